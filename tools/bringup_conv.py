@@ -1,0 +1,175 @@
+"""GPU bring-up for K1 (tcgen05 implicit-GEMM conv): numerics vs torch fp32 conv on the same bf16-rounded
+operands, then a timing sweep of the dominant shapes.  Run on a B200 via gpurun:
+    python tools/bringup_conv.py [--time]
+"""
+import ctypes
+import json
+import sys
+import time
+from pathlib import Path
+
+import torch
+import torch.nn.functional as F
+
+ROOT = Path(__file__).resolve().parents[1]
+lib = ctypes.CDLL(str(ROOT / "climate2weather_b200" / "libc2w_b200.so"))
+lib.c2w_op_conv.restype = ctypes.c_int
+lib.c2w_op_conv.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                            ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                            ctypes.c_void_p]
+try:
+    lib.c2w_last_error.restype = ctypes.c_char_p
+except AttributeError:
+    pass
+
+dev = torch.device("cuda:0")
+
+
+def pack_w(w, cin_pad, cout_pad):
+    cout, cin, kh, kw = w.shape
+    wp = torch.zeros(cout_pad, kh, kw, cin_pad, device=w.device, dtype=torch.float32)
+    wp[:cout, :, :, :cin] = w.permute(0, 2, 3, 1)
+    return wp.reshape(cout_pad, kh * kw * cin_pad).to(torch.bfloat16).contiguous()
+
+
+def run_conv(x_nhwc, wp, bias, mode, res=None, conv3x3=True, f32=False, bn=0, max_ctas=0):
+    n, H, W, cin = x_nhwc.shape
+    cout_pad = wp.shape[0]
+    M = n * H * W
+    out = torch.empty(M, cout_pad, device=dev, dtype=torch.bfloat16) if not f32 else None
+    out32 = torch.empty(M, cout_pad, device=dev, dtype=torch.float32) if f32 else None
+    if mode == 2 and res is not None:
+        out.copy_(res)  # in-place residual
+    rc = lib.c2w_op_conv(x_nhwc.data_ptr(), n, H, W, cin, wp.data_ptr(), cout_pad, bias.data_ptr(), mode,
+                         out.data_ptr() if (mode == 2) else None, out.data_ptr() if out is not None else None,
+                         out32.data_ptr() if f32 else None, 1 if conv3x3 else 0, bn, max_ctas,
+                         torch.cuda.current_stream().cuda_stream)
+    if rc != 0:
+        raise RuntimeError(f"c2w_op_conv rc={rc}")
+    torch.cuda.synchronize()
+    return out32 if f32 else out
+
+
+def check(name, n, H, W, cin, cout, mode, seed=0, **kw):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    cin_pad = (cin + 63) // 64 * 64
+    cout_pad = (cout + 63) // 64 * 64
+    x = torch.randn(n, cin, H, W, generator=g).to(dev)
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)).to(dev)
+    b = torch.randn(cout, generator=g).to(dev)
+    xb = torch.zeros(n, H, W, cin_pad, device=dev, dtype=torch.bfloat16)
+    xb[..., :cin] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+    wp = pack_w(w, cin_pad, cout_pad)
+    bp = torch.zeros(cout_pad, device=dev)
+    bp[:cout] = b
+    res = None
+    if mode == 2:
+        res = torch.randn(n * H * W, cout_pad, generator=g).to(dev).to(torch.bfloat16)
+    got = run_conv(xb, wp, bp, 4 if mode == 4 else mode, res=res, f32=(mode == 4), **kw).float()
+    # reference on the same rounded operands, fp32 math
+    xr = xb[..., :cin].float().permute(0, 3, 1, 2)
+    wr = w.to(torch.bfloat16).float()
+    ref = F.conv2d(xr, wr, b, padding=1)
+    if mode == 1:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 3, 1).reshape(n * H * W, cout)
+    if mode == 2:
+        ref = ref + res[:, :cout].float()
+    err = (got[:, :cout] - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    tol = 2e-2 * scale if mode != 4 else 2e-3 * scale
+    ok = err <= tol and torch.isfinite(got).all().item()
+    print(f"{'PASS' if ok else 'FAIL'} {name}: n={n} {H}x{W} {cin}->{cout} mode={mode} max_err={err:.3e} "
+          f"ref_max={scale:.3e}", flush=True)
+    return ok
+
+
+def check_gemm(name, M, K, N, seed=1):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    a = torch.randn(M, K, generator=g).to(dev).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev).to(torch.bfloat16)
+    b = torch.randn(N, generator=g).to(dev)
+    got = run_conv(a.reshape(1, 1, M, K), w, b, 4, conv3x3=False, f32=True)
+    ref = a.float() @ w.float().t() + b
+    err = (got - ref).abs().max().item()
+    ok = err <= 2e-3 * ref.abs().max().item()
+    print(f"{'PASS' if ok else 'FAIL'} {name}: gemm M={M} K={K} N={N} max_err={err:.3e}", flush=True)
+    return ok
+
+
+def timeit(name, n, H, W, cin, cout, iters=20, **kw):
+    cin_pad = (cin + 63) // 64 * 64
+    cout_pad = (cout + 63) // 64 * 64
+    xb = torch.randn(n, H, W, cin_pad, device=dev).to(torch.bfloat16)
+    wp = (torch.randn(cout_pad, 9 * cin_pad, device=dev) / 30).to(torch.bfloat16)
+    bp = torch.zeros(cout_pad, device=dev)
+    out = torch.empty(n * H * W, cout_pad, device=dev, dtype=torch.bfloat16)
+    st = torch.cuda.current_stream().cuda_stream
+    bn = kw.get("bn", 0)
+
+    def call():
+        rc = lib.c2w_op_conv(xb.data_ptr(), n, H, W, cin_pad, wp.data_ptr(), cout_pad, bp.data_ptr(), 1, None,
+                             out.data_ptr(), None, 1, bn, 0, st)
+        assert rc == 0
+
+    for _ in range(3):
+        call()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    flops = 2.0 * n * H * W * cout_pad * 9 * cin_pad
+    tf = flops / ms / 1e9
+    # cuDNN bf16 channels_last for comparison (library bar)
+    xc = xb.permute(0, 3, 1, 2)  # NCHW view of NHWC memory == channels_last
+    wc = wp.reshape(cout_pad, 3, 3, cin_pad).permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
+    for _ in range(3):
+        F.conv2d(xc, wc, None, padding=1)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        F.conv2d(xc, wc, None, padding=1)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_dnn = e0.elapsed_time(e1) / iters
+    print(json.dumps({"shape": name, "n": n, "H": H, "W": W, "cin": cin, "cout": cout, "ms": round(ms, 4),
+                      "tflops": round(tf, 1), "cudnn_ms": round(ms_dnn, 4),
+                      "cudnn_tflops": round(flops / ms_dnn / 1e9, 1)}), flush=True)
+
+
+def main():
+    print(torch.cuda.get_device_name(0), flush=True)
+    ok = True
+    ok &= check_gemm("gemm-basic", 256, 128, 128)
+    ok &= check_gemm("gemm-k512-n256", 384, 512, 256)
+    ok &= check_gemm("gemm-m64", 64, 512, 1536)
+    ok &= check("conv-w128-c64", 1, 128, 128, 64, 128, 0)
+    ok &= check("conv-G2", 2, 128, 128, 128, 128, 1)
+    ok &= check("conv-G2-res", 2, 128, 128, 128, 128, 2)
+    ok &= check("conv-G1(52)", 2, 128, 128, 52, 128, 0)
+    ok &= check("conv-G3(->52) f32", 2, 128, 128, 128, 52, 4)
+    ok &= check("conv-w64", 3, 64, 64, 128, 128, 1)
+    ok &= check("conv-w32-256", 3, 32, 32, 256, 256, 2)
+    ok &= check("conv-w16-384", 3, 16, 16, 384, 384, 1)
+    ok &= check("conv-w8-512", 3, 8, 8, 512, 512, 2)
+    ok &= check("conv-w16-512->384", 2, 16, 16, 512, 384, 0)
+    ok &= check("conv-G2-bn64", 2, 128, 128, 128, 128, 1, bn=64)
+    ok &= check("conv-G2-few-ctas", 4, 128, 128, 128, 128, 1, max_ctas=7)
+    print("ALL PASS" if ok else "SOME FAILED", flush=True)
+    if "--time" in sys.argv:
+        timeit("G2", 32, 128, 128, 128, 128)
+        timeit("G2-bn64", 32, 128, 128, 128, 128, bn=64)
+        timeit("G5", 64, 64, 64, 128, 128)
+        timeit("G8", 64, 32, 32, 256, 256)
+        timeit("G11", 128, 16, 16, 384, 384)
+        timeit("G14", 156, 8, 8, 512, 512)
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
