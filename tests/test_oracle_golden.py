@@ -1,0 +1,137 @@
+"""Pins the CPU oracle (oracle/) against outputs of the reference's own code (tests/golden/*.npz,
+written by tests/golden/make_golden.py from /root/reference).  Integer/index work: bit-exact.
+Floating point: same ATen kernels on a possibly different host CPU -> rel 2e-5 of the tensor scale."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pipeline_ref, score_ref, unet_ref
+
+SMALL = dict(channels=20, embedding_dim=64, hidden_channels=(64, 128), hidden_blocks=(1, 2), attention_levels=(1,),
+             kernel_size=3)
+STD = [0.1692666615037876, 0.0425178630338289, 0.3268027589410125, 0.3268027589410125]
+GAMMA = 0.0007196856730011522
+
+
+def close(a, b, rel=2e-5):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() <= rel * max(np.abs(b).max(), 1e-30)
+
+
+def test_full_arch_names_shapes_and_init(golden_dir):
+    g = np.load(golden_dir / "full_arch.npz")
+    sd = unet_ref.init_state_dict(unet_ref.SDA_UNET, seed=0)
+    assert len(sd) == 228 and sum(v.numel() for v in sd.values()) == 72102964
+    assert set(sd) == set(g["names"].tolist())
+    for name, shape, s, a in zip(g["names"], g["shapes"], g["sums"], g["asums"]):
+        v = sd[str(name)]
+        assert ",".join(map(str, v.shape)) == str(shape), name
+        assert abs(v.double().sum().item() - s) <= 1e-9 * max(1.0, abs(a)), name
+        assert abs(v.double().abs().sum().item() - a) <= 1e-9 * max(1.0, abs(a)), name
+
+
+def test_full_arch_forward(golden_dir):
+    g = np.load(golden_dir / "full_arch.npz")
+    sd = unet_ref.init_state_dict(unet_ref.SDA_UNET, seed=0)
+    x = torch.randn(1, 52, 128, 128, generator=torch.Generator().manual_seed(int(g["x_seed"])))
+    with torch.no_grad():
+        y = unet_ref.score_unet_forward(sd, unet_ref.SDA_UNET, x, torch.tensor(float(g["t"])))
+    assert close(y[0, :, ::8, ::8].numpy(), g["out_slice"])
+    assert abs(y.double().std().item() - float(g["out_std"])) < 1e-5
+
+
+@pytest.fixture(scope="module")
+def small(golden_dir):
+    g = np.load(golden_dir / "small_path.npz")
+    sd = unet_ref.init_state_dict(SMALL, seed=3)
+    for name, s, a in zip(g["names"], g["sums"], g["asums"]):
+        assert abs(sd[str(name)].double().sum().item() - s) <= 1e-9 * max(1.0, abs(a)), name
+    return g, unet_ref.RefNet(sd, SMALL)
+
+
+def test_small_window_scores(small):
+    g, net = small
+    x, t = torch.from_numpy(g["x"]), torch.tensor(float(g["t"]))
+    with torch.no_grad():
+        e = score_ref.window_score(net, x, t, k=2)
+        assert close(e.numpy(), g["eps_default"])
+        for bs in (2, 3, 5):
+            eb = score_ref.window_score(net, x, t, k=2, batch_size=bs)
+            assert close(eb.numpy(), g[f"eps_batched_{bs}"])
+            # Default == Batched
+            assert close(eb.numpy(), e.numpy(), rel=1e-5)
+
+
+def test_small_guided_scores(small):
+    g, net = small
+    x, t = torch.from_numpy(g["x"]), torch.tensor(float(g["t"]))
+    y = torch.from_numpy(g["yobs"])
+    std = torch.tensor(STD).reshape(1, 4, 1, 1)
+    for exact, key in ((False, "eps_guided_approx"), (True, "eps_guided_exact")):
+        e = score_ref.guided_score(net, x, t, 2, y, std, GAMMA, t_step=3, s_step=8, exact_grad=exact)
+        assert close(e.numpy(), g[key], rel=5e-5), key
+    with torch.no_grad():
+        eps = score_ref.window_score(net, x, t, k=2)
+    cf = score_ref.guided_score_closed_form(eps, x, t, y, std, GAMMA, 3, 8)
+    assert close(cf.numpy(), g["eps_guided_approx"], rel=5e-5)
+    assert not close(g["eps_guided_exact"], g["eps_guided_approx"], rel=1e-3)
+
+
+def test_small_schedule(small):
+    g, _ = small
+    p = pipeline_ref.RefPipeline()
+    ts = torch.from_numpy(g["ts"])
+    assert close(p.mu(ts).numpy(), g["mu"], rel=1e-6) and close(p.sigma(ts).numpy(), g["sigma"], rel=1e-6)
+    assert abs(p.mu(torch.tensor(1.0)).item() - 1e-3) < 1e-6 and abs(p.sigma(torch.tensor(0.0)).item() - 1e-3) < 1e-6
+
+
+def test_small_sampler(small):
+    g, net = small
+    x = torch.from_numpy(g["x"])
+    y = torch.from_numpy(g["yobs"])
+    std = torch.tensor(STD).reshape(1, 4, 1, 1)
+    p = pipeline_ref.RefPipeline()
+
+    def guided(xx, tt):
+        with torch.no_grad():
+            eps = score_ref.window_score(net, xx, tt, k=2, batch_size=4)
+        return score_ref.guided_score_closed_form(eps, xx, tt, y, std, GAMMA, 3, 8)
+
+    torch.manual_seed(5)
+    s1 = p.sample(guided, x, steps=3, corrections=1, tau=0.5)
+    assert close(s1.numpy(), g["sample_c1"], rel=2e-4)
+    s0 = p.sample(guided, x, steps=4, corrections=0, tau=0.5)
+    assert close(s0.numpy(), g["sample_c0"], rel=2e-4)
+    with torch.no_grad():
+        s2 = p.sample(lambda xx, tt: score_ref.window_score(net, xx, tt, k=2), x[:5], steps=3)
+    assert close(s2.numpy(), g["sample_one_window"], rel=2e-4)
+
+
+def test_small_loss(small):
+    g, net = small
+    p = pipeline_ref.RefPipeline()
+    xw = torch.from_numpy(g["loss_x"])
+    torch.manual_seed(7)
+    with torch.no_grad():
+        l = p.loss(net, xw)
+    assert close(l.numpy(), g["loss"], rel=5e-5)
+
+
+@pytest.mark.parametrize("L,k,C", [(13, 6, 4), (14, 6, 4), (26, 6, 4), (40, 6, 4), (5, 2, 4), (9, 2, 3), (7, 1, 1)])
+def test_index_maps_bit_exact(golden_dir, L, k, C):
+    g = np.load(golden_dir / "index_maps.npz")
+    u = score_ref.unfold_index(L, k, C)
+    code = u[..., 0] * 1000 + u[..., 1] * 10
+    ref = g[f"unfold_{L}_{k}_{C}"]  # [Nw, wC, 2, 2] with + 2*h + w added
+    assert np.array_equal(code, ref[:, :, 0, 0])
+    f = score_ref.fold_index(L, k, C)
+    assert np.array_equal(f[..., 0] * 1000 + f[..., 1], g[f"fold_{L}_{k}_{C}"][:, :, 0, 0])
+    # batched compose: apply the plan to the unfolded integer code with an identity network
+    for bs in (1, 2, 3, 16):
+        rows = []
+        for s, n, items in score_ref.batched_fold_plan(L, k, bs):
+            for win, slot in items:
+                rows.append(code[win, slot * C:(slot + 1) * C])
+        assert np.array_equal(np.stack(rows), g[f"batched_{L}_{k}_{C}_{bs}"][:, :, 0, 0])
+        # fold(unfold(x)) == x  
+        assert np.array_equal(np.stack(rows)[:, :] // 1000, np.arange(L)[:, None].repeat(C, 1))
