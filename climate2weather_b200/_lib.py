@@ -1,0 +1,108 @@
+"""ctypes binding of libc2w_b200.so (include/c2w_b200.h).  There is no CPU fallback: if the CUDA library is
+missing or a call fails, this raises."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "libc2w_b200.so"
+MAX_LEVELS = 8
+
+
+class C2WError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("frame_channels", C.c_int32),
+        ("window", C.c_int32),
+        ("height", C.c_int32),
+        ("width", C.c_int32),
+        ("embedding_dim", C.c_int32),
+        ("noise_features", C.c_int32),
+        ("n_levels", C.c_int32),
+        ("hidden_channels", C.c_int32 * MAX_LEVELS),
+        ("hidden_blocks", C.c_int32 * MAX_LEVELS),
+        ("attention_mask", C.c_int32),
+    ]
+
+
+class Guide(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("eps", C.c_void_p),
+        ("eps_out", C.c_void_p),
+        ("y", C.c_void_p),
+        ("std2", C.c_float * 4),
+        ("gamma", C.c_float * 4),
+        ("mu", C.c_float),
+        ("sigma", C.c_float),
+        ("mu_next", C.c_float),
+        ("sigma_next", C.c_float),
+        ("t_step", C.c_int32),
+        ("s_step", C.c_int32),
+        ("H", C.c_int32),
+        ("W", C.c_int32),
+        ("frame_global0", C.c_int32),
+        ("own_lo", C.c_int32),
+        ("own_n", C.c_int32),
+        ("mode", C.c_int32),
+        ("partials", C.c_void_p),
+        ("nan_flag", C.c_void_p),
+    ]
+
+
+_vp, _i, _i64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
+
+# name -> (restype, argtypes); every symbol include/c2w_b200.h declares
+SIGNATURES = {
+    "c2w_create": (_i, [C.POINTER(Config), C.POINTER(_vp)]),
+    "c2w_destroy": (None, [_vp]),
+    "c2w_last_error": (C.c_char_p, []),
+    "c2w_abi_version": (_i, []),
+    "c2w_load_weight": (_i, [_vp, C.c_char_p, _vp, _i64]),
+    "c2w_finalize_weights": (_i, [_vp]),
+    "c2w_workspace_bytes": (_i64, [_vp, C.c_int32]),
+    "c2w_bind_workspace": (_i, [_vp, C.c_int32, _vp, _i64]),
+    "c2w_unet_forward": (_i, [_vp, _vp, C.c_int32, _f, _vp, _vp]),
+    "c2w_window_score": (_i, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f, _vp, _vp]),
+    "c2w_traj_pack": (_i, [_vp, _vp, _i64, C.c_int32, C.c_int32, _vp]),
+    "c2w_traj_unpack": (_i, [_vp, _vp, _i64, C.c_int32, C.c_int32, _vp]),
+    "c2w_guided_step": (_i, [C.POINTER(Guide), _vp]),
+    "c2w_reduce_partials": (_i, [_vp, C.c_int32, _vp, _vp]),
+    "c2w_corrector_update": (_i, [_vp, _vp, _vp, _vp, _d, _f, _f, _i64, _i64, C.c_uint64, C.c_uint32, _vp, _vp]),
+    "c2w_op_conv": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "c2w_op_layernorm": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "c2w_op_attention": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "c2w_op_im2col_s2": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "c2w_op_gather_windows": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "c2w_op_modulation": (_i, [_vp, _f, _vp, _vp, _vp]),
+    "c2w_total_mod_channels": (_i, [_vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (once).  Raises C2WError with the build recipe if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise C2WError(
+            f"{LIB_PATH} not found: the CUDA extension is required (no CPU fallback). Build it with "
+            "`python -m climate2weather_b200.build` or `python -c 'import __graft_entry__ as g; g.build()'`.")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().c2w_last_error()
+        raise C2WError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")

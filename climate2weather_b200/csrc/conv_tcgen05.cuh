@@ -54,6 +54,7 @@ struct ConvParams {
   int win_first;    // global index of the first window of this launch
   int win_last_global;  // global index of the last window of the trajectory (Nw - 1)
   int frame_base;   // global frame index of eps[0]
+  int dbg_skip_loads;  // diagnostics only: after the ring is primed, signal `full` without issuing TMA loads
 };
 
 constexpr int kBlockM = 128;
@@ -124,6 +125,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int issued = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int nt = tile % p.num_n_tiles;
         const int mt = tile / p.num_n_tiles;
@@ -143,9 +145,14 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           const int ds = (p.taps == 9) ? tap % 3 - 1 : 0;
           for (int cb = 0; cb < p.cin_blocks; ++cb, ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-            tma_load_4d(&tmA, &full[stage], smA + stage * kATileBytes, cb * kBlockK, b1 + ds, b2 + dr, b3);
-            tma_load_2d(&tmB, &full[stage], smB + stage * Cfg::kBTileBytes, kb * kBlockK, nt * BN);
+            if (p.dbg_skip_loads && issued >= Cfg::kStages) {
+              mbar_arrive(&full[stage]);
+            } else {
+              mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+              tma_load_4d(&tmA, &full[stage], smA + stage * kATileBytes, cb * kBlockK, b1 + ds, b2 + dr, b3);
+              tma_load_2d(&tmB, &full[stage], smB + stage * Cfg::kBTileBytes, kb * kBlockK, nt * BN);
+            }
+            ++issued;
             if (++stage == Cfg::kStages) {
               stage = 0;
               phase ^= 1;
@@ -224,7 +231,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const int win = p.win_first + n_img;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-              const int tau = (c >> 2) + g;  // window slot of channels [4*tau, 4*tau+4)
+              const int tau = (col0 >> 2) + g;  // window slot of channels [4*tau, 4*tau+4)
               const bool take = (tau == p.order_k) || (win == 0 && tau < p.order_k) ||
                                 (win == p.win_last_global && tau > p.order_k && tau <= 2 * p.order_k);
               if (take) {

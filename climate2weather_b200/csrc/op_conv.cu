@@ -1,5 +1,6 @@
 // Op-level C-ABI entry for K1 (used by the parity tests and by tools/; the engine calls
 // conv_launch_init/conv_launch directly with prebuilt tensor maps).
+#include "c2w_b200.h"
 #include "common.cuh"
 #include "conv_tcgen05.cuh"
 
@@ -29,6 +30,8 @@ int c2w_op_conv(const void* x, int n_img, int H, int W, int cin, const void* w_p
               "c2w_op_conv: unsupported mode %d", mode);
   const int sms = c2w_num_sms();
   C2W_REQUIRE(sms > 0, "c2w_op_conv: no CUDA device");
+  const int dbg = bn >> 12;  // diagnostics: bit 12 of `bn` = skip TMA loads once the ring is primed
+  bn &= 0xfff;
   if (bn == 0) bn = conv_pick_bn(cout_pad);
   ConvLaunch L;
   if (!conv_launch_init(&L, conv3x3 != 0, static_cast<const __nv_bfloat16*>(x), n_img, H, W, cin,
@@ -40,6 +43,7 @@ int c2w_op_conv(const void* x, int n_img, int H, int W, int cin, const void* w_p
   L.p.res = static_cast<const __nv_bfloat16*>(res);
   L.p.out = static_cast<__nv_bfloat16*>(out);
   L.p.out_f32 = out_f32;
+  L.p.dbg_skip_loads = dbg & 1;
   C2W_CUDA(conv_launch(L, static_cast<cudaStream_t>(stream)));
   return C2W_OK;
 }

@@ -1,0 +1,260 @@
+"""Host-side mirror of `model.score.ScoreUNet` (reference model/score.py:37-70, model/nn.py:88-242).
+
+Same constructor signature, same parameter names / shapes / initialisation order as the reference module, so
+reference state_dicts and pickled snapshots load unchanged; the arithmetic is done by the CUDA library
+(climate2weather_b200/csrc via include/c2w_b200.h).  There is no torch-op forward and no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib
+
+NOISE_FEATURES = 32  # model/score.py:53
+
+
+def _layer_specs(channels: int, embedding_dim: int, hidden_channels: Sequence[int], hidden_blocks: Sequence[int],
+                 attention_levels: Sequence[int], ks: int) -> List[Tuple[str, Tuple[int, ...]]]:
+    """state_dict prefixes and weight shapes in the reference's construction order (model/nn.py:165-218;
+    `tails` / `ascent` are stored reversed, :216,218), followed by the time MLP (model/score.py:56-57)."""
+    nl = len(hidden_blocks)
+    ch = list(hidden_channels)
+    specs: List[Tuple[str, Tuple[int, ...]]] = []
+    for lvl in range(nl):
+        rev = nl - 1 - lvl
+        if lvl == 0:
+            specs.append(("unet.heads.0", (ch[0], channels, ks, ks)))
+            specs.append((f"unet.tails.{rev}", (channels, ch[0], ks, ks)))
+        else:
+            specs.append((f"unet.heads.{lvl}.0", (ch[lvl], ch[lvl - 1], ks, ks)))
+            specs.append((f"unet.tails.{rev}.2", (ch[lvl - 1], ch[lvl], ks, ks)))
+        has_attn = lvl in attention_levels
+        step = 2 if has_attn else 1
+        for b in range(hidden_blocks[lvl]):
+            sides = (("descent", lvl), ("ascent", rev))
+            for side, idx in sides:
+                p = f"unet.{side}.{idx}.{b * step}"
+                specs.append((p + ".project.0", (ch[lvl], embedding_dim)))
+                specs.append((p + ".residue.1", (ch[lvl], ch[lvl], ks, ks)))
+                specs.append((p + ".residue.3", (ch[lvl], ch[lvl], ks, ks)))
+            if has_attn:
+                for side, idx in sides:
+                    p = f"unet.{side}.{idx}.{b * step + 1}"
+                    specs.append((p + ".qkv", (3 * ch[lvl], ch[lvl], 1)))
+                    specs.append((p + ".proj_out", (ch[lvl], ch[lvl], 1)))
+    specs.append(("map_layer0", (embedding_dim, NOISE_FEATURES)))
+    specs.append(("map_layer1", (embedding_dim, embedding_dim)))
+    return specs
+
+
+class _Node(nn.Module):
+    """Anonymous container: gives parameters the dotted names of the reference module tree."""
+
+
+def _register(root: nn.Module, dotted: str, param: nn.Parameter) -> None:
+    parts = dotted.split(".")
+    node = root
+    for part in parts[:-1]:
+        if part not in node._modules:
+            node.add_module(part, _Node())
+        node = node._modules[part]
+    node.register_parameter(parts[-1], param)
+
+
+class Engine:
+    """One c2w handle: packed weights + workspace for a fixed (frame_channels, window, H, W)."""
+
+    def __init__(self, net: "ScoreUNet", frame_channels: int, window: int, height: int, width: int,
+                 device: torch.device, max_windows: int):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.C2WError("climate2weather_b200 runs on CUDA devices only (no CPU path)")
+        cfg = _lib.Config()
+        cfg.frame_channels, cfg.window, cfg.height, cfg.width = frame_channels, window, height, width
+        cfg.embedding_dim, cfg.noise_features = net.embedding_dim, NOISE_FEATURES
+        cfg.n_levels = len(net.hidden_blocks)
+        if cfg.n_levels > _lib.MAX_LEVELS:
+            raise _lib.C2WError("too many UNet levels")
+        for i, (c, b) in enumerate(zip(net.hidden_channels, net.hidden_blocks)):
+            cfg.hidden_channels[i], cfg.hidden_blocks[i] = c, b
+        cfg.attention_mask = sum(1 << l for l in net.attention_levels)
+        self.frame_channels, self.window, self.height, self.width = frame_channels, window, height, width
+        self.handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.c2w_create(ctypes.byref(cfg), ctypes.byref(self.handle)), "c2w_create")
+            for name, p in net.state_dict().items():
+                w = p.detach().to(device="cpu", dtype=torch.float32).contiguous()
+                _lib.check(self.lib.c2w_load_weight(self.handle, name.encode(), w.data_ptr(), w.numel()),
+                           f"c2w_load_weight({name})")
+            _lib.check(self.lib.c2w_finalize_weights(self.handle), "c2w_finalize_weights")
+            self.max_windows = 0
+            self.workspace = None
+            self.bind(max_windows)
+
+    def bind(self, max_windows: int) -> None:
+        with torch.cuda.device(self.device):
+            nbytes = self.lib.c2w_workspace_bytes(self.handle, max_windows)
+            if nbytes < 0:
+                _lib.check(-1, "c2w_workspace_bytes")
+            self.workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
+            _lib.check(self.lib.c2w_bind_workspace(self.handle, max_windows, self.workspace.data_ptr(),
+                                                   self.workspace.numel()), "c2w_bind_workspace")
+            self.max_windows = max_windows
+
+    @property
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def unet_forward(self, x: Tensor, t: float) -> Tensor:
+        """x: fp32 NCHW [n, C*window, H, W] on self.device."""
+        out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.c2w_unet_forward(self.handle, x.data_ptr(), x.shape[0], float(t), out.data_ptr(),
+                                                 self.stream), "c2w_unet_forward")
+        return out
+
+    def window_score(self, traj: Tensor, frame_global0: int, win_first: int, n_win: int, n_win_global: int, t: float,
+                     eps: Tensor) -> None:
+        """traj / eps: fp32 [frames_local, H, W, C] device layout."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.c2w_window_score(self.handle, traj.data_ptr(), traj.shape[0], frame_global0, win_first,
+                                                 n_win, n_win_global, float(t), eps.data_ptr(), self.stream),
+                       "c2w_window_score")
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and self.handle.value:
+                self.lib.c2w_destroy(self.handle)
+                self.handle = ctypes.c_void_p()
+        except Exception:
+            pass
+
+
+class ScoreUNet(nn.Module):
+    r"""Drop-in for `model.score.ScoreUNet(channels, embedding_dim, forcing_dim=0, **unet_kwargs)`.
+
+    Arguments mirror model/score.py:46 and model/nn.py:108-121.  Supported: kernel_size=3, stride=2, spatial=2,
+    SiLU activation, zero padding, forcing_dim=0 — i.e. configs/sda_unet.yml with train.py:164-173 — with any
+    hidden_channels (multiples of 64, <= 512), hidden_blocks and attention_levels.
+    """
+
+    DEFAULT_MAX_WINDOWS = 16
+
+    def __init__(self, channels: int, embedding_dim: int, forcing_dim: int = 0,
+                 hidden_channels: Sequence[int] = (32, 64, 128), hidden_blocks: Sequence[int] = (2, 3, 5),
+                 attention_levels: Sequence[int] = (), kernel_size=3, stride=2, activation=nn.SiLU, spatial: int = 2,
+                 padding_mode: str = "zeros", **kwargs):
+        super().__init__()
+        ks = kernel_size if isinstance(kernel_size, int) else kernel_size[0]
+        st = stride if isinstance(stride, int) else stride[0]
+        unsupported = []
+        if forcing_dim != 0:
+            unsupported.append("forcing_dim != 0")
+        if ks != 3 or st != 2 or spatial != 2:
+            unsupported.append("kernel_size/stride/spatial other than 3/2/2")
+        if padding_mode != "zeros":
+            unsupported.append(f"padding_mode={padding_mode!r}")
+        if activation is not nn.SiLU and not isinstance(activation, nn.SiLU):
+            unsupported.append("activation other than SiLU")
+        if kwargs:
+            unsupported.append(f"extra conv kwargs {sorted(kwargs)}")
+        if unsupported:
+            raise NotImplementedError("climate2weather_b200.ScoreUNet: " + "; ".join(unsupported))
+        self.channels = int(channels)
+        self.embedding_dim = int(embedding_dim)
+        self.noise_features = NOISE_FEATURES
+        self.hidden_channels = [int(c) for c in hidden_channels]
+        self.hidden_blocks = [int(b) for b in hidden_blocks]
+        self.attention_levels = sorted(int(a) for a in attention_levels)
+        self.map_forcing = None
+        # Parameters are created by torch's own Conv/Linear initialisers in the reference's construction order, so
+        # `torch.manual_seed(s); ScoreUNet(...)` yields the same weights as the reference module.
+        for prefix, shape in _layer_specs(self.channels, self.embedding_dim, self.hidden_channels, self.hidden_blocks,
+                                          self.attention_levels, ks):
+            w = torch.empty(shape)
+            nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+            bound = 1.0 / math.sqrt(w[0].numel())
+            b = torch.empty(shape[0]).uniform_(-bound, bound)
+            _register(self, prefix + ".weight", nn.Parameter(w))
+            _register(self, prefix + ".bias", nn.Parameter(b))
+        self._engines: Dict[tuple, Engine] = {}
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_engines"] = {}  # device handles are rebuilt lazily after unpickling / deepcopy
+        return state
+
+    # ---------------------------------------------------------------------------------------------- engines
+    def _fingerprint(self) -> tuple:
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def engine(self, frame_channels: int, window: int, height: int, width: int, device, max_windows: Optional[int] = None
+               ) -> Engine:
+        """Packed-weight engine for this geometry; rebuilt if the parameters changed since it was packed."""
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        if frame_channels * window != self.channels:
+            raise ValueError(f"frame_channels*window = {frame_channels * window} != channels = {self.channels}")
+        key = (frame_channels, window, height, width, str(device))
+        fp = self._fingerprint()
+        hit = self._engines.get(key)
+        want = max_windows or self.DEFAULT_MAX_WINDOWS
+        if hit is not None and hit[1] == fp:
+            eng = hit[0]
+            if max_windows is not None and eng.max_windows != max_windows:
+                eng.bind(max_windows)
+            return eng
+        eng = Engine(self, frame_channels, window, height, width, device, want)
+        self._engines[key] = (eng, fp)
+        return eng
+
+    def from_reference(self, module: nn.Module) -> "ScoreUNet":
+        """Copies the weights of a reference `model.score.ScoreUNet` (any dtype; snapshots are fp16)."""
+        self.load_state_dict({k: v.float() for k, v in module.state_dict().items()})
+        return self
+
+    # ---------------------------------------------------------------------------------------------- forward
+    def forward(self, x: Tensor, t: Tensor, forcing: Optional[Tensor] = None) -> Tensor:
+        """model/score.py:59-70.  x: [B, channels, H, W] on a CUDA device; t: one diffusion time for the batch."""
+        if forcing is not None:
+            raise NotImplementedError("forcing is not supported (forcing_dim=0 in every reference config)")
+        if not x.is_cuda:
+            raise _lib.C2WError("ScoreUNet.forward: input must live on a CUDA device (no CPU path); "
+                                "BatchedScoreFunction moves window batches for you")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            if x.requires_grad:
+                raise NotImplementedError("ScoreUNet VJP (exact_grad=True / training) is not built yet")
+        tt = torch.as_tensor(t).reshape(-1).float()
+        if tt.numel() != 1 and not bool((tt == tt[0]).all()):
+            raise NotImplementedError("per-sample diffusion times are not built yet (sampling uses one t per call)")
+        B, Cc, H, W = x.shape
+        eng = self.engine(Cc, 1, H, W, x.device)
+        out = eng.unet_forward(x.detach().float().contiguous(), float(tt[0]))
+        return out.to(x.dtype).reshape(x.shape)
+
+
+def build_from_reference(module: nn.Module) -> ScoreUNet:
+    """New ScoreUNet with the architecture and weights of a reference `model.score.ScoreUNet` instance."""
+    sd = module.state_dict()
+    nl = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("unet.heads."))
+    ch, blocks, attn = [], [], []
+    for lvl in range(nl):
+        wkey = "unet.heads.0.weight" if lvl == 0 else f"unet.heads.{lvl}.0.weight"
+        ch.append(sd[wkey].shape[0])
+        idxs = sorted({int(k.split(".")[3]) for k in sd if k.startswith(f"unet.descent.{lvl}.")})
+        has_attn = any(k.startswith(f"unet.descent.{lvl}.") and ".qkv." in k for k in sd)
+        if has_attn:
+            attn.append(lvl)
+            blocks.append(len(idxs) // 2)
+        else:
+            blocks.append(len(idxs))
+    net = ScoreUNet(channels=sd["unet.heads.0.weight"].shape[1], embedding_dim=sd["map_layer1.weight"].shape[0],
+                    hidden_channels=ch, hidden_blocks=blocks, attention_levels=attn)
+    return net.from_reference(module)

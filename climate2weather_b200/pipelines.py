@@ -1,0 +1,146 @@
+"""Host-side mirror of `thor.pipelines.SDAPipeline` (reference src/thor/pipelines.py:8-97): cosine VP schedule,
+DSM loss, predictor-corrector sampler — same method names and signatures.
+
+`sample()` with one of this package's score functions runs device-resident: the trajectory never leaves HBM
+between steps, each step is  window score (K0/K1/K2/K4/K5)  ->  fused guidance + predictor (K6)  [-> corrector
+(K7)]  [-> halo exchange when time-sharded].  The reference keeps x on the CPU and round-trips every window batch
+(src/thor/score.py:170-181).
+"""
+from __future__ import annotations
+
+import math
+import time
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from .score import AbstractScoreFunction, _mu_sigma
+from .sharding import all_gather_frames
+
+
+class SDAPipeline:
+    #: corrector noise: "device" = on-chip Philox keyed by the global pixel index (default, sharding-invariant);
+    #: "reference" = z.normal_() from the global CPU generator exactly like src/thor/pipelines.py:82 (parity runs).
+    rng: str = "device"
+    #: check the device NaN flag every this many steps (0 = only at the end); the reference syncs every step (:90)
+    nan_check_every: int = 0
+
+    def __init__(self, eta=1e-3):
+        self.eta = eta  # src/thor/pipelines.py:9-11
+
+    # ---------------------------------------------------------------- schedule (src/thor/pipelines.py:13-20)
+    def alpha(self, t):
+        return torch.cos(math.acos(math.sqrt(self.eta)) * t) ** 2
+
+    def mu(self, t):
+        return self.alpha(t)
+
+    def sigma(self, t):
+        return (1 - self.alpha(t) ** 2 + self.eta ** 2).sqrt()
+
+    # ---------------------------------------------------------------- training objective (:22-35)
+    def forward(self, x, t):
+        eps = torch.randn_like(x)
+        return self.mu(t) * x + self.sigma(t) * eps, eps
+
+    def loss(self, net, x, forcing=None):
+        t = torch.rand(x.shape[0], 1, 1, 1, dtype=x.dtype, device=x.device)
+        xt, eps = self.forward(x, t)
+        return (net(xt, t, forcing=forcing) - eps) ** 2
+
+    def pred_eps(self, score_fn, x, t):
+        return score_fn(x, t)
+
+    def _sample_step(self, score_fn, x, t, dt, proc_x0=None):
+        """:41-46 (generic form, used only for foreign score functions)."""
+        eps_pred = self.pred_eps(score_fn, x, t)
+        pred_x0 = (x - self.sigma(t) * eps_pred) / self.mu(t)
+        if proc_x0 is not None:
+            pred_x0 = proc_x0(pred_x0)
+        return self.mu(t - dt) * pred_x0 + self.sigma(t - dt) * eps_pred
+
+    # ---------------------------------------------------------------- sampler (:48-97)
+    def sample(self, score_fn, noise, steps: int = 64, corrections: int = 0, tau: float = 1.0, proc_x0=None,
+               device=None, show_progressbar=True, seed: Optional[int] = None):
+        if isinstance(score_fn, AbstractScoreFunction) and proc_x0 is None:
+            return self._sample_resident(score_fn, noise, steps, corrections, tau, device, show_progressbar, seed)
+        return self._sample_generic(score_fn, noise, steps, corrections, tau, proc_x0, device, show_progressbar)
+
+    def _sample_resident(self, sf: AbstractScoreFunction, noise: Tensor, steps: int, corrections: int, tau: float,
+                         device, show_progressbar: bool, seed: Optional[int]) -> Tensor:
+        if device is not None and torch.device(device).type == "cuda":
+            sf.device = torch.device(device)
+        rt = sf.runtime(noise)
+        group = sf.shard[2] if sf.shard else None
+        rt.nan_flag.zero_()
+        rt.load(noise)
+        time_steps = torch.linspace(1, 0, steps + 1).to(dtype=torch.float32)
+        dt = 1 / steps
+        z_dev = None
+        if seed is None:
+            seed = int(torch.empty((), dtype=torch.int64).random_().item()) if corrections > 0 else 0
+        iterator = time_steps[:-1]
+        if show_progressbar:
+            try:
+                from tqdm.auto import tqdm
+                iterator = tqdm(iterator, desc="Sampling")
+            except Exception:  # pragma: no cover
+                pass
+        total_start_time = time.time()
+        z_host = torch.empty(noise.shape, dtype=torch.float32) if (corrections > 0 and self.rng == "reference") else None
+        for istep, t in enumerate(iterator):
+            t_next = t - dt
+            mu, sigma = _mu_sigma(self, t)
+            mu_n, sigma_n = _mu_sigma(self, t_next)
+            # predictor
+            rt.score(float(t))
+            rt.predictor(mu, sigma, mu_n, sigma_n)
+            rt.halo(group)
+            # corrector
+            for ic in range(corrections):
+                if z_host is not None:
+                    z_host.normal_()
+                    p = rt.plan
+                    if z_dev is None:
+                        z_dev = torch.empty_like(rt.x)
+                    src = z_host[p.frame_lo:p.frame_hi].to(rt.device, non_blocking=False).contiguous()
+                    from . import _lib
+                    with torch.cuda.device(rt.device):
+                        _lib.check(rt.lib.c2w_traj_pack(src.data_ptr(), z_dev.data_ptr(), p.n_local, rt.C, rt.H * rt.W,
+                                                        rt.stream), "c2w_traj_pack")
+                rt.score(float(t_next))
+                rt.guided_eps(mu_n, sigma_n)
+                rt.corrector(tau, sigma_n, z_dev, seed, istep * max(corrections, 1) + ic, group)
+                rt.halo(group)
+            if self.nan_check_every and (istep + 1) % self.nan_check_every == 0:
+                rt.check_finite()
+        rt.check_finite()
+        out = rt.owned(rt.x)
+        if sf.shard:
+            out = all_gather_frames(out, rt.plan, group)
+        total_time = time.time() - total_start_time
+        print(f"Total sampling time: {total_time:.2f} s  = {total_time / 60:.3f} min = {total_time / 3600:.4f} h")
+        target = noise.device if device is None else torch.device(device)
+        return out.to(device=target, dtype=noise.dtype).reshape(noise.shape)
+
+    def _sample_generic(self, score_fn, noise, steps, corrections, tau, proc_x0, device, show_progressbar):
+        """The reference loop for score functions this package does not own (plain callables, proc_x0 hooks)."""
+        if device is None:
+            device = torch.device("cpu")
+        x = noise.to(device=device)
+        dims = tuple(range(-len(noise.shape), 0))
+        time_steps = torch.linspace(1, 0, steps + 1).to(dtype=x.dtype, device=device)
+        dt = 1 / steps
+        z = torch.empty_like(x) if corrections > 0 else None
+        with torch.no_grad():
+            for t in time_steps[:-1]:
+                x = self._sample_step(score_fn, x, t, dt, proc_x0=proc_x0)
+                for _ in range(corrections):
+                    z.normal_()
+                    eps = score_fn(x, t - dt)
+                    delta = tau / eps.square().mean(dim=dims, keepdim=True)
+                    x = x - (delta * eps + torch.sqrt(2 * delta) * z) * self.sigma(t - dt)
+                if torch.isnan(x).any():
+                    raise ValueError("NaN detected in sample")
+        return x.reshape(noise.shape)

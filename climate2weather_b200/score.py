@@ -1,0 +1,328 @@
+"""Host-side mirror of `thor.score` (reference src/thor/score.py:7-185): AbstractScoreFunction,
+DefaultScoreFunction, BatchedScoreFunction — same constructors, `condition_on`, `__call__`, `score_fn`.
+
+What differs is where the work happens: the trajectory lives in HBM as fp32 [frames, H, W, C]; unfold, the UNet,
+the centre-pick compose, the likelihood guidance and the predictor/corrector updates are CUDA kernels behind
+include/c2w_b200.h.  Nothing here computes on the CPU and nothing falls back to torch ops.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Callable, Optional, Sequence, Union
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+from torch import Tensor
+
+from . import _lib
+from .model import ScoreUNet, build_from_reference
+from .sharding import ShardPlan, all_gather_frames, exchange_halos, make_plan
+
+
+class CoarseGrain:
+    """The reference's observation operator (exp/downscaling.py:129-132): every `t_step`-th frame, mean over
+    `s_step` x `s_step` tiles.  Passing an instance as `A=` lets `condition_on` skip operator recognition."""
+
+    def __init__(self, t_step: int, s_step: int):
+        self.t_step, self.s_step = int(t_step), int(s_step)
+
+    def __call__(self, x: Tensor) -> Tensor:
+        return F.avg_pool2d(x[..., ::self.t_step, :, :, :], self.s_step, stride=self.s_step)
+
+    def __repr__(self):
+        return f"CoarseGrain(t_step={self.t_step}, s_step={self.s_step})"
+
+
+def _per_channel(v, C: int, name: str):
+    """float | Tensor[1,C,1,1] | sequence  ->  4 floats (exp/downscaling.py:218-234)."""
+    t = torch.as_tensor(v, dtype=torch.float32).reshape(-1).cpu()
+    if t.numel() == 1:
+        t = t.expand(C)
+    if t.numel() != C:
+        raise ValueError(f"{name}: expected a scalar or {C} per-variable values, got {t.numel()}")
+    out = [float(x) for x in t]
+    return out + [1.0] * (4 - len(out))
+
+
+def _recognise_operator(A: Callable, L: int, C: int, H: int, W: int, y_shape) -> CoarseGrain:
+    """`A` is an opaque Python callable in the reference API.  The fused path implements exactly one operator
+    family (every t-th frame, s x s mean); identify (t, s) from the shapes and verify on a random probe."""
+    if isinstance(A, CoarseGrain):
+        return A
+    Lo, Cy, Hs, Ws = y_shape
+    if Cy != C or H % Hs or W % Ws or H // Hs != W // Ws:
+        raise NotImplementedError(f"observation of shape {tuple(y_shape)} is not a tile average of [{L},{C},{H},{W}]")
+    s = H // Hs
+    g = torch.Generator().manual_seed(1234)
+    probe = torch.randn(L, C, H, W, generator=g)
+    got = A(probe)
+    for t in range(1, L + 1):
+        if -(-L // t) != Lo:
+            continue
+        cand = CoarseGrain(t, s)
+        ref = cand(probe)
+        if ref.shape == got.shape and torch.allclose(ref, got, rtol=1e-5, atol=1e-6):
+            return cand
+    raise NotImplementedError("observation operator A was not recognised as `AvgPool2d(s)(x[::t])`; the fused "
+                              "guidance kernel supports only that family (pass climate2weather_b200.CoarseGrain)")
+
+
+class _Runtime:
+    """Device-resident state of one trajectory (or of this rank's time shard of it)."""
+
+    def __init__(self, sf: "AbstractScoreFunction", L: int, C: int, H: int, W: int, device: torch.device,
+                 plan: ShardPlan, max_windows: int):
+        if C != 4:
+            raise NotImplementedError(f"the fused path keeps 4 variables per pixel (float4); got C={C}")
+        self.sf, self.L, self.C, self.H, self.W, self.device, self.plan = sf, L, C, H, W, device, plan
+        self.lib = _lib.load()
+        k = sf.markov_order
+        self.engine = sf.unet.engine(C, 2 * k + 1, H, W, device, max_windows=min(max_windows, plan.win_hi - plan.win_lo))
+        f32 = dict(dtype=torch.float32, device=device)
+        self.x = torch.zeros(plan.n_local, H, W, C, **f32)
+        self.eps = torch.zeros_like(self.x)
+        self.eps_g: Optional[Tensor] = None
+        self.nan_flag = torch.zeros(1, dtype=torch.int32, device=device)
+        self.sumsq = torch.zeros(1, dtype=torch.float64, device=device)
+        self.partials: Optional[Tensor] = None
+        self.cond = None
+        self.s_tile = next(s for s in (16, 8, 32, 4, 64, 2, 128, 1) if H % s == 0 and W % s == 0 and W // s <= 32)
+
+    # ------------------------------------------------------------------------------------------------ state io
+    @property
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def load(self, x_nchw: Tensor) -> None:
+        """x_nchw: the FULL trajectory [L, C, H, W] (any device); keeps this rank's frames (with halos)."""
+        p = self.plan
+        src = x_nchw[p.frame_lo:p.frame_hi].to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.c2w_traj_pack(src.data_ptr(), self.x.data_ptr(), p.n_local, self.C, self.H * self.W,
+                                              self.stream), "c2w_traj_pack")
+
+    def unpack(self, buf: Tensor, lo: int, n: int) -> Tensor:
+        out = torch.empty(n, self.C, self.H, self.W, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.c2w_traj_unpack(buf[lo:lo + n].data_ptr(), out.data_ptr(), n, self.C, self.H * self.W,
+                                                self.stream), "c2w_traj_unpack")
+        return out
+
+    def owned(self, buf: Tensor) -> Tensor:
+        """NCHW copy of this rank's owned frames of `buf`."""
+        p = self.plan
+        return self.unpack(buf, p.own_lo - p.frame_lo, p.own_n)
+
+    # ------------------------------------------------------------------------------------------------ kernels
+    def score(self, t: float) -> None:
+        """eps <- composed window score of x at time t (src/thor/score.py:90-93 / :156-185)."""
+        p = self.plan
+        self.engine.window_score(self.x, p.frame_lo, p.win_lo, p.win_hi - p.win_lo, p.n_win_global, t, self.eps)
+
+    def set_condition(self, cond) -> None:
+        self.cond = cond
+        if cond is not None:
+            self.y_dev = cond["y"].to(device=self.device, dtype=torch.float32).contiguous()
+
+    def _guide(self, mode: int, mu: float, sigma: float, mu_next: float, sigma_next: float) -> None:
+        p = self.plan
+        g = _lib.Guide()
+        g.x, g.eps = self.x.data_ptr(), self.eps.data_ptr()
+        s = self.s_tile
+        if self.cond is not None:
+            cg: CoarseGrain = self.cond["op"]
+            s = cg.s_step
+            g.y = self.y_dev.data_ptr()
+            g.t_step = cg.t_step
+            for i in range(4):
+                g.std2[i] = self.cond["std"][i] ** 2
+                g.gamma[i] = self.cond["gamma"][i]
+        else:
+            g.y = None
+            g.t_step = 1
+        g.s_step, g.H, g.W = s, self.H, self.W
+        g.mu, g.sigma, g.mu_next, g.sigma_next = mu, sigma, mu_next, sigma_next
+        g.frame_global0, g.own_lo, g.own_n = p.frame_lo, p.own_lo - p.frame_lo, p.own_n
+        g.mode = mode
+        g.nan_flag = self.nan_flag.data_ptr()
+        if mode == 1:
+            n_part = p.own_n * (self.H // s)
+            if self.partials is None or self.partials.numel() < n_part:
+                self.partials = torch.zeros(n_part, dtype=torch.float32, device=self.device)
+            if self.eps_g is None:
+                self.eps_g = torch.zeros_like(self.x)
+            g.eps_out, g.partials = self.eps_g.data_ptr(), self.partials.data_ptr()
+            self._n_part = n_part
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.c2w_guided_step(ctypes.byref(g), self.stream), "c2w_guided_step")
+
+    def predictor(self, mu: float, sigma: float, mu_next: float, sigma_next: float) -> None:
+        """x <- mu' (x - sigma eps_g)/mu + sigma' eps_g on the owned frames (src/thor/pipelines.py:41-46)."""
+        self._guide(0, mu, sigma, mu_next, sigma_next)
+
+    def guided_eps(self, mu: float, sigma: float) -> None:
+        """eps_g <- eps - sigma * grad_x log p(y | x) (src/thor/score.py:24-35) and the partial sums of eps_g^2."""
+        self._guide(1, mu, sigma, 0.0, 0.0)
+
+    def corrector(self, tau: float, sigma_next: float, z: Optional[Tensor], seed: int, step_id: int,
+                  group=None) -> None:
+        """One Langevin correction with eps_g already computed (src/thor/pipelines.py:81-88)."""
+        p = self.plan
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.c2w_reduce_partials(self.partials.data_ptr(), self._n_part, self.sumsq.data_ptr(),
+                                                    self.stream), "c2w_reduce_partials")
+            if p.world > 1:
+                dist.all_reduce(self.sumsq, group=group)  # trajectory-global mean(eps^2): one scalar per correction
+            lo = p.own_lo - p.frame_lo
+            hw = self.H * self.W
+            zp = None
+            if z is not None:
+                zl = z[lo:lo + p.own_n]
+                assert zl.is_contiguous()
+                zp = zl.data_ptr()
+            _lib.check(self.lib.c2w_corrector_update(
+                self.x[lo:].data_ptr(), self.eps_g[lo:].data_ptr(), zp, self.sumsq.data_ptr(),
+                float(self.L * self.C * hw), float(tau), float(sigma_next), p.own_lo * hw, p.own_n * hw, int(seed),
+                int(step_id), self.nan_flag.data_ptr(), self.stream), "c2w_corrector_update")
+
+    def halo(self, group=None) -> None:
+        exchange_halos(self.x, self.plan, group)
+
+    def check_finite(self) -> None:
+        if int(self.nan_flag.item()) != 0:
+            raise ValueError("NaN detected in sample")  # same error as src/thor/pipelines.py:90-91
+
+
+class AbstractScoreFunction:
+    """src/thor/score.py:7-60."""
+
+    #: windows per UNet launch; None = the subclass default.  Results do not depend on it.
+    max_windows: Optional[int] = None
+
+    def __init__(self, unet, noise_process, unet_kwargs=None):
+        if not isinstance(unet, ScoreUNet):
+            # a reference `model.score.ScoreUNet` (e.g. snapshot["ema"]): take its architecture and weights
+            unet = build_from_reference(unet)
+        self.unet = unet
+        self.noise_process = noise_process
+        self.unet_kwargs = unet_kwargs if unet_kwargs is not None else {}
+        self.likelihood = None
+        self.device: Optional[torch.device] = None
+        self.shard = None  # (rank, world, group) once enable_time_sharding() was called
+        self._runtimes = {}
+        self.unet.eval()
+
+    # ------------------------------------------------------------------------------------------------ reference API
+    @property
+    def is_conditioned(self):
+        return self.likelihood is not None
+
+    def net_forward(self, x: Tensor, t: Tensor) -> Tensor:
+        return self.unet(x, t)
+
+    def condition_on(self, *, A, y, std, gamma=1e-2, exact_grad=True):
+        """src/thor/score.py:44-60.  `exact_grad=False` (every shipped config) is the closed-form guidance
+        J = A^T((y - A x0)/var)/mu; `exact_grad=True` needs the UNet VJP."""
+        if self.likelihood is not None:
+            print("Warning: Overwriting old conditioning")
+        if exact_grad:
+            raise NotImplementedError("exact_grad=True (UNet vector-Jacobian product) is not built yet; "
+                                      "the reference's experiment configs all use use_exact_grad: false")
+        self.likelihood = dict(A=A, y=torch.as_tensor(y), std=std, gamma=gamma, op=None)
+        for rt in self._runtimes.values():
+            rt.set_condition(None)
+        self._runtimes.clear()
+        return self
+
+    def __call__(self, x: Tensor, t: Tensor) -> Tensor:
+        """src/thor/score.py:24-35: the (guided) noise prediction for the whole trajectory x[L, C, H, W]."""
+        rt = self.runtime(x)
+        rt.load(x)
+        rt.score(float(t))
+        if not self.is_conditioned:
+            out = rt.owned(rt.eps)
+        else:
+            mu, sigma = _mu_sigma(self.noise_process, t)
+            rt.guided_eps(mu, sigma)
+            out = rt.owned(rt.eps_g)
+        return out.to(device=x.device, dtype=x.dtype)
+
+    def score_fn(self, x: Tensor, t: Tensor) -> Tensor:
+        """Unguided composed score (src/thor/score.py:90-93, :156-185)."""
+        rt = self.runtime(x)
+        rt.load(x)
+        rt.score(float(t))
+        return rt.owned(rt.eps).to(device=x.device, dtype=x.dtype)
+
+    # ------------------------------------------------------------------------------------------------ runtime
+    def enable_time_sharding(self, group=None) -> "AbstractScoreFunction":
+        """Partition trajectories along time over the ranks of `group` (default: the world group)."""
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.shard = (dist.get_rank(group), dist.get_world_size(group), group)
+        self._runtimes.clear()
+        return self
+
+    def _compute_device(self, x: Tensor) -> torch.device:
+        if x.is_cuda:
+            return x.device
+        if self.device is not None and torch.device(self.device).type == "cuda":
+            return torch.device(self.device)
+        p = next(self.unet.parameters())
+        if p.is_cuda:
+            return p.device
+        if torch.cuda.is_available():
+            return torch.device("cuda", torch.cuda.current_device())
+        raise _lib.C2WError("no CUDA device: climate2weather_b200 has no CPU path")
+
+    def _default_windows(self, n_win: int) -> int:
+        return min(n_win, 32)
+
+    def runtime(self, x: Tensor) -> _Runtime:
+        L, C, H, W = x.shape
+        dev = self._compute_device(x)
+        rank, world = (self.shard[0], self.shard[1]) if self.shard else (0, 1)
+        key = (L, C, H, W, str(dev), rank, world)
+        rt = self._runtimes.get(key)
+        if rt is None:
+            plan = make_plan(L, self.markov_order, rank, world)
+            mw = self.max_windows or self._default_windows(plan.win_hi - plan.win_lo)
+            rt = _Runtime(self, L, C, H, W, dev, plan, mw)
+            if self.likelihood is not None:
+                lk = self.likelihood
+                if lk["op"] is None:
+                    lk["op"] = _recognise_operator(lk["A"], L, C, H, W, lk["y"].shape)
+                    lk["std_c"] = _per_channel(lk["std"], C, "std")
+                    lk["gamma_c"] = _per_channel(lk["gamma"], C, "gamma")
+                rt.set_condition(dict(op=lk["op"], y=lk["y"], std=lk["std_c"], gamma=lk["gamma_c"]))
+            self._runtimes = {key: rt}  # one live trajectory geometry at a time
+        return rt
+
+
+def _mu_sigma(noise_process, t) -> tuple:
+    tt = torch.as_tensor(t, dtype=torch.float32).cpu()
+    return float(noise_process.mu(tt)), float(noise_process.sigma(tt))
+
+
+class DefaultScoreFunction(AbstractScoreFunction):
+    """src/thor/score.py:63-93."""
+
+    def __init__(self, unet, markov_order, **kwargs):
+        super().__init__(unet=unet, **kwargs)
+        self.markov_order = markov_order
+
+
+class BatchedScoreFunction(AbstractScoreFunction):
+    """src/thor/score.py:96-185.  `batch_size` windows go through the UNet per launch; `device` is where the
+    trajectory is kept resident (the reference streams every batch host->device->host, :170-181)."""
+
+    def __init__(self, unet, markov_order, batch_size=16, device=None, **kwargs):
+        super().__init__(unet=unet, **kwargs)
+        self.markov_order = markov_order
+        self.batch_size = batch_size
+        self.device = device if device is not None else torch.device("cuda")
+        print(f">>> Initialized batched score function to use device: {self.device}")
+
+    def _default_windows(self, n_win: int) -> int:
+        return min(n_win, int(self.batch_size))

@@ -1,0 +1,99 @@
+"""Time-axis sharding of a trajectory across ranks (new in this build).
+
+Frame i's score depends only on frames i-k .. i+k (src/thor/score.py:68-93), so the Nw = L - 2k window CENTRES
+are split evenly over the ranks; the edge ranks additionally own the k edge frames (which cost no extra windows,
+src/thor/score.py:76-88).  Before every score evaluation each rank needs the k boundary frames of its neighbours'
+current state: one send/recv pair per neighbour (NCCL over NVLink on GPUs; gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass(frozen=True)
+class ShardPlan:
+    L: int          # trajectory length (frames)
+    k: int          # Markov order
+    rank: int
+    world: int
+    win_lo: int     # windows [win_lo, win_hi) are evaluated on this rank (global window indices)
+    win_hi: int
+
+    @property
+    def n_win_global(self) -> int:
+        return self.L - 2 * self.k
+
+    @property
+    def frame_lo(self) -> int:
+        """first global frame held locally (including the left halo)"""
+        return self.win_lo
+
+    @property
+    def frame_hi(self) -> int:
+        """one past the last global frame held locally (including the right halo)"""
+        return self.win_hi + 2 * self.k
+
+    @property
+    def n_local(self) -> int:
+        return self.frame_hi - self.frame_lo
+
+    @property
+    def own_lo(self) -> int:
+        """first OWNED global frame: window centres, plus the k leading frames on rank 0"""
+        return 0 if self.rank == 0 else self.win_lo + self.k
+
+    @property
+    def own_hi(self) -> int:
+        return self.L if self.rank == self.world - 1 else self.win_hi + self.k
+
+    @property
+    def own_n(self) -> int:
+        return self.own_hi - self.own_lo
+
+
+def make_plan(L: int, k: int, rank: int = 0, world: int = 1) -> ShardPlan:
+    nw = L - 2 * k
+    if nw < 1:
+        raise ValueError(f"trajectory of {L} frames is shorter than one window of {2 * k + 1}")
+    if world > 1 and nw // world < max(k, 1):
+        raise ValueError(f"{nw} windows over {world} ranks leaves fewer than k={k} windows per rank; use fewer ranks")
+    base, rem = divmod(nw, world)
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return ShardPlan(L, k, rank, world, lo, hi)
+
+
+def exchange_halos(x_local: torch.Tensor, plan: ShardPlan, group: Optional[dist.ProcessGroup] = None) -> None:
+    """Refreshes the k halo frames on each side of `x_local` ([n_local, ...], frames outermost, contiguous) from the
+    neighbours' owned boundary frames.  No-op for a single rank."""
+    if plan.world == 1:
+        return
+    k = plan.k
+    ops: List[dist.P2POp] = []
+    n = plan.n_local
+    if plan.rank > 0:  # left neighbour: my first k owned frames -> its right halo; its last k owned -> my left halo
+        ops.append(dist.P2POp(dist.isend, x_local[k:2 * k], plan.rank - 1, group))
+        ops.append(dist.P2POp(dist.irecv, x_local[0:k], plan.rank - 1, group))
+    if plan.rank < plan.world - 1:
+        ops.append(dist.P2POp(dist.isend, x_local[n - 2 * k:n - k], plan.rank + 1, group))
+        ops.append(dist.P2POp(dist.irecv, x_local[n - k:n], plan.rank + 1, group))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+
+
+def all_gather_frames(x_owned: torch.Tensor, plan: ShardPlan, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """Concatenates every rank's owned frames into the full [L, ...] trajectory (end of sampling only)."""
+    if plan.world == 1:
+        return x_owned
+    counts = [make_plan(plan.L, plan.k, r, plan.world).own_n for r in range(plan.world)]
+    cmax = max(counts)
+    tail = tuple(x_owned.shape[1:])
+    mine = torch.zeros((cmax,) + tail, dtype=x_owned.dtype, device=x_owned.device)
+    mine[:plan.own_n] = x_owned
+    bufs = [torch.empty_like(mine) for _ in counts]
+    dist.all_gather(bufs, mine, group=group)  # equal-sized buffers: valid on both nccl and gloo
+    return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)

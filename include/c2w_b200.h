@@ -1,0 +1,120 @@
+/* c2w_b200 — C ABI of the B200-native guided-sampling hot path of Climate2Weather.
+ *
+ * The reference (schmidtjonathan/Climate2Weather) has NO plugin / operator / FFI interface: its hot path is
+ * three Python classes calling PyTorch library ops.  Each entry point below therefore cites
+ * the reference *function* (file:line under the reference root) whose arithmetic it replaces; the Python
+ * mirror of those classes in climate2weather_b200/ is the only caller (ctypes).
+ *
+ * Conventions: plain C, `int` return (0 = ok, negative = error, text via c2w_last_error()); the caller owns every
+ * tensor and passes raw DEVICE pointers plus a cudaStream_t (as void*); the library owns only its handle, the
+ * packed weights and the tensor maps it builds over the caller's workspace.  No hidden allocation and no
+ * synchronisation on the hot calls.  One handle per device/process, not re-entrant per handle.
+ *
+ * Device layouts
+ *   trajectory / score / noise : fp32 [frames, H, W, C]   (C = 4 variables -> one float4 per pixel)
+ *   reference-facing tensors   : fp32 NCHW, converted by c2w_traj_pack / c2w_traj_unpack
+ *   activations (internal)     : bf16 NHWC, channel counts padded to multiples of 64
+ */
+#ifndef C2W_B200_H
+#define C2W_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define C2W_MAX_LEVELS 8
+
+/* Architecture of model.score.ScoreUNet (model/score.py:37-57, model/nn.py:108-218, configs/sda_unet.yml). */
+typedef struct c2w_config {
+  int32_t frame_channels;                  /* C: variables per frame (train.py:169: channels = C * window) */
+  int32_t window;                          /* w = 2k+1 frames per Markov window (run_training.sh:41)       */
+  int32_t height, width;                   /* patch size (run_training.sh:39)                               */
+  int32_t embedding_dim;                   /* configs/sda_unet.yml:1                                        */
+  int32_t noise_features;                  /* model/score.py:53 (32)                                        */
+  int32_t n_levels;
+  int32_t hidden_channels[C2W_MAX_LEVELS]; /* configs/sda_unet.yml:8-13                                     */
+  int32_t hidden_blocks[C2W_MAX_LEVELS];   /* configs/sda_unet.yml:2-7                                      */
+  int32_t attention_mask;                  /* bit l set: AttentionBlock after every block of level l        */
+} c2w_config;
+
+typedef struct c2w_handle c2w_handle;
+
+/* Guided predictor / corrector arithmetic on the resident trajectory.
+ * Replaces AbstractScoreFunction.condition_on/log_p + __call__ (src/thor/score.py:24-60, exact_grad=False closed
+ * form), the observation operator A and its adjoint (exp/downscaling.py:129-132) and SDAPipeline._sample_step
+ * (src/thor/pipelines.py:41-46) / the corrector body (src/thor/pipelines.py:81-88). */
+typedef struct c2w_guide {
+  float* x;             /* [frames_local, H, W, 4] state, updated in place (mode 0)                       */
+  const float* eps;     /* [frames_local, H, W, 4] window-composed score                                   */
+  float* eps_out;       /* mode 1: guided score                                                            */
+  const float* y;       /* [ceil(L / t_step), 4, H / s_step, W / s_step] observation; NULL = unconditioned */
+  float std2[4];        /* likelihood std^2 per variable (exp/downscaling.py:221-227)                      */
+  float gamma[4];
+  float mu, sigma;           /* schedule at the score's time (src/thor/pipelines.py:13-20)                 */
+  float mu_next, sigma_next; /* schedule at t - dt                                                         */
+  int32_t t_step, s_step, H, W;
+  int32_t frame_global0; /* global frame index of local frame 0 (time sharding)                            */
+  int32_t own_lo, own_n; /* local frames [own_lo, own_lo + own_n) are updated                              */
+  int32_t mode;          /* 0 predictor update, 1 guided eps + per-CTA partial sums of eps^2               */
+  float* partials;       /* mode 1: >= own_n * (H / s_step) floats                                         */
+  int32_t* nan_flag;     /* set to 1 if any updated value is not finite (src/thor/pipelines.py:90-91)      */
+} c2w_guide;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------ */
+int c2w_create(const c2w_config* cfg, c2w_handle** out);
+void c2w_destroy(c2w_handle* h);
+const char* c2w_last_error(void);
+int c2w_abi_version(void);
+
+/* ---- weights: reference state_dict entries by name, fp32 host memory -------------------- */
+int c2w_load_weight(c2w_handle* h, const char* name, const float* host_data, int64_t numel);
+int c2w_finalize_weights(c2w_handle* h); /* packs to bf16 K-major [Cout, 9*Cin] and uploads; checks completeness */
+
+/* ---- workspace ------------------------------------------------------------------------------------------- */
+int64_t c2w_workspace_bytes(c2w_handle* h, int32_t max_windows);
+int c2w_bind_workspace(c2w_handle* h, int32_t max_windows, void* dev_ptr, int64_t bytes);
+
+/* ---- ScoreUNet.forward (model/score.py:59-70 -> model/nn.py:220-242) --------------------------------------
+ * x, out: fp32 NCHW [n, C*window, H, W] on the device; scalar diffusion time t (sampling: one t per call). */
+int c2w_unet_forward(c2w_handle* h, const float* x_nchw, int32_t n, float t, float* out_nchw, void* stream);
+
+/* ---- DefaultScoreFunction/BatchedScoreFunction.score_fn (src/thor/score.py:68-93, :111-185) ---------------
+ * unfold -> UNet -> centre-pick/edge-fill compose, without materialising the unfold in fp32 or the unused
+ * 12/13 of the UNet output.  traj/eps: [n_frames_local, H, W, C].  Computes windows
+ * [win_first, win_first + n_win) (global indices; window j covers global frames j .. j+2k) of a trajectory with
+ * n_win_global windows; local frame 0 is global frame frame_global0. */
+int c2w_window_score(c2w_handle* h, const float* traj, int32_t n_frames_local, int32_t frame_global0,
+                     int32_t win_first, int32_t n_win, int32_t n_win_global, float t, float* eps, void* stream);
+
+/* ---- layout: reference NCHW fp32 [frames, C, H, W] <-> device [frames, H, W, C] --------------------------- */
+int c2w_traj_pack(const float* nchw, float* fhwc, int64_t frames, int32_t C, int32_t hw, void* stream);
+int c2w_traj_unpack(const float* fhwc, float* nchw, int64_t frames, int32_t C, int32_t hw, void* stream);
+
+/* ---- guided predictor / corrector (see c2w_guide) --------------------------------------------------------- */
+int c2w_guided_step(const c2w_guide* g, void* stream);
+int c2w_reduce_partials(const float* partials, int32_t n, double* sumsq, void* stream);
+/* x <- x - (delta eps + sqrt(2 delta) z) sigma_next, delta = tau / (sumsq / count)  (src/thor/pipelines.py:84-87).
+ * z == NULL: on-chip Philox4x32-10 keyed by (seed, step_id, global pixel index). */
+int c2w_corrector_update(float* x, const float* eps, const float* z, const double* sumsq, double count, float tau,
+                         float sigma_next, int64_t pix0_global, int64_t npix, uint64_t seed, uint32_t step_id,
+                         int32_t* nan_flag, void* stream);
+
+/* ---- op-level hooks (parity tests of single kernels; same kernels the calls above launch) ----------------- */
+int c2w_op_conv(const void* x, int n_img, int H, int W, int cin, const void* w_packed, int cout_pad,
+                const float* bias, int mode, const void* res, void* out, float* out_f32, int conv3x3, int bn,
+                int max_ctas, void* stream);
+int c2w_op_layernorm(const void* x_bf16, const float* mod, void* out_bf16, int64_t npix, int C, int H, int W,
+                     int upsample, void* stream);
+int c2w_op_attention(const void* qkv_bf16, void* out_bf16, int n, int T, int C, void* stream);
+int c2w_op_im2col_s2(const void* x_bf16, void* col_bf16, int n, int H, int W, int C, void* stream);
+int c2w_op_gather_windows(const float* traj, void* out_bf16, int n, int hw, int C, int window, int cin_pad,
+                          int frame0, void* stream);
+int c2w_op_modulation(c2w_handle* h, float t, float* emb_out, float* mods_out, void* stream);
+int c2w_total_mod_channels(c2w_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* C2W_B200_H */

@@ -163,6 +163,9 @@ def main():
     print("ALL PASS" if ok else "SOME FAILED", flush=True)
     if "--time" in sys.argv:
         timeit("G2", 32, 128, 128, 128, 128)
+        # diagnostics: no TMA traffic after priming -> MMA + smem-read + epilogue ceiling of this kernel structure
+        timeit("G2-noloads", 32, 128, 128, 128, 128, bn=128 | 0x1000)
+        timeit("G8-noloads", 64, 32, 32, 256, 256, bn=256 | 0x1000)
         timeit("G2-bn64", 32, 128, 128, 128, 128, bn=64)
         timeit("G5", 64, 64, 64, 128, 128)
         timeit("G8", 64, 32, 32, 256, 256)
