@@ -79,6 +79,9 @@ SIGNATURES = {
     "c2w_op_gather_windows": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "c2w_op_modulation": (_i, [_vp, _f, _vp, _vp, _vp]),
     "c2w_total_mod_channels": (_i, [_vp]),
+    "c2w_launch_count": (_i64, []),
+    "c2w_set_timing": (_i, [_vp, _i]),
+    "c2w_timing_read": (_i, [_vp, _vp, _vp]),
 }
 
 _lib = None

@@ -72,11 +72,85 @@ struct ConvCfg {
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + 1024;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static_assert(BN % 32 == 0 && BN >= 64 && BN <= 256, "BN must be 64..256, multiple of 32");
+  static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN must be 64..256, multiple of 64");
   static_assert(kStages >= 3, "pipeline too shallow");
 };
 
-__device__ __forceinline__ float silu_f(float x) { return x * (1.0f / (1.0f + __expf(-x))); }
+// SiLU without the IEEE-division slow path: ex2.approx + rcp.approx, branch-free so the 32 independent
+// evaluations of a chunk interleave (the IEEE form serialises into ~100 clk per element).
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+// One 32-column chunk of one accumulator row: v = raw fp32 bits from TMEM, col0 = first output channel.
+__device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32_t (&v)[32], int col0, int m,
+                                               bool valid) {
+  float f[32];
+  const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 b = __ldg(b4 + i);
+    f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b.x;
+    f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b.y;
+    f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z;
+    f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
+  }
+  if (p.mode == EPI_COMPOSE) {
+    if (valid) {
+      const int n_img = m / p.hw;
+      const int pix = m - n_img * p.hw;
+      const int win = p.win_first + n_img;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const int tau = (col0 >> 2) + g;  // window slot of channels [4*tau, 4*tau+4)
+        const bool take = (tau == p.order_k) || (win == 0 && tau < p.order_k) ||
+                          (win == p.win_last_global && tau > p.order_k && tau <= 2 * p.order_k);
+        if (take) {
+          const long long fl = static_cast<long long>(win + tau - p.frame_base);
+          float4 o = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+          *reinterpret_cast<float4*>(p.eps + (fl * p.hw + pix) * 4) = o;
+        }
+      }
+    }
+  } else if (p.mode == EPI_F32) {
+    if (valid) {
+      float4* o4 = reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(m) * p.ldc + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+    }
+  } else {
+    if (p.mode == EPI_BIAS_SILU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = silu_f(f[i]);
+    }
+    if (valid) {
+      const size_t off = static_cast<size_t>(m) * p.ldc + col0;
+      if (p.mode == EPI_BIAS_RES) {
+        const uint4* r4 = reinterpret_cast<const uint4*>(p.res + off);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 r = r4[i];
+          const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+            f[8 * i + 2 * j] += __low2float(h);
+            f[8 * i + 2 * j + 1] += __high2float(h);
+          }
+        }
+      }
+      uint4* o4 = reinterpret_cast<uint4*>(p.out + off);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(f[8 * i + 2 * j], f[8 * i + 2 * j + 1]);
+          w[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        o4[i] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -208,79 +282,17 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      // two register buffers: the tcgen05.ld of chunk i+1 is in flight while chunk i is processed
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(taddr, va);
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c, v);
+      for (int c = 0; c < BN; c += 64) {
         tmem_ld_wait();
-        const int col0 = nt * BN + c;
-        float f[32];
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b = __ldg(b4 + i);
-          f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b.x;
-          f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b.y;
-          f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z;
-          f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
-        }
-        if (p.mode == EPI_COMPOSE) {
-          if (valid) {
-            const int n_img = m / p.hw;
-            const int pix = m - n_img * p.hw;
-            const int win = p.win_first + n_img;
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const int tau = (col0 >> 2) + g;  // window slot of channels [4*tau, 4*tau+4)
-              const bool take = (tau == p.order_k) || (win == 0 && tau < p.order_k) ||
-                                (win == p.win_last_global && tau > p.order_k && tau <= 2 * p.order_k);
-              if (take) {
-                const long long fl = static_cast<long long>(win + tau - p.frame_base);
-                float4 o = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
-                *reinterpret_cast<float4*>(p.eps + (fl * p.hw + pix) * 4) = o;
-              }
-            }
-          }
-        } else if (p.mode == EPI_F32) {
-          if (valid) {
-            float4* o4 = reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(m) * p.ldc + col0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-          }
-        } else {
-          if (p.mode == EPI_BIAS_SILU) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = silu_f(f[i]);
-          }
-          if (valid) {
-            const size_t off = static_cast<size_t>(m) * p.ldc + col0;
-            if (p.mode == EPI_BIAS_RES) {
-              const uint4* r4 = reinterpret_cast<const uint4*>(p.res + off);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint4 r = r4[i];
-                const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
-                  f[8 * i + 2 * j] += __low2float(h);
-                  f[8 * i + 2 * j + 1] += __high2float(h);
-                }
-              }
-            }
-            uint4* o4 = reinterpret_cast<uint4*>(p.out + off);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint32_t w[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(f[8 * i + 2 * j], f[8 * i + 2 * j + 1]);
-                w[j] = *reinterpret_cast<uint32_t*>(&h);
-              }
-              o4[i] = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-          }
-        }
+        tmem_ld_32x32(taddr + c + 32, vb);
+        epilogue_chunk(p, va, nt * BN + c, m, valid);
+        tmem_ld_wait();
+        if (c + 64 < BN) tmem_ld_32x32(taddr + c + 64, va);
+        epilogue_chunk(p, vb, nt * BN + c + 32, m, valid);
       }
       tc_fence_before();
       __syncwarp();

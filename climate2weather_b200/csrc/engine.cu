@@ -14,7 +14,16 @@ using namespace c2w;
 
 int c2w_num_sms();
 
+static long long g_launches = 0;  // kernels launched by this library (bench.py's gpu_launches)
+
 namespace {
+
+// Optional per-launch CUDA-event timing (bench.py roofline pass): events are recorded on the launch stream around
+// every kernel of the forward pass and summed per class when read.
+struct TimedSpan {
+  int cls;  // 0 = K1 conv/GEMM (tensor cores), 1 = everything else in the forward pass
+  cudaEvent_t e0, e1;
+};
 
 struct ConvW {
   bf16* w = nullptr;   // [cout_pad, taps * cin_pad], k = tap * cin_pad + c
@@ -78,6 +87,9 @@ struct c2w_handle {
   std::vector<LevelW> levels;
   Plan plan;
   int sms = 0;
+  bool timing = false;
+  std::vector<TimedSpan> spans;
+  size_t spans_used = 0;
 };
 
 namespace {
@@ -203,6 +215,7 @@ int run_modulation(c2w_handle* h, float t, float* h0, float* emb, float* mods, c
   matvec_kernel<<<ceil_div(static_cast<long long>(E) * 32, 256), 256, 0, st>>>(h->map1_w, h->map1_b, h0, emb, E, E, 1);
   matvec_kernel<<<ceil_div(static_cast<long long>(h->total_mod) * 32, 256), 256, 0, st>>>(h->proj_w, h->proj_b, emb, mods,
                                                                                          h->total_mod, E, 0);
+  g_launches += 3;
   C2W_CUDA(cudaGetLastError());
   return C2W_OK;
 }
@@ -354,6 +367,29 @@ int build_plan(c2w_handle* h, int n, void* base, size_t* bytes_out) {
   return C2W_OK;
 }
 
+struct SpanGuard {
+  c2w_handle* h;
+  cudaStream_t st;
+  TimedSpan* sp = nullptr;
+  SpanGuard(c2w_handle* h_, int cls, cudaStream_t st_) : h(h_), st(st_) {
+    ++g_launches;
+    if (!h->timing) return;
+    if (h->spans_used == h->spans.size()) {
+      TimedSpan t;
+      t.cls = cls;
+      cudaEventCreate(&t.e0);
+      cudaEventCreate(&t.e1);
+      h->spans.push_back(t);
+    }
+    sp = &h->spans[h->spans_used++];
+    sp->cls = cls;
+    cudaEventRecord(sp->e0, st);
+  }
+  ~SpanGuard() {
+    if (sp) cudaEventRecord(sp->e1, st);
+  }
+};
+
 struct FinalSpec {
   int mode;  // EPI_F32 or EPI_COMPOSE
   float* eps = nullptr;
@@ -382,22 +418,28 @@ int run_plan(c2w_handle* h, int nn, const FinalSpec& fs, cudaStream_t st) {
           L.p.win_last_global = fs.win_last_global;
           L.p.frame_base = fs.frame_base;
         }
-        C2W_CUDA(conv_launch(L, st));
+        {
+          SpanGuard sg(h, 0, st);
+          C2W_CUDA(conv_launch(L, st));
+        }
         break;
       }
       case OP_LN: {
+        SpanGuard sg(h, 1, st);
         int rc = launch_ln(op.in, op.mod_off >= 0 ? P.mods + op.mod_off : nullptr, op.out,
                            static_cast<long long>(nn) * op.H * op.W, op.C, op.H, op.W, op.up, h->sms, st);
         if (rc) return rc;
         break;
       }
       case OP_IM2COL: {
+        SpanGuard sg(h, 1, st);
         const long long items = static_cast<long long>(nn) * (op.H / 2) * (op.W / 2) * 9 * (op.C / 8);
         im2col_s2_kernel<<<grid_for(items, 256, h->sms), 256, 0, st>>>(op.in, op.out, nn, op.H, op.W, op.C);
         C2W_CUDA(cudaGetLastError());
         break;
       }
       case OP_ATTN: {
+        SpanGuard sg(h, 1, st);
         int rc = launch_attention(op.in, op.out, nn, op.T, op.C, st);
         if (rc) return rc;
         break;
@@ -531,6 +573,33 @@ int c2w_finalize_weights(c2w_handle* h) {
 
 int c2w_total_mod_channels(c2w_handle* h) { return h ? h->total_mod : 0; }
 
+int64_t c2w_launch_count(void) { return g_launches; }
+
+int c2w_set_timing(c2w_handle* h, int enable) {
+  C2W_REQUIRE(h, "null handle");
+  h->timing = enable != 0;
+  h->spans_used = 0;
+  return C2W_OK;
+}
+
+// Sums the event-timed spans recorded since the last read: ms[0] / n[0] = K1 conv/GEMM launches, ms[1] / n[1] = the
+// other forward-pass kernels.  Synchronises on the recorded events.
+int c2w_timing_read(c2w_handle* h, double* ms, int64_t* n) {
+  C2W_REQUIRE(h && ms && n, "c2w_timing_read: bad argument");
+  ms[0] = ms[1] = 0.0;
+  n[0] = n[1] = 0;
+  for (size_t i = 0; i < h->spans_used; ++i) {
+    TimedSpan& s = h->spans[i];
+    C2W_CUDA(cudaEventSynchronize(s.e1));
+    float t = 0.f;
+    C2W_CUDA(cudaEventElapsedTime(&t, s.e0, s.e1));
+    ms[s.cls] += t;
+    n[s.cls] += 1;
+  }
+  h->spans_used = 0;
+  return C2W_OK;
+}
+
 int64_t c2w_workspace_bytes(c2w_handle* h, int32_t max_windows) {
   if (!h || !h->finalized || max_windows < 1) {
     fail(C2W_ERR_STATE, "c2w_workspace_bytes: finalise the weights first");
@@ -614,6 +683,7 @@ int c2w_window_score(c2w_handle* h, const float* traj, int32_t n_frames_local, i
     const long long items = static_cast<long long>(nn) * hw * (h->cin_pad / 8);
     gather_windows_kernel<<<grid_for(items, 256, h->sms), 256, 0, st>>>(traj, P.xin, nn, hw, C, w * C, h->cin_pad,
                                                                         j0 - frame_global0);
+    ++g_launches;
     C2W_CUDA(cudaGetLastError());
     FinalSpec fs;
     fs.mode = EPI_COMPOSE;
@@ -673,6 +743,7 @@ int c2w_guided_step(const c2w_guide* g, void* stream) {
   p.nan_flag = g->nan_flag;
   dim3 grid(g->H / g->s_step, g->own_n);
   guided_step_kernel<<<grid, 32 * (g->W / g->s_step), 0, static_cast<cudaStream_t>(stream)>>>(p);
+  ++g_launches;
   C2W_CUDA(cudaGetLastError());
   return C2W_OK;
 }
@@ -680,6 +751,7 @@ int c2w_guided_step(const c2w_guide* g, void* stream) {
 int c2w_reduce_partials(const float* partials, int32_t n, double* sumsq, void* stream) {
   C2W_REQUIRE(partials && sumsq && n >= 1, "c2w_reduce_partials: bad argument");
   reduce_partials_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, n, sumsq);
+  ++g_launches;
   C2W_CUDA(cudaGetLastError());
   return C2W_OK;
 }
@@ -690,6 +762,7 @@ int c2w_corrector_update(float* x, const float* eps, const float* z, const doubl
   C2W_REQUIRE(x && eps && sumsq && nan_flag && npix >= 1 && count > 0, "c2w_corrector_update: bad argument");
   corrector_update_kernel<<<grid_for(npix, 256, c2w_num_sms()), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, eps, z, sumsq, count, tau, sigma_next, pix0_global, npix, seed, step_id, nan_flag);
+  ++g_launches;
   C2W_CUDA(cudaGetLastError());
   return C2W_OK;
 }

@@ -114,6 +114,12 @@ int c2w_op_gather_windows(const float* traj, void* out_bf16, int n, int hw, int 
 int c2w_op_modulation(c2w_handle* h, float t, float* emb_out, float* mods_out, void* stream);
 int c2w_total_mod_channels(c2w_handle* h);
 
+/* ---- measurement hooks (bench.py): kernel launches issued by this library so far; optional CUDA-event timing of
+ * every forward-pass launch on its own stream, summed per class: [0] K1 conv/GEMM (tensor cores), [1] the rest --- */
+int64_t c2w_launch_count(void);
+int c2w_set_timing(c2w_handle* h, int enable);
+int c2w_timing_read(c2w_handle* h, double* ms, int64_t* n);
+
 #ifdef __cplusplus
 }
 #endif
