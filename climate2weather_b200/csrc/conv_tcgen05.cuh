@@ -194,31 +194,34 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Producer and MMA warps run CONVERGED (all 32 lanes wait on the barriers) and issue under elect_one():
+  // operands stay warp-uniform, so ptxas keeps descriptors/coordinates in uniform registers instead of wrapping
+  // every tcgen05/TMA instruction in an R2UR waterfall (measured: 41% -> tensor pipe, see profiles/).
   if (warp_idx == 0) {
-    // ------------------------------------------------------------ TMA producer (one lane)
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int issued = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int nt = tile % p.num_n_tiles;
-        const int mt = tile / p.num_n_tiles;
-        int b1, b2, b3;
-        if (p.taps == 9) {
-          b1 = 0;
-          b2 = (mt % p.tiles_per_img) * p.tile_h;
-          b3 = (mt / p.tiles_per_img) * p.tile_n;
-        } else {
-          b1 = mt * kBlockM;
-          b2 = 0;
-          b3 = 0;
-        }
-        int kb = 0;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int dr = (p.taps == 9) ? tap / 3 - 1 : 0;
-          const int ds = (p.taps == 9) ? tap % 3 - 1 : 0;
-          for (int cb = 0; cb < p.cin_blocks; ++cb, ++kb) {
-            mbar_wait(&empty[stage], phase ^ 1);
+    // ------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    int issued = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int nt = tile % p.num_n_tiles;
+      const int mt = tile / p.num_n_tiles;
+      int b1, b2, b3;
+      if (p.taps == 9) {
+        b1 = 0;
+        b2 = (mt % p.tiles_per_img) * p.tile_h;
+        b3 = (mt / p.tiles_per_img) * p.tile_n;
+      } else {
+        b1 = mt * kBlockM;
+        b2 = 0;
+        b3 = 0;
+      }
+      int kb = 0;
+      for (int tap = 0; tap < p.taps; ++tap) {
+        const int dr = (p.taps == 9) ? tap / 3 - 1 : 0;
+        const int ds = (p.taps == 9) ? tap % 3 - 1 : 0;
+        for (int cb = 0; cb < p.cin_blocks; ++cb, ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (elect_one()) {
             if (p.dbg_skip_loads && issued >= Cfg::kStages) {
               mbar_arrive(&full[stage]);
             } else {
@@ -226,47 +229,50 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               tma_load_4d(&tmA, &full[stage], smA + stage * kATileBytes, cb * kBlockK, b1 + ds, b2 + dr, b3);
               tma_load_2d(&tmB, &full[stage], smB + stage * Cfg::kBTileBytes, kb * kBlockK, nt * BN);
             }
-            ++issued;
-            if (++stage == Cfg::kStages) {
-              stage = 0;
-              phase ^= 1;
-            }
           }
-        }
-      }
-    }
-  } else if (warp_idx == 1) {
-    // ------------------------------------------------------------ MMA issuer (one lane)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(smA + stage * kATileBytes));
-          const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(smB + stage * Cfg::kBTileBytes));
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          }
-          umma_commit(&empty[stage]);
-          if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+          __syncwarp();
+          ++issued;
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
       }
+    }
+  } else if (warp_idx == 1) {
+    // ------------------------------------------------------------ MMA issuer (one elected lane issues)
+    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
+    const uint64_t adesc0 = umma_desc_kmajor_sw128(smem_u32(smA));
+    const uint64_t bdesc0 = umma_desc_kmajor_sw128(smem_u32(smB));
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          // descriptor start-address field is (addr >> 4): stage stride and the 32 B K-advance are plain adds
+          const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (kATileBytes >> 4));
+          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * (Cfg::kBTileBytes >> 4));
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&empty[stage]);
+          if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp_idx >= 4) {
     // ------------------------------------------------------------ epilogue (4 warps = 128 rows)

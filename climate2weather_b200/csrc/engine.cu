@@ -188,15 +188,28 @@ int launch_ln(const bf16* x, const float* mod, bf16* out, long long npix, int C,
 
 int launch_attention(const bf16* qkv, bf16* out, int n, int T, int C, cudaStream_t st) {
   C2W_REQUIRE(T % 4 == 0 && C % 8 == 0, "attention: T %% 4 and C %% 8 must be 0 (T=%d C=%d)", T, C);
-  const size_t smem = attention_smem_bytes(T, C);
+  // 64-query CTAs when they already fill the machine twice over, else 16-query CTAs (4x the parallelism)
+  const int sms = c2w_num_sms();
+  const bool big = static_cast<long long>(n) * ((T + 63) / 64) >= 2LL * sms;
+  const int qb = big ? 64 : 16;
+  const size_t smem = attention_smem_bytes(T, C, qb);
   C2W_REQUIRE(smem <= static_cast<size_t>(kSmemLimit), "attention: T=%d C=%d needs %zu B of shared memory", T, C, smem);
-  static size_t configured = 0;
-  if (smem > configured) {
-    C2W_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
+  static size_t configured[2] = {0, 0};
+  const float scale2 = 1.0f / sqrtf(static_cast<float>(C));
+  dim3 grid((T + qb - 1) / qb, n);
+  if (big) {
+    if (smem > configured[0]) {
+      C2W_CUDA(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      configured[0] = smem;
+    }
+    attention_kernel<64><<<grid, kAttnThreads, smem, st>>>(qkv, out, T, C, scale2);
+  } else {
+    if (smem > configured[1]) {
+      C2W_CUDA(cudaFuncSetAttribute(attention_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      configured[1] = smem;
+    }
+    attention_kernel<16><<<grid, kAttnThreads, smem, st>>>(qkv, out, T, C, scale2);
   }
-  dim3 grid((T + kAttnQB - 1) / kAttnQB, n);
-  attention_kernel<<<grid, kAttnThreads, smem, st>>>(qkv, out, T, C, 1.0f / sqrtf(static_cast<float>(C)));
   C2W_CUDA(cudaGetLastError());
   return C2W_OK;
 }

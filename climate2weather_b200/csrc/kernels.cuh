@@ -204,43 +204,44 @@ __global__ void matvec_kernel(const float* __restrict__ W, const float* __restri
 
 // ------------------------------------------------------------------------------------------------ K4
 // qkv: bf16 [n*T, 3C] (q | k | v along channels, model/nn.py:74), out: bf16 [n*T, C].
-// CTA = (query block of 64, window).  S^T = (K Q^T) / sqrt(C) in fp32 smem, fp32 softmax over keys, O = P V.
-constexpr int kAttnQB = 64;
+// CTA = (query block of QB, window).  S^T = (K Q^T) / sqrt(C) in fp32 smem, fp32 softmax over keys, O = P V.
+// QB = 64 when there are enough windows to fill the SMs, 16 otherwise (4x the CTAs; K and V are re-read from L2).
 constexpr int kAttnThreads = 256;
-inline size_t attention_smem_bytes(int T, int C) {
+inline size_t attention_smem_bytes(int T, int C, int QB = 64) {
   const size_t pitch = (C + 2) * 2;
-  return (kAttnQB + 2 * static_cast<size_t>(T)) * pitch + static_cast<size_t>(T) * (kAttnQB + 4) * 4;
+  return (QB + 2 * static_cast<size_t>(T)) * pitch + static_cast<size_t>(T) * (QB + 4) * 4;
 }
+template <int QB>
 __global__ void __launch_bounds__(kAttnThreads)
 attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, int C, float scale2) {
   extern __shared__ __align__(16) uint8_t smraw[];
   const int pitch = C + 2;  // bf16 elements; +2 shifts consecutive rows by one bank
   bf16* sq = reinterpret_cast<bf16*>(smraw);
-  bf16* sk = sq + kAttnQB * pitch;
+  bf16* sk = sq + QB * pitch;
   bf16* sv = sk + static_cast<size_t>(T) * pitch;
-  const int sp = kAttnQB + 4;  // pitch of S^T rows (floats), keeps float4 alignment
+  const int sp = QB + 4;  // pitch of S^T rows (floats), keeps float4 alignment
   float* st = reinterpret_cast<float*>(sv + static_cast<size_t>(T) * pitch);
-  const int q0 = blockIdx.x * kAttnQB;
-  const int nq = min(kAttnQB, T - q0);
+  const int q0 = blockIdx.x * QB;
+  const int nq = min(QB, T - q0);
   const bf16* base = qkv + static_cast<size_t>(blockIdx.y) * T * 3 * C;
   const int tid = threadIdx.x;
   const int c8 = C / 8;
   // ---- load q block, k, v (16 B global reads, 4 B smem writes because of the padded pitch)
-  for (int idx = tid; idx < (kAttnQB + 2 * T) * c8; idx += kAttnThreads) {
+  for (int idx = tid; idx < (QB + 2 * T) * c8; idx += kAttnThreads) {
     const int row = idx / c8, g = idx - row * c8;
     const bf16* src;
     bf16* dst;
     bool ok = true;
-    if (row < kAttnQB) {
+    if (row < QB) {
       ok = row < nq;
       src = base + static_cast<size_t>(q0 + row) * 3 * C + g * 8;
       dst = sq + row * pitch + g * 8;
-    } else if (row < kAttnQB + T) {
-      const int r = row - kAttnQB;
+    } else if (row < QB + T) {
+      const int r = row - QB;
       src = base + static_cast<size_t>(r) * 3 * C + C + g * 8;
       dst = sk + static_cast<size_t>(r) * pitch + g * 8;
     } else {
-      const int r = row - kAttnQB - T;
+      const int r = row - QB - T;
       src = base + static_cast<size_t>(r) * 3 * C + 2 * C + g * 8;
       dst = sv + static_cast<size_t>(r) * pitch + g * 8;
     }
@@ -253,39 +254,40 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, in
     d[3] = v.w;
   }
   __syncthreads();
-  // ---- S^T[s][tq] = scale2 * q[tq] . k[s]   (4 x 4 register micro-tiles)
-  const int tiles = (kAttnQB / 4) * (T / 4);
+  // ---- S^T[s][tq] = scale2 * q[tq] . k[s]   (MQ x 4 register micro-tiles; 16 query groups x T/4 key groups)
+  constexpr int MQ = QB / 16;
+  const int tiles = 16 * (T / 4);
   for (int mt = tid; mt < tiles; mt += kAttnThreads) {
-    const int tq4 = mt % (kAttnQB / 4), s4 = mt / (kAttnQB / 4);
-    float acc[4][4];
+    const int tqg = mt % 16, s4 = mt / 16;
+    float acc[MQ][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MQ; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    const uint32_t* qp = reinterpret_cast<const uint32_t*>(sq + (tq4 * 4) * pitch);
+    const uint32_t* qp = reinterpret_cast<const uint32_t*>(sq + (tqg * MQ) * pitch);
     const uint32_t* kp = reinterpret_cast<const uint32_t*>(sk + static_cast<size_t>(s4 * 4) * pitch);
     const int pw = pitch / 2;
     for (int c = 0; c < C / 2; ++c) {
-      float2 qv[4], kv[4];
+      float2 qv[MQ], kv[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) qv[i] = unpack_bf16x2(qp[i * pw + c]);
+      for (int i = 0; i < MQ; ++i) qv[i] = unpack_bf16x2(qp[i * pw + c]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) kv[j] = unpack_bf16x2(kp[j * pw + c]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < MQ; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] += qv[i].x * kv[j].x + qv[i].y * kv[j].y;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      *reinterpret_cast<float4*>(st + (s4 * 4 + j) * sp + tq4 * 4) =
-          make_float4(acc[0][j] * scale2, acc[1][j] * scale2, acc[2][j] * scale2, acc[3][j] * scale2);
+#pragma unroll
+      for (int i = 0; i < MQ; ++i) st[(s4 * 4 + j) * sp + tqg * MQ + i] = acc[i][j] * scale2;
   }
   __syncthreads();
   // ---- softmax over keys s for each query column tq (fp32, model/nn.py:82)
   {
     const int warp = tid >> 5, lane = tid & 31;
-    for (int tq = warp; tq < kAttnQB; tq += kAttnThreads / 32) {
+    for (int tq = warp; tq < QB; tq += kAttnThreads / 32) {
       float mx = -INFINITY;
       for (int s = lane; s < T; s += 32) mx = fmaxf(mx, st[s * sp + tq]);
       mx = warp_max(mx);
@@ -303,7 +305,7 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, in
   __syncthreads();
   // ---- O[tq][c] = sum_s P[tq][s] v[s][c]; thread = (channel pair, 8 queries)
   const int pairs = C / 2;
-  for (int item = tid; item < pairs * (kAttnQB / 8); item += kAttnThreads) {
+  for (int item = tid; item < pairs * (QB / 8); item += kAttnThreads) {
     const int c2 = item % pairs, qb = item / pairs;
     float a0[8], a1[8];
 #pragma unroll
