@@ -65,8 +65,13 @@ constexpr int kSmemLimit = 232448;  // 227 KB
 
 template <int BN>
 struct ConvCfg {
+  // A pipeline stage holds kSub K-sub-blocks of 64 (one 128 B swizzle row each).  With BN <= 128 a 64-wide
+  // sub-block is only 256 tensor-pipe cycles of work, less than one barrier round trip of the issuing thread,
+  // so two sub-blocks share one full/empty barrier pair (measured: issue-bound at kSub = 1, profiles/).
+  static constexpr int kSub = (BN <= 128) ? 2 : 1;
   static constexpr int kBTileBytes = BN * kBlockK * 2;
-  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kSubBytes = kATileBytes + kBTileBytes;
+  static constexpr int kStageBytes = kSub * kSubBytes;
   static constexpr int kBarrierBytes = 256;
   static constexpr int kStagesRaw = (kSmemLimit - 1024 - kBarrierBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -160,7 +165,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;
-  uint8_t* smB = smem + Cfg::kStages * kATileBytes;
+  uint8_t* smB = smem + Cfg::kStages * Cfg::kSub * kATileBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::kStages;
@@ -215,27 +220,31 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         b2 = 0;
         b3 = 0;
       }
-      int kb = 0;
-      for (int tap = 0; tap < p.taps; ++tap) {
-        const int dr = (p.taps == 9) ? tap / 3 - 1 : 0;
-        const int ds = (p.taps == 9) ? tap % 3 - 1 : 0;
-        for (int cb = 0; cb < p.cin_blocks; ++cb, ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          if (elect_one()) {
-            if (p.dbg_skip_loads && issued >= Cfg::kStages) {
-              mbar_arrive(&full[stage]);
-            } else {
-              mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-              tma_load_4d(&tmA, &full[stage], smA + stage * kATileBytes, cb * kBlockK, b1 + ds, b2 + dr, b3);
-              tma_load_2d(&tmB, &full[stage], smB + stage * Cfg::kBTileBytes, kb * kBlockK, nt * BN);
+      for (int kb = 0; kb < num_kb; kb += Cfg::kSub) {
+        const int nsub = (num_kb - kb) < Cfg::kSub ? (num_kb - kb) : Cfg::kSub;
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          if (p.dbg_skip_loads && issued >= Cfg::kStages) {
+            mbar_arrive(&full[stage]);
+          } else {
+            mbar_arrive_expect_tx(&full[stage], nsub * Cfg::kSubBytes);
+            for (int sub = 0; sub < nsub; ++sub) {
+              const int kk = kb + sub;
+              const int tap = kk / p.cin_blocks;
+              const int cb = kk - tap * p.cin_blocks;
+              const int dr = (p.taps == 9) ? tap / 3 - 1 : 0;
+              const int ds = (p.taps == 9) ? tap % 3 - 1 : 0;
+              const int slot = stage * Cfg::kSub + sub;
+              tma_load_4d(&tmA, &full[stage], smA + slot * kATileBytes, cb * kBlockK, b1 + ds, b2 + dr, b3);
+              tma_load_2d(&tmB, &full[stage], smB + slot * Cfg::kBTileBytes, kk * kBlockK, nt * BN);
             }
           }
-          __syncwarp();
-          ++issued;
-          if (++stage == Cfg::kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        ++issued;
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
@@ -252,18 +261,25 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = 0; kb < num_kb; kb += Cfg::kSub) {
+        const int nsub = (num_kb - kb) < Cfg::kSub ? (num_kb - kb) : Cfg::kSub;
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         if (elect_one()) {
-          // descriptor start-address field is (addr >> 4): stage stride and the 32 B K-advance are plain adds
-          const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (kATileBytes >> 4));
-          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * (Cfg::kBTileBytes >> 4));
+          // descriptor start-address field is (addr >> 4): slot stride and the 32 B K-advance are plain adds
+          const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * Cfg::kSub * (kATileBytes >> 4));
+          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * Cfg::kSub * (Cfg::kBTileBytes >> 4));
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          for (int sub = 0; sub < Cfg::kSub; ++sub) {
+            if (sub < nsub) {
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_bf16(tmem_d, adesc + sub * (kATileBytes >> 4) + 2 * k, bdesc + sub * (Cfg::kBTileBytes >> 4) + 2 * k,
+                          idesc, (kb | sub | k) != 0);
+            }
+          }
           umma_commit(&empty[stage]);
-          if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+          if (kb + Cfg::kSub >= num_kb) umma_commit(&tmem_full[acc]);
         }
         __syncwarp();
         if (++stage == Cfg::kStages) {
