@@ -1,0 +1,174 @@
+"""CPU tests (pytest -m "not gpu") of the host side: the C-ABI library loads and exports every symbol the header
+declares (no compute calls), the time-shard plan partitions trajectories correctly, and the halo exchange /
+frame gather work with world_size 2 over gloo.  The sharded-score equivalence is checked with the oracle's window
+composition standing in for the UNet (src/thor/score.py:68-93 makes frame i depend on frames i-k..i+k only).
+"""
+import os
+import re
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from climate2weather_b200 import _lib, sharding
+from oracle import score_ref
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+# ------------------------------------------------------------------------------------------------ C ABI
+def test_library_exports_every_header_symbol():
+    """include/c2w_b200.h is the boundary: every function it declares must resolve in libc2w_b200.so, and the ctypes
+    table must cover exactly that set."""
+    text = (ROOT / "include" / "c2w_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    declared = set(re.findall(r"\b(c2w_[a-z0-9_]+)\s*\(", text))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    lib = _lib.load()  # raises C2WError if the library is missing, AttributeError if a symbol is
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.c2w_abi_version() >= 1
+
+
+def test_no_cpu_path():
+    """The product must fail loudly without a CUDA device (no CPU fallback)."""
+    import climate2weather_b200 as c2w
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    net = c2w.ScoreUNet(channels=20, embedding_dim=64, hidden_channels=(64,), hidden_blocks=(1,), attention_levels=())
+    with pytest.raises(_lib.C2WError):
+        net(torch.zeros(1, 20, 16, 16), torch.tensor(0.5))
+    sf = c2w.DefaultScoreFunction(net, markov_order=2, noise_process=c2w.SDAPipeline())
+    with pytest.raises(_lib.C2WError):
+        sf(torch.zeros(8, 4, 16, 16), torch.tensor(0.5))
+
+
+def test_package_never_imports_oracle():
+    """oracle/ is test infrastructure: nothing under climate2weather_b200/ may import it."""
+    for f in (ROOT / "climate2weather_b200").rglob("*.py"):
+        src = f.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+# ------------------------------------------------------------------------------------------------ shard plan
+@pytest.mark.parametrize("L,k,world", [(168, 6, 1), (168, 6, 2), (720, 6, 8), (25, 6, 2), (30, 2, 4), (8760, 6, 8),
+                                       (13, 6, 1), (181, 6, 7)])
+def test_plan_partitions_windows_and_frames(L, k, world):
+    plans = [sharding.make_plan(L, k, r, world) for r in range(world)]
+    nw = L - 2 * k
+    # windows: contiguous, disjoint, cover [0, nw), balanced to within one
+    assert plans[0].win_lo == 0 and plans[-1].win_hi == nw
+    for a, b in zip(plans, plans[1:]):
+        assert a.win_hi == b.win_lo
+    sizes = [p.win_hi - p.win_lo for p in plans]
+    assert max(sizes) - min(sizes) <= 1
+    # owned frames: contiguous, disjoint, cover [0, L)
+    assert plans[0].own_lo == 0 and plans[-1].own_hi == L
+    for a, b in zip(plans, plans[1:]):
+        assert a.own_hi == b.own_lo
+    for p in plans:
+        # local frames = every frame any local window touches; owned frames lie inside with k halo frames
+        assert p.frame_lo == p.win_lo and p.frame_hi == p.win_hi + 2 * k
+        assert p.frame_lo <= p.own_lo and p.own_hi <= p.frame_hi
+        if p.rank > 0:
+            assert p.own_lo - p.frame_lo == k
+        if p.rank < world - 1:
+            assert p.frame_hi - p.own_hi == k
+        # every owned frame's score source (fold index map) is a window of this rank
+        fi = score_ref.fold_index(L, k, 1)[:, 0, 0]
+        src = fi[p.own_lo:p.own_hi]
+        assert src.min() >= p.win_lo and src.max() < p.win_hi
+
+
+def test_plan_rejects_too_many_ranks():
+    with pytest.raises(ValueError):
+        sharding.make_plan(12, 6, 0, 1)
+    with pytest.raises(ValueError):
+        sharding.make_plan(30, 6, 0, 8)
+
+
+def _fake_net(u, t):
+    """A window-local map with the UNet's signature: mixes every slot of a window into every output slot."""
+    n, wc, H, W = u.shape
+    return torch.tanh(u.flip(1) * 0.7 + u.mean(dim=1, keepdim=True) * (1.0 + t))
+
+
+@pytest.mark.parametrize("L,k,world", [(40, 3, 2), (61, 6, 4), (25, 2, 3)])
+def test_simulated_shards_reproduce_unsharded_score_bit_exact(L, k, world):
+    """Each simulated rank evaluates only its windows on its local frames (with halos) and keeps its owned
+    frames; the concatenation must equal the unsharded composition exactly (index work: bit-exact)."""
+    C, H, W = 4, 4, 4
+    x = torch.randn(L, C, H, W, generator=torch.Generator().manual_seed(L))
+    t = torch.tensor(0.3)
+    full = score_ref.window_score(_fake_net, x, t, k)
+    nw = L - 2 * k
+    parts = []
+    for r in range(world):
+        p = sharding.make_plan(L, k, r, world)
+        u = score_ref.unfold(x[p.frame_lo:p.frame_hi], k)  # local windows == global windows [win_lo, win_hi)
+        out = _fake_net(u, t)
+        loc = torch.empty(p.own_n, C, H, W)
+        for i in range(p.own_lo, p.own_hi):  # src/thor/score.py:76-88 on global indices
+            if i < k:
+                win, slot = 0, i
+            elif i < L - k:
+                win, slot = i - k, k
+            else:
+                win, slot = nw - 1, i - (L - 2 * k - 1)
+            loc[i - p.own_lo] = out[win - p.win_lo, slot * C:(slot + 1) * C]
+        parts.append(loc)
+    assert torch.equal(torch.cat(parts), full)
+
+
+# ------------------------------------------------------------------------------------------------ gloo, world 2
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank: int, world: int, port: int, L: int, k: int, out_dir: str):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        shape = (4, 3, 2)
+        x = torch.randn(L, *shape)
+        p = sharding.make_plan(L, k, rank, world)
+        # local copy with POISONED halos: only owned frames are valid before the exchange
+        loc = x[p.frame_lo:p.frame_hi].clone()
+        lo, hi = p.own_lo - p.frame_lo, p.own_hi - p.frame_lo
+        loc[:lo] = float("nan")
+        loc[hi:] = float("nan")
+        sharding.exchange_halos(loc, p)
+        ok_halo = torch.equal(loc, x[p.frame_lo:p.frame_hi])
+        # "update" the owned frames rank-locally, exchange again, gather
+        loc[lo:hi] = loc[lo:hi] * 2 + 1
+        sharding.exchange_halos(loc, p)
+        ok_halo2 = torch.equal(loc, x[p.frame_lo:p.frame_hi] * 2 + 1)
+        full = sharding.all_gather_frames(loc[lo:hi].contiguous(), p)
+        ok_gather = torch.equal(full, x * 2 + 1)
+        # the corrector's scalar: sum over ranks of owned-frame sums == global sum
+        s = (loc[lo:hi].double() ** 2).sum().reshape(1)
+        dist.all_reduce(s)
+        ok_sum = abs(s.item() - ((x * 2 + 1).double() ** 2).sum().item()) < 1e-6 * s.item()
+        Path(out_dir, f"ok{rank}").write_text(f"{int(ok_halo)}{int(ok_halo2)}{int(ok_gather)}{int(ok_sum)}")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("L,k", [(40, 6), (31, 3)])
+def test_halo_exchange_and_gather_gloo_world2(tmp_path, L, k):
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, L, k, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert (tmp_path / f"ok{r}").read_text() == "1111"
