@@ -53,6 +53,30 @@ class Guide(C.Structure):
     ]
 
 
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("n_img", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("cin", C.c_int32),
+        ("stride", C.c_int32),
+        ("conv3x3", C.c_int32),
+        ("w_packed", C.c_void_p),
+        ("cout_pad", C.c_int32),
+        ("bias", C.c_void_p),
+        ("mode", C.c_int32),
+        ("res", C.c_void_p),
+        ("out", C.c_void_p),
+        ("out_f32", C.c_void_p),
+        ("bn", C.c_int32),
+        ("variant", C.c_int32),
+        ("max_ctas", C.c_int32),
+        ("skip_loads", C.c_int32),
+        ("ln_out", C.c_void_p),
+        ("ln_mod", C.c_void_p),
+        ("ln_upsample", C.c_int32),
+    ]
+
+
 _vp, _i, _i64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 
 # name -> (restype, argtypes); every symbol include/c2w_b200.h declares
@@ -72,10 +96,10 @@ SIGNATURES = {
     "c2w_guided_step": (_i, [C.POINTER(Guide), _vp]),
     "c2w_reduce_partials": (_i, [_vp, C.c_int32, _vp, _vp]),
     "c2w_corrector_update": (_i, [_vp, _vp, _vp, _vp, _d, _f, _f, _i64, _i64, C.c_uint64, C.c_uint32, _vp, _vp]),
+    "c2w_op_conv_ex": (_i, [C.POINTER(ConvDesc), _vp]),
     "c2w_op_conv": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "c2w_op_layernorm": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
     "c2w_op_attention": (_i, [_vp, _vp, _i, _i, _i, _vp]),
-    "c2w_op_im2col_s2": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "c2w_op_gather_windows": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "c2w_op_modulation": (_i, [_vp, _f, _vp, _vp, _vp]),
     "c2w_total_mod_channels": (_i, [_vp]),

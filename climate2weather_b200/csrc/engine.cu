@@ -1,5 +1,7 @@
 // Host side of the C-ABI: handle, weight packing, workspace plan and the static launch sequence of the
 // ScoreUNet forward (model/nn.py:220-242) over a batch of Markov windows.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <map>
 #include <string>
@@ -45,7 +47,7 @@ struct LevelW {
   std::vector<AttnW> dattn, aattn;
 };
 
-enum OpKind { OP_CONV, OP_LN, OP_IM2COL, OP_ATTN };
+enum OpKind { OP_CONV, OP_LN, OP_ATTN };
 struct Op {
   OpKind kind;
   // conv
@@ -88,6 +90,7 @@ struct c2w_handle {
   Plan plan;
   int sms = 0;
   bool timing = false;
+  bool fuse_ln = true;  // C2W_NO_FUSE_LN=1 keeps every LayerNorm a separate kernel (A/B runs)
   std::vector<TimedSpan> spans;
   size_t spans_used = 0;
 };
@@ -250,7 +253,7 @@ int build_plan(c2w_handle* h, int n, void* base, size_t* bytes_out) {
   float* mods = B.take<float>(h->total_mod);
   float* out32 = B.take<float>(n * HW0 * h->levels[0].tail.cout_pad);
   std::vector<bf16*> xs(nl), as(nl), hs(nl);
-  size_t up_elems = 0, col_elems = 0, qkv_elems = 0, att_elems = 0;
+  size_t up_elems = 0, qkv_elems = 0, att_elems = 0;
   for (int l = 0; l < nl; ++l) {
     const LevelW& L = h->levels[l];
     const size_t e = static_cast<size_t>(n) * L.H * L.W * L.C;
@@ -260,7 +263,6 @@ int build_plan(c2w_handle* h, int n, void* base, size_t* bytes_out) {
     if (l > 0) {
       const LevelW& U = h->levels[l - 1];
       up_elems = std::max(up_elems, static_cast<size_t>(n) * U.H * U.W * L.C);
-      col_elems = std::max(col_elems, static_cast<size_t>(n) * L.H * L.W * 9 * U.C);
     }
     if (L.attn) {
       qkv_elems = std::max(qkv_elems, static_cast<size_t>(n) * L.H * L.W * 3 * L.C);
@@ -268,7 +270,6 @@ int build_plan(c2w_handle* h, int n, void* base, size_t* bytes_out) {
     }
   }
   bf16* up = B.take<bf16>(up_elems);
-  bf16* col = B.take<bf16>(col_elems);
   bf16* qkv = B.take<bf16>(qkv_elems);
   bf16* att = B.take<bf16>(att_elems);
   *bytes_out = B.off + 1024;
@@ -279,24 +280,35 @@ int build_plan(c2w_handle* h, int n, void* base, size_t* bytes_out) {
   P.mods = mods;
   P.out32 = out32;
 
+  // H, W: INPUT image size; stride 2 halves it (heads of levels > 0, model/nn.py:169-176)
   auto add_conv = [&](bool c3, const bf16* in, int H, int W, int cin, const ConvW& w, int mode, const bf16* res,
-                      bf16* out, bool is_final) -> int {
+                      bf16* out, bool is_final, int stride = 1) -> int {
     Op op;
     op.kind = OP_CONV;
     const int bn = conv_pick_bn(w.cout_pad);
-    if (!conv_launch_init(&op.conv, c3, in, n, H, W, cin, w.w, w.cout_pad, bn, h->sms))
-      return fail(C2W_ERR_INVALID, "cannot build conv launch (H=%d W=%d cin=%d cout=%d): W must divide 128", H, W, cin,
-                  w.cout_pad);
+    if (!conv_launch_init(&op.conv, c3, in, n, H, W, cin, w.w, w.cout_pad, bn, h->sms, stride))
+      return fail(C2W_ERR_INVALID, "cannot build conv launch (H=%d W=%d cin=%d cout=%d stride=%d)", H, W, cin,
+                  w.cout_pad, stride);
     op.conv.p.mode = mode;
     op.conv.p.bias = w.b;
-    op.conv.p.res = res;
-    op.conv.p.out = out;
-    op.pix_per_img = H * W;
+    if (mode == EPI_BIAS_RES && res != out)
+      return fail(C2W_ERR_INVALID, "residual convs accumulate in place (res must be out)");
+    if (out && !conv_launch_set_out(&op.conv, out)) return fail(C2W_ERR_CUDA, "cannot encode the output tensor map");
+    op.pix_per_img = (H / stride) * (W / stride);
     op.is_final = is_final;
     P.ops.push_back(op);
     return C2W_OK;
   };
+  // Channel LayerNorm of `in` (+ modulation) -> `out`.  When `in` was just produced by a conv whose single N tile
+  // holds all C channels of a pixel, the normalisation is done in that conv's epilogue (no extra pass over HBM).
   auto add_ln = [&](const bf16* in, bf16* out, int C, int H, int W, int upf, int mod_off) {
+    if (h->fuse_ln && !P.ops.empty()) {
+      Op& prev = P.ops.back();
+      if (prev.kind == OP_CONV && !prev.is_final && prev.conv.out_ptr == in && prev.conv.cout_pad == C &&
+          conv_launch_can_ln(&prev.conv, upf) &&
+          conv_launch_set_ln(&prev.conv, out, mod_off >= 0 ? mods + mod_off : nullptr, upf))
+        return;
+    }
     Op op;
     op.kind = OP_LN;
     op.in = in;
@@ -349,15 +361,7 @@ int build_plan(c2w_handle* h, int n, void* base, size_t* bytes_out) {
       rc = add_conv(true, xin, L.H, L.W, h->cin_pad, L.head, EPI_BIAS, nullptr, xs[0], false);
     } else {
       const LevelW& U = h->levels[l - 1];
-      Op op;
-      op.kind = OP_IM2COL;
-      op.in = xs[l - 1];
-      op.out = col;
-      op.H = U.H;
-      op.W = U.W;
-      op.C = U.C;
-      P.ops.push_back(op);
-      rc = add_conv(false, col, L.H, L.W, 9 * U.C, L.head, EPI_BIAS, nullptr, xs[l], false);
+      rc = add_conv(true, xs[l - 1], U.H, U.W, U.C, L.head, EPI_BIAS, nullptr, xs[l], false, 2);
     }
     if (rc) return rc;
     rc = add_blocks(l, L.desc, L.dattn);
@@ -419,8 +423,7 @@ int run_plan(c2w_handle* h, int nn, const FinalSpec& fs, cudaStream_t st) {
         const long long m_total = static_cast<long long>(nn) * op.pix_per_img;
         L.p.m_total = static_cast<int>(m_total);
         L.p.num_m_tiles = ceil_div(m_total, kBlockM);
-        const int tiles = L.p.num_m_tiles * L.p.num_n_tiles;
-        L.grid = tiles < h->sms ? tiles : h->sms;
+        conv_set_grid(&L, h->sms);
         if (op.is_final) {
           L.p.mode = fs.mode;
           L.p.out_f32 = P.out32;
@@ -442,13 +445,6 @@ int run_plan(c2w_handle* h, int nn, const FinalSpec& fs, cudaStream_t st) {
         int rc = launch_ln(op.in, op.mod_off >= 0 ? P.mods + op.mod_off : nullptr, op.out,
                            static_cast<long long>(nn) * op.H * op.W, op.C, op.H, op.W, op.up, h->sms, st);
         if (rc) return rc;
-        break;
-      }
-      case OP_IM2COL: {
-        SpanGuard sg(h, 1, st);
-        const long long items = static_cast<long long>(nn) * (op.H / 2) * (op.W / 2) * 9 * (op.C / 8);
-        im2col_s2_kernel<<<grid_for(items, 256, h->sms), 256, 0, st>>>(op.in, op.out, nn, op.H, op.W, op.C);
-        C2W_CUDA(cudaGetLastError());
         break;
       }
       case OP_ATTN: {
@@ -497,6 +493,10 @@ int c2w_create(const c2w_config* cfg, c2w_handle** out) {
   h->cin = cfg->frame_channels * cfg->window;
   h->cin_pad = pad64(h->cin);
   h->sms = sms;
+  {
+    const char* e = getenv("C2W_NO_FUSE_LN");
+    h->fuse_ln = !(e && e[0] == '1');
+  }
   *out = h;
   return C2W_OK;
 }
@@ -791,14 +791,6 @@ int c2w_op_attention(const void* qkv, void* out, int n, int T, int C, void* stre
   C2W_REQUIRE(qkv && out && n >= 1, "c2w_op_attention: bad argument");
   return launch_attention(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), n, T, C,
                           static_cast<cudaStream_t>(stream));
-}
-int c2w_op_im2col_s2(const void* x, void* col, int n, int H, int W, int C, void* stream) {
-  C2W_REQUIRE(x && col && n >= 1 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "c2w_op_im2col_s2: bad argument");
-  const long long items = static_cast<long long>(n) * (H / 2) * (W / 2) * 9 * (C / 8);
-  im2col_s2_kernel<<<grid_for(items, 256, c2w_num_sms()), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(x), static_cast<bf16*>(col), n, H, W, C);
-  C2W_CUDA(cudaGetLastError());
-  return C2W_OK;
 }
 int c2w_op_gather_windows(const float* traj, void* out, int n, int hw, int C, int window, int cin_pad, int frame0,
                           void* stream) {

@@ -3,7 +3,6 @@
 //   K2  channel_layernorm   model/nn.py:154,183,44 (zuko LayerNorm over C) + modulation add (+ 2x nearest upsample)
 //   K3  time embedding MLP + all modulation projections        model/score.py:14-34,61-67 ; model/nn.py:149
 //   K4  attention core      model/nn.py:64-85
-//   im2col for the four stride-2 head convs                    model/nn.py:169-176
 //   K6  guided eps + predictor update                          src/thor/score.py:44-60,24-35 ; pipelines.py:41-46
 //   K7  corrector (guided eps, ||eps||^2, Langevin update)     src/thor/pipelines.py:81-88
 //   layout converters between the reference's NCHW fp32 tensors and the device layouts
@@ -330,29 +329,6 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, in
         *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(blockIdx.y) * T + q0 + tq) * C + 2 * c2) =
             pack_bf16x2(a0[i], a1[i]);
     }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ im2col (stride 2)
-// x: bf16 [n, H, W, C] -> col: bf16 [n*(H/2)*(W/2), 9*C], k = (r*3+s)*C + c, ih = 2*oh + r - 1, iw = 2*ow + s - 1.
-__global__ void im2col_s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ col, int n, int H, int W, int C) {
-  const int Ho = H / 2, Wo = W / 2, c8 = C / 8;
-  const long long total = static_cast<long long>(n) * Ho * Wo * 9 * c8;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(idx % c8);
-    long long r = idx / c8;
-    const int tap = static_cast<int>(r % 9);
-    r /= 9;
-    const int ow = static_cast<int>(r % Wo);
-    r /= Wo;
-    const int oh = static_cast<int>(r % Ho);
-    const long long img = r / Ho;
-    const int ih = 2 * oh + tap / 3 - 1, iw = 2 * ow + tap % 3 - 1;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (ih >= 0 && ih < H && iw >= 0 && iw < W)
-      v = *reinterpret_cast<const uint4*>(x + ((img * H + ih) * W + iw) * C + g * 8);
-    *reinterpret_cast<uint4*>(col + (((img * Ho + oh) * Wo + ow) * 9 + tap) * C + g * 8) = v;
   }
 }
 

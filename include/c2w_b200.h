@@ -102,13 +102,36 @@ int c2w_corrector_update(float* x, const float* eps, const float* z, const doubl
                          int32_t* nan_flag, void* stream);
 
 /* ---- op-level hooks (parity tests of single kernels; same kernels the calls above launch) ----------------- */
+/* One launch of K1 (Conv2d 3x3 pad 1, stride 1 or 2 — model/nn.py:155,157,169,185,193,194 — or a plain GEMM for the
+ * 1x1 Conv1d of model/nn.py:45,47) with every epilogue option the engine uses. */
+typedef struct c2w_conv_desc {
+  const void* x;        /* bf16 NHWC [n_img, H, W, cin] (conv3x3) or [n_img*H*W, cin] row-major (GEMM)            */
+  int32_t n_img, H, W;  /* INPUT image size                                                                       */
+  int32_t cin;          /* multiple of 64                                                                         */
+  int32_t stride;       /* 1 or 2 (conv3x3 only); output is [n_img, H/stride, W/stride, cout_pad]                 */
+  int32_t conv3x3;      /* 0: GEMM                                                                                */
+  const void* w_packed; /* bf16 [cout_pad, taps*cin], k = (r*3+s)*cin + c                                         */
+  int32_t cout_pad;     /* multiple of 64                                                                         */
+  const float* bias;    /* fp32 [cout_pad]                                                                        */
+  int32_t mode;         /* 0 bias, 1 bias+SiLU, 2 bias+residual, 4 fp32 output                                    */
+  const void* res;      /* bf16 [M, cout_pad] (mode 2; may alias out)                                             */
+  void* out;            /* bf16 [M, cout_pad]                                                                     */
+  float* out_f32;       /* mode 4                                                                                 */
+  int32_t bn;           /* N tile (0 = pick)                                                                      */
+  int32_t variant;      /* -1 pick; else bit 0: CTA pair (cta_group::2)                                            */
+  int32_t max_ctas;     /* 0 = one per SM                                                                         */
+  int32_t skip_loads;   /* diagnostics: stop issuing TMA loads once the ring is primed (results are garbage)      */
+  void* ln_out;         /* non-NULL: fused channel LayerNorm of (bf16(out) + ln_mod) -> bf16 (bn == cout_pad)     */
+  const float* ln_mod;  /* fp32 [cout_pad] or NULL                                                                */
+  int32_t ln_upsample;  /* write each normalised pixel to its 2x2 block of [n_img, 2Ho, 2Wo, cout_pad]            */
+} c2w_conv_desc;
+int c2w_op_conv_ex(const c2w_conv_desc* d, void* stream);
 int c2w_op_conv(const void* x, int n_img, int H, int W, int cin, const void* w_packed, int cout_pad,
                 const float* bias, int mode, const void* res, void* out, float* out_f32, int conv3x3, int bn,
                 int max_ctas, void* stream);
 int c2w_op_layernorm(const void* x_bf16, const float* mod, void* out_bf16, int64_t npix, int C, int H, int W,
                      int upsample, void* stream);
 int c2w_op_attention(const void* qkv_bf16, void* out_bf16, int n, int T, int C, void* stream);
-int c2w_op_im2col_s2(const void* x_bf16, void* col_bf16, int n, int H, int W, int C, void* stream);
 int c2w_op_gather_windows(const float* traj, void* out_bf16, int n, int hw, int C, int window, int cin_pad,
                           int frame0, void* stream);
 int c2w_op_modulation(c2w_handle* h, float t, float* emb_out, float* mods_out, void* stream);

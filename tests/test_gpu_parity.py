@@ -106,7 +106,105 @@ def test_gemm_mode_vs_torch(lib, dev):
         assert relerr(out32, a.float() @ w.float().t() + b) < 1e-4
 
 
-# ------------------------------------------------------------------------------------------------ K2 / K4 / im2col / K0
+def _conv_ex(lib, xb, wp, bp, mode, n, H, W, stride=1, res=None, variant=-1, bn=0, ln_mod=None, ln=False, ln_up=0,
+             f32=False, max_ctas=0):
+    """One c2w_op_conv_ex launch on NHWC bf16 input xb [n, H, W, cin_pad]; returns (out, ln_out)."""
+    from climate2weather_b200 import _lib
+    dev = xb.device
+    cout_pad = wp.shape[0]
+    Ho, Wo = H // stride, W // stride
+    M = n * Ho * Wo
+    out = res.clone() if mode == 2 else torch.empty(M, cout_pad, device=dev, dtype=torch.bfloat16)
+    out32 = torch.empty(M, cout_pad, device=dev) if f32 else None
+    up = 2 if ln_up else 1
+    ln_out = torch.full((n, Ho * up, Wo * up, cout_pad), 7.0, device=dev, dtype=torch.bfloat16) if ln else None
+    d = _lib.ConvDesc()
+    d.x, d.n_img, d.H, d.W, d.cin, d.stride, d.conv3x3 = xb.data_ptr(), n, H, W, xb.shape[-1], stride, 1
+    d.w_packed, d.cout_pad, d.bias, d.mode = wp.data_ptr(), cout_pad, bp.data_ptr(), mode
+    d.res = out.data_ptr() if mode == 2 else None
+    d.out = out.data_ptr()
+    d.out_f32 = out32.data_ptr() if f32 else None
+    d.bn, d.variant, d.max_ctas, d.skip_loads = bn, variant, max_ctas, 0
+    d.ln_out = ln_out.data_ptr() if ln else None
+    d.ln_mod = ln_mod.data_ptr() if ln_mod is not None else None
+    d.ln_upsample = ln_up
+    _lib.check(lib.c2w_op_conv_ex(ctypes.byref(d), stream()), "c2w_op_conv_ex")
+    torch.cuda.synchronize()
+    return (out32 if f32 else out), ln_out
+
+
+def _conv_problem(dev, n, H, W, cin, cout, seed):
+    g = torch.Generator().manual_seed(seed)
+    cin_pad, cout_pad = (cin + 63) // 64 * 64, (cout + 63) // 64 * 64
+    x = torch.randn(n, cin, H, W, generator=g).to(dev)
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (3 * math.sqrt(cin))).to(dev)
+    b = torch.randn(cout, generator=g).to(dev)
+    xb = torch.zeros(n, H, W, cin_pad, device=dev, dtype=torch.bfloat16)
+    xb[..., :cin] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+    wp = pack_w(w, cin_pad, cout_pad)
+    bp = torch.zeros(cout_pad, device=dev)
+    bp[:cout] = b
+    return g, xb, w, b, wp, bp
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n,H,W,cin,cout,mode", [
+    (2, 128, 128, 128, 128, 1), (3, 64, 64, 128, 128, 2), (5, 32, 32, 128, 128, 0), (1, 128, 128, 64, 128, 1)])
+def test_conv3x3_kernel_variants(lib, dev, variant, n, H, W, cin, cout, mode):
+    """Single CTA (0) and CTA pair / cta_group::2 (1) compute the same conv; odd tile counts exercise the pair's
+    out-of-range half."""
+    g, xb, w, b, wp, bp = _conv_problem(dev, n, H, W, cin, cout, 11 * n + cin)
+    M = n * H * W
+    res = torch.randn(M, wp.shape[0], generator=g).to(dev).to(torch.bfloat16)
+    got, _ = _conv_ex(lib, xb, wp, bp, mode, n, H, W, res=res, variant=variant)
+    ref = F.conv2d(xb[..., :cin].float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), b, padding=1)
+    if mode == 1:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 3, 1).reshape(M, cout)
+    if mode == 2:
+        ref = ref + res[:, :cout].float()
+    assert relerr(got.float()[:, :cout], ref) < 2 ** -7
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n,H,W,cin,cout", [(2, 128, 128, 128, 128), (3, 64, 64, 128, 256), (3, 32, 32, 256, 384),
+                                            (5, 16, 16, 384, 512), (1, 16, 32, 64, 64)])
+def test_conv3x3_stride2_vs_torch(lib, dev, variant, n, H, W, cin, cout):
+    """Head convs of levels > 0 (model/nn.py:169-176): stride 2, pad 1, read straight from the NHWC input through
+    an element-strided tensor map."""
+    g, xb, w, b, wp, bp = _conv_problem(dev, n, H, W, cin, cout, 5 * n + cout)
+    got, _ = _conv_ex(lib, xb, wp, bp, 0, n, H, W, stride=2, variant=variant)
+    ref = F.conv2d(xb[..., :cin].float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), b, padding=1, stride=2)
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, cout)
+    assert relerr(got.float()[:, :cout], ref) < 2 ** -7
+
+
+@pytest.mark.parametrize("n,H,W,C,mode,up,use_mod,variant", [
+    (2, 128, 128, 128, 2, 0, True, 1), (2, 64, 64, 128, 0, 0, True, 1), (3, 32, 32, 256, 2, 0, True, 1),
+    (3, 32, 32, 256, 2, 1, False, 1), (2, 64, 64, 128, 2, 1, False, 0), (1, 16, 16, 64, 0, 0, True, 0)])
+def test_conv3x3_fused_layernorm(lib, dev, n, H, W, C, mode, up, use_mod, variant):
+    """Conv epilogue that also emits LN(out + mod) (model/nn.py:154,183-184): must equal the standalone K2 semantics
+    applied to the bf16 conv output -> 2^-7 of the normalised scale."""
+    g, xb, w, b, wp, bp = _conv_problem(dev, n, H, W, C, C, 17 * n + C + up)
+    M = n * H * W
+    res = torch.randn(M, C, generator=g).to(dev).to(torch.bfloat16)
+    mod = torch.randn(C, generator=g).to(dev) if use_mod else None
+    out, ln_out = _conv_ex(lib, xb, wp, bp, mode, n, H, W, res=res, variant=variant, ln=True, ln_mod=mod, ln_up=up)
+    ref = F.conv2d(xb.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), b, padding=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(M, C)
+    if mode == 2:
+        ref = ref + res.float()
+    assert relerr(out.float(), ref) < 2 ** -7
+    v = out.float().reshape(n, H, W, C).permute(0, 3, 1, 2).cpu()
+    if use_mod:
+        v = v + mod.cpu()[None, :, None, None]
+    lref = unet_ref.channel_layernorm(v)
+    if up:
+        lref = F.interpolate(lref, scale_factor=2, mode="nearest")
+    assert relerr(ln_out.float().cpu().permute(0, 3, 1, 2), lref) < 2 ** -7
+
+
+# ------------------------------------------------------------------------------------------------ K2 / K4 / K0
 @pytest.mark.parametrize("C", [64, 128, 256, 384, 512])
 @pytest.mark.parametrize("up", [0, 1])
 def test_channel_layernorm(lib, dev, C, up):
@@ -142,18 +240,6 @@ def test_attention_core(lib, dev, T, C):
     w = torch.softmax(torch.einsum("btc,bsc->bts", q * s, k * s), dim=-1)
     ref = torch.einsum("bts,bsc->btc", w, v)
     assert relerr(out.float().cpu(), ref) < 2 ** -7
-
-
-def test_im2col_s2_bit_exact(lib, dev):
-    from climate2weather_b200 import _lib
-    n, H, W, C = 2, 16, 16, 64
-    x = torch.randn(n, H, W, C, generator=torch.Generator().manual_seed(3)).to(dev).to(torch.bfloat16)
-    col = torch.empty(n * (H // 2) * (W // 2), 9 * C, device=dev, dtype=torch.bfloat16)
-    _lib.check(lib.c2w_op_im2col_s2(x.data_ptr(), col.data_ptr(), n, H, W, C, stream()), "c2w_op_im2col_s2")
-    torch.cuda.synchronize()
-    u = F.unfold(x.float().permute(0, 3, 1, 2), kernel_size=3, padding=1, stride=2)  # [n, C*9, Ho*Wo], (c, tap)
-    ref = u.reshape(n, C, 9, -1).permute(0, 3, 2, 1).reshape(-1, 9 * C)
-    assert torch.equal(col.float(), ref)
 
 
 @pytest.mark.parametrize("L,k,first,n", [(16, 6, 0, 4), (16, 6, 2, 2), (9, 2, 1, 4)])

@@ -98,20 +98,31 @@ def check_gemm(name, M, K, N, seed=1):
     return ok
 
 
-def timeit(name, n, H, W, cin, cout, iters=20, **kw):
+def timeit(name, n, H, W, cin, cout, iters=20, variant=-1, bn=0, skip_loads=0, ln=False, res=False, cudnn=True, **kw):
+    sys.path.insert(0, str(ROOT))
+    from climate2weather_b200 import _lib
     cin_pad = (cin + 63) // 64 * 64
     cout_pad = (cout + 63) // 64 * 64
     xb = torch.randn(n, H, W, cin_pad, device=dev).to(torch.bfloat16)
     wp = (torch.randn(cout_pad, 9 * cin_pad, device=dev) / 30).to(torch.bfloat16)
     bp = torch.zeros(cout_pad, device=dev)
     out = torch.empty(n * H * W, cout_pad, device=dev, dtype=torch.bfloat16)
+    ln_out = torch.empty(n * H * W, cout_pad, device=dev, dtype=torch.bfloat16) if ln else None
+    mod = torch.randn(cout_pad, device=dev)
     st = torch.cuda.current_stream().cuda_stream
-    bn = kw.get("bn", 0)
+    L = _lib.load()
+    d = _lib.ConvDesc()
+    d.x, d.n_img, d.H, d.W, d.cin, d.stride, d.conv3x3 = xb.data_ptr(), n, H, W, cin_pad, 1, 1
+    d.w_packed, d.cout_pad, d.bias, d.mode = wp.data_ptr(), cout_pad, bp.data_ptr(), (2 if (ln or res) else 1)
+    d.res = out.data_ptr() if (ln or res) else None
+    d.out = out.data_ptr()
+    d.bn, d.variant, d.max_ctas, d.skip_loads = bn, variant, 0, skip_loads
+    d.ln_out = ln_out.data_ptr() if ln else None
+    d.ln_mod = mod.data_ptr() if ln else None
 
     def call():
-        rc = lib.c2w_op_conv(xb.data_ptr(), n, H, W, cin_pad, wp.data_ptr(), cout_pad, bp.data_ptr(), 1, None,
-                             out.data_ptr(), None, 1, bn, 0, st)
-        assert rc == 0
+        rc = L.c2w_op_conv_ex(ctypes.byref(d), st)
+        assert rc == 0, L.c2w_last_error()
 
     for _ in range(3):
         call()
@@ -125,6 +136,10 @@ def timeit(name, n, H, W, cin, cout, iters=20, **kw):
     ms = e0.elapsed_time(e1) / iters
     flops = 2.0 * n * H * W * cout_pad * 9 * cin_pad
     tf = flops / ms / 1e9
+    if not cudnn:
+        print(json.dumps({"shape": name, "n": n, "H": H, "W": W, "cin": cin, "cout": cout, "ms": round(ms, 4),
+                          "tflops": round(tf, 1)}), flush=True)
+        return
     # cuDNN bf16 channels_last for comparison (library bar)
     xc = xb.permute(0, 3, 1, 2)  # NCHW view of NHWC memory == channels_last
     wc = wp.reshape(cout_pad, 3, 3, cin_pad).permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
@@ -145,7 +160,7 @@ def timeit(name, n, H, W, cin, cout, iters=20, **kw):
 def main():
     print(torch.cuda.get_device_name(0), flush=True)
     if "--only-g2" in sys.argv:  # short run for `ncu --set full -k regex:conv_gemm`
-        timeit("G2", 32, 128, 128, 128, 128, iters=5)
+        timeit("G2", 32, 128, 128, 128, 128, iters=5, cudnn=False)
         return 0
     ok = True
     ok &= check_gemm("gemm-basic", 256, 128, 128)
@@ -165,15 +180,21 @@ def main():
     ok &= check("conv-G2-few-ctas", 4, 128, 128, 128, 128, 1, max_ctas=7)
     print("ALL PASS" if ok else "SOME FAILED", flush=True)
     if "--time" in sys.argv:
-        timeit("G2", 32, 128, 128, 128, 128)
+        timeit("G2 cg1", 32, 128, 128, 128, 128, variant=0)
+        timeit("G2 cg2", 32, 128, 128, 128, 128, variant=1, cudnn=False)
+        timeit("G2 cg2 res", 32, 128, 128, 128, 128, variant=1, res=True, cudnn=False)
+        timeit("G2 cg2+LN", 32, 128, 128, 128, 128, variant=1, ln=True, cudnn=False)
+        timeit("G5 cg2", 64, 64, 64, 128, 128, variant=1, cudnn=False)
         # diagnostics: no TMA traffic after priming -> MMA + smem-read + epilogue ceiling of this kernel structure
-        timeit("G2-noloads", 32, 128, 128, 128, 128, bn=128 | 0x1000)
-        timeit("G8-noloads", 64, 32, 32, 256, 256, bn=256 | 0x1000)
-        timeit("G2-bn64", 32, 128, 128, 128, 128, bn=64)
-        timeit("G5", 64, 64, 64, 128, 128)
-        timeit("G8", 64, 32, 32, 256, 256)
-        timeit("G11", 128, 16, 16, 384, 384)
-        timeit("G14", 156, 8, 8, 512, 512)
+        timeit("G2 cg1 noloads", 32, 128, 128, 128, 128, variant=0, skip_loads=1, cudnn=False)
+        timeit("G2 cg2 noloads", 32, 128, 128, 128, 128, variant=1, skip_loads=1, cudnn=False)
+        timeit("G5 cg2 (cudnn)", 64, 64, 64, 128, 128, variant=1)
+        timeit("G8 cg1", 64, 32, 32, 256, 256, variant=0)
+        timeit("G8 cg2", 64, 32, 32, 256, 256, variant=1, cudnn=False)
+        timeit("G11 cg1", 128, 16, 16, 384, 384, variant=0)
+        timeit("G11 cg2", 128, 16, 16, 384, 384, variant=1, cudnn=False)
+        timeit("G14 cg1", 156, 8, 8, 512, 512, variant=0)
+        timeit("G14 cg2", 156, 8, 8, 512, 512, variant=1, cudnn=False)
     return 0 if ok else 1
 
 
