@@ -447,57 +447,76 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
       if (LN) {
         // ---- channel LayerNorm of the staged rows (two-pass variance in registers) -> global, coalesced: the
-        //      kLPR lanes of a row write its C channels as one contiguous segment (x4 when upsampling)
+        //      kLPR lanes of a row write its C channels as one contiguous segment (x4 when upsampling).
+        //      Batches of kBatch rows per lane keep the shuffle reductions of different rows in flight together.
+        constexpr int kBatch = kIters < 8 ? kIters : 8;
+#pragma unroll 1
+        for (int it0 = 0; it0 < kIters; it0 += kBatch) {
+          float v[kBatch][8];
+          float s[kBatch];
 #pragma unroll
-        for (int it = 0; it < kIters; ++it) {
-          const int r = ew * 16 + it * kRPI + lane / kLPR;
-          const uint32_t addr = stg_u32 + static_cast<uint32_t>(ln_chunk >> 3) * kATileBytes +
-                                static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>((ln_chunk & 7) ^ (r & 7)) << 4);
-          const uint4 xr = ld_shared_v4(addr);
-          const uint32_t w[4] = {xr.x, xr.y, xr.z, xr.w};
-          float v[8];
-          float s = 0.f;
+          for (int b = 0; b < kBatch; ++b) {
+            const int r = ew * 16 + (it0 + b) * kRPI + lane / kLPR;
+            const uint32_t addr = stg_u32 + static_cast<uint32_t>(ln_chunk >> 3) * kATileBytes +
+                                  static_cast<uint32_t>(r) * 128u +
+                                  (static_cast<uint32_t>((ln_chunk & 7) ^ (r & 7)) << 4);
+            const uint4 xr = ld_shared_v4(addr);
+            const uint32_t w[4] = {xr.x, xr.y, xr.z, xr.w};
+            s[b] = 0.f;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
-            v[2 * j] = __low2float(h) + ln_m[2 * j];
-            v[2 * j + 1] = __high2float(h) + ln_m[2 * j + 1];
-            s += v[2 * j] + v[2 * j + 1];
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+              v[b][2 * j] = __low2float(h) + ln_m[2 * j];
+              v[b][2 * j + 1] = __high2float(h) + ln_m[2 * j + 1];
+              s[b] += v[b][2 * j] + v[b][2 * j + 1];
+            }
           }
 #pragma unroll
-          for (int o = kLPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          const float mean = s * (1.0f / BN);
-          float ss = 0.f;
+          for (int o = kLPR / 2; o > 0; o >>= 1)
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            v[e] -= mean;
-            ss += v[e] * v[e];
+            for (int b = 0; b < kBatch; ++b) s[b] += __shfl_xor_sync(0xffffffffu, s[b], o);
+#pragma unroll
+          for (int b = 0; b < kBatch; ++b) {
+            const float mean = s[b] * (1.0f / BN);
+            float ss = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              v[b][e] -= mean;
+              ss += v[b][e] * v[b][e];
+            }
+            s[b] = ss;
           }
 #pragma unroll
-          for (int o = kLPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-          const float inv = 1.0f / sqrtf(ss * (1.0f / (BN - 1)) + p.ln_eps);
-          uint32_t o4[4];
+          for (int o = kLPR / 2; o > 0; o >>= 1)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j] * inv, v[2 * j + 1] * inv);
-            o4[j] = *reinterpret_cast<uint32_t*>(&h);
-          }
-          const uint4 yv = make_uint4(o4[0], o4[1], o4[2], o4[3]);
-          const int mr = mt * kBlockM + r;
-          if (mr < p.m_total) {
-            if (p.ln_up) {
-              const int w0 = mr % p.ln_W;
-              const int t = mr / p.ln_W;
-              const int h0 = t % p.ln_H;
-              const long long n = t / p.ln_H;
-              const long long o00 = (n * 2 * p.ln_H + 2 * h0) * 2 * p.ln_W + 2 * w0;
-              __nv_bfloat16* dst = p.ln_out + o00 * BN + ln_chunk * 8;
-              *reinterpret_cast<uint4*>(dst) = yv;
-              *reinterpret_cast<uint4*>(dst + BN) = yv;
-              *reinterpret_cast<uint4*>(dst + 2ll * p.ln_W * BN) = yv;
-              *reinterpret_cast<uint4*>(dst + (2ll * p.ln_W + 1) * BN) = yv;
-            } else {
-              *reinterpret_cast<uint4*>(p.ln_out + static_cast<long long>(mr) * BN + ln_chunk * 8) = yv;
+            for (int b = 0; b < kBatch; ++b) s[b] += __shfl_xor_sync(0xffffffffu, s[b], o);
+#pragma unroll
+          for (int b = 0; b < kBatch; ++b) {
+            const float inv = rsqrtf(s[b] * (1.0f / (BN - 1)) + p.ln_eps);
+            uint32_t o4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(v[b][2 * j] * inv, v[b][2 * j + 1] * inv);
+              o4[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            const uint4 yv = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+            const int r = ew * 16 + (it0 + b) * kRPI + lane / kLPR;
+            const int mr = mt * kBlockM + r;
+            if (mr < p.m_total) {
+              if (p.ln_up) {
+                const int w0 = mr % p.ln_W;
+                const int t = mr / p.ln_W;
+                const int h0 = t % p.ln_H;
+                const long long n = t / p.ln_H;
+                const long long o00 = (n * 2 * p.ln_H + 2 * h0) * 2 * p.ln_W + 2 * w0;
+                __nv_bfloat16* dst = p.ln_out + o00 * BN + ln_chunk * 8;
+                *reinterpret_cast<uint4*>(dst) = yv;
+                *reinterpret_cast<uint4*>(dst + BN) = yv;
+                *reinterpret_cast<uint4*>(dst + 2ll * p.ln_W * BN) = yv;
+                *reinterpret_cast<uint4*>(dst + (2ll * p.ln_W + 1) * BN) = yv;
+              } else {
+                *reinterpret_cast<uint4*>(p.ln_out + static_cast<long long>(mr) * BN + ln_chunk * 8) = yv;
+              }
             }
           }
         }
