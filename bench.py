@@ -336,8 +336,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=None, help="override L (default 12 + 156 * gpus)")
-    ap.add_argument("--chunk", type=int, default=int(os.environ.get("C2W_CHUNK", 32)), help="windows per UNet launch")
-    ap.add_argument("--e2e-steps", type=int, default=16)
+    ap.add_argument("--chunk", type=int, default=int(os.environ.get("C2W_CHUNK", 156)), help="windows per UNet launch")
+    ap.add_argument("--e2e-steps", type=int, default=32)
     ap.add_argument("--cpu-windows", type=int, default=13)
     ap.add_argument("--ref-steps", type=int, default=3)
     ap.add_argument("--warmup-ref", type=int, default=1)

@@ -1,11 +1,8 @@
 #!/bin/bash
-# Quick GPU session: parity tests, K1 timing sweep, chunk-size sweep of the bench step.
+# Chunk-size sweep of the bench step (windows per UNet launch).
 TAG=${1:-s01}
-OUT=gpurun_out
-mkdir -p $OUT
-timeout 900 python -m pytest tests -m gpu -x -q > $OUT/test_$TAG.log 2>&1; echo "pytest exit=$?"; tail -3 $OUT/test_$TAG.log
-timeout 300 python tools/bringup_conv.py --time > $OUT/bringup_$TAG.log 2>&1; tail -9 $OUT/bringup_$TAG.log
-for ch in ${CHUNKS:-8 16 32 64 156}; do
+OUT=gpurun_out; mkdir -p $OUT
+for ch in ${CHUNKS:-16 26 32 39 52 78 156}; do
   timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu --no-e2e --chunk $ch 2>&1 | grep '^{' | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); r=d['roofline']
