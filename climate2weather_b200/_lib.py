@@ -50,6 +50,8 @@ class Guide(C.Structure):
         ("mode", C.c_int32),
         ("partials", C.c_void_p),
         ("nan_flag", C.c_void_p),
+        ("vjp", C.c_void_p),
+        ("cot_out", C.c_void_p),
     ]
 
 
@@ -89,6 +91,10 @@ SIGNATURES = {
     "c2w_finalize_weights": (_i, [_vp]),
     "c2w_workspace_bytes": (_i64, [_vp, C.c_int32]),
     "c2w_bind_workspace": (_i, [_vp, C.c_int32, _vp, _i64]),
+    "c2w_workspace_bytes_vjp": (_i64, [_vp, C.c_int32]),
+    "c2w_bind_workspace_vjp": (_i, [_vp, C.c_int32, _vp, _i64]),
+    "c2w_unet_vjp": (_i, [_vp, _vp, C.c_int32, _f, _vp, _vp, _vp, _vp]),
+    "c2w_window_score_backward": (_i, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp]),
     "c2w_unet_forward": (_i, [_vp, _vp, C.c_int32, _f, _vp, _vp]),
     "c2w_window_score": (_i, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f, _vp, _vp]),
     "c2w_traj_pack": (_i, [_vp, _vp, _i64, C.c_int32, C.c_int32, _vp]),
@@ -100,6 +106,9 @@ SIGNATURES = {
     "c2w_op_conv": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "c2w_op_layernorm": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
     "c2w_op_attention": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "c2w_op_layernorm_inv": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
+    "c2w_op_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "c2w_op_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "c2w_op_gather_windows": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "c2w_op_modulation": (_i, [_vp, _f, _vp, _vp, _vp]),
     "c2w_total_mod_channels": (_i, [_vp]),

@@ -37,6 +37,7 @@ enum EpiMode : int {
   EPI_BIAS_RES = 2,   // out += acc + bias                      -> bf16   (in place)
   EPI_COMPOSE = 3,    // centre-pick / edge-fill compose        -> fp32 eps [L, H, W, 4]
   EPI_F32 = 4,        // out = acc + bias                       -> fp32 [M, ldc]
+  EPI_DSILU = 5,      // out = (acc + bias) * silu'(aux)        -> bf16   (VJP: aux = stashed pre-activation)
 };
 
 struct ConvParams {
@@ -48,7 +49,8 @@ struct ConvParams {
   int m_total;  // valid rows
   int tile_h, tile_n, tiles_per_img;
   int num_stages;   // depth of the A/B ring
-  int num_staging;  // epilogue staging tiles (2 for residual convs)
+  int num_staging;  // epilogue staging tiles (2 for convs with an auxiliary input tile or a second output)
+  int dual_out;     // EPI_BIAS_SILU only: also store the pre-activation (acc + bias) as a second bf16 tensor
   // epilogue
   int mode;
   int ldc;  // output row pitch (elements)
@@ -58,6 +60,7 @@ struct ConvParams {
   //   ln_out[pixel] = (v - mean_C v) / sqrt(var_C v + eps),  v = bf16(out) + ln_mod, unbiased variance;
   //   ln_up: every pixel is written to its 2x2 nearest-neighbour block of a [n, 2H, 2W, C] tensor (model/nn.py:184)
   __nv_bfloat16* ln_out;
+  float* ln_inv;  // optional: 1 / sqrt(var + eps) per row (stash for the LayerNorm backward)
   const float* ln_mod;
   int ln_up, ln_H, ln_W;  // ln_H x ln_W: output image of this conv (for the upsampled addressing)
   float ln_eps;
@@ -155,10 +158,17 @@ __device__ __forceinline__ void epilogue_chunk_direct(const ConvParams& p, const
   }
 }
 
-// Staged epilogue of one 32-column chunk: bf16 result into the 128B-swizzled staging tile (in place over the
-// prefetched residual in EPI_BIAS_RES).  `stg_row` = shared address of this row in box 0; col = column in the tile.
+// silu'(x) = s (1 + x (1 - s)), s = sigmoid(x) = (1 + tanh(x/2)) / 2
+__device__ __forceinline__ float dsilu_f(float x) {
+  const float sg = fmaf(0.5f, tanh_approx(0.5f * x), 0.5f);
+  return sg * fmaf(x, 1.0f - sg, 1.0f);
+}
+
+// Staged epilogue of one 32-column chunk: bf16 result into the 128B-swizzled staging tile — in place over the
+// TMA-prefetched auxiliary tile (residual in EPI_BIAS_RES, stashed pre-activation in EPI_DSILU).  `stg_row` = shared
+// address of this row in box 0 of the tile; `stg2_row` = same for the second output tile (dual_out).
 __device__ __forceinline__ void epilogue_chunk_staged(const ConvParams& p, const uint32_t (&v)[32], int gcol, int col,
-                                                      uint32_t stg_row, int row) {
+                                                      uint32_t stg_row, uint32_t stg2_row, int row) {
   float f[32];
   const float4* b4 = reinterpret_cast<const float4*>(p.bias + gcol);
 #pragma unroll
@@ -169,23 +179,40 @@ __device__ __forceinline__ void epilogue_chunk_staged(const ConvParams& p, const
     f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z;
     f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
   }
+  const uint32_t boff = static_cast<uint32_t>(col >> 6) * kATileBytes;
+  const int j0 = (col & 63) >> 3;  // first 16 B chunk of this 32-column group inside the 128 B row
   if (p.mode == EPI_BIAS_SILU) {
+    if (p.dual_out) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(f[8 * i + 2 * j], f[8 * i + 2 * j + 1]);
+          o[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        st_shared_v4(stg2_row + boff + (static_cast<uint32_t>((j0 + i) ^ (row & 7)) << 4), o[0], o[1], o[2], o[3]);
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = silu_f(f[i]);
   }
-  const uint32_t box = stg_row + static_cast<uint32_t>(col >> 6) * kATileBytes;
-  const int j0 = (col & 63) >> 3;  // first 16 B chunk of this 32-column group inside the 128 B row
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const uint32_t addr = box + (static_cast<uint32_t>((j0 + i) ^ (row & 7)) << 4);
-    if (p.mode == EPI_BIAS_RES) {
+    const uint32_t addr = stg_row + boff + (static_cast<uint32_t>((j0 + i) ^ (row & 7)) << 4);
+    if (p.mode == EPI_BIAS_RES || p.mode == EPI_DSILU) {
       const uint4 r = ld_shared_v4(addr);
       const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
-        f[8 * i + 2 * j] += __low2float(h);
-        f[8 * i + 2 * j + 1] += __high2float(h);
+        if (p.mode == EPI_BIAS_RES) {
+          f[8 * i + 2 * j] += __low2float(h);
+          f[8 * i + 2 * j + 1] += __high2float(h);
+        } else {
+          f[8 * i + 2 * j] *= dsilu_f(__low2float(h));
+          f[8 * i + 2 * j + 1] *= dsilu_f(__high2float(h));
+        }
       }
     }
     uint32_t o[4];
@@ -201,7 +228,8 @@ __device__ __forceinline__ void epilogue_chunk_staged(const ConvParams& p, const
 template <int BN, int CG, bool LN>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmOut, const ConvParams p) {
+                         const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux,
+                         const __grid_constant__ CUtensorMap tmOut2, const ConvParams p) {
   using Cfg = ConvCfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -224,12 +252,15 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int num_groups = gridDim.x / CG;
   const int num_tiles = ((p.num_m_tiles + CG - 1) / CG) * p.num_n_tiles;
   const int num_kb = p.taps * p.cin_blocks;
-  const bool staged = p.mode == EPI_BIAS || p.mode == EPI_BIAS_SILU || p.mode == EPI_BIAS_RES;
+  const bool staged = p.mode != EPI_COMPOSE && p.mode != EPI_F32;
+  const bool has_aux = p.mode == EPI_BIAS_RES || p.mode == EPI_DSILU;  // TMA-prefetched input tile, double-buffered
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (staged) tma_prefetch_desc(&tmOut);
+    if (has_aux) tma_prefetch_desc(&tmAux);
+    if (p.dual_out) tma_prefetch_desc(&tmOut2);
   }
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < num_stages; ++s) {
@@ -388,16 +419,16 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       nt = tile % p.num_n_tiles;
       mt = (tile / p.num_n_tiles) * CG + rank;
     };
-    auto prefetch_residual = [&](int tile, int buf) {  // leader only: staging[buf] <- out[tile] (residual, in place)
+    auto prefetch_residual = [&](int tile, int buf) {  // leader only: staging[buf] <- aux[tile]
       int nt, mt;
       tile_coords(tile, nt, mt);
       uint8_t* dst = stg0 + buf * Cfg::kStagingBytes;
       mbar_arrive_expect_tx(&res_full[buf], Cfg::kStagingBytes);
 #pragma unroll
       for (int b = 0; b < BN / 64; ++b)
-        tma_load_2d(&tmOut, &res_full[buf], dst + b * kATileBytes, nt * BN + b * 64, mt * kBlockM);
+        tma_load_2d(&tmAux, &res_full[buf], dst + b * kATileBytes, nt * BN + b * 64, mt * kBlockM);
     };
-    if (p.mode == EPI_BIAS_RES && leader) {  // residual convs run with two staging tiles: prefetch two tiles ahead
+    if (has_aux && leader) {  // two staging tiles: the auxiliary tile is prefetched two tiles ahead
       if (group_id < num_tiles) prefetch_residual(group_id, 0);
       if (group_id + num_groups < num_tiles) prefetch_residual(group_id + num_groups, 1);
     }
@@ -410,11 +441,13 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col_base;
-      const int buf = (p.num_staging == 2) ? (it_local & 1) : 0;
+      const int buf = has_aux ? (it_local & 1) : 0;
       uint8_t* stg = stg0 + buf * Cfg::kStagingBytes;
+      uint8_t* stg2 = stg0 + Cfg::kStagingBytes;  // second output tile (dual_out; never together with has_aux)
       const uint32_t stg_u32 = smem_u32(stg);
       const uint32_t stg_row = stg_u32 + static_cast<uint32_t>(row) * 128u;
-      if (p.mode == EPI_BIAS_RES) mbar_wait(&res_full[buf], (it_local >> 1) & 1);
+      const uint32_t stg2_row = smem_u32(stg2) + static_cast<uint32_t>(row) * 128u;
+      if (has_aux) mbar_wait(&res_full[buf], (it_local >> 1) & 1);
       // two register buffers: the tcgen05.ld of chunk i+1 is in flight while chunk i is processed
       uint32_t va[32], vb[32];
       tmem_ld_32x32(taddr, va);
@@ -423,7 +456,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         tmem_ld_wait();
         if (c + 1 < kChunks) tmem_ld_32x32(taddr + 32 * (c + 1), (c & 1) ? va : vb);
         const int col = col_base + 32 * c;
-        if (staged) epilogue_chunk_staged(p, (c & 1) ? vb : va, nt * BN + col, col, stg_row, row);
+        if (staged) epilogue_chunk_staged(p, (c & 1) ? vb : va, nt * BN + col, col, stg_row, stg2_row, row);
         else epilogue_chunk_direct(p, (c & 1) ? vb : va, nt * BN + col, m, valid);
       }
       tc_fence_before();
@@ -443,6 +476,11 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       if (leader) {
 #pragma unroll
         for (int b = 0; b < BN / 64; ++b) tma_store_2d(&tmOut, stg + b * kATileBytes, nt * BN + b * 64, mt * kBlockM);
+        if (p.dual_out) {
+#pragma unroll
+          for (int b = 0; b < BN / 64; ++b)
+            tma_store_2d(&tmOut2, stg2 + b * kATileBytes, nt * BN + b * 64, mt * kBlockM);
+        }
         bulk_commit();
       }
       if (LN) {
@@ -503,6 +541,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const int r = ew * 16 + (it0 + b) * kRPI + lane / kLPR;
             const int mr = mt * kBlockM + r;
             if (mr < p.m_total) {
+              if (p.ln_inv != nullptr && ln_chunk == 0) p.ln_inv[mr] = inv;
               if (p.ln_up) {
                 const int w0 = mr % p.ln_W;
                 const int t = mr / p.ln_W;
@@ -524,7 +563,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       // ---- the staging tile is reused by the next tile once these stores have read it
       if (leader) bulk_wait_read_all();
       named_bar_sync(kEpiBarrier, kEpiThreads);  // store has read the tile AND every warp is done reading it (LN)
-      if (leader && p.mode == EPI_BIAS_RES) {
+      if (leader && has_aux) {
         const int next = tile + 2 * num_groups;  // this staging tile's next user
         if (next < num_tiles) prefetch_residual(next, buf);
       }
@@ -562,6 +601,11 @@ inline PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
+inline char* tmap_error_slot() {
+  static thread_local char buf[256] = {0};
+  return buf;
+}
+
 // bf16 tensor map with 128B swizzle and zero OOB fill.  dims/box/estride are innermost-first; with an element
 // stride e > 1 in a dimension the box TRAVERSES box[i] elements and loads every e-th one (ceil(box/e) elements).
 // strides_bytes (rank - 1 entries, for dims 1..rank-1) defaults to the packed layout.
@@ -569,6 +613,13 @@ inline bool make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uin
                            const uint32_t* estride = nullptr, const uint64_t* strides_bytes = nullptr) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return false;
+  // The driver entry point needs the primary context current on THIS thread; a thread that has made no runtime call
+  // yet (e.g. PyTorch's autograd worker) has none.  cudaFree(0) is the canonical no-op that binds it.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(0);
+    ctx_bound = true;
+  }
   cuuint64_t gdim[5];
   cuuint64_t gstride[4];
   cuuint32_t bdim[5];
@@ -584,12 +635,17 @@ inline bool make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uin
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstride, bdim, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char* e = tmap_error_slot();
+    int o = snprintf(e, 256, "cuTensorMapEncodeTiled -> %d: base %p rank %d dims", (int)r, base, rank);
+    for (int i = 0; i < rank && o < 230; ++i) o += snprintf(e + o, 256 - o, " %llu/%u", (unsigned long long)gdim[i], bdim[i]);
+  }
   return r == CUDA_SUCCESS;
 }
 
 // One prepared launch of K1: tensor maps + parameters.  Built once per (layer, batch) and replayed.
 struct ConvLaunch {
-  CUtensorMap tmA, tmB, tmOut;
+  CUtensorMap tmA, tmB, tmOut, tmAux, tmOut2;
   ConvParams p;
   int bn;
   int cg;     // CTAs per MMA (1 or 2)
@@ -620,6 +676,8 @@ inline bool conv_launch_init(ConvLaunch* L, bool is_conv3x3, const __nv_bfloat16
   ConvParams& p = L->p;
   memset(&p, 0, sizeof(p));
   memset(&L->tmOut, 0, sizeof(CUtensorMap));
+  memset(&L->tmAux, 0, sizeof(CUtensorMap));
+  memset(&L->tmOut2, 0, sizeof(CUtensorMap));
   L->bn = bn;
   L->ln = 0;
   L->out_ptr = nullptr;
@@ -671,12 +729,28 @@ inline bool conv_launch_init(ConvLaunch* L, bool is_conv3x3, const __nv_bfloat16
   return true;
 }
 
-// bf16 output [M, cout_pad] (modes 0..2; mode 2 accumulates in place, so `out` is also the residual)
+// bf16 output [M, cout_pad] (modes 0..2, 5).  Mode 2 accumulates in place: `out` is also the auxiliary (residual) tile.
 inline bool conv_launch_set_out(ConvLaunch* L, __nv_bfloat16* out) {
   const uint64_t dims[2] = {(uint64_t)L->cout_pad, (uint64_t)L->p.m_total};
   const uint32_t box[2] = {64u, (uint32_t)kBlockM};
   L->out_ptr = out;
-  return make_tmap_bf16(&L->tmOut, out, 2, dims, box);
+  if (!make_tmap_bf16(&L->tmOut, out, 2, dims, box)) return false;
+  if (L->p.mode == EPI_BIAS_RES) L->tmAux = L->tmOut;
+  return true;
+}
+// Auxiliary input tile of mode 5 (the stashed pre-activation), same shape as the output.
+inline bool conv_launch_set_aux(ConvLaunch* L, const __nv_bfloat16* aux) {
+  const uint64_t dims[2] = {(uint64_t)L->cout_pad, (uint64_t)L->p.m_total};
+  const uint32_t box[2] = {64u, (uint32_t)kBlockM};
+  return make_tmap_bf16(&L->tmAux, aux, 2, dims, box);
+}
+// Second output of mode 1: the pre-activation acc + bias (stash for the VJP).
+inline bool conv_launch_set_out2(ConvLaunch* L, __nv_bfloat16* out2) {
+  const uint64_t dims[2] = {(uint64_t)L->cout_pad, (uint64_t)L->p.m_total};
+  const uint32_t box[2] = {64u, (uint32_t)kBlockM};
+  if (L->p.mode != EPI_BIAS_SILU) return false;
+  L->p.dual_out = 1;
+  return make_tmap_bf16(&L->tmOut2, out2, 2, dims, box);
 }
 
 // Whether this launch can also emit the channel LayerNorm of its output (one N tile = all channels of a pixel).
@@ -707,12 +781,12 @@ inline cudaError_t conv_launch_variant(const ConvLaunch& L, cudaStream_t stream)
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<BN, CG, LN>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes(1));
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
   ConvParams p = L.p;
-  p.num_staging = (p.mode == EPI_BIAS_RES) ? 2 : 1;
+  p.num_staging = (p.mode == EPI_BIAS_RES || p.mode == EPI_DSILU || p.dual_out) ? 2 : 1;
   p.num_stages = Cfg::stages_for(p.num_staging);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -727,7 +801,7 @@ inline cudaError_t conv_launch_variant(const ConvLaunch& L, cudaStream_t stream)
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<BN, CG, LN>, L.tmA, L.tmB, L.tmOut, p);
+  return cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<BN, CG, LN>, L.tmA, L.tmB, L.tmOut, L.tmAux, L.tmOut2, p);
 }
 
 template <int BN, bool LN>

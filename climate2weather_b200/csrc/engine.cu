@@ -30,6 +30,7 @@ struct TimedSpan {
 struct ConvW {
   bf16* w = nullptr;   // [cout_pad, taps * cin_pad], k = tap * cin_pad + c
   float* b = nullptr;  // [cout_pad]
+  bf16* wd = nullptr;  // input-gradient weights [cin_pad, taps * cout_pad], k = (8 - tap) * cout_pad + o  (flipped)
   int cin = 0, cout = 0, cin_pad = 0, cout_pad = 0, taps = 0;
 };
 struct BlockW {
@@ -47,16 +48,19 @@ struct LevelW {
   std::vector<AttnW> dattn, aattn;
 };
 
-enum OpKind { OP_CONV, OP_LN, OP_ATTN };
+enum OpKind { OP_CONV, OP_LN, OP_ATTN, OP_LN_BWD, OP_ATTN_BWD, OP_ZERO_UP };
 struct Op {
   OpKind kind;
   // conv
   ConvLaunch conv;
   int pix_per_img = 0;
   bool is_final = false;
-  // layernorm
+  // layernorm (forward: in -> out [+ inv]; backward: in = g_y, aux = y stash, res = incoming gradient or null)
   const bf16* in = nullptr;
   bf16* out = nullptr;
+  float* inv = nullptr;
+  const bf16* aux = nullptr;
+  const bf16* res = nullptr;
   int C = 0, H = 0, W = 0, up = 0, mod_off = -1;
   // attention
   int T = 0;
@@ -64,7 +68,11 @@ struct Op {
 
 struct Plan {
   int n_max = 0;
+  bool vjp = false;        // forward ops stash what the backward ops need
   std::vector<Op> ops;
+  std::vector<Op> bwd;     // input-gradient pass (vjp plans only), in execution order
+  bf16* cot = nullptr;     // UNet-output cotangent [n, HW, cout_pad(window channels)] bf16
+  bf16* g0 = nullptr;
   bf16* xin = nullptr;
   float* h0 = nullptr;
   float* emb = nullptr;
@@ -85,6 +93,7 @@ struct c2w_handle {
   std::vector<void*> allocs;
   float *map0_w = nullptr, *map0_b = nullptr, *map1_w = nullptr, *map1_b = nullptr;
   float *proj_w = nullptr, *proj_b = nullptr;
+  float* zero_bias = nullptr;  // 512 zeros: the input-gradient convs have no bias
   int total_mod = 0;
   std::vector<LevelW> levels;
   Plan plan;
@@ -151,7 +160,17 @@ int pack_conv(c2w_handle* h, const std::string& prefix, int cout, int cin, int t
   for (int o = 0; o < cout; ++o) bias[o] = (*b)[o];
   rc = dev_upload(h, packed.data(), packed.size() * sizeof(bf16), reinterpret_cast<void**>(&cw->w));
   if (rc) return rc;
-  return dev_upload(h, bias.data(), bias.size() * sizeof(float), reinterpret_cast<void**>(&cw->b));
+  rc = dev_upload(h, bias.data(), bias.size() * sizeof(float), reinterpret_cast<void**>(&cw->b));
+  if (rc) return rc;
+  // input-gradient weights: rows = input channels, k = (taps - 1 - t) * cout_pad + o  (spatially flipped kernel)
+  const size_t Kd = static_cast<size_t>(taps) * cw->cout_pad;
+  std::vector<bf16> packed_d(static_cast<size_t>(cw->cin_pad) * Kd, __float2bfloat16_rn(0.f));
+  for (int o = 0; o < cout; ++o)
+    for (int c = 0; c < cin; ++c)
+      for (int t = 0; t < taps; ++t)
+        packed_d[c * Kd + static_cast<size_t>(taps - 1 - t) * cw->cout_pad + o] =
+            __float2bfloat16_rn((*w)[(static_cast<size_t>(o) * cin + c) * taps + t]);
+  return dev_upload(h, packed_d.data(), packed_d.size() * sizeof(bf16), reinterpret_cast<void**>(&cw->wd));
 }
 
 int upload_named(c2w_handle* h, const std::string& name, size_t numel, float** out) {
@@ -162,29 +181,83 @@ int upload_named(c2w_handle* h, const std::string& name, size_t numel, float** o
 }
 
 template <int C>
-void launch_ln_c(const bf16* x, const float* mod, bf16* out, long long npix, int H, int W, int up, int sms,
+void launch_ln_c(const bf16* x, const float* mod, bf16* out, float* inv, long long npix, int H, int W, int up, int sms,
                  cudaStream_t st) {
   const int threads = 256;
   long long blocks = (npix + 7) / 8;
   const long long cap = static_cast<long long>(sms) * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  channel_layernorm_kernel<C><<<static_cast<int>(blocks), threads, 0, st>>>(x, mod, out, npix, H, W, up, 1e-5f);
+  channel_layernorm_kernel<C><<<static_cast<int>(blocks), threads, 0, st>>>(x, mod, out, inv, npix, H, W, up, 1e-5f);
+}
+template <int C>
+void launch_ln_bwd_c(const bf16* gy, const bf16* y, const float* inv, const bf16* gres, bf16* out, long long npix, int H,
+                     int W, int down, int sms, cudaStream_t st) {
+  const int threads = 256;
+  long long blocks = (npix + 7) / 8;
+  const long long cap = static_cast<long long>(sms) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  channel_layernorm_bwd_kernel<C><<<static_cast<int>(blocks), threads, 0, st>>>(gy, y, inv, gres, out, npix, H, W, down);
 }
 
-int launch_ln(const bf16* x, const float* mod, bf16* out, long long npix, int C, int H, int W, int up, int sms,
-              cudaStream_t st) {
-  switch (C) {
-    case 64: launch_ln_c<64>(x, mod, out, npix, H, W, up, sms, st); break;
-    case 128: launch_ln_c<128>(x, mod, out, npix, H, W, up, sms, st); break;
-    case 192: launch_ln_c<192>(x, mod, out, npix, H, W, up, sms, st); break;
-    case 256: launch_ln_c<256>(x, mod, out, npix, H, W, up, sms, st); break;
-    case 320: launch_ln_c<320>(x, mod, out, npix, H, W, up, sms, st); break;
-    case 384: launch_ln_c<384>(x, mod, out, npix, H, W, up, sms, st); break;
-    case 448: launch_ln_c<448>(x, mod, out, npix, H, W, up, sms, st); break;
-    case 512: launch_ln_c<512>(x, mod, out, npix, H, W, up, sms, st); break;
-    default: return fail(C2W_ERR_INVALID, "channel LayerNorm: unsupported C=%d (multiple of 64, <= 512)", C);
+#define C2W_LN_DISPATCH(C, CALL)                                                                           \
+  switch (C) {                                                                                             \
+    case 64: CALL(64); break;                                                                              \
+    case 128: CALL(128); break;                                                                            \
+    case 192: CALL(192); break;                                                                            \
+    case 256: CALL(256); break;                                                                            \
+    case 320: CALL(320); break;                                                                            \
+    case 384: CALL(384); break;                                                                            \
+    case 448: CALL(448); break;                                                                            \
+    case 512: CALL(512); break;                                                                            \
+    default: return fail(C2W_ERR_INVALID, "channel LayerNorm: unsupported C=%d (multiple of 64, <= 512)", C); \
   }
+
+int launch_ln(const bf16* x, const float* mod, bf16* out, float* inv, long long npix, int C, int H, int W, int up,
+              int sms, cudaStream_t st) {
+#define C2W_CALL(CC) launch_ln_c<CC>(x, mod, out, inv, npix, H, W, up, sms, st)
+  C2W_LN_DISPATCH(C, C2W_CALL)
+#undef C2W_CALL
+  C2W_CUDA(cudaGetLastError());
+  return C2W_OK;
+}
+
+int launch_ln_bwd(const bf16* gy, const bf16* y, const float* inv, const bf16* gres, bf16* out, long long npix, int C,
+                  int H, int W, int down, int sms, cudaStream_t st) {
+#define C2W_CALL(CC) launch_ln_bwd_c<CC>(gy, y, inv, gres, out, npix, H, W, down, sms, st)
+  C2W_LN_DISPATCH(C, C2W_CALL)
+#undef C2W_CALL
+  C2W_CUDA(cudaGetLastError());
+  return C2W_OK;
+}
+
+// scratch: fp32 [2][n][T][T] (P and gS)
+int launch_attention_bwd(const bf16* qkv, const bf16* go, bf16* gqkv, float* scratch, int n, int T, int C,
+                         cudaStream_t st) {
+  C2W_REQUIRE(T % 8 == 0 && C % 8 == 0 && scratch, "attention backward: T %% 8 and C %% 8 must be 0 (T=%d C=%d)", T, C);
+  const int QB = std::min(T, kAttnBwdRows);
+  const size_t smem1 = attention_bwd_scores_smem(T, C, QB), smem2 = attention_bwd_grads_smem(T, C, QB);
+  C2W_REQUIRE(std::max(smem1, smem2) <= static_cast<size_t>(kSmemLimit),
+              "attention backward: T=%d C=%d needs %zu B of shared memory", T, C, std::max(smem1, smem2));
+  static size_t conf1 = 0, conf2 = 0;
+  if (smem1 > conf1) {
+    C2W_CUDA(cudaFuncSetAttribute(attention_bwd_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem1)));
+    conf1 = smem1;
+  }
+  if (smem2 > conf2) {
+    C2W_CUDA(cudaFuncSetAttribute(attention_bwd_grads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem2)));
+    conf2 = smem2;
+  }
+  float* Pm = scratch;
+  float* gSm = scratch + static_cast<size_t>(n) * T * T;
+  const float scale2 = 1.0f / sqrtf(static_cast<float>(C));
+  const int nb = (T + QB - 1) / QB;
+  attention_bwd_scores_kernel<<<dim3(nb, n), kAttnThreads, smem1, st>>>(qkv, go, Pm, gSm, T, C, QB, scale2);
+  C2W_CUDA(cudaGetLastError());
+  attention_bwd_grads_kernel<<<dim3(nb, n, 3), kAttnThreads, smem2, st>>>(qkv, go, Pm, gSm, gqkv, T, C, QB, scale2);
   C2W_CUDA(cudaGetLastError());
   return C2W_OK;
 }
@@ -236,8 +309,10 @@ int run_modulation(c2w_handle* h, float t, float* h0, float* emb, float* mods, c
   return C2W_OK;
 }
 
-// Lays the workspace out and (if base != null) builds every launch of the forward pass over it.
-int build_plan(c2w_handle* h, int n, void* base, size_t* bytes_out) {
+// Lays the workspace out and (if base != null) builds every launch of the forward pass over it.  vjp: the forward
+// ops additionally stash (per block) the LayerNorm output + 1/std and the SiLU pre-activation, (per attention block)
+// qkv, and the plan gets the input-gradient pass `bwd`.
+int build_plan(c2w_handle* h, int n, bool vjp, void* base, size_t* bytes_out) {
   Plan& P = h->plan;
   const bool real = base != nullptr;
   Bump B(base);
@@ -245,21 +320,28 @@ int build_plan(c2w_handle* h, int n, void* base, size_t* bytes_out) {
   const long long HW0 = static_cast<long long>(h->cfg.height) * h->cfg.width;
   if (real) {
     P.ops.clear();
+    P.bwd.clear();
     P.n_max = n;
+    P.vjp = vjp;
   }
   bf16* xin = B.take<bf16>(n * HW0 * h->cin_pad);
   float* h0 = B.take<float>(h->cfg.embedding_dim);
   float* emb = B.take<float>(h->cfg.embedding_dim);
   float* mods = B.take<float>(h->total_mod);
   float* out32 = B.take<float>(n * HW0 * h->levels[0].tail.cout_pad);
-  std::vector<bf16*> xs(nl), as(nl), hs(nl);
+  std::vector<bf16*> xs(nl), as(nl), hs(nl), gs(nl), ga(nl), gh(nl);
   size_t up_elems = 0, qkv_elems = 0, att_elems = 0;
   for (int l = 0; l < nl; ++l) {
     const LevelW& L = h->levels[l];
     const size_t e = static_cast<size_t>(n) * L.H * L.W * L.C;
     xs[l] = B.take<bf16>(e);
-    as[l] = B.take<bf16>(e);
+    as[l] = vjp ? nullptr : B.take<bf16>(e);  // vjp: every LayerNorm output gets its own stash buffer
     hs[l] = B.take<bf16>(e);
+    if (vjp) {
+      gs[l] = B.take<bf16>(e);
+      ga[l] = B.take<bf16>(e);
+      gh[l] = B.take<bf16>(e);
+    }
     if (l > 0) {
       const LevelW& U = h->levels[l - 1];
       up_elems = std::max(up_elems, static_cast<size_t>(n) * U.H * U.W * L.C);
@@ -269,50 +351,94 @@ int build_plan(c2w_handle* h, int n, void* base, size_t* bytes_out) {
       att_elems = std::max(att_elems, e);
     }
   }
-  bf16* up = B.take<bf16>(up_elems);
-  bf16* qkv = B.take<bf16>(qkv_elems);
+  bf16* up = vjp ? nullptr : B.take<bf16>(up_elems);
+  bf16* qkv = vjp ? nullptr : B.take<bf16>(qkv_elems);
   bf16* att = B.take<bf16>(att_elems);
-  *bytes_out = B.off + 1024;
-  if (!real) return C2W_OK;
-  P.xin = xin;
-  P.h0 = h0;
-  P.emb = emb;
-  P.mods = mods;
-  P.out32 = out32;
+  bf16 *gup = nullptr, *gz = nullptr, *gqkv = nullptr, *gatt = nullptr, *cot = nullptr;
+  float* attn_scratch = nullptr;
+  if (vjp) {
+    size_t sc = 0;
+    for (int l = 0; l < nl; ++l)
+      if (h->levels[l].attn) {
+        const size_t T = static_cast<size_t>(h->levels[l].H) * h->levels[l].W;
+        sc = std::max(sc, 2 * static_cast<size_t>(n) * T * T);
+      }
+    attn_scratch = B.take<float>(sc);
+    gup = B.take<bf16>(up_elems);    // gradient w.r.t. the upsampled LayerNorm output of a tail
+    gz = B.take<bf16>(up_elems);     // zero-inserted gradient of a stride-2 head
+    gqkv = B.take<bf16>(qkv_elems);
+    gatt = B.take<bf16>(att_elems);
+    cot = B.take<bf16>(n * HW0 * h->levels[0].tail.cout_pad);
+  }
+  // per-block stash buffers are taken on the fly below (same order in the sizing and the real pass)
+  auto stash = [&](size_t elems) -> bf16* { return B.take<bf16>(elems); };
+  auto stash_f = [&](size_t elems) -> float* { return B.take<float>(elems); };
+
+  if (real) {
+    P.xin = xin;
+    P.h0 = h0;
+    P.emb = emb;
+    P.mods = mods;
+    P.out32 = out32;
+    P.cot = cot;
+    P.g0 = vjp ? gs[0] : nullptr;
+  }
 
   // H, W: INPUT image size; stride 2 halves it (heads of levels > 0, model/nn.py:169-176)
-  auto add_conv = [&](bool c3, const bf16* in, int H, int W, int cin, const ConvW& w, int mode, const bf16* res,
-                      bf16* out, bool is_final, int stride = 1) -> int {
+  auto make_conv = [&](Op* op, bool c3, const bf16* in, int H, int W, int cin, const bf16* wts, const float* bias,
+                       int cout_pad, int mode, bf16* out, bool is_final, int stride) -> int {
+    op->kind = OP_CONV;
+    const int bn = conv_pick_bn(cout_pad);
+    if (!conv_launch_init(&op->conv, c3, in, n, H, W, cin, wts, cout_pad, bn, h->sms, stride))
+      return fail(C2W_ERR_INVALID, "cannot build conv launch (n=%d H=%d W=%d cin=%d cout=%d stride=%d) %s", n, H, W, cin,
+                  cout_pad, stride, tmap_error_slot());
+    op->conv.p.mode = mode;
+    op->conv.p.bias = bias;
+    if (out && !conv_launch_set_out(&op->conv, out)) return fail(C2W_ERR_CUDA, "cannot encode the output tensor map");
+    op->pix_per_img = (H / stride) * (W / stride);
+    op->is_final = is_final;
+    return C2W_OK;
+  };
+  auto add_conv = [&](bool c3, const bf16* in, int H, int W, int cin, const ConvW& w, int mode, bf16* out, bool is_final,
+                      int stride = 1) -> int {
+    if (!real) return C2W_OK;
     Op op;
-    op.kind = OP_CONV;
-    const int bn = conv_pick_bn(w.cout_pad);
-    if (!conv_launch_init(&op.conv, c3, in, n, H, W, cin, w.w, w.cout_pad, bn, h->sms, stride))
-      return fail(C2W_ERR_INVALID, "cannot build conv launch (H=%d W=%d cin=%d cout=%d stride=%d)", H, W, cin,
-                  w.cout_pad, stride);
-    op.conv.p.mode = mode;
-    op.conv.p.bias = w.b;
-    if (mode == EPI_BIAS_RES && res != out)
-      return fail(C2W_ERR_INVALID, "residual convs accumulate in place (res must be out)");
-    if (out && !conv_launch_set_out(&op.conv, out)) return fail(C2W_ERR_CUDA, "cannot encode the output tensor map");
-    op.pix_per_img = (H / stride) * (W / stride);
-    op.is_final = is_final;
+    int rc = make_conv(&op, c3, in, H, W, cin, w.w, w.b, w.cout_pad, mode, out, is_final, stride);
+    if (rc) return rc;
     P.ops.push_back(op);
     return C2W_OK;
   };
-  // Channel LayerNorm of `in` (+ modulation) -> `out`.  When `in` was just produced by a conv whose single N tile
-  // holds all C channels of a pixel, the normalisation is done in that conv's epilogue (no extra pass over HBM).
-  auto add_ln = [&](const bf16* in, bf16* out, int C, int H, int W, int upf, int mod_off) {
+  // input-gradient conv: the transposed / flipped weights, no bias; pushed on `unit` (a backward op group)
+  auto add_dconv = [&](std::vector<Op>& unit, bool c3, const bf16* gin, int H, int W, const ConvW& w, int mode,
+                       bf16* gout, const bf16* aux) -> int {
+    if (!real) return C2W_OK;
+    Op op;
+    // forward cout is this conv's K side, forward cin its N side
+    int rc = make_conv(&op, c3, gin, H, W, w.cout_pad, w.wd, h->zero_bias, w.cin_pad, mode, gout, false, 1);
+    if (rc) return rc;
+    if (mode == EPI_DSILU && !conv_launch_set_aux(&op.conv, aux))
+      return fail(C2W_ERR_CUDA, "cannot encode the stash tensor map");
+    unit.push_back(op);
+    return C2W_OK;
+  };
+  // Channel LayerNorm of `in` (+ modulation) -> `out` (+ inv).  When `in` was just produced by a conv whose single N
+  // tile holds all C channels of a pixel, the normalisation is done in that conv's epilogue (no extra HBM pass).
+  auto add_ln = [&](const bf16* in, bf16* out, float* inv, int C, int H, int W, int upf, int mod_off) {
+    if (!real) return;
     if (h->fuse_ln && !P.ops.empty()) {
       Op& prev = P.ops.back();
       if (prev.kind == OP_CONV && !prev.is_final && prev.conv.out_ptr == in && prev.conv.cout_pad == C &&
           conv_launch_can_ln(&prev.conv, upf) &&
-          conv_launch_set_ln(&prev.conv, out, mod_off >= 0 ? mods + mod_off : nullptr, upf))
+          conv_launch_set_ln(&prev.conv, out, mod_off >= 0 ? mods + mod_off : nullptr, upf)) {
+        prev.conv.p.ln_inv = inv;
         return;
+      }
     }
     Op op;
     op.kind = OP_LN;
     op.in = in;
     op.out = out;
+    op.inv = inv;
     op.C = C;
     op.H = H;
     op.W = W;
@@ -320,34 +446,92 @@ int build_plan(c2w_handle* h, int n, void* base, size_t* bytes_out) {
     op.mod_off = mod_off;
     P.ops.push_back(op);
   };
+  auto add_ln_bwd = [&](std::vector<Op>& unit, const bf16* gy, const bf16* y, const float* inv, const bf16* gres,
+                        bf16* out, int C, int H, int W, int down) {
+    if (!real) return;
+    Op op;
+    op.kind = OP_LN_BWD;
+    op.in = gy;
+    op.aux = y;
+    op.inv = const_cast<float*>(inv);
+    op.res = gres;
+    op.out = out;
+    op.C = C;
+    op.H = H;
+    op.W = W;
+    op.up = down;
+    unit.push_back(op);
+  };
+
+  // Backward op groups are collected per forward unit and replayed in reverse unit order.
+  std::vector<std::vector<Op>> units;
+
   auto add_blocks = [&](int l, const std::vector<BlockW>& blocks, const std::vector<AttnW>& attns) -> int {
     const LevelW& L = h->levels[l];
+    const size_t e = static_cast<size_t>(n) * L.H * L.W * L.C;
+    const size_t npix = static_cast<size_t>(n) * L.H * L.W;
     for (size_t b = 0; b < blocks.size(); ++b) {
       const BlockW& bw = blocks[b];
       // x + conv2(SiLU(conv1(LN(x + proj(emb)))))    model/nn.py:27-28,151-158
-      add_ln(xs[l], as[l], L.C, L.H, L.W, 0, bw.mod_off);
-      int rc = add_conv(true, as[l], L.H, L.W, L.C, bw.c1, EPI_BIAS_SILU, nullptr, hs[l], false);
+      bf16* y = vjp ? stash(e) : as[l];
+      bf16* pre = vjp ? stash(e) : nullptr;
+      float* inv = vjp ? stash_f(npix) : nullptr;
+      add_ln(xs[l], y, inv, L.C, L.H, L.W, 0, bw.mod_off);
+      int rc = add_conv(true, y, L.H, L.W, L.C, bw.c1, EPI_BIAS_SILU, hs[l], false);
       if (rc) return rc;
-      rc = add_conv(true, hs[l], L.H, L.W, L.C, bw.c2, EPI_BIAS_RES, xs[l], xs[l], false);
+      if (vjp && real && !conv_launch_set_out2(&P.ops.back().conv, pre))
+        return fail(C2W_ERR_CUDA, "cannot encode the pre-activation stash tensor map");
+      rc = add_conv(true, hs[l], L.H, L.W, L.C, bw.c2, EPI_BIAS_RES, xs[l], false);
       if (rc) return rc;
+      if (vjp) {
+        units.emplace_back();
+        std::vector<Op>& u = units.back();
+        if ((rc = add_dconv(u, true, gs[l], L.H, L.W, bw.c2, EPI_DSILU, gh[l], pre))) return rc;
+        if ((rc = add_dconv(u, true, gh[l], L.H, L.W, bw.c1, EPI_BIAS, ga[l], nullptr))) return rc;
+        add_ln_bwd(u, ga[l], y, inv, gs[l], gs[l], L.C, L.H, L.W, 0);
+      }
       if (L.attn) {
         // x + proj(attn(qkv(LN(x))))    model/nn.py:50-60
         const AttnW& aw = attns[b];
-        add_ln(xs[l], as[l], L.C, L.H, L.W, 0, -1);
-        rc = add_conv(false, as[l], L.H, L.W, L.C, aw.qkv, EPI_BIAS, nullptr, qkv, false);
+        const int T = L.H * L.W;
+        bf16* ya = vjp ? stash(e) : as[l];
+        float* inva = vjp ? stash_f(npix) : nullptr;
+        bf16* q = vjp ? stash(3 * e) : qkv;
+        add_ln(xs[l], ya, inva, L.C, L.H, L.W, 0, -1);
+        rc = add_conv(false, ya, L.H, L.W, L.C, aw.qkv, EPI_BIAS, q, false);
         if (rc) return rc;
-        Op op;
-        op.kind = OP_ATTN;
-        op.in = qkv;
-        op.out = att;
-        op.T = L.H * L.W;
-        op.C = L.C;
-        P.ops.push_back(op);
-        P.attn_smem = std::max(P.attn_smem, attention_smem_bytes(op.T, op.C));
-        if (P.attn_smem > static_cast<size_t>(kSmemLimit))
-          return fail(C2W_ERR_INVALID, "attention at level %d (T=%d, C=%d) exceeds shared memory", l, op.T, op.C);
-        rc = add_conv(false, att, L.H, L.W, L.C, aw.proj, EPI_BIAS_RES, xs[l], xs[l], false);
+        if (real) {
+          Op op;
+          op.kind = OP_ATTN;
+          op.in = q;
+          op.out = att;
+          op.T = T;
+          op.C = L.C;
+          P.ops.push_back(op);
+          P.attn_smem = std::max(P.attn_smem, attention_smem_bytes(op.T, op.C));
+          if (P.attn_smem > static_cast<size_t>(kSmemLimit))
+            return fail(C2W_ERR_INVALID, "attention at level %d (T=%d, C=%d) exceeds shared memory", l, op.T, op.C);
+        }
+        rc = add_conv(false, att, L.H, L.W, L.C, aw.proj, EPI_BIAS_RES, xs[l], false);
         if (rc) return rc;
+        if (vjp) {
+          units.emplace_back();
+          std::vector<Op>& u = units.back();
+          if ((rc = add_dconv(u, false, gs[l], L.H, L.W, aw.proj, EPI_BIAS, gatt, nullptr))) return rc;
+          if (real) {
+            Op op;
+            op.kind = OP_ATTN_BWD;
+            op.inv = attn_scratch;
+            op.in = gatt;
+            op.aux = q;
+            op.out = gqkv;
+            op.T = T;
+            op.C = L.C;
+            u.push_back(op);
+          }
+          if ((rc = add_dconv(u, false, gqkv, L.H, L.W, aw.qkv, EPI_BIAS, ga[l], nullptr))) return rc;
+          add_ln_bwd(u, ga[l], ya, inva, gs[l], gs[l], L.C, L.H, L.W, 0);
+        }
       }
     }
     return C2W_OK;
@@ -358,12 +542,33 @@ int build_plan(c2w_handle* h, int n, void* base, size_t* bytes_out) {
     const LevelW& L = h->levels[l];
     int rc;
     if (l == 0) {
-      rc = add_conv(true, xin, L.H, L.W, h->cin_pad, L.head, EPI_BIAS, nullptr, xs[0], false);
+      rc = add_conv(true, xin, L.H, L.W, h->cin_pad, L.head, EPI_BIAS, xs[0], false);
+      if (rc) return rc;
+      if (vjp) {  // gradient w.r.t. the window batch, fp32 [n, HW, cin_pad] into out32
+        units.emplace_back();
+        if ((rc = add_dconv(units.back(), true, gs[0], L.H, L.W, L.head, EPI_F32, nullptr, nullptr))) return rc;
+        if (real) units.back().back().conv.p.out_f32 = out32;
+      }
     } else {
       const LevelW& U = h->levels[l - 1];
-      rc = add_conv(true, xs[l - 1], U.H, U.W, U.C, L.head, EPI_BIAS, nullptr, xs[l], false, 2);
+      rc = add_conv(true, xs[l - 1], U.H, U.W, U.C, L.head, EPI_BIAS, xs[l], false, 2);
+      if (rc) return rc;
+      if (vjp) {  // g[l-1] += conv_flipped(zero-upsampled g[l])
+        units.emplace_back();
+        std::vector<Op>& u = units.back();
+        if (real) {
+          Op op;
+          op.kind = OP_ZERO_UP;
+          op.in = gs[l];
+          op.out = gz;
+          op.H = L.H;
+          op.W = L.W;
+          op.C = L.C;
+          u.push_back(op);
+        }
+        if ((rc = add_dconv(u, true, gz, U.H, U.W, L.head, EPI_BIAS_RES, gs[l - 1], nullptr))) return rc;
+      }
     }
-    if (rc) return rc;
     rc = add_blocks(l, L.desc, L.dattn);
     if (rc) return rc;
   }
@@ -374,13 +579,31 @@ int build_plan(c2w_handle* h, int n, void* base, size_t* bytes_out) {
     if (rc) return rc;
     if (l > 0) {
       const LevelW& U = h->levels[l - 1];
-      add_ln(xs[l], up, L.C, L.H, L.W, 1, -1);
-      rc = add_conv(true, up, U.H, U.W, L.C, L.tail, EPI_BIAS_RES, xs[l - 1], xs[l - 1], false);
+      const size_t eu = static_cast<size_t>(n) * U.H * U.W * L.C;
+      bf16* upl = vjp ? stash(eu) : up;
+      float* invt = vjp ? stash_f(static_cast<size_t>(n) * L.H * L.W) : nullptr;
+      add_ln(xs[l], upl, invt, L.C, L.H, L.W, 1, -1);
+      rc = add_conv(true, upl, U.H, U.W, L.C, L.tail, EPI_BIAS_RES, xs[l - 1], false);
+      if (rc) return rc;
+      if (vjp) {  // g[l] = LN_bwd(sum_2x2 conv_flipped(g[l-1]))   (xs[l] feeds nothing else)
+        units.emplace_back();
+        std::vector<Op>& u = units.back();
+        if ((rc = add_dconv(u, true, gs[l - 1], U.H, U.W, L.tail, EPI_BIAS, gup, nullptr))) return rc;
+        add_ln_bwd(u, gup, upl, invt, nullptr, gs[l], L.C, L.H, L.W, 1);
+      }
     } else {
-      rc = add_conv(true, xs[0], L.H, L.W, L.C, L.tail, EPI_F32, nullptr, nullptr, true);
+      rc = add_conv(true, xs[0], L.H, L.W, L.C, L.tail, EPI_F32, nullptr, true);
+      if (rc) return rc;
+      if (vjp) {
+        units.emplace_back();
+        if ((rc = add_dconv(units.back(), true, cot, L.H, L.W, L.tail, EPI_BIAS, gs[0], nullptr))) return rc;
+      }
     }
-    if (rc) return rc;
   }
+  *bytes_out = B.off + 1024;
+  if (real && vjp)
+    for (auto it = units.rbegin(); it != units.rend(); ++it)
+      for (const Op& op : *it) P.bwd.push_back(op);
   return C2W_OK;
 }
 
@@ -413,10 +636,10 @@ struct FinalSpec {
   int order_k = 0, win_first = 0, win_last_global = 0, frame_base = 0;
 };
 
-// Runs the forward pass on the first nn windows of plan.xin.
-int run_plan(c2w_handle* h, int nn, const FinalSpec& fs, cudaStream_t st) {
+// Runs an op list (the forward pass, or the input-gradient pass) on the first nn windows of the plan.
+int run_ops(c2w_handle* h, std::vector<Op>& ops, int nn, const FinalSpec& fs, cudaStream_t st) {
   Plan& P = h->plan;
-  for (Op& op : P.ops) {
+  for (Op& op : ops) {
     switch (op.kind) {
       case OP_CONV: {
         ConvLaunch L = op.conv;
@@ -442,7 +665,7 @@ int run_plan(c2w_handle* h, int nn, const FinalSpec& fs, cudaStream_t st) {
       }
       case OP_LN: {
         SpanGuard sg(h, 1, st);
-        int rc = launch_ln(op.in, op.mod_off >= 0 ? P.mods + op.mod_off : nullptr, op.out,
+        int rc = launch_ln(op.in, op.mod_off >= 0 ? P.mods + op.mod_off : nullptr, op.out, op.inv,
                            static_cast<long long>(nn) * op.H * op.W, op.C, op.H, op.W, op.up, h->sms, st);
         if (rc) return rc;
         break;
@@ -453,10 +676,32 @@ int run_plan(c2w_handle* h, int nn, const FinalSpec& fs, cudaStream_t st) {
         if (rc) return rc;
         break;
       }
+      case OP_LN_BWD: {
+        SpanGuard sg(h, 1, st);
+        int rc = launch_ln_bwd(op.in, op.aux, op.inv, op.res, op.out, static_cast<long long>(nn) * op.H * op.W, op.C, op.H,
+                               op.W, op.up, h->sms, st);
+        if (rc) return rc;
+        break;
+      }
+      case OP_ATTN_BWD: {
+        SpanGuard sg(h, 1, st);
+        int rc = launch_attention_bwd(op.aux, op.in, op.out, op.inv, nn, op.T, op.C, st);
+        if (rc) return rc;
+        break;
+      }
+      case OP_ZERO_UP: {
+        SpanGuard sg(h, 1, st);
+        const long long items = static_cast<long long>(nn) * (2 * op.H) * (2 * op.W) * (op.C / 8);
+        zero_upsample_kernel<<<grid_for(items, 256, h->sms), 256, 0, st>>>(op.in, op.out, nn, op.H, op.W, op.C);
+        C2W_CUDA(cudaGetLastError());
+        break;
+      }
     }
   }
   return C2W_OK;
 }
+
+int run_plan(c2w_handle* h, int nn, const FinalSpec& fs, cudaStream_t st) { return run_ops(h, h->plan.ops, nn, fs, st); }
 
 }  // namespace
 
@@ -576,6 +821,10 @@ int c2w_finalize_weights(c2w_handle* h) {
     H /= 2;
     W /= 2;
   }
+  {
+    std::vector<float> z(2048, 0.f);
+    if ((rc = dev_upload(h, z.data(), z.size() * sizeof(float), reinterpret_cast<void**>(&h->zero_bias)))) return rc;
+  }
   h->total_mod = static_cast<int>(proj_b.size());
   if ((rc = dev_upload(h, proj_w.data(), proj_w.size() * sizeof(float), reinterpret_cast<void**>(&h->proj_w)))) return rc;
   if ((rc = dev_upload(h, proj_b.data(), proj_b.size() * sizeof(float), reinterpret_cast<void**>(&h->proj_b)))) return rc;
@@ -613,25 +862,33 @@ int c2w_timing_read(c2w_handle* h, double* ms, int64_t* n) {
   return C2W_OK;
 }
 
-int64_t c2w_workspace_bytes(c2w_handle* h, int32_t max_windows) {
+static int64_t workspace_bytes(c2w_handle* h, int32_t max_windows, bool vjp) {
   if (!h || !h->finalized || max_windows < 1) {
     fail(C2W_ERR_STATE, "c2w_workspace_bytes: finalise the weights first");
     return -1;
   }
   size_t bytes = 0;
-  if (build_plan(h, max_windows, nullptr, &bytes)) return -1;
+  if (build_plan(h, max_windows, vjp, nullptr, &bytes)) return -1;
   return static_cast<int64_t>(bytes);
 }
-
-int c2w_bind_workspace(c2w_handle* h, int32_t max_windows, void* dev_ptr, int64_t bytes) {
+static int bind_workspace(c2w_handle* h, int32_t max_windows, bool vjp, void* dev_ptr, int64_t bytes) {
   C2W_REQUIRE(h && dev_ptr && max_windows >= 1, "c2w_bind_workspace: bad argument");
   if (!h->finalized) return fail(C2W_ERR_STATE, "finalise the weights first");
   size_t need_bytes = 0;
-  int rc = build_plan(h, max_windows, nullptr, &need_bytes);
+  int rc = build_plan(h, max_windows, vjp, nullptr, &need_bytes);
   if (rc) return rc;
   C2W_REQUIRE(static_cast<size_t>(bytes) >= need_bytes, "workspace too small: %lld < %zu", (long long)bytes, need_bytes);
   void* aligned = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(dev_ptr) + 1023) & ~uintptr_t(1023));
-  return build_plan(h, max_windows, aligned, &need_bytes);
+  return build_plan(h, max_windows, vjp, aligned, &need_bytes);
+}
+
+int64_t c2w_workspace_bytes(c2w_handle* h, int32_t max_windows) { return workspace_bytes(h, max_windows, false); }
+int c2w_bind_workspace(c2w_handle* h, int32_t max_windows, void* dev_ptr, int64_t bytes) {
+  return bind_workspace(h, max_windows, false, dev_ptr, bytes);
+}
+int64_t c2w_workspace_bytes_vjp(c2w_handle* h, int32_t max_windows) { return workspace_bytes(h, max_windows, true); }
+int c2w_bind_workspace_vjp(c2w_handle* h, int32_t max_windows, void* dev_ptr, int64_t bytes) {
+  return bind_workspace(h, max_windows, true, dev_ptr, bytes);
 }
 
 int c2w_op_modulation(c2w_handle* h, float t, float* emb_out, float* mods_out, void* stream) {
@@ -711,6 +968,73 @@ int c2w_window_score(c2w_handle* h, const float* traj, int32_t n_frames_local, i
   return C2W_OK;
 }
 
+// J^T g of ScoreUNet.forward w.r.t. its input: forward (stashing) + input-gradient pass, n <= max_windows.
+int c2w_unet_vjp(c2w_handle* h, const float* x_nchw, int32_t n, float t, const float* gout_nchw, float* out_nchw,
+                 float* gin_nchw, void* stream) {
+  C2W_REQUIRE(h && x_nchw && gout_nchw && gin_nchw && n >= 1, "c2w_unet_vjp: bad argument");
+  Plan& P = h->plan;
+  if (P.n_max < 1 || !P.vjp) return fail(C2W_ERR_STATE, "bind a VJP workspace first (c2w_bind_workspace_vjp)");
+  C2W_REQUIRE(n <= P.n_max, "c2w_unet_vjp: %d windows exceed the bound workspace (%d)", n, P.n_max);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int hw = h->cfg.height * h->cfg.width;
+  const int cout_pad = h->levels[0].tail.cout_pad;
+  int rc = run_modulation(h, t, P.h0, P.emb, P.mods, st);
+  if (rc) return rc;
+  dim3 blk(32, 8);
+  dim3 g1(ceil_div(hw, 32), ceil_div(h->cin_pad, 32), n);
+  nchw_to_nhwc_bf16_kernel<<<g1, blk, 0, st>>>(x_nchw, P.xin, h->cin, hw, h->cin_pad);
+  C2W_CUDA(cudaGetLastError());
+  FinalSpec fs;
+  fs.mode = EPI_F32;
+  if ((rc = run_ops(h, P.ops, n, fs, st))) return rc;
+  dim3 g2(ceil_div(hw, 32), ceil_div(cout_pad, 32), n);
+  if (out_nchw) {
+    nhwc_f32_to_nchw_kernel<<<g2, blk, 0, st>>>(P.out32, out_nchw, h->cin, hw, cout_pad);
+    C2W_CUDA(cudaGetLastError());
+  }
+  nchw_to_nhwc_bf16_kernel<<<g2, blk, 0, st>>>(gout_nchw, P.cot, h->cin, hw, cout_pad);
+  C2W_CUDA(cudaGetLastError());
+  if ((rc = run_ops(h, P.bwd, n, fs, st))) return rc;
+  dim3 g3(ceil_div(hw, 32), ceil_div(h->cin_pad, 32), n);
+  nhwc_f32_to_nchw_kernel<<<g3, blk, 0, st>>>(P.out32, gin_nchw, h->cin, hw, h->cin_pad);
+  C2W_CUDA(cudaGetLastError());
+  return C2W_OK;
+}
+
+// Input-gradient pass of the windows whose forward c2w_window_score has JUST run on a VJP workspace (one chunk:
+// n_win <= max_windows).  cot: fp32 [n_frames_local, H, W, C] cotangent w.r.t. the composed score; vjp (same shape)
+// is ACCUMULATED: vjp[f] += sum over the windows of this call of d eps / d traj[f] ^T cot.
+int c2w_window_score_backward(c2w_handle* h, const float* cot, int32_t n_frames_local, int32_t frame_global0,
+                              int32_t win_first, int32_t n_win, int32_t n_win_global, float* vjp, void* stream) {
+  C2W_REQUIRE(h && cot && vjp, "c2w_window_score_backward: bad argument");
+  Plan& P = h->plan;
+  if (P.n_max < 1 || !P.vjp) return fail(C2W_ERR_STATE, "bind a VJP workspace first (c2w_bind_workspace_vjp)");
+  const int w = h->cfg.window, k = w / 2, C = h->cfg.frame_channels;
+  C2W_REQUIRE(n_win >= 1 && n_win <= P.n_max, "backward handles one chunk: %d windows, workspace %d", n_win, P.n_max);
+  C2W_REQUIRE(win_first >= frame_global0 && win_first + n_win - 1 + w <= frame_global0 + n_frames_local,
+              "windows [%d,%d) need frames outside the local range [%d,%d)", win_first, win_first + n_win,
+              frame_global0, frame_global0 + n_frames_local);
+  C2W_REQUIRE(C == 4, "fused compose supports 4 variables per frame (got %d)", C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int hw = h->cfg.height * h->cfg.width;
+  const int cpad = h->levels[0].tail.cout_pad;
+  const long long items = static_cast<long long>(n_win) * hw * (cpad / 8);
+  compose_adjoint_kernel<<<grid_for(items, 256, h->sms), 256, 0, st>>>(cot, P.cot, n_win, hw, cpad, k, win_first,
+                                                                         n_win_global - 1, frame_global0);
+  ++g_launches;
+  C2W_CUDA(cudaGetLastError());
+  FinalSpec fs;
+  fs.mode = EPI_F32;
+  int rc = run_ops(h, P.bwd, n_win, fs, st);
+  if (rc) return rc;
+  const long long items2 = static_cast<long long>(n_win + w - 1) * hw;
+  unfold_adjoint_kernel<<<grid_for(items2, 256, h->sms), 256, 0, st>>>(P.out32, vjp, n_win, hw, h->cin_pad, w, win_first,
+                                                                         frame_global0);
+  ++g_launches;
+  C2W_CUDA(cudaGetLastError());
+  return C2W_OK;
+}
+
 int c2w_traj_pack(const float* nchw, float* fhwc, int64_t frames, int32_t C, int32_t hw, void* stream) {
   C2W_REQUIRE(nchw && fhwc && frames >= 1, "c2w_traj_pack: bad argument");
   nchw_to_fhwc_kernel<<<grid_for(frames * hw, 256, c2w_num_sms()), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -730,7 +1054,8 @@ int c2w_guided_step(const c2w_guide* g, void* stream) {
   C2W_REQUIRE(g && g->x && g->eps && g->nan_flag, "c2w_guided_step: bad argument");
   C2W_REQUIRE(g->s_step >= 1 && g->H % g->s_step == 0 && g->W % g->s_step == 0 && g->W / g->s_step <= 32,
               "s_step=%d must divide %dx%d with at most 32 tiles per row", g->s_step, g->H, g->W);
-  C2W_REQUIRE(g->mode == 0 || (g->eps_out && g->partials), "mode 1 needs eps_out and partials");
+  C2W_REQUIRE(g->mode != 1 || (g->eps_out && g->partials), "mode 1 needs eps_out and partials");
+  C2W_REQUIRE(g->mode != 2 || (g->cot_out && g->y), "mode 2 needs cot_out and an observation");
   C2W_REQUIRE(g->own_n >= 1 && g->t_step >= 1, "own_n and t_step must be positive");
   GuideParams p;
   p.x = g->x;
@@ -754,6 +1079,8 @@ int c2w_guided_step(const c2w_guide* g, void* stream) {
   p.mode = g->mode;
   p.partials = g->partials;
   p.nan_flag = g->nan_flag;
+  p.vjp = g->vjp;
+  p.cot_out = g->cot_out;
   dim3 grid(g->H / g->s_step, g->own_n);
   guided_step_kernel<<<grid, 32 * (g->W / g->s_step), 0, static_cast<cudaStream_t>(stream)>>>(p);
   ++g_launches;
@@ -784,8 +1111,25 @@ int c2w_corrector_update(float* x, const float* eps, const float* z, const doubl
 int c2w_op_layernorm(const void* x, const float* mod, void* out, int64_t npix, int C, int H, int W, int upsample,
                      void* stream) {
   C2W_REQUIRE(x && out && npix >= 1, "c2w_op_layernorm: bad argument");
-  return launch_ln(static_cast<const bf16*>(x), mod, static_cast<bf16*>(out), npix, C, H, W, upsample, c2w_num_sms(),
+  return launch_ln(static_cast<const bf16*>(x), mod, static_cast<bf16*>(out), nullptr, npix, C, H, W, upsample, c2w_num_sms(),
                    static_cast<cudaStream_t>(stream));
+}
+int c2w_op_layernorm_bwd(const void* gy, const void* y, const float* inv, const void* gres, void* out, int64_t npix,
+                         int C, int H, int W, int down, void* stream) {
+  C2W_REQUIRE(gy && y && inv && out && npix >= 1, "c2w_op_layernorm_bwd: bad argument");
+  return launch_ln_bwd(static_cast<const bf16*>(gy), static_cast<const bf16*>(y), inv, static_cast<const bf16*>(gres),
+                       static_cast<bf16*>(out), npix, C, H, W, down, c2w_num_sms(), static_cast<cudaStream_t>(stream));
+}
+int c2w_op_layernorm_inv(const void* x, const float* mod, void* out, float* inv, int64_t npix, int C, void* stream) {
+  C2W_REQUIRE(x && out && inv && npix >= 1, "c2w_op_layernorm_inv: bad argument");
+  return launch_ln(static_cast<const bf16*>(x), mod, static_cast<bf16*>(out), inv, npix, C, 1, 1, 0, c2w_num_sms(),
+                   static_cast<cudaStream_t>(stream));
+}
+int c2w_op_attention_bwd(const void* qkv, const void* go, void* gqkv, float* scratch, int n, int T, int C,
+                         void* stream) {
+  C2W_REQUIRE(qkv && go && gqkv && scratch && n >= 1, "c2w_op_attention_bwd: bad argument");
+  return launch_attention_bwd(static_cast<const bf16*>(qkv), static_cast<const bf16*>(go), static_cast<bf16*>(gqkv),
+                              scratch, n, T, C, static_cast<cudaStream_t>(stream));
 }
 int c2w_op_attention(const void* qkv, void* out, int n, int T, int C, void* stream) {
   C2W_REQUIRE(qkv && out && n >= 1, "c2w_op_attention: bad argument");

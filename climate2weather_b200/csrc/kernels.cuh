@@ -82,8 +82,8 @@ __global__ void gather_windows_kernel(const float* __restrict__ traj, bf16* __re
 // block of a [n, 2H, 2W, C] tensor (model/nn.py:183-184 fused).
 template <int C>
 __global__ void channel_layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ mod,
-                                         bf16* __restrict__ out, long long npix, int H, int W, int upsample,
-                                         float eps) {
+                                         bf16* __restrict__ out, float* __restrict__ inv_out, long long npix, int H,
+                                         int W, int upsample, float eps) {
   constexpr int VEC = (C % 128 == 0) ? 4 : 2;
   constexpr int NCH = C / (32 * VEC);
   static_assert(C % 64 == 0 && NCH >= 1, "C must be a multiple of 64");
@@ -127,6 +127,7 @@ __global__ void channel_layernorm_kernel(const bf16* __restrict__ x, const float
     }
     const float var = warp_sum(ss) * (1.0f / (C - 1));
     const float inv = 1.0f / sqrtf(var + eps);
+    if (inv_out != nullptr && lane == 0) inv_out[pix] = inv;
     long long obase[4];
     int nout = 1;
     if (upsample) {
@@ -383,6 +384,346 @@ __global__ void nhwc_f32_to_nchw_kernel(const float* __restrict__ in, float* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------ VJP kernels
+// Backward of the channel LayerNorm (model/nn.py:154,183; zuko LayerNorm, unbiased variance):
+//   g_v = inv * (g_y - mean_C(g_y) - y * sum_C(g_y y) / (C - 1)),   out = gres + g_v
+// y is the stashed normalised output, inv the stashed 1/sqrt(var + eps).  down != 0: the LayerNorm output had been
+// nearest-upsampled 2x (model/nn.py:184): g_y is the sum of the 2x2 block of gy [n, 2H, 2W, C] and y is read from
+// the block's first pixel.  One warp per pixel, same lane -> channel mapping as the forward kernel.
+template <int C>
+__global__ void channel_layernorm_bwd_kernel(const bf16* __restrict__ gy, const bf16* __restrict__ y,
+                                             const float* __restrict__ inv, const bf16* gres, bf16* out,
+                                             long long npix, int H, int W, int down) {
+  constexpr int VEC = (C % 128 == 0) ? 4 : 2;
+  constexpr int NCH = C / (32 * VEC);
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long pix = warp0; pix < npix; pix += nwarps) {
+    long long src[4];
+    int nsrc = 1;
+    if (down) {
+      const int w = static_cast<int>(pix % W);
+      const long long t = pix / W;
+      const int h = static_cast<int>(t % H);
+      const long long n = t / H;
+      const long long o00 = ((n * 2 * H + 2 * h) * 2 * W + 2 * w);
+      src[0] = o00;
+      src[1] = o00 + 1;
+      src[2] = o00 + 2 * W;
+      src[3] = o00 + 2 * W + 1;
+      nsrc = 4;
+    } else {
+      src[0] = pix;
+    }
+    float g[NCH * VEC], yv[NCH * VEC];
+#pragma unroll
+    for (int i = 0; i < NCH * VEC; ++i) g[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int c0 = j * 32 * VEC + lane * VEC;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (q < nsrc) {
+          if (VEC == 4) {
+            const uint2 r = *reinterpret_cast<const uint2*>(gy + src[q] * C + c0);
+            const float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y);
+            g[j * 4 + 0] += a.x;
+            g[j * 4 + 1] += a.y;
+            g[j * 4 + 2] += b.x;
+            g[j * 4 + 3] += b.y;
+          } else {
+            const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(gy + src[q] * C + c0));
+            g[j * 2 + 0] += a.x;
+            g[j * 2 + 1] += a.y;
+          }
+        }
+      }
+      const bf16* yp = y + src[0] * C + c0;
+      if (VEC == 4) {
+        const uint2 r = *reinterpret_cast<const uint2*>(yp);
+        const float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y);
+        yv[j * 4 + 0] = a.x;
+        yv[j * 4 + 1] = a.y;
+        yv[j * 4 + 2] = b.x;
+        yv[j * 4 + 3] = b.y;
+      } else {
+        const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(yp));
+        yv[j * 2 + 0] = a.x;
+        yv[j * 2 + 1] = a.y;
+      }
+    }
+    float s = 0.f, sy = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH * VEC; ++i) {
+      s += g[i];
+      sy += g[i] * yv[i];
+    }
+    s = warp_sum(s) * (1.0f / C);
+    sy = warp_sum(sy) * (1.0f / (C - 1));
+    const float iv = inv[pix];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int c0 = j * 32 * VEC + lane * VEC;
+      float o[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) o[e] = iv * (g[j * VEC + e] - s - yv[j * VEC + e] * sy);
+      if (gres != nullptr) {
+        if (VEC == 4) {
+          const uint2 r = *reinterpret_cast<const uint2*>(gres + pix * C + c0);
+          const float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y);
+          o[0] += a.x;
+          o[1] += a.y;
+          o[2] += b.x;
+          o[3] += b.y;
+        } else {
+          const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(gres + pix * C + c0));
+          o[0] += a.x;
+          o[1] += a.y;
+        }
+      }
+      if (VEC == 4)
+        *reinterpret_cast<uint2*>(out + pix * C + c0) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+      else
+        *reinterpret_cast<uint32_t*>(out + pix * C + c0) = pack_bf16x2(o[0], o[1]);
+    }
+  }
+}
+
+// Backward of the attention core (model/nn.py:74-85).  qkv: bf16 [n*T, 3C] (stash), go: bf16 [n*T, C] (gradient w.r.t.
+// the attention output), gqkv: bf16 [n*T, 3C].
+//   S = scale2 q k^T, P = softmax_s(S), o = P v
+//   gv = P^T go ; gP = go v^T ; gS = P * (gP - rowsum(gP * P)) ; gq = scale2 gS k ; gk = scale2 gS^T q
+// Two kernels: (1) per (query block, window): P and gS rows -> fp32 scratch [n, T, T];  (2) per (row block, window,
+// {q, k, v}): the three products against k, q, go.
+constexpr int kAttnBwdRows = 64;
+inline size_t attention_bwd_scores_smem(int T, int C, int QB) {
+  return (static_cast<size_t>(T) + QB) * (C + 2) * 2 + 2 * static_cast<size_t>(QB) * (T + 1) * 4;
+}
+inline size_t attention_bwd_grads_smem(int T, int C, int RB) {
+  return static_cast<size_t>(T) * (C + 2) * 2 + static_cast<size_t>(RB) * (T + 1) * 4;
+}
+// dst[r][pitch] <- src[(row0 + r) * ld + coff + c], r < rows
+__device__ __forceinline__ void attn_load_tile(bf16* dst, const bf16* src, size_t row0, int rows, int ld, int coff, int C,
+                                               int pitch) {
+  const int c8 = C / 8;
+  for (int idx = threadIdx.x; idx < rows * c8; idx += kAttnThreads) {
+    const int r = idx / c8, g = idx - r * c8;
+    const uint4 v = *reinterpret_cast<const uint4*>(src + (row0 + r) * ld + coff + g * 8);
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(r) * pitch + g * 8);
+    d[0] = v.x;
+    d[1] = v.y;
+    d[2] = v.z;
+    d[3] = v.w;
+  }
+}
+// out[i][j] = scale * sum_c a[i][c] * b[j][c],  i < rows_a, j < T  (tiles [.][pitch] bf16; out [.][sp] fp32)
+__device__ __forceinline__ void attn_abt(const bf16* a, const bf16* b, float* out, int rows_a, int T, int C, int pitch,
+                                         int sp, float scale) {
+  const int pw = pitch / 2;
+  for (int item = threadIdx.x; item < rows_a * (T / 4); item += kAttnThreads) {
+    const int i = item / (T / 4), j4 = (item - i * (T / 4)) * 4;
+    const uint32_t* ap = reinterpret_cast<const uint32_t*>(a + static_cast<size_t>(i) * pitch);
+    const uint32_t* bp = reinterpret_cast<const uint32_t*>(b + static_cast<size_t>(j4) * pitch);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < C / 2; ++c) {
+      const float2 av = unpack_bf16x2(ap[c]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 bv = unpack_bf16x2(bp[j * pw + c]);
+        acc[j] += av.x * bv.x + av.y * bv.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[i * sp + j4 + j] = acc[j] * scale;
+  }
+}
+__global__ void __launch_bounds__(kAttnThreads)
+attention_bwd_scores_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ go, float* __restrict__ Pm,
+                            float* __restrict__ gSm, int T, int C, int QB, float scale2) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int pitch = C + 2, sp = T + 1;
+  bf16* sx = reinterpret_cast<bf16*>(smraw);                  // [T][pitch]: k, then v
+  bf16* sq = sx + static_cast<size_t>(T) * pitch;             // [QB][pitch]: q block, then go block
+  float* P = reinterpret_cast<float*>(sq + static_cast<size_t>(QB) * pitch);
+  float* gS = P + static_cast<size_t>(QB) * sp;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t row0 = static_cast<size_t>(blockIdx.y) * T;
+  const int i0 = blockIdx.x * QB;
+  const int nq = min(QB, T - i0);
+  attn_load_tile(sx, qkv, row0, T, 3 * C, C, C, pitch);
+  attn_load_tile(sq, qkv, row0 + i0, nq, 3 * C, 0, C, pitch);
+  __syncthreads();
+  attn_abt(sq, sx, P, nq, T, C, pitch, sp, scale2);
+  __syncthreads();
+  for (int i = warp; i < nq; i += kAttnThreads / 32) {
+    float mx = -INFINITY;
+    for (int j = lane; j < T; j += 32) mx = fmaxf(mx, P[i * sp + j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < T; j += 32) {
+      const float e = expf(P[i * sp + j] - mx);
+      P[i * sp + j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    for (int j = lane; j < T; j += 32) P[i * sp + j] *= inv;
+  }
+  __syncthreads();
+  attn_load_tile(sx, qkv, row0, T, 3 * C, 2 * C, C, pitch);
+  attn_load_tile(sq, go, row0 + i0, nq, C, 0, C, pitch);
+  __syncthreads();
+  attn_abt(sq, sx, gS, nq, T, C, pitch, sp, 1.0f);  // gP
+  __syncthreads();
+  for (int i = warp; i < nq; i += kAttnThreads / 32) {
+    float dot = 0.f;
+    for (int j = lane; j < T; j += 32) dot += gS[i * sp + j] * P[i * sp + j];
+    dot = warp_sum(dot);
+    float* prow = Pm + (row0 + i0 + i) * T;
+    float* grow = gSm + (row0 + i0 + i) * T;
+    for (int j = lane; j < T; j += 32) {
+      const float pv = P[i * sp + j];
+      prow[j] = pv;
+      grow[j] = pv * (gS[i * sp + j] - dot);
+    }
+  }
+}
+// blockIdx.z: 0 -> gq = scale2 gS k ; 1 -> gk = scale2 gS^T q ; 2 -> gv = P^T go.  Rows [r0, r0 + RB) of the output.
+__global__ void __launch_bounds__(kAttnThreads)
+attention_bwd_grads_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ go, const float* __restrict__ Pm,
+                           const float* __restrict__ gSm, bf16* __restrict__ gqkv, int T, int C, int RB, float scale2) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int pitch = C + 2, sp = T + 1;
+  bf16* sx = reinterpret_cast<bf16*>(smraw);  // [T][pitch]
+  float* sm = reinterpret_cast<float*>(sx + static_cast<size_t>(T) * pitch);  // [RB][sp]
+  const int tid = threadIdx.x;
+  const size_t row0 = static_cast<size_t>(blockIdx.y) * T;
+  const int r0 = blockIdx.x * RB;
+  const int nr = min(RB, T - r0);
+  const int z = blockIdx.z;
+  const float* M = (z == 2 ? Pm : gSm) + row0 * T;
+  if (z == 0) {
+    attn_load_tile(sx, qkv, row0, T, 3 * C, C, C, pitch);
+    for (int idx = tid; idx < nr * T; idx += kAttnThreads) {
+      const int r = idx / T, t = idx - r * T;
+      sm[r * sp + t] = M[static_cast<size_t>(r0 + r) * T + t];
+    }
+  } else {
+    if (z == 1) attn_load_tile(sx, qkv, row0, T, 3 * C, 0, C, pitch);
+    else attn_load_tile(sx, go, row0, T, C, 0, C, pitch);
+    for (int idx = tid; idx < nr * T; idx += kAttnThreads) {  // transposed read: sm[r][t] = M[t][r0 + r]
+      const int t = idx / nr, r = idx - t * nr;
+      sm[r * sp + t] = M[static_cast<size_t>(t) * T + r0 + r];
+    }
+  }
+  __syncthreads();
+  const float scale = (z == 2) ? 1.0f : scale2;
+  const int pairs = C / 2, pw = pitch / 2;
+  for (int item = tid; item < pairs * (RB / 8); item += kAttnThreads) {
+    const int c2 = item % pairs, ib = (item / pairs) * 8;
+    float a0[8], a1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
+    const uint32_t* bp = reinterpret_cast<const uint32_t*>(sx) + c2;
+    for (int t = 0; t < T; ++t) {
+      const float2 bv = unpack_bf16x2(bp[static_cast<size_t>(t) * pw]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float mv = sm[(ib + i) * sp + t];
+        a0[i] += mv * bv.x;
+        a1[i] += mv * bv.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (ib + i < nr)
+        *reinterpret_cast<uint32_t*>(gqkv + (row0 + r0 + ib + i) * 3 * C + z * C + 2 * c2) =
+            pack_bf16x2(a0[i] * scale, a1[i] * scale);
+  }
+}
+
+// Zero-insertion 2x upsample: out[n, 2h, 2w, :] = in[n, h, w, :], every other pixel zero.  The stride-2 conv's input
+// gradient is then a stride-1 conv of `out` with the flipped kernel.
+__global__ void zero_upsample_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, long long n, int H, int W,
+                                     int C) {
+  const int c8 = C / 8;
+  const long long total = n * (2 * H) * (2 * W) * c8;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(idx % c8);
+    long long r = idx / c8;
+    const int w2 = static_cast<int>(r % (2 * W));
+    r /= 2 * W;
+    const int h2 = static_cast<int>(r % (2 * H));
+    const long long img = r / (2 * H);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (((w2 | h2) & 1) == 0) v = *reinterpret_cast<const uint4*>(in + ((img * H + (h2 >> 1)) * W + (w2 >> 1)) * C + g * 8);
+    *reinterpret_cast<uint4*>(out + idx * 8) = v;
+  }
+}
+
+// Adjoint of the window compose (src/thor/score.py:76-88,111-141): UNet-output cotangent of window i, slot tau is
+// the frame cotangent g[win + tau] where that slot is the frame's source, zero elsewhere.
+// g: fp32 [frames, HW, 4] ; cot: bf16 [n, HW, cpad]
+__global__ void compose_adjoint_kernel(const float* __restrict__ g, bf16* __restrict__ cot, int n, int hw, int cpad,
+                                       int order_k, int win_first, int win_last_global, int frame_base) {
+  const int groups = cpad >> 3;
+  const long long total = static_cast<long long>(n) * hw * groups;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int gq = static_cast<int>(idx % groups);
+    const long long pw = idx / groups;
+    const int pix = static_cast<int>(pw % hw);
+    const int i = static_cast<int>(pw / hw);
+    const int win = win_first + i;
+    float v[8];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int tau = 2 * gq + hf;
+      const bool take = (tau == order_k) || (win == 0 && tau < order_k) ||
+                        (win == win_last_global && tau > order_k && tau <= 2 * order_k);
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (take) q = __ldg(reinterpret_cast<const float4*>(g + (static_cast<long long>(win + tau - frame_base) * hw + pix) * 4));
+      v[4 * hf + 0] = q.x;
+      v[4 * hf + 1] = q.y;
+      v[4 * hf + 2] = q.z;
+      v[4 * hf + 3] = q.w;
+    }
+    *reinterpret_cast<uint4*>(cot + (static_cast<long long>(i) * hw + pix) * cpad + 8 * gq) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
+// Adjoint of unfold (src/thor/score.py:68-74): vjp[f] += sum_tau gin[f - tau - win_first][slot tau] over the windows
+// of this launch.  gin: fp32 [n, HW, cpad] ; vjp: fp32 [frames, HW, 4] ; frames f in [win_first, win_first + n + 2k).
+__global__ void unfold_adjoint_kernel(const float* __restrict__ gin, float* __restrict__ vjp, int n, int hw, int cpad,
+                                      int window, int win_first, int frame_base) {
+  const long long total = static_cast<long long>(n + window - 1) * hw;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int pix = static_cast<int>(idx % hw);
+    const int fo = static_cast<int>(idx / hw);  // frame offset from win_first
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int tau = 0; tau < window; ++tau) {
+      const int i = fo - tau;
+      if (i < 0 || i >= n) continue;
+      const float4 q = *reinterpret_cast<const float4*>(gin + (static_cast<long long>(i) * hw + pix) * cpad + 4 * tau);
+      acc.x += q.x;
+      acc.y += q.y;
+      acc.z += q.z;
+      acc.w += q.w;
+    }
+    float4* dst = reinterpret_cast<float4*>(vjp + (static_cast<long long>(win_first + fo - frame_base) * hw + pix) * 4);
+    float4 o = *dst;
+    o.x += acc.x;
+    o.y += acc.y;
+    o.z += acc.z;
+    o.w += acc.w;
+    *dst = o;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ K6 / K7
 // State layout: x, eps, z are fp32 [frames, H, W, 4] (one float4 per pixel).  Observation y: fp32 [n_obs, 4, Hs, Ws]
 // exactly as the reference builds it (exp/downscaling.py:129-132: every t_step-th frame, s x s tile means).
@@ -401,6 +742,8 @@ struct GuideParams {
   int mode;           // 0: predictor update of x in place; 1: guided eps -> eps_out + partial sum of squares
   float* partials;    // mode 1: one float per CTA
   int* nan_flag;
+  const float* vjp;   // exact_grad: J_eps^T g per pixel (UNet vector-Jacobian product), null = closed-form guidance
+  float* cot_out;     // mode 2: g = A^T((y - A x0) / var), the cotangent fed to the UNet VJP
 };
 
 // CTA = one s-row strip of one frame; one warp per s x s observation tile (warp-shuffle tile mean, deterministic).
@@ -437,20 +780,38 @@ __global__ void guided_step_kernel(const GuideParams p) {
       const float yv = __ldg(p.y + ((static_cast<long long>(m) * 4 + ch) * Hs + blockIdx.x) * Ws + warp);
       const float err = yv - mean[ch];
       const float var = p.std2[ch] + p.gamma[ch] * r2;
-      // J = A^T(err / var) / mu  (each pixel of the tile gets err/var / s^2);  corr = sigma * J
-      c[ch] = p.sigma * (err / var) * inv_area * inv_mu;
+      // g = A^T(err / var): each pixel of the tile gets err/var / s^2
+      c[ch] = (err / var) * inv_area;
     }
     corr = make_float4(c[0], c[1], c[2], c[3]);
   }
+  if (p.mode == 2) {
+    for (int i = lane; i < s * s; i += 32) {
+      const long long o = (fbase + static_cast<long long>(h0 + i / s) * p.W + (w0 + i % s)) * 4;
+      *reinterpret_cast<float4*>(p.cot_out + o) = corr;
+    }
+    return;
+  }
+  // grad_x log p = (g - sigma J_eps^T g) / mu  (src/thor/score.py:48-60; the second term only with exact_grad);
+  // eps_guided = eps - sigma * grad  =>  per-pixel correction sigma (g - sigma vjp) / mu
+  const float sg_mu = p.sigma * inv_mu;
   float sq = 0.f;
   bool bad = false;
   for (int i = lane; i < s * s; i += 32) {
     const long long o = (fbase + static_cast<long long>(h0 + i / s) * p.W + (w0 + i % s)) * 4;
     float4 ev = *reinterpret_cast<const float4*>(p.eps + o);
-    ev.x -= corr.x;
-    ev.y -= corr.y;
-    ev.z -= corr.z;
-    ev.w -= corr.w;
+    float4 gv = corr;
+    if (p.vjp != nullptr) {
+      const float4 jv = *reinterpret_cast<const float4*>(p.vjp + o);
+      gv.x -= p.sigma * jv.x;
+      gv.y -= p.sigma * jv.y;
+      gv.z -= p.sigma * jv.z;
+      gv.w -= p.sigma * jv.w;
+    }
+    ev.x -= sg_mu * gv.x;
+    ev.y -= sg_mu * gv.y;
+    ev.z -= sg_mu * gv.z;
+    ev.w -= sg_mu * gv.w;
     if (p.mode == 0) {
       float4 xv = *reinterpret_cast<const float4*>(p.x + o);
       // x0 = (x - sigma eps)/mu ; x <- mu' x0 + sigma' eps     (src/thor/pipelines.py:41-46)

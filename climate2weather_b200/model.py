@@ -70,7 +70,7 @@ class Engine:
     """One c2w handle: packed weights + workspace for a fixed (frame_channels, window, H, W)."""
 
     def __init__(self, net: "ScoreUNet", frame_channels: int, window: int, height: int, width: int,
-                 device: torch.device, max_windows: int):
+                 device: torch.device, max_windows: int, vjp: bool = False):
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -95,16 +95,20 @@ class Engine:
             _lib.check(self.lib.c2w_finalize_weights(self.handle), "c2w_finalize_weights")
             self.max_windows = 0
             self.workspace = None
+            self.vjp = bool(vjp)
             self.bind(max_windows)
 
     def bind(self, max_windows: int) -> None:
+        size_fn = self.lib.c2w_workspace_bytes_vjp if self.vjp else self.lib.c2w_workspace_bytes
+        bind_fn = self.lib.c2w_bind_workspace_vjp if self.vjp else self.lib.c2w_bind_workspace
         with torch.cuda.device(self.device):
-            nbytes = self.lib.c2w_workspace_bytes(self.handle, max_windows)
+            nbytes = size_fn(self.handle, max_windows)
             if nbytes < 0:
                 _lib.check(-1, "c2w_workspace_bytes")
+            self.workspace = None  # release the old arena before taking the new one
             self.workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
-            _lib.check(self.lib.c2w_bind_workspace(self.handle, max_windows, self.workspace.data_ptr(),
-                                                   self.workspace.numel()), "c2w_bind_workspace")
+            _lib.check(bind_fn(self.handle, max_windows, self.workspace.data_ptr(), self.workspace.numel()),
+                       "c2w_bind_workspace")
             self.max_windows = max_windows
 
     @property
@@ -118,6 +122,25 @@ class Engine:
             _lib.check(self.lib.c2w_unet_forward(self.handle, x.data_ptr(), x.shape[0], float(t), out.data_ptr(),
                                                  self.stream), "c2w_unet_forward")
         return out
+
+    def unet_vjp(self, x: Tensor, t: float, gout: Tensor):
+        """(out, gin): forward and (d out / d x)^T gout for x, gout: fp32 NCHW [n, C*window, H, W], chunked."""
+        assert self.vjp, "engine was built without a VJP workspace"
+        out, gin = torch.empty_like(x), torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            for i in range(0, x.shape[0], self.max_windows):
+                xs, gs = x[i:i + self.max_windows], gout[i:i + self.max_windows]
+                _lib.check(self.lib.c2w_unet_vjp(self.handle, xs.data_ptr(), xs.shape[0], float(t), gs.data_ptr(),
+                                                 out[i:].data_ptr(), gin[i:].data_ptr(), self.stream), "c2w_unet_vjp")
+        return out, gin
+
+    def window_score_backward(self, cot: Tensor, frame_global0: int, win_first: int, n_win: int, n_win_global: int,
+                              vjp: Tensor) -> None:
+        """Adjoint of the last window_score call (same window range, one chunk); accumulates into vjp."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.c2w_window_score_backward(self.handle, cot.data_ptr(), cot.shape[0], frame_global0,
+                                                          win_first, n_win, n_win_global, vjp.data_ptr(), self.stream),
+                       "c2w_window_score_backward")
 
     def window_score(self, traj: Tensor, frame_global0: int, win_first: int, n_win: int, n_win_global: int, t: float,
                      eps: Tensor) -> None:
@@ -194,15 +217,15 @@ class ScoreUNet(nn.Module):
     def _fingerprint(self) -> tuple:
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
-    def engine(self, frame_channels: int, window: int, height: int, width: int, device, max_windows: Optional[int] = None
-               ) -> Engine:
+    def engine(self, frame_channels: int, window: int, height: int, width: int, device, max_windows: Optional[int] = None,
+               vjp: bool = False) -> Engine:
         """Packed-weight engine for this geometry; rebuilt if the parameters changed since it was packed."""
         device = torch.device(device)
         if device.type == "cuda" and device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
         if frame_channels * window != self.channels:
             raise ValueError(f"frame_channels*window = {frame_channels * window} != channels = {self.channels}")
-        key = (frame_channels, window, height, width, str(device))
+        key = (frame_channels, window, height, width, str(device), bool(vjp))
         fp = self._fingerprint()
         hit = self._engines.get(key)
         want = max_windows or self.DEFAULT_MAX_WINDOWS
@@ -211,7 +234,7 @@ class ScoreUNet(nn.Module):
             if max_windows is not None and eng.max_windows != max_windows:
                 eng.bind(max_windows)
             return eng
-        eng = Engine(self, frame_channels, window, height, width, device, want)
+        eng = Engine(self, frame_channels, window, height, width, device, want, vjp=vjp)
         self._engines[key] = (eng, fp)
         return eng
 
@@ -228,16 +251,41 @@ class ScoreUNet(nn.Module):
         if not x.is_cuda:
             raise _lib.C2WError("ScoreUNet.forward: input must live on a CUDA device (no CPU path); "
                                 "BatchedScoreFunction moves window batches for you")
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            if x.requires_grad:
-                raise NotImplementedError("ScoreUNet VJP (exact_grad=True / training) is not built yet")
         tt = torch.as_tensor(t).reshape(-1).float()
         if tt.numel() != 1 and not bool((tt == tt[0]).all()):
             raise NotImplementedError("per-sample diffusion times are not built yet (sampling uses one t per call)")
         B, Cc, H, W = x.shape
+        if torch.is_grad_enabled() and x.requires_grad:
+            # input gradients only (model/nn.py weights are frozen in sampling, training_loop.py:257); parameter
+            # gradients (training) are not built
+            return _UNetInputVJP.apply(x, self, float(tt[0]))
         eng = self.engine(Cc, 1, H, W, x.device)
         out = eng.unet_forward(x.detach().float().contiguous(), float(tt[0]))
         return out.to(x.dtype).reshape(x.shape)
+
+
+class _UNetInputVJP(torch.autograd.Function):
+    """ScoreUNet.forward under autograd: the backward is c2w_unet_vjp (forward recomputed with stashing + the
+    input-gradient pass on tensor cores).  Gradients flow to x only."""
+
+    VJP_WINDOWS = 8
+
+    @staticmethod
+    def forward(ctx, x, net, t):
+        B, Cc, H, W = x.shape
+        eng = net.engine(Cc, 1, H, W, x.device)
+        ctx.save_for_backward(x)
+        ctx.net, ctx.t = net, t
+        out = eng.unet_forward(x.detach().float().contiguous(), t)
+        return out.to(x.dtype).reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (x,) = ctx.saved_tensors
+        B, Cc, H, W = x.shape
+        eng = ctx.net.engine(Cc, 1, H, W, x.device, max_windows=min(B, _UNetInputVJP.VJP_WINDOWS), vjp=True)
+        _, gin = eng.unet_vjp(x.detach().float().contiguous(), ctx.t, gout.detach().float().contiguous())
+        return gin.to(x.dtype), None, None
 
 
 def build_from_reference(module: nn.Module) -> ScoreUNet:

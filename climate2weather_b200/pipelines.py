@@ -94,7 +94,7 @@ class SDAPipeline:
             mu, sigma = _mu_sigma(self, t)
             mu_n, sigma_n = _mu_sigma(self, t_next)
             # predictor
-            rt.score(float(t))
+            rt.score(float(t), group)
             rt.predictor(mu, sigma, mu_n, sigma_n)
             rt.halo(group)
             # corrector
@@ -109,7 +109,7 @@ class SDAPipeline:
                     with torch.cuda.device(rt.device):
                         _lib.check(rt.lib.c2w_traj_pack(src.data_ptr(), z_dev.data_ptr(), p.n_local, rt.C, rt.H * rt.W,
                                                         rt.stream), "c2w_traj_pack")
-                rt.score(float(t_next))
+                rt.score(float(t_next), group)
                 rt.guided_eps(mu_n, sigma_n)
                 rt.corrector(tau, sigma_n, z_dev, seed, istep * max(corrections, 1) + ic, group)
                 rt.halo(group)

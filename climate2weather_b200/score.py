@@ -17,7 +17,7 @@ from torch import Tensor
 
 from . import _lib
 from .model import ScoreUNet, build_from_reference
-from .sharding import ShardPlan, all_gather_frames, exchange_halos, make_plan
+from .sharding import ShardPlan, all_gather_frames, exchange_halos, exchange_halos_adjoint, make_plan
 
 
 class CoarseGrain:
@@ -72,17 +72,21 @@ class _Runtime:
     """Device-resident state of one trajectory (or of this rank's time shard of it)."""
 
     def __init__(self, sf: "AbstractScoreFunction", L: int, C: int, H: int, W: int, device: torch.device,
-                 plan: ShardPlan, max_windows: int):
+                 plan: ShardPlan, max_windows: int, exact: bool = False):
         if C != 4:
             raise NotImplementedError(f"the fused path keeps 4 variables per pixel (float4); got C={C}")
         self.sf, self.L, self.C, self.H, self.W, self.device, self.plan = sf, L, C, H, W, device, plan
         self.lib = _lib.load()
         k = sf.markov_order
-        self.engine = sf.unet.engine(C, 2 * k + 1, H, W, device, max_windows=min(max_windows, plan.win_hi - plan.win_lo))
+        self.exact = bool(exact)  # exact_grad=True: guidance through the UNet VJP (src/thor/score.py:28-33,51-52)
+        self.engine = sf.unet.engine(C, 2 * k + 1, H, W, device, max_windows=min(max_windows, plan.win_hi - plan.win_lo),
+                                     vjp=self.exact)
         f32 = dict(dtype=torch.float32, device=device)
         self.x = torch.zeros(plan.n_local, H, W, C, **f32)
         self.eps = torch.zeros_like(self.x)
         self.eps_g: Optional[Tensor] = None
+        self.vjp = torch.zeros_like(self.x) if self.exact else None   # J_eps^T g, accumulated per score evaluation
+        self.cot = torch.zeros_like(self.x) if self.exact else None   # g = A^T((y - A x0)/var)
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=device)
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=device)
         self.partials: Optional[Tensor] = None
@@ -115,17 +119,33 @@ class _Runtime:
         return self.unpack(buf, p.own_lo - p.frame_lo, p.own_n)
 
     # ------------------------------------------------------------------------------------------------ kernels
-    def score(self, t: float) -> None:
-        """eps <- composed window score of x at time t (src/thor/score.py:90-93 / :156-185)."""
+    def score(self, t: float, group=None) -> None:
+        """eps <- composed window score of x at time t (src/thor/score.py:90-93 / :156-185).  With exact_grad the
+        likelihood cotangent is pushed back through the same windows chunk by chunk: vjp <- J_eps^T g."""
         p = self.plan
-        self.engine.window_score(self.x, p.frame_lo, p.win_lo, p.win_hi - p.win_lo, p.n_win_global, t, self.eps)
+        if not (self.exact and self.cond is not None):
+            self.engine.window_score(self.x, p.frame_lo, p.win_lo, p.win_hi - p.win_lo, p.n_win_global, t, self.eps)
+            return
+        mu, sigma = _mu_sigma(self.sf.noise_process, t)
+        k = self.sf.markov_order
+        self.vjp.zero_()
+        step = self.engine.max_windows
+        for j0 in range(p.win_lo, p.win_hi, step):
+            n = min(step, p.win_hi - j0)
+            self.engine.window_score(self.x, p.frame_lo, j0, n, p.n_win_global, t, self.eps)
+            # frames whose score these windows produce: their centres, plus the trajectory's edge frames
+            f_lo = 0 if j0 == 0 else j0 + k
+            f_hi = self.L if j0 + n == p.n_win_global else j0 + n + k
+            self._guide(2, mu, sigma, 0.0, 0.0, frames=(f_lo - p.frame_lo, f_hi - f_lo))
+            self.engine.window_score_backward(self.cot, p.frame_lo, j0, n, p.n_win_global, self.vjp)
+        exchange_halos_adjoint(self.vjp, p, group)
 
     def set_condition(self, cond) -> None:
         self.cond = cond
         if cond is not None:
             self.y_dev = cond["y"].to(device=self.device, dtype=torch.float32).contiguous()
 
-    def _guide(self, mode: int, mu: float, sigma: float, mu_next: float, sigma_next: float) -> None:
+    def _guide(self, mode: int, mu: float, sigma: float, mu_next: float, sigma_next: float, frames=None) -> None:
         p = self.plan
         g = _lib.Guide()
         g.x, g.eps = self.x.data_ptr(), self.eps.data_ptr()
@@ -144,8 +164,12 @@ class _Runtime:
         g.s_step, g.H, g.W = s, self.H, self.W
         g.mu, g.sigma, g.mu_next, g.sigma_next = mu, sigma, mu_next, sigma_next
         g.frame_global0, g.own_lo, g.own_n = p.frame_lo, p.own_lo - p.frame_lo, p.own_n
+        if frames is not None:
+            g.own_lo, g.own_n = frames
         g.mode = mode
         g.nan_flag = self.nan_flag.data_ptr()
+        g.vjp = self.vjp.data_ptr() if (self.exact and self.cond is not None and mode != 2) else None
+        g.cot_out = self.cot.data_ptr() if mode == 2 else None
         if mode == 1:
             n_part = p.own_n * (self.H // s)
             if self.partials is None or self.partials.numel() < n_part:
@@ -223,13 +247,11 @@ class AbstractScoreFunction:
 
     def condition_on(self, *, A, y, std, gamma=1e-2, exact_grad=True):
         """src/thor/score.py:44-60.  `exact_grad=False` (every shipped config) is the closed-form guidance
-        J = A^T((y - A x0)/var)/mu; `exact_grad=True` needs the UNet VJP."""
+        J = A^T((y - A x0)/var)/mu; `exact_grad=True` adds the term through the network,
+        J = (g - sigma J_eps^T g)/mu with g = A^T((y - A x0)/var), computed by the UNet input-gradient kernels."""
         if self.likelihood is not None:
             print("Warning: Overwriting old conditioning")
-        if exact_grad:
-            raise NotImplementedError("exact_grad=True (UNet vector-Jacobian product) is not built yet; "
-                                      "the reference's experiment configs all use use_exact_grad: false")
-        self.likelihood = dict(A=A, y=torch.as_tensor(y), std=std, gamma=gamma, op=None)
+        self.likelihood = dict(A=A, y=torch.as_tensor(y), std=std, gamma=gamma, op=None, exact=bool(exact_grad))
         for rt in self._runtimes.values():
             rt.set_condition(None)
         self._runtimes.clear()
@@ -239,7 +261,7 @@ class AbstractScoreFunction:
         """src/thor/score.py:24-35: the (guided) noise prediction for the whole trajectory x[L, C, H, W]."""
         rt = self.runtime(x)
         rt.load(x)
-        rt.score(float(t))
+        rt.score(float(t), self.shard[2] if self.shard else None)
         if not self.is_conditioned:
             out = rt.owned(rt.eps)
         else:
@@ -280,6 +302,8 @@ class AbstractScoreFunction:
     #: (156) keeps every level of the UNet at full machine occupancy: measured 20.9 ms/step vs 24.9 ms at 32 windows
     #: (profiles/r01_chunk_sweep.log).  The workspace is ~24 MiB per window.
     DEFAULT_WINDOWS = 192
+    #: windows per forward+backward chunk with exact_grad=True
+    VJP_WINDOWS = 64
 
     def _default_windows(self, n_win: int) -> int:
         return min(n_win, self.DEFAULT_WINDOWS)
@@ -288,12 +312,15 @@ class AbstractScoreFunction:
         L, C, H, W = x.shape
         dev = self._compute_device(x)
         rank, world = (self.shard[0], self.shard[1]) if self.shard else (0, 1)
-        key = (L, C, H, W, str(dev), rank, world)
+        exact = bool(self.likelihood is not None and self.likelihood.get("exact"))
+        key = (L, C, H, W, str(dev), rank, world, exact)
         rt = self._runtimes.get(key)
         if rt is None:
             plan = make_plan(L, self.markov_order, rank, world)
             mw = self.max_windows or self._default_windows(plan.win_hi - plan.win_lo)
-            rt = _Runtime(self, L, C, H, W, dev, plan, mw)
+            if exact:
+                mw = min(mw, self.VJP_WINDOWS)  # the stash costs ~110 MiB per window at the reference shapes
+            rt = _Runtime(self, L, C, H, W, dev, plan, mw, exact=exact)
             if self.likelihood is not None:
                 lk = self.likelihood
                 if lk["op"] is None:

@@ -85,6 +85,32 @@ def exchange_halos(x_local: torch.Tensor, plan: ShardPlan, group: Optional[dist.
         req.wait()
 
 
+def exchange_halos_adjoint(v_local: torch.Tensor, plan: ShardPlan, group: Optional[dist.ProcessGroup] = None) -> None:
+    """Adjoint of `exchange_halos`: what this rank accumulated in its k halo frames belongs to the neighbour that
+    owns them — send it there and ADD what the neighbours accumulated for this rank's boundary frames (the UNet
+    vector-Jacobian product reaches k frames beyond the owned range).  No-op for a single rank."""
+    if plan.world == 1:
+        return
+    k = plan.k
+    n = plan.n_local
+    ops: List[dist.P2POp] = []
+    recv_l = recv_r = None
+    if plan.rank > 0:
+        recv_l = torch.empty_like(v_local[k:2 * k])
+        ops.append(dist.P2POp(dist.isend, v_local[0:k].contiguous(), plan.rank - 1, group))
+        ops.append(dist.P2POp(dist.irecv, recv_l, plan.rank - 1, group))
+    if plan.rank < plan.world - 1:
+        recv_r = torch.empty_like(v_local[n - 2 * k:n - k])
+        ops.append(dist.P2POp(dist.isend, v_local[n - k:n].contiguous(), plan.rank + 1, group))
+        ops.append(dist.P2POp(dist.irecv, recv_r, plan.rank + 1, group))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    if recv_l is not None:
+        v_local[k:2 * k] += recv_l
+    if recv_r is not None:
+        v_local[n - 2 * k:n - k] += recv_r
+
+
 def all_gather_frames(x_owned: torch.Tensor, plan: ShardPlan, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
     """Concatenates every rank's owned frames into the full [L, ...] trajectory (end of sampling only)."""
     if plan.world == 1:

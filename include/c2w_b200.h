@@ -57,9 +57,13 @@ typedef struct c2w_guide {
   int32_t t_step, s_step, H, W;
   int32_t frame_global0; /* global frame index of local frame 0 (time sharding)                            */
   int32_t own_lo, own_n; /* local frames [own_lo, own_lo + own_n) are updated                              */
-  int32_t mode;          /* 0 predictor update, 1 guided eps + per-CTA partial sums of eps^2               */
+  int32_t mode;          /* 0 predictor update, 1 guided eps + per-CTA partial sums of eps^2,
+                            2 likelihood cotangent g = A^T((y - A x0)/var) -> cot_out (exact_grad)          */
   float* partials;       /* mode 1: >= own_n * (H / s_step) floats                                         */
   int32_t* nan_flag;     /* set to 1 if any updated value is not finite (src/thor/pipelines.py:90-91)      */
+  const float* vjp;      /* exact_grad=True: J_eps^T g from c2w_window_score_backward (src/thor/score.py:28-35,
+                            48-60 with grad enabled); NULL = closed-form guidance (exact_grad=False)        */
+  float* cot_out;        /* mode 2 output, [frames_local, H, W, 4]                                         */
 } c2w_guide;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------ */
@@ -76,9 +80,20 @@ int c2w_finalize_weights(c2w_handle* h); /* packs to bf16 K-major [Cout, 9*Cin] 
 int64_t c2w_workspace_bytes(c2w_handle* h, int32_t max_windows);
 int c2w_bind_workspace(c2w_handle* h, int32_t max_windows, void* dev_ptr, int64_t bytes);
 
+/* VJP workspaces additionally hold the per-block stashes (LayerNorm outputs, SiLU pre-activations, qkv) and the
+ * gradient buffers (about 4.5x the forward-only workspace); forward calls on them stash as they go. */
+int64_t c2w_workspace_bytes_vjp(c2w_handle* h, int32_t max_windows);
+int c2w_bind_workspace_vjp(c2w_handle* h, int32_t max_windows, void* dev_ptr, int64_t bytes);
+
 /* ---- ScoreUNet.forward (model/score.py:59-70 -> model/nn.py:220-242) --------------------------------------
  * x, out: fp32 NCHW [n, C*window, H, W] on the device; scalar diffusion time t (sampling: one t per call). */
 int c2w_unet_forward(c2w_handle* h, const float* x_nchw, int32_t n, float t, float* out_nchw, void* stream);
+
+/* Vector-Jacobian product of ScoreUNet.forward w.r.t. x (what torch.func.jacrev / autograd computes through the UNet
+ * when condition_on(exact_grad=True), src/thor/score.py:28-33,51-52): gin = (d out / d x)^T gout.  n <= max_windows
+ * of a VJP workspace; out_nchw (the forward result) may be NULL. */
+int c2w_unet_vjp(c2w_handle* h, const float* x_nchw, int32_t n, float t, const float* gout_nchw, float* out_nchw,
+                 float* gin_nchw, void* stream);
 
 /* ---- DefaultScoreFunction/BatchedScoreFunction.score_fn (src/thor/score.py:68-93, :111-185) ---------------
  * unfold -> UNet -> centre-pick/edge-fill compose, without materialising the unfold in fp32 or the unused
@@ -87,6 +102,11 @@ int c2w_unet_forward(c2w_handle* h, const float* x_nchw, int32_t n, float t, flo
  * n_win_global windows; local frame 0 is global frame frame_global0. */
 int c2w_window_score(c2w_handle* h, const float* traj, int32_t n_frames_local, int32_t frame_global0,
                      int32_t win_first, int32_t n_win, int32_t n_win_global, float t, float* eps, void* stream);
+
+/* Adjoint of c2w_window_score for the windows whose forward has JUST run on a VJP workspace (one chunk): compose
+ * adjoint -> UNet input-gradient pass -> unfold adjoint.  cot: cotangent w.r.t. the composed score; vjp is accumulated. */
+int c2w_window_score_backward(c2w_handle* h, const float* cot, int32_t n_frames_local, int32_t frame_global0,
+                              int32_t win_first, int32_t n_win, int32_t n_win_global, float* vjp, void* stream);
 
 /* ---- layout: reference NCHW fp32 [frames, C, H, W] <-> device [frames, H, W, C] --------------------------- */
 int c2w_traj_pack(const float* nchw, float* fhwc, int64_t frames, int32_t C, int32_t hw, void* stream);
@@ -132,6 +152,14 @@ int c2w_op_conv(const void* x, int n_img, int H, int W, int cin, const void* w_p
 int c2w_op_layernorm(const void* x_bf16, const float* mod, void* out_bf16, int64_t npix, int C, int H, int W,
                      int upsample, void* stream);
 int c2w_op_attention(const void* qkv_bf16, void* out_bf16, int n, int T, int C, void* stream);
+/* backward kernels of the VJP path: LayerNorm forward with its 1/std stash, LayerNorm backward (down: the forward
+ * output was 2x nearest-upsampled, gy is [n, 2H, 2W, C]), attention-core backward (scratch: 2*n*T*T floats) */
+int c2w_op_layernorm_inv(const void* x_bf16, const float* mod, void* out_bf16, float* inv, int64_t npix, int C,
+                         void* stream);
+int c2w_op_layernorm_bwd(const void* gy_bf16, const void* y_bf16, const float* inv, const void* gres_bf16,
+                         void* out_bf16, int64_t npix, int C, int H, int W, int down, void* stream);
+int c2w_op_attention_bwd(const void* qkv_bf16, const void* go_bf16, void* gqkv_bf16, float* scratch_2nTT, int n, int T,
+                         int C, void* stream);
 int c2w_op_gather_windows(const float* traj, void* out_bf16, int n, int hw, int C, int window, int cin_pad,
                           int frame0, void* stream);
 int c2w_op_modulation(c2w_handle* h, float t, float* emb_out, float* mods_out, void* stream);

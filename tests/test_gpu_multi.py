@@ -34,12 +34,12 @@ def _problem(L):
     return net, noise, y
 
 
-def _sample(net, noise, y, dev, corrections, shard):
+def _sample(net, noise, y, dev, corrections, shard, exact=False):
     import climate2weather_b200 as c2w
 
     pipe = c2w.SDAPipeline()
     sf = c2w.BatchedScoreFunction(net.to(dev), markov_order=2, noise_process=pipe, batch_size=5, device=dev)
-    sf.condition_on(A=c2w.CoarseGrain(3, 8), y=y, std=0.1, gamma=1e-3, exact_grad=False)
+    sf.condition_on(A=c2w.CoarseGrain(3, 8), y=y, std=0.1, gamma=1e-3, exact_grad=exact)
     if shard:
         sf.enable_time_sharding()
     return pipe.sample(sf, noise, steps=4, corrections=corrections, tau=0.5, show_progressbar=False, seed=77)
@@ -57,6 +57,9 @@ def _worker(rank, world, port, L, out_dir):
             out = _sample(net, noise, y, dev, corr, shard=True)
             if rank == 0:
                 torch.save(out.cpu(), os.path.join(out_dir, f"sharded_c{corr}.pt"))
+        out = _sample(net, noise, y, dev, 0, shard=True, exact=True)
+        if rank == 0:
+            torch.save(out.cpu(), os.path.join(out_dir, "sharded_exact.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -76,3 +79,10 @@ def test_time_sharded_sampling_matches_single_gpu(tmp_path, world):
     assert torch.equal(got0, ref[0]), float((got0 - ref[0]).abs().max())
     rel = ((got1 - ref[1]).abs().max() / ref[1].abs().max()).item()
     assert rel < 1e-5, rel
+    # exact_grad: the UNet VJP reaches k frames into the neighbours' shards (reverse halo exchange, send-and-add);
+    # the fp32 accumulation order over windows differs between the sharded and the unsharded run -> 1e-4
+    want = _sample(net, noise, y, dev, 0, shard=False, exact=True).cpu()
+    gote = torch.load(tmp_path / "sharded_exact.pt")
+    rel = ((gote - want).abs().max() / want.abs().max()).item()
+    assert rel < 1e-4, rel
+    assert not torch.equal(want, ref[0])

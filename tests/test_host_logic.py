@@ -160,7 +160,19 @@ def _worker(rank: int, world: int, port: int, L: int, k: int, out_dir: str):
         s = (loc[lo:hi].double() ** 2).sum().reshape(1)
         dist.all_reduce(s)
         ok_sum = abs(s.item() - ((x * 2 + 1).double() ** 2).sum().item()) < 1e-6 * s.item()
-        Path(out_dir, f"ok{rank}").write_text(f"{int(ok_halo)}{int(ok_halo2)}{int(ok_gather)}{int(ok_sum)}")
+        # adjoint exchange: every rank accumulated a contribution on ALL its local frames (halos included); after the
+        # exchange each owned frame holds the sum over the ranks whose local range covers it
+        def contrib(r):
+            q = sharding.make_plan(L, k, r, world)
+            return q, torch.randn(q.n_local, *shape, generator=torch.Generator().manual_seed(100 + r))
+        total = torch.zeros(L, *shape)
+        for r in range(world):
+            q, c = contrib(r)
+            total[q.frame_lo:q.frame_hi] += c
+        _, mine = contrib(rank)
+        sharding.exchange_halos_adjoint(mine, p)
+        ok_adj = torch.allclose(mine[lo:hi], total[p.own_lo:p.own_hi], rtol=0, atol=1e-6)
+        Path(out_dir, f"ok{rank}").write_text(f"{int(ok_halo)}{int(ok_halo2)}{int(ok_gather)}{int(ok_sum)}{int(ok_adj)}")
     finally:
         dist.destroy_process_group()
 
@@ -171,4 +183,4 @@ def test_halo_exchange_and_gather_gloo_world2(tmp_path, L, k):
     port = _free_port()
     mp.spawn(_worker, args=(world, port, L, k, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
-        assert (tmp_path / f"ok{r}").read_text() == "1111"
+        assert (tmp_path / f"ok{r}").read_text() == "11111"
