@@ -138,7 +138,7 @@ def run_ours(args):
     net = net.to(dev)
     pipe = c2w.SDAPipeline()
     sf = c2w.BatchedScoreFunction(net, markov_order=K_ORDER, noise_process=pipe, batch_size=args.chunk, device=dev)
-    sf.condition_on(A=cg, y=y, std=torch.tensor(STD).reshape(1, C, 1, 1), gamma=GAMMA, exact_grad=False)
+    sf.condition_on(A=cg, y=y, std=torch.tensor(STD).reshape(1, C, 1, 1), gamma=GAMMA, exact_grad=args.exact_grad)
     if world > 1:
         sf.enable_time_sharding()
     rt = sf.runtime(noise)
@@ -151,7 +151,7 @@ def run_ours(args):
         t = times[i % SAMPLER_STEPS]
         mu, sigma = _mu_sigma(pipe, t)
         mu_n, sigma_n = _mu_sigma(pipe, t - dt)
-        rt.score(float(t))
+        rt.score(float(t), group)
         rt.predictor(mu, sigma, mu_n, sigma_n)
         rt.halo(group)
 
@@ -243,7 +243,8 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"config2: guided PC sampling, L={L} frames ({n_win_local} windows/GPU) of "
                                    f"{C}x{H}x{W}, sda_unet.yml ScoreUNet k={K_ORDER}, {SAMPLER_STEPS} steps, "
-                                   "0 corrections, approx-grad guidance t_step=6 s_step=16",
+                                   f"0 corrections, {'exact-grad (UNet VJP)' if args.exact_grad else 'approx-grad'} guidance "
+                                   "t_step=6 s_step=16",
                        "frames": L, "sampler_steps": SAMPLER_STEPS, "windows_per_gpu": n_win_local,
                        "chunk_windows": rt.engine.max_windows, "parallelism": f"time-shard x{world}",
                        "l2": "per-step working set (activations of a chunk + 144 MB packed weights) exceeds the 126 MB "
@@ -341,6 +342,9 @@ def main():
     ap.add_argument("--cpu-windows", type=int, default=13)
     ap.add_argument("--ref-steps", type=int, default=3)
     ap.add_argument("--warmup-ref", type=int, default=1)
+    ap.add_argument("--exact-grad", action="store_true",
+                    help="guidance through the UNet vector-Jacobian product (condition_on(exact_grad=True)); the shipped "
+                         "experiment configs and the default bench line use the closed-form guidance")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: no warm-up floor, no roofline/e2e/cpu legs")

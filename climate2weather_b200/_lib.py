@@ -76,6 +76,7 @@ class ConvDesc(C.Structure):
         ("ln_out", C.c_void_p),
         ("ln_mod", C.c_void_p),
         ("ln_upsample", C.c_int32),
+        ("stats", C.c_void_p),
     ]
 
 

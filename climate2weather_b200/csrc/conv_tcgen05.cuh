@@ -37,7 +37,6 @@ enum EpiMode : int {
   EPI_BIAS_RES = 2,   // out += acc + bias                      -> bf16   (in place)
   EPI_COMPOSE = 3,    // centre-pick / edge-fill compose        -> fp32 eps [L, H, W, 4]
   EPI_F32 = 4,        // out = acc + bias                       -> fp32 [M, ldc]
-  EPI_DSILU = 5,      // out = (acc + bias) * silu'(aux)        -> bf16   (VJP: aux = stashed pre-activation)
 };
 
 struct ConvParams {
@@ -48,9 +47,10 @@ struct ConvParams {
   int num_m_tiles, num_n_tiles;
   int m_total;  // valid rows
   int tile_h, tile_n, tiles_per_img;
+  int tiles_w;      // AR: 16 x 8 spatial tiles per image row (W / 8); tiles_per_img = (H / 16) * tiles_w
+  int img_h, img_w; // AR: output image size
   int num_stages;   // depth of the A/B ring
-  int num_staging;  // epilogue staging tiles (2 for convs with an auxiliary input tile or a second output)
-  int dual_out;     // EPI_BIAS_SILU only: also store the pre-activation (acc + bias) as a second bf16 tensor
+  int num_staging;  // epilogue staging tiles (2: used alternately)
   // epilogue
   int mode;
   int ldc;  // output row pitch (elements)
@@ -71,6 +71,7 @@ struct ConvParams {
   int win_first;    // global index of the first window of this launch
   int win_last_global;  // global index of the last window of the trajectory (Nw - 1)
   int frame_base;   // global frame index of eps[0]
+  long long* dbg_stats;  // diagnostics only: per-CTA wait cycles [grid][12] (see tools/bringup_conv.py --stats)
   int dbg_skip_loads;  // diagnostics only: after the ring is primed, signal `full` without issuing TMA loads
 };
 
@@ -99,8 +100,24 @@ struct ConvCfg {
   static constexpr int kSubBytes = kATileBytes + kBTileBytes;
   static constexpr int kStageBytes = kSub * kSubBytes;
   static constexpr int kStagingBytes = (BN / 64) * kATileBytes;  // bf16 [BN/64 boxes][128 rows][64 ch], swizzled
-  static constexpr int kBarrierBytes = 256;
+  static constexpr int kBarrierBytes = 256 + 4096;  // mbarriers, TMEM slot; LN row statistics float2[2 tiles][2][128]
   static constexpr int kMaxStages = 8;
+  // AR (activation reuse, 3x3 stride 1): the M tile is a 16 x 8 spatial block; a stage holds, for one (channel
+  // block, filter column s), the block's input with a one-row halo above and below shifted by s-1 columns
+  // ([18 x 8 pixels][64 ch] = 18 KB) and the three B tiles of filter rows r = 0..2.  Filter row r is the sub-view
+  // starting r * 8 rows (r KB) into the unit, so the unit is loaded once and multiplied three times: 6 KB of A per
+  // K block instead of 16 KB.  (K1 with streamed operands is bound by the chip-wide L2 -> SM TMA throughput,
+  // ~12 TB/s: profiles/r01c_*.)
+  static constexpr int kARTileH = 16, kARTileW = 8;
+  static constexpr int kARUnitBytes = (kARTileH + 2) * kARTileW * kBlockK * 2;  // 18 KB
+  static constexpr int kARStageBytes = kARUnitBytes + 3 * kBTileBytes;
+  static constexpr int ar_stages_for(int num_staging) {
+    const int n = (kSmemLimit - 1024 - kBarrierBytes - num_staging * kStagingBytes) / kARStageBytes;
+    return n > kMaxStages ? kMaxStages : n;
+  }
+  static constexpr int ar_smem_bytes(int num_staging) {
+    return ar_stages_for(num_staging) * kARStageBytes + num_staging * kStagingBytes + kBarrierBytes + 1024;
+  }
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int stages_for(int num_staging) {
     const int n = (kSmemLimit - 1024 - kBarrierBytes - num_staging * kStagingBytes) / kStageBytes;
@@ -111,8 +128,8 @@ struct ConvCfg {
   }
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN must be 64..256, multiple of 64");
   static_assert(CG == 1 || CG == 2, "cta_group is 1 or 2");
-  static_assert(stages_for(2) >= 2, "pipeline too shallow");
-  static_assert(2 * kMaxStages + 6 <= kBarrierBytes / 8 - 1, "barrier block too small");
+  static_assert(stages_for(2) >= 1 && stages_for(1) >= 2, "pipeline too shallow");
+  static_assert(2 * kMaxStages + 10 <= 256 / 8 - 1, "barrier block too small");
 };
 
 // SiLU = x * sigmoid(x) = h + h * tanh(h), h = x / 2: one MUFU op per element (tanh.approx, rel. error 2^-11, far
@@ -158,17 +175,12 @@ __device__ __forceinline__ void epilogue_chunk_direct(const ConvParams& p, const
   }
 }
 
-// silu'(x) = s (1 + x (1 - s)), s = sigmoid(x) = (1 + tanh(x/2)) / 2
-__device__ __forceinline__ float dsilu_f(float x) {
-  const float sg = fmaf(0.5f, tanh_approx(0.5f * x), 0.5f);
-  return sg * fmaf(x, 1.0f - sg, 1.0f);
-}
-
-// Staged epilogue of one 32-column chunk: bf16 result into the 128B-swizzled staging tile — in place over the
-// TMA-prefetched auxiliary tile (residual in EPI_BIAS_RES, stashed pre-activation in EPI_DSILU).  `stg_row` = shared
-// address of this row in box 0 of the tile; `stg2_row` = same for the second output tile (dual_out).
+// Staged epilogue of one 32-column chunk: bf16 result into the 128B-swizzled staging tile, in place over the
+// TMA-prefetched residual tile in EPI_BIAS_RES.  `stg_row` = this row in box 0 of the tile.  LN: also accumulates the
+// row's LayerNorm statistics (sums of v = out + mod and v^2 over this thread's columns).
+template <bool LN>
 __device__ __forceinline__ void epilogue_chunk_staged(const ConvParams& p, const uint32_t (&v)[32], int gcol, int col,
-                                                      uint32_t stg_row, uint32_t stg2_row, int row) {
+                                                      uint8_t* stg_row, int row, float& s1, float& s2) {
   float f[32];
   const float4* b4 = reinterpret_cast<const float4*>(p.bias + gcol);
 #pragma unroll
@@ -182,68 +194,75 @@ __device__ __forceinline__ void epilogue_chunk_staged(const ConvParams& p, const
   const uint32_t boff = static_cast<uint32_t>(col >> 6) * kATileBytes;
   const int j0 = (col & 63) >> 3;  // first 16 B chunk of this 32-column group inside the 128 B row
   if (p.mode == EPI_BIAS_SILU) {
-    if (p.dual_out) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint32_t o[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          __nv_bfloat162 h = __floats2bfloat162_rn(f[8 * i + 2 * j], f[8 * i + 2 * j + 1]);
-          o[j] = *reinterpret_cast<uint32_t*>(&h);
-        }
-        st_shared_v4(stg2_row + boff + (static_cast<uint32_t>((j0 + i) ^ (row & 7)) << 4), o[0], o[1], o[2], o[3]);
-      }
-    }
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = silu_f(f[i]);
-  }
+  } else if (p.mode == EPI_BIAS_RES) {
+    // all residual loads of the chunk first: the in-place stores below alias them as far as the compiler can tell
+    uint4 aux[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t addr = stg_row + boff + (static_cast<uint32_t>((j0 + i) ^ (row & 7)) << 4);
-    if (p.mode == EPI_BIAS_RES || p.mode == EPI_DSILU) {
-      const uint4 r = ld_shared_v4(addr);
-      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    for (int i = 0; i < 4; ++i) aux[i] = ld_shared_v4(stg_row, boff + (static_cast<uint32_t>((j0 + i) ^ (row & 7)) << 4));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t w[4] = {aux[i].x, aux[i].y, aux[i].z, aux[i].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
-        if (p.mode == EPI_BIAS_RES) {
-          f[8 * i + 2 * j] += __low2float(h);
-          f[8 * i + 2 * j + 1] += __high2float(h);
-        } else {
-          f[8 * i + 2 * j] *= dsilu_f(__low2float(h));
-          f[8 * i + 2 * j + 1] *= dsilu_f(__high2float(h));
-        }
+        f[8 * i + 2 * j] += __low2float(h);
+        f[8 * i + 2 * j + 1] += __high2float(h);
       }
     }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
     uint32_t o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       __nv_bfloat162 h = __floats2bfloat162_rn(f[8 * i + 2 * j], f[8 * i + 2 * j + 1]);
       o[j] = *reinterpret_cast<uint32_t*>(&h);
     }
-    st_shared_v4(addr, o[0], o[1], o[2], o[3]);
+    st_shared_v4(stg_row, boff + (static_cast<uint32_t>((j0 + i) ^ (row & 7)) << 4), o[0], o[1], o[2], o[3]);
+  }
+  if (LN) {
+    float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 mv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.ln_mod) mv = __ldg(reinterpret_cast<const float4*>(p.ln_mod + gcol) + i);
+      const float mm[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float vv = f[4 * i + e] + mm[e];
+        sa[e] += vv;
+        sb[e] = fmaf(vv, vv, sb[e]);
+      }
+    }
+    s1 += (sa[0] + sa[1]) + (sa[2] + sa[3]);
+    s2 += (sb[0] + sb[1]) + (sb[2] + sb[3]);
   }
 }
 
-template <int BN, int CG, bool LN>
+template <int BN, int CG, bool LN, bool AR>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux,
-                         const __grid_constant__ CUtensorMap tmOut2, const ConvParams p) {
+                         const __grid_constant__ CUtensorMap tmOut, const ConvParams p) {
   using Cfg = ConvCfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int num_stages = p.num_stages;
   uint8_t* smA = smem;
-  uint8_t* smB = smem + num_stages * Cfg::kSub * kATileBytes;
-  uint8_t* stg0 = smem + num_stages * Cfg::kStageBytes;  // epilogue staging tile(s)
+  uint8_t* smB = smem + num_stages * Cfg::kSub * kATileBytes;  // (AR: stages are [A unit][B r0][B r1][B r2])
+  uint8_t* stg0 = smem + num_stages * (AR ? Cfg::kARStageBytes : Cfg::kStageBytes);  // epilogue staging tile(s)
   uint64_t* bars = reinterpret_cast<uint64_t*>(stg0 + p.num_staging * Cfg::kStagingBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::kMaxStages;
   uint64_t* tmem_full = bars + 2 * Cfg::kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_full = tmem_empty + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
+  uint64_t* res_full = tmem_empty + 2;  // [2] auxiliary tile landed in staging[b]
+  uint64_t* stg_full = res_full + 2;    // [2] staging[b] written by the epilogue warps
+  uint64_t* stg_free = stg_full + 2;    // [2] staging[b] read by its store (and the LayerNorm pass)
+  uint64_t* ln_done = stg_free + 2;     // [2] LayerNorm pass over staging[b] finished (all epilogue warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_done + 2);
+  float2* ln_stats = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2][2][128]
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -252,15 +271,17 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int num_groups = gridDim.x / CG;
   const int num_tiles = ((p.num_m_tiles + CG - 1) / CG) * p.num_n_tiles;
   const int num_kb = p.taps * p.cin_blocks;
-  const bool staged = p.mode != EPI_COMPOSE && p.mode != EPI_F32;
-  const bool has_aux = p.mode == EPI_BIAS_RES || p.mode == EPI_DSILU;  // TMA-prefetched input tile, double-buffered
+  // direct (fp32 / compose) epilogues exist for the 64-wide tile only: the last conv of the UNet
+  const bool staged = BN != 64 || (p.mode != EPI_COMPOSE && p.mode != EPI_F32);
+  const bool has_aux = p.mode == EPI_BIAS_RES;  // TMA-prefetched residual tile, double-buffered
+  // two staging tiles used alternately (always with a residual tile; for narrow tiles also to take the TMA store's
+  // read of tile i off the critical path of tile i+1)
+  const bool two_bufs = p.num_staging == 2;
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (staged) tma_prefetch_desc(&tmOut);
-    if (has_aux) tma_prefetch_desc(&tmAux);
-    if (p.dual_out) tma_prefetch_desc(&tmOut2);
   }
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < num_stages; ++s) {
@@ -271,8 +292,12 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], kEpiWarps * CG);
     }
-    mbar_init(&res_full[0], 1);
-    mbar_init(&res_full[1], 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&res_full[b], 1);
+      mbar_init(&stg_full[b], kEpiWarps);
+      mbar_init(&stg_free[b], 1);
+      mbar_init(&ln_done[b], kEpiWarps);
+    }
     fence_mbar_init();
   }
   if (warp_idx == 2) {
@@ -293,7 +318,46 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     int stage = 0;
     uint32_t phase = 0;
     int issued = 0;
-    for (int tile = group_id; tile < num_tiles; tile += num_groups) {
+    long long w_empty = 0;
+    const long long t_begin = clock64();
+    for (int tile = group_id; AR && tile < num_tiles; tile += num_groups) {
+      const int nt = tile % p.num_n_tiles;
+      const int mt = (tile / p.num_n_tiles) * CG + rank;
+      const int img = mt / p.tiles_per_img, tt = mt % p.tiles_per_img;
+      const int h0 = (tt / p.tiles_w) * Cfg::kARTileH, w0 = (tt % p.tiles_w) * Cfg::kARTileW;
+      for (int kb = 0; kb < 3 * p.cin_blocks; ++kb) {  // kb = cb * 3 + s
+        const int cb = kb / 3, s3 = kb - cb * 3;
+        {
+          const long long t0 = clock64();
+          mbar_wait(&empty[stage], phase ^ 1);
+          w_empty += clock64() - t0;
+        }
+        if (elect_one()) {
+          const uint32_t full_bar = (CG == 2) ? mapa_shared(smem_u32(&full[stage]), 0) : smem_u32(&full[stage]);
+          uint8_t* sbase = smem + stage * Cfg::kARStageBytes;
+          if (p.dbg_skip_loads && issued >= num_stages) {
+            if (rank == 0) mbar_arrive(&full[stage]);
+          } else {
+            if (rank == 0) mbar_arrive_expect_tx(&full[stage], CG * Cfg::kARStageBytes);
+            if (CG == 2) tma_load_4d_pair(&tmA, full_bar, sbase, cb * kBlockK, w0 + s3 - 1, h0 - 1, img);
+            else tma_load_4d(&tmA, &full[stage], sbase, cb * kBlockK, w0 + s3 - 1, h0 - 1, img);
+            for (int r = 0; r < 3; ++r) {
+              const int kk = (r * 3 + s3) * p.cin_blocks + cb;  // K block of tap (r, s) in the packed weights
+              uint8_t* bdst = sbase + Cfg::kARUnitBytes + r * Cfg::kBTileBytes;
+              if (CG == 2) tma_load_2d_pair(&tmB, full_bar, bdst, kk * kBlockK, nt * BN + rank * Cfg::kBRows);
+              else tma_load_2d(&tmB, &full[stage], bdst, kk * kBlockK, nt * BN);
+            }
+          }
+        }
+        __syncwarp();
+        ++issued;
+        if (++stage == num_stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    for (int tile = group_id; !AR && tile < num_tiles; tile += num_groups) {
       const int nt = tile % p.num_n_tiles;
       const int mt = (tile / p.num_n_tiles) * CG + rank;
       int b1, b2, b3;
@@ -308,7 +372,11 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
       for (int kb = 0; kb < num_kb; kb += Cfg::kSub) {
         const int nsub = (num_kb - kb) < Cfg::kSub ? (num_kb - kb) : Cfg::kSub;
-        mbar_wait(&empty[stage], phase ^ 1);
+        {
+          const long long t0 = clock64();
+          mbar_wait(&empty[stage], phase ^ 1);
+          w_empty += clock64() - t0;
+        }
         if (elect_one()) {
           const uint32_t full_bar = (CG == 2) ? mapa_shared(smem_u32(&full[stage]), 0) : smem_u32(&full[stage]);
           if (p.dbg_skip_loads && issued >= num_stages) {
@@ -341,6 +409,10 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
       }
     }
+    if (p.dbg_stats && lane == 0) {
+      p.dbg_stats[blockIdx.x * 12 + 0] = clock64() - t_begin;
+      p.dbg_stats[blockIdx.x * 12 + 1] = w_empty;
+    }
   } else if (warp_idx == 1 && rank == 0) {
     // ------------------------------------------------------------ MMA issuer (leader CTA, one elected lane issues)
     constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * CG, BN);
@@ -350,13 +422,58 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    long long w_full = 0, w_tmem = 0;
+    const long long t_begin = clock64();
     for (int tile = group_id; tile < num_tiles; tile += num_groups) {
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      {
+        const long long t0 = clock64();
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        w_tmem += clock64() - t0;
+      }
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
-      for (int kb = 0; kb < num_kb; kb += Cfg::kSub) {
+      for (int kb = 0; AR && kb < 3 * p.cin_blocks; ++kb) {
+        {
+          const long long t0 = clock64();
+          mbar_wait(&full[stage], phase);
+          w_full += clock64() - t0;
+        }
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (Cfg::kARStageBytes >> 4));
+          const uint64_t bdesc = adesc + static_cast<uint64_t>(Cfg::kARUnitBytes >> 4);
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // filter row r = the unit from its r-th pixel row on: + r * 8 rows * 128 B (keeps the swizzle phase)
+              const uint64_t a = adesc + r * ((Cfg::kARTileW * 128) >> 4) + 2 * k;
+              const uint64_t b = bdesc + r * (Cfg::kBTileBytes >> 4) + 2 * k;
+              if (CG == 2) umma_bf16_pair(tmem_d, a, b, idesc, (kb | r | k) != 0);
+              else umma_bf16(tmem_d, a, b, idesc, (kb | r | k) != 0);
+            }
+          }
+          if (CG == 2) {
+            umma_commit_pair(&empty[stage]);
+            if (kb + 1 >= 3 * p.cin_blocks) umma_commit_pair(&tmem_full[acc]);
+          } else {
+            umma_commit(&empty[stage]);
+            if (kb + 1 >= 3 * p.cin_blocks) umma_commit(&tmem_full[acc]);
+          }
+        }
+        __syncwarp();
+        if (++stage == num_stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      for (int kb = 0; !AR && kb < num_kb; kb += Cfg::kSub) {
         const int nsub = (num_kb - kb) < Cfg::kSub ? (num_kb - kb) : Cfg::kSub;
-        mbar_wait(&full[stage], phase);
+        {
+          const long long t0 = clock64();
+          mbar_wait(&full[stage], phase);
+          w_full += clock64() - t0;
+        }
         tc_fence_after();
         if (elect_one()) {
           // descriptor start-address field is (addr >> 4): slot stride and the 32 B K-advance are plain adds
@@ -391,182 +508,277 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (p.dbg_stats && lane == 0) {
+      p.dbg_stats[blockIdx.x * 12 + 2] = clock64() - t_begin;
+      p.dbg_stats[blockIdx.x * 12 + 3] = w_full;
+      p.dbg_stats[blockIdx.x * 12 + 4] = w_tmem;
+    }
   } else if (warp_idx >= 4) {
     // ------------------------------------------------------------ epilogue: 8 warps = 128 rows x 2 column halves
+    // TMEM -> registers -> (accumulator released) -> bias / SiLU / residual -> bf16 -> staging tile -> stg_full.
+    // The stores, the LayerNorm pass and the auxiliary-tile prefetch belong to warps 2-3 (below): these warps never
+    // wait for a TMA transfer they issued.
     const int ew = warp_idx - 4;
     const int q = ew & 3;       // TMEM lane quarter this warp may access (warp_idx % 4)
     const int half = ew >> 2;   // column half
     const int row = q * 32 + lane;
-    const bool leader = threadIdx.x == 128;  // issues the staging tile's TMA loads / stores
     constexpr int kHalfCols = BN / 2;
     constexpr int kChunks = kHalfCols / 32;  // 32-column chunks per warp (BN = 64: 1 ... BN = 256: 4)
     const int col_base = half * kHalfCols;
     int acc = 0;
     uint32_t acc_phase = 0;
-    int it_local = 0;  // tiles processed by this CTA: staging tile it_local % num_staging
-
-    // fused LayerNorm: warp `ew` normalises rows [16 ew, 16 ew + 16); a row is spread over kLPR lanes x 16 B
-    constexpr int kLPR = BN / 8;                        // lanes per row (8 channels each)
+    int it_local = 0;  // tiles processed by this CTA: staging tile it_local % 2 when double-buffered
+    long long w_tfull = 0, w_stg = 0, c_pass1 = 0, w_lnfull = 0, c_ln = 0;
+    const long long t_epi_begin = clock64();
+    // fused LayerNorm: warp `ew` normalises rows [16 ew, 16 ew + 16) of the staged tile
+    constexpr int kLPR = BN / 8;                  // lanes per row (8 channels = 16 B each)
     constexpr int kRPI = (kLPR >= 32) ? 1 : 32 / kLPR;  // rows per warp iteration
-    constexpr int kIters = 16 / kRPI;
     static_assert(!LN || (kLPR == 8 || kLPR == 16 || kLPR == 32), "fused LayerNorm needs BN in {64, 128, 256}");
-    const int ln_chunk = lane % kLPR;  // 16 B chunk of the row this lane owns (channels 8*ln_chunk .. +8)
+    const int ln_chunk = lane % kLPR;             // 16 B chunk of the row this lane owns (channels 8 ln_chunk .. +8)
     float ln_m[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) ln_m[e] = (LN && p.ln_mod) ? __ldg(p.ln_mod + (ln_chunk * 8 + e) % BN) : 0.f;
 
-    auto tile_coords = [&](int tile, int& nt, int& mt) {
-      nt = tile % p.num_n_tiles;
-      mt = (tile / p.num_n_tiles) * CG + rank;
-    };
-    auto prefetch_residual = [&](int tile, int buf) {  // leader only: staging[buf] <- aux[tile]
-      int nt, mt;
-      tile_coords(tile, nt, mt);
-      uint8_t* dst = stg0 + buf * Cfg::kStagingBytes;
-      mbar_arrive_expect_tx(&res_full[buf], Cfg::kStagingBytes);
-#pragma unroll
-      for (int b = 0; b < BN / 64; ++b)
-        tma_load_2d(&tmAux, &res_full[buf], dst + b * kATileBytes, nt * BN + b * 64, mt * kBlockM);
-    };
-    if (has_aux && leader) {  // two staging tiles: the auxiliary tile is prefetched two tiles ahead
-      if (group_id < num_tiles) prefetch_residual(group_id, 0);
-      if (group_id + num_groups < num_tiles) prefetch_residual(group_id + num_groups, 1);
-    }
 
     for (int tile = group_id; tile < num_tiles; tile += num_groups) {
-      int nt, mt;
-      tile_coords(tile, nt, mt);
-      const int m = mt * kBlockM + row;
+      const int nt = tile % p.num_n_tiles;
+      const int mt = (tile / p.num_n_tiles) * CG + rank;
+      int m = mt * kBlockM + row;
+      if (AR) {
+        const int img = mt / p.tiles_per_img, tt = mt % p.tiles_per_img;
+        m = (img * p.img_h + (tt / p.tiles_w) * Cfg::kARTileH + (row >> 3)) * p.img_w + (tt % p.tiles_w) * Cfg::kARTileW +
+            (row & 7);
+      }
       const bool valid = m < p.m_total;
-      mbar_wait(&tmem_full[acc], acc_phase);
+      {
+        const long long t0 = clock64();
+        mbar_wait(&tmem_full[acc], acc_phase);
+        w_tfull += clock64() - t0;
+      }
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col_base;
-      const int buf = has_aux ? (it_local & 1) : 0;
+      const int buf = two_bufs ? (it_local & 1) : 0;
+      const int use = two_bufs ? (it_local >> 1) : it_local;  // how often this staging tile has been used before
       uint8_t* stg = stg0 + buf * Cfg::kStagingBytes;
-      uint8_t* stg2 = stg0 + Cfg::kStagingBytes;  // second output tile (dual_out; never together with has_aux)
-      const uint32_t stg_u32 = smem_u32(stg);
-      const uint32_t stg_row = stg_u32 + static_cast<uint32_t>(row) * 128u;
-      const uint32_t stg2_row = smem_u32(stg2) + static_cast<uint32_t>(row) * 128u;
-      if (has_aux) mbar_wait(&res_full[buf], (it_local >> 1) & 1);
-      // two register buffers: the tcgen05.ld of chunk i+1 is in flight while chunk i is processed
-      uint32_t va[32], vb[32];
-      tmem_ld_32x32(taddr, va);
-#pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        tmem_ld_wait();
-        if (c + 1 < kChunks) tmem_ld_32x32(taddr + 32 * (c + 1), (c & 1) ? va : vb);
-        const int col = col_base + 32 * c;
-        if (staged) epilogue_chunk_staged(p, (c & 1) ? vb : va, nt * BN + col, col, stg_row, stg2_row, row);
-        else epilogue_chunk_direct(p, (c & 1) ? vb : va, nt * BN + col, m, valid);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CG == 2 && rank != 0) mbar_arrive_remote(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
-        else mbar_arrive(&tmem_empty[acc]);
-      }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-      ++it_local;
-      if (!staged) continue;
-
-      // ---- staged tile -> global (TMA store); rows past the tensor end are clipped by the tensor map
-      fence_proxy_async();
-      named_bar_sync(kEpiBarrier, kEpiThreads);
-      if (leader) {
-#pragma unroll
-        for (int b = 0; b < BN / 64; ++b) tma_store_2d(&tmOut, stg + b * kATileBytes, nt * BN + b * 64, mt * kBlockM);
-        if (p.dual_out) {
-#pragma unroll
-          for (int b = 0; b < BN / 64; ++b)
-            tma_store_2d(&tmOut2, stg2 + b * kATileBytes, nt * BN + b * 64, mt * kBlockM);
+      uint8_t* stg_row = stg + row * 128;
+      // The accumulator is handed back to the MMA warp as soon as its last tcgen05.ld has landed in registers, before
+      // the epilogue math: the MMAs of the next tile but one only ever wait for TMEM reads.
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2 && rank != 0) mbar_arrive_remote(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+          else mbar_arrive(&tmem_empty[acc]);
         }
-        bulk_commit();
+      };
+      // staging tile ready to be written: its auxiliary tile has landed, or its previous store has read it
+      auto wait_staging = [&]() {
+        if (!staged) return;
+        const long long t0 = clock64();
+        if (has_aux) mbar_wait(&res_full[buf], use & 1);
+        else mbar_wait(&stg_free[buf], (use & 1) ^ 1);
+        w_stg += clock64() - t0;
+      };
+      const long long t_p1 = clock64();
+      float s1 = 0.f, s2 = 0.f;
+      uint32_t va[32], vb[32];
+      if constexpr (kChunks <= 2) {
+        tmem_ld_32x32(taddr, va);
+        if (kChunks == 2) tmem_ld_32x32(taddr + 32, vb);
+        tmem_ld_wait();
+        release_acc();
+        wait_staging();
+        if (staged) epilogue_chunk_staged<LN>(p, va, nt * BN + col_base, col_base, stg_row, row, s1, s2);
+        else if constexpr (BN == 64) epilogue_chunk_direct(p, va, nt * BN + col_base, m, valid);
+        if (kChunks == 2) {
+          if (staged) epilogue_chunk_staged<LN>(p, vb, nt * BN + col_base + 32, col_base + 32, stg_row, row, s1, s2);
+          else if constexpr (BN == 64) epilogue_chunk_direct(p, vb, nt * BN + col_base + 32, m, valid);
+        }
+      } else {
+        // two register buffers: the tcgen05.ld of chunk i+1 is in flight while chunk i is processed
+        tmem_ld_32x32(taddr, va);
+        wait_staging();
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          tmem_ld_wait();
+          if (c + 1 < kChunks) tmem_ld_32x32(taddr + 32 * (c + 1), (c & 1) ? va : vb);
+          else release_acc();
+          const int col = col_base + 32 * c;
+          if (staged) epilogue_chunk_staged<LN>(p, (c & 1) ? vb : va, nt * BN + col, col, stg_row, row, s1, s2);
+        }
       }
+      if (staged) {
+        if (LN) ln_stats[(buf * 2 + half) * kBlockM + row] = make_float2(s1, s2);
+        fence_proxy_async();  // generic-proxy writes of the tile -> visible to the TMA store
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&stg_full[buf]);
+      }
+      c_pass1 += clock64() - t_p1;
+      const long long t_ln0 = clock64();
       if (LN) {
-        // ---- channel LayerNorm of the staged rows (two-pass variance in registers) -> global, coalesced: the
-        //      kLPR lanes of a row write its C channels as one contiguous segment (x4 when upsampling).
-        //      Batches of kBatch rows per lane keep the shuffle reductions of different rows in flight together.
-        constexpr int kBatch = kIters < 8 ? kIters : 8;
+        mbar_wait(&stg_full[buf], use & 1);  // every warp's columns of the tile and the row statistics are in place
+        w_lnfull += clock64() - t_ln0;
+        // ---- channel LayerNorm of the staged rows: y = (x + mod - mean) * inv with the row statistics the epilogue
+        //      warps summed (unbiased variance, model/nn.py:154,183); kLPR lanes write a row's C channels as one
+        //      contiguous segment (x4 when the output is 2x nearest-upsampled, model/nn.py:184)
+        const float2* st0 = ln_stats + (buf * 2 + 0) * kBlockM;
+        const float2* st1 = ln_stats + (buf * 2 + 1) * kBlockM;
+        int img = 0, th0 = 0, tw0 = 0;
+        if (AR) {
+          const int tt = mt % p.tiles_per_img;
+          img = mt / p.tiles_per_img;
+          th0 = (tt / p.tiles_w) * Cfg::kARTileH;
+          tw0 = (tt % p.tiles_w) * Cfg::kARTileW;
+        }
+        constexpr int kIters = 16 / kRPI;
+        constexpr int kBatch = kIters < 4 ? kIters : 4;
 #pragma unroll 1
         for (int it0 = 0; it0 < kIters; it0 += kBatch) {
-          float v[kBatch][8];
-          float s[kBatch];
+          // loads of the whole batch, then the math, then the stores: the global stores alias the shared-memory
+          // loads as far as the compiler can tell and would otherwise serialise the rows
+          uint4 xr[kBatch];
+          float2 sa[kBatch], sb[kBatch];
 #pragma unroll
-          for (int b = 0; b < kBatch; ++b) {
-            const int r = ew * 16 + (it0 + b) * kRPI + lane / kLPR;
-            const uint32_t addr = stg_u32 + static_cast<uint32_t>(ln_chunk >> 3) * kATileBytes +
-                                  static_cast<uint32_t>(r) * 128u +
-                                  (static_cast<uint32_t>((ln_chunk & 7) ^ (r & 7)) << 4);
-            const uint4 xr = ld_shared_v4(addr);
-            const uint32_t w[4] = {xr.x, xr.y, xr.z, xr.w};
-            s[b] = 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
-              v[b][2 * j] = __low2float(h) + ln_m[2 * j];
-              v[b][2 * j + 1] = __high2float(h) + ln_m[2 * j + 1];
-              s[b] += v[b][2 * j] + v[b][2 * j + 1];
-            }
+          for (int bb = 0; bb < kBatch; ++bb) {
+            const int r = ew * 16 + (it0 + bb) * kRPI + lane / kLPR;
+            xr[bb] = ld_shared_v4(stg, static_cast<uint32_t>(ln_chunk >> 3) * kATileBytes + static_cast<uint32_t>(r) * 128u +
+                                           (static_cast<uint32_t>((ln_chunk & 7) ^ (r & 7)) << 4));
+            sa[bb] = st0[r];
+            sb[bb] = st1[r];
           }
+          uint4 yv[kBatch];
+          float invv[kBatch];
 #pragma unroll
-          for (int o = kLPR / 2; o > 0; o >>= 1)
-#pragma unroll
-            for (int b = 0; b < kBatch; ++b) s[b] += __shfl_xor_sync(0xffffffffu, s[b], o);
-#pragma unroll
-          for (int b = 0; b < kBatch; ++b) {
-            const float mean = s[b] * (1.0f / BN);
-            float ss = 0.f;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              v[b][e] -= mean;
-              ss += v[b][e] * v[b][e];
-            }
-            s[b] = ss;
-          }
-#pragma unroll
-          for (int o = kLPR / 2; o > 0; o >>= 1)
-#pragma unroll
-            for (int b = 0; b < kBatch; ++b) s[b] += __shfl_xor_sync(0xffffffffu, s[b], o);
-#pragma unroll
-          for (int b = 0; b < kBatch; ++b) {
-            const float inv = rsqrtf(s[b] * (1.0f / (BN - 1)) + p.ln_eps);
+          for (int bb = 0; bb < kBatch; ++bb) {
+            const float sum = sa[bb].x + sb[bb].x, sq = sa[bb].y + sb[bb].y;
+            const float mean = sum * (1.0f / BN);
+            const float var = fmaxf(sq - sum * mean, 0.f) * (1.0f / (BN - 1));
+            const float inv = rsqrtf(var + p.ln_eps);
+            const float nmi = -mean * inv;
+            const uint32_t w[4] = {xr[bb].x, xr[bb].y, xr[bb].z, xr[bb].w};
             uint32_t o4[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(v[b][2 * j] * inv, v[b][2 * j + 1] * inv);
-              o4[j] = *reinterpret_cast<uint32_t*>(&h);
+              __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+              const float y0 = fmaf(__low2float(h), inv, fmaf(ln_m[2 * j], inv, nmi));
+              const float y1 = fmaf(__high2float(h), inv, fmaf(ln_m[2 * j + 1], inv, nmi));
+              __nv_bfloat162 y = __floats2bfloat162_rn(y0, y1);
+              o4[j] = *reinterpret_cast<uint32_t*>(&y);
             }
-            const uint4 yv = make_uint4(o4[0], o4[1], o4[2], o4[3]);
-            const int r = ew * 16 + (it0 + b) * kRPI + lane / kLPR;
-            const int mr = mt * kBlockM + r;
-            if (mr < p.m_total) {
-              if (p.ln_inv != nullptr && ln_chunk == 0) p.ln_inv[mr] = inv;
+            yv[bb] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+            invv[bb] = inv;
+          }
+#pragma unroll
+          for (int bb = 0; bb < kBatch; ++bb) {
+            const int r = ew * 16 + (it0 + bb) * kRPI + lane / kLPR;
+            int hh, ww, nimg;  // output pixel of this row
+            if (AR) {
+              hh = th0 + (r >> 3);
+              ww = tw0 + (r & 7);
+              nimg = img;
+            } else {
+              const int mr = mt * kBlockM + r;
+              ww = mr % p.ln_W;
+              const int t = mr / p.ln_W;
+              hh = t % p.ln_H;
+              nimg = t / p.ln_H;
+            }
+            const long long pix = (static_cast<long long>(nimg) * p.ln_H + hh) * p.ln_W + ww;
+            if (pix < p.m_total) {
+              if (p.ln_inv != nullptr && ln_chunk == 0) p.ln_inv[pix] = invv[bb];
               if (p.ln_up) {
-                const int w0 = mr % p.ln_W;
-                const int t = mr / p.ln_W;
-                const int h0 = t % p.ln_H;
-                const long long n = t / p.ln_H;
-                const long long o00 = (n * 2 * p.ln_H + 2 * h0) * 2 * p.ln_W + 2 * w0;
+                const long long o00 = (static_cast<long long>(nimg) * 2 * p.ln_H + 2 * hh) * 2 * p.ln_W + 2 * ww;
                 __nv_bfloat16* dst = p.ln_out + o00 * BN + ln_chunk * 8;
-                *reinterpret_cast<uint4*>(dst) = yv;
-                *reinterpret_cast<uint4*>(dst + BN) = yv;
-                *reinterpret_cast<uint4*>(dst + 2ll * p.ln_W * BN) = yv;
-                *reinterpret_cast<uint4*>(dst + (2ll * p.ln_W + 1) * BN) = yv;
+                *reinterpret_cast<uint4*>(dst) = yv[bb];
+                *reinterpret_cast<uint4*>(dst + BN) = yv[bb];
+                *reinterpret_cast<uint4*>(dst + 2ll * p.ln_W * BN) = yv[bb];
+                *reinterpret_cast<uint4*>(dst + (2ll * p.ln_W + 1) * BN) = yv[bb];
               } else {
-                *reinterpret_cast<uint4*>(p.ln_out + static_cast<long long>(mr) * BN + ln_chunk * 8) = yv;
+                *reinterpret_cast<uint4*>(p.ln_out + pix * BN + ln_chunk * 8) = yv[bb];
               }
             }
           }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ln_done[buf]);
+        c_ln += clock64() - t_ln0;
       }
-      // ---- the staging tile is reused by the next tile once these stores have read it
-      if (leader) bulk_wait_read_all();
-      named_bar_sync(kEpiBarrier, kEpiThreads);  // store has read the tile AND every warp is done reading it (LN)
-      if (leader && has_aux) {
-        const int next = tile + 2 * num_groups;  // this staging tile's next user
-        if (next < num_tiles) prefetch_residual(next, buf);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+      ++it_local;
+    }
+    if (p.dbg_stats && threadIdx.x == 128) {
+      p.dbg_stats[blockIdx.x * 12 + 5] = clock64() - t_epi_begin;
+      p.dbg_stats[blockIdx.x * 12 + 6] = w_tfull;
+      p.dbg_stats[blockIdx.x * 12 + 7] = w_stg;
+      p.dbg_stats[blockIdx.x * 12 + 8] = c_pass1;
+      p.dbg_stats[blockIdx.x * 12 + 9] = w_lnfull;
+      p.dbg_stats[blockIdx.x * 12 + 10] = c_ln;
+    }
+  } else if (staged && warp_idx == 2) {
+    // ------------------------------------------------------------ warp 2: staging tile -> global
+    // TMA store of the finished tile and the prefetch of the auxiliary tile of the staging tile's next user; the
+    // epilogue warps never wait for a TMA transfer.
+    const bool leader = lane == 0;                // owns every bulk async-group of this CTA
+    auto box_coords = [&](int mt, int& c1, int& c2, int& c3) {
+      const int img = mt / p.tiles_per_img, tt = mt % p.tiles_per_img;
+      c1 = (tt % p.tiles_w) * Cfg::kARTileW;
+      c2 = (tt / p.tiles_w) * Cfg::kARTileH;
+      c3 = img;
+    };
+    auto prefetch_aux = [&](int tile, int buf) {  // leader only: staging[buf] <- aux[tile]
+      const int nt = tile % p.num_n_tiles;
+      const int mt = (tile / p.num_n_tiles) * CG + rank;
+      uint8_t* dst = stg0 + buf * Cfg::kStagingBytes;
+      mbar_arrive_expect_tx(&res_full[buf], Cfg::kStagingBytes);
+#pragma unroll
+      for (int b = 0; b < BN / 64; ++b) {
+        if (AR) {
+          int c1, c2, c3;
+          box_coords(mt, c1, c2, c3);
+          tma_load_4d(&tmOut, &res_full[buf], dst + b * kATileBytes, nt * BN + b * 64, c1, c2, c3);
+        } else {
+          tma_load_2d(&tmOut, &res_full[buf], dst + b * kATileBytes, nt * BN + b * 64, mt * kBlockM);
+        }
       }
+    };
+    if (has_aux && leader) {  // two staging tiles: the auxiliary tile is prefetched two tiles ahead
+      if (group_id < num_tiles) prefetch_aux(group_id, 0);
+      if (group_id + num_groups < num_tiles) prefetch_aux(group_id + num_groups, 1);
+    }
+    int it_local = 0;
+    for (int tile = group_id; tile < num_tiles; tile += num_groups) {
+      const int nt = tile % p.num_n_tiles;
+      const int mt = (tile / p.num_n_tiles) * CG + rank;
+      const int buf = two_bufs ? (it_local & 1) : 0;
+      const int use = two_bufs ? (it_local >> 1) : it_local;
+      uint8_t* stg = stg0 + buf * Cfg::kStagingBytes;
+      mbar_wait(&stg_full[buf], use & 1);
+      if (leader) {
+#pragma unroll
+        for (int b = 0; b < BN / 64; ++b) {
+          if (AR) {
+            int c1, c2, c3;
+            box_coords(mt, c1, c2, c3);
+            tma_store_4d(&tmOut, stg + b * kATileBytes, nt * BN + b * 64, c1, c2, c3);
+          } else {
+            tma_store_2d(&tmOut, stg + b * kATileBytes, nt * BN + b * 64, mt * kBlockM);
+          }
+        }
+        bulk_commit();
+      }
+      // ---- the staging tile is free once the store has read it and every epilogue warp is done with its LayerNorm rows
+      if (LN) mbar_wait(&ln_done[buf], use & 1);
+      if (leader) {
+        bulk_wait_read_all();
+        const int next = tile + (two_bufs ? 2 : 1) * num_groups;  // this staging tile's next user
+        if (has_aux) {
+          if (next < num_tiles) prefetch_aux(next, buf);
+        } else {
+          mbar_arrive(&stg_free[buf]);
+        }
+      }
+      ++it_local;
     }
     if (leader) bulk_wait_all();  // global writes of the last stores are complete before the CTA retires
   }
@@ -645,11 +857,12 @@ inline bool make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uin
 
 // One prepared launch of K1: tensor maps + parameters.  Built once per (layer, batch) and replayed.
 struct ConvLaunch {
-  CUtensorMap tmA, tmB, tmOut, tmAux, tmOut2;
+  CUtensorMap tmA, tmB, tmOut;
   ConvParams p;
   int bn;
   int cg;     // CTAs per MMA (1 or 2)
   int ln;     // fused LayerNorm output
+  int ar;     // activation-reuse main loop (16 x 8 spatial tiles)
   int grid;   // CTAs (a multiple of cg)
   int n_img, Ho, Wo, cout_pad;
   const void* out_ptr;  // bf16 output bound by conv_launch_set_out (LayerNorm fusion matches on it)
@@ -669,15 +882,13 @@ inline void conv_set_grid(ConvLaunch* L, int num_sms) {
 //  conv3x3: x is NHWC [n_img, H, W, cin] bf16 (cin % 64 == 0); stride 1: output [n_img, H, W], stride 2: output
 //           [n_img, H/2, W/2] (pad 1 either way)
 //  gemm   : x is [m, k] bf16 row-major (k % 64 == 0) with m = n_img * H * W
-// variant: -1 = pick; else bit 0 = CTA pair (cta_group::2)
+// variant: -1 = pick; else bit 0 = CTA pair (cta_group::2), bit 2 = activation-reuse main loop
 inline bool conv_launch_init(ConvLaunch* L, bool is_conv3x3, const __nv_bfloat16* x, int n_img, int H, int W, int cin,
                              const __nv_bfloat16* w_packed, int cout_pad, int bn, int num_sms, int stride = 1,
                              int variant = -1) {
   ConvParams& p = L->p;
   memset(&p, 0, sizeof(p));
   memset(&L->tmOut, 0, sizeof(CUtensorMap));
-  memset(&L->tmAux, 0, sizeof(CUtensorMap));
-  memset(&L->tmOut2, 0, sizeof(CUtensorMap));
   L->bn = bn;
   L->ln = 0;
   L->out_ptr = nullptr;
@@ -695,6 +906,8 @@ inline bool conv_launch_init(ConvLaunch* L, bool is_conv3x3, const __nv_bfloat16
   const long long m_total = static_cast<long long>(n_img) * Ho * Wo;
   p.m_total = static_cast<int>(m_total);
   p.num_m_tiles = static_cast<int>((m_total + kBlockM - 1) / kBlockM);
+  L->cg = variant < 0 ? conv_pick_cg(p.num_m_tiles) : ((variant & 1) ? 2 : 1);
+  L->ar = 0;
   if (is_conv3x3) {
     if (Wo > kBlockM || kBlockM % Wo != 0) return false;
     int th = kBlockM / Wo;
@@ -705,10 +918,29 @@ inline bool conv_launch_init(ConvLaunch* L, bool is_conv3x3, const __nv_bfloat16
     p.tile_h = th;
     p.tile_n = tn;
     p.tiles_per_img = Ho / th;
-    const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)n_img};
-    const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)(Wo * stride), (uint32_t)(th * stride), (uint32_t)tn};
-    const uint32_t est[4] = {1u, (uint32_t)stride, (uint32_t)stride, 1u};
-    if (!make_tmap_bf16(&L->tmA, x, 4, dims, box, est)) return false;
+    // activation reuse: stride-1 convs with one 128-wide N tile per CTA pair on images that tile into 16 x 8 blocks
+    static int ar_ok = -1;
+    if (ar_ok < 0) {
+      const char* e = getenv("C2W_NO_AR");
+      ar_ok = (e && e[0] == '1') ? 0 : 1;
+    }
+    const bool want_ar = (variant < 0) ? ar_ok != 0 : (variant & 4) != 0;
+    if (want_ar && stride == 1 && bn == 128 && L->cg == 2 && H % 16 == 0 && W % 8 == 0) {
+      L->ar = 1;
+      p.tiles_w = W / 8;
+      p.tiles_per_img = (H / 16) * p.tiles_w;
+      p.img_h = H;
+      p.img_w = W;
+      const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)n_img};
+      const uint32_t box[4] = {(uint32_t)kBlockK, 8u, 18u, 1u};
+      if (!make_tmap_bf16(&L->tmA, x, 4, dims, box)) return false;
+    } else {
+      if (variant >= 0 && (variant & 4)) return false;  // AR was requested explicitly but does not apply
+      const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)n_img};
+      const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)(Wo * stride), (uint32_t)(th * stride), (uint32_t)tn};
+      const uint32_t est[4] = {1u, (uint32_t)stride, (uint32_t)stride, 1u};
+      if (!make_tmap_bf16(&L->tmA, x, 4, dims, box, est)) return false;
+    }
   } else {
     p.taps = 1;
     p.tile_h = 1;
@@ -718,7 +950,6 @@ inline bool conv_launch_init(ConvLaunch* L, bool is_conv3x3, const __nv_bfloat16
     const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)kBlockM, 1, 1};
     if (!make_tmap_bf16(&L->tmA, x, 4, dims, box)) return false;
   }
-  L->cg = variant < 0 ? conv_pick_cg(p.num_m_tiles) : ((variant & 1) ? 2 : 1);
   {
     const uint64_t dims[2] = {(uint64_t)p.taps * cin, (uint64_t)cout_pad};
     const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)(bn / L->cg)};
@@ -729,28 +960,22 @@ inline bool conv_launch_init(ConvLaunch* L, bool is_conv3x3, const __nv_bfloat16
   return true;
 }
 
-// bf16 output [M, cout_pad] (modes 0..2, 5).  Mode 2 accumulates in place: `out` is also the auxiliary (residual) tile.
+// Tensor map of a bf16 [M, cout_pad] epilogue tensor: rows of 128 pixels, or (AR) 16 x 8 spatial blocks of the
+// [n, H, W, cout_pad] view of the same memory.
+inline bool conv_make_epi_map(const ConvLaunch* L, CUtensorMap* m, const void* ptr) {
+  if (L->ar) {
+    const uint64_t dims[4] = {(uint64_t)L->cout_pad, (uint64_t)L->Wo, (uint64_t)L->Ho, (uint64_t)L->n_img};
+    const uint32_t box[4] = {64u, 8u, 16u, 1u};
+    return make_tmap_bf16(m, ptr, 4, dims, box);
+  }
+  const uint64_t dims[2] = {(uint64_t)L->cout_pad, (uint64_t)L->p.m_total};
+  const uint32_t box[2] = {64u, (uint32_t)kBlockM};
+  return make_tmap_bf16(m, ptr, 2, dims, box);
+}
+// bf16 output [M, cout_pad] (modes 0..2).  Mode 2 accumulates in place: `out` is also the residual.
 inline bool conv_launch_set_out(ConvLaunch* L, __nv_bfloat16* out) {
-  const uint64_t dims[2] = {(uint64_t)L->cout_pad, (uint64_t)L->p.m_total};
-  const uint32_t box[2] = {64u, (uint32_t)kBlockM};
   L->out_ptr = out;
-  if (!make_tmap_bf16(&L->tmOut, out, 2, dims, box)) return false;
-  if (L->p.mode == EPI_BIAS_RES) L->tmAux = L->tmOut;
-  return true;
-}
-// Auxiliary input tile of mode 5 (the stashed pre-activation), same shape as the output.
-inline bool conv_launch_set_aux(ConvLaunch* L, const __nv_bfloat16* aux) {
-  const uint64_t dims[2] = {(uint64_t)L->cout_pad, (uint64_t)L->p.m_total};
-  const uint32_t box[2] = {64u, (uint32_t)kBlockM};
-  return make_tmap_bf16(&L->tmAux, aux, 2, dims, box);
-}
-// Second output of mode 1: the pre-activation acc + bias (stash for the VJP).
-inline bool conv_launch_set_out2(ConvLaunch* L, __nv_bfloat16* out2) {
-  const uint64_t dims[2] = {(uint64_t)L->cout_pad, (uint64_t)L->p.m_total};
-  const uint32_t box[2] = {64u, (uint32_t)kBlockM};
-  if (L->p.mode != EPI_BIAS_SILU) return false;
-  L->p.dual_out = 1;
-  return make_tmap_bf16(&L->tmOut2, out2, 2, dims, box);
+  return conv_make_epi_map(L, &L->tmOut, out);
 }
 
 // Whether this launch can also emit the channel LayerNorm of its output (one N tile = all channels of a pixel).
@@ -775,24 +1000,26 @@ inline bool conv_launch_set_ln(ConvLaunch* L, __nv_bfloat16* ln_out, const float
   return true;
 }
 
-template <int BN, int CG, bool LN>
+template <int BN, int CG, bool LN, bool AR>
 inline cudaError_t conv_launch_variant(const ConvLaunch& L, cudaStream_t stream) {
   using Cfg = ConvCfg<BN, CG>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<BN, CG, LN>,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<BN, CG, LN, AR>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
   ConvParams p = L.p;
-  p.num_staging = (p.mode == EPI_BIAS_RES || p.mode == EPI_DSILU || p.dual_out) ? 2 : 1;
-  p.num_stages = Cfg::stages_for(p.num_staging);
+  const bool staged = p.mode != EPI_COMPOSE && p.mode != EPI_F32;
+  if (!staged && BN != 64) return cudaErrorInvalidValue;  // fp32 / compose epilogues: 64-wide tiles only
+  p.num_staging = (p.mode == EPI_BIAS_RES || (staged && BN <= 128)) ? 2 : 1;
+  p.num_stages = AR ? Cfg::ar_stages_for(p.num_staging) : Cfg::stages_for(p.num_staging);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(L.grid);
   cfg.blockDim = dim3(kConvThreads);
-  cfg.dynamicSmemBytes = Cfg::smem_bytes(p.num_staging);
+  cfg.dynamicSmemBytes = AR ? Cfg::ar_smem_bytes(p.num_staging) : Cfg::smem_bytes(p.num_staging);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -801,13 +1028,18 @@ inline cudaError_t conv_launch_variant(const ConvLaunch& L, cudaStream_t stream)
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<BN, CG, LN>, L.tmA, L.tmB, L.tmOut, L.tmAux, L.tmOut2, p);
+  return cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<BN, CG, LN, AR>, L.tmA, L.tmB, L.tmOut, p);
 }
 
 template <int BN, bool LN>
 inline cudaError_t conv_launch_bn_ln(const ConvLaunch& L, cudaStream_t stream) {
-  if (L.cg == 2) return conv_launch_variant<BN, 2, LN>(L, stream);
-  return conv_launch_variant<BN, 1, LN>(L, stream);
+  if (L.cg == 2) {
+    if constexpr (BN == 128) {
+      if (L.ar) return conv_launch_variant<BN, 2, LN, true>(L, stream);
+    }
+    return conv_launch_variant<BN, 2, LN, false>(L, stream);
+  }
+  return conv_launch_variant<BN, 1, LN, false>(L, stream);
 }
 
 template <int BN>

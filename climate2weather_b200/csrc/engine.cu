@@ -48,7 +48,7 @@ struct LevelW {
   std::vector<AttnW> dattn, aattn;
 };
 
-enum OpKind { OP_CONV, OP_LN, OP_ATTN, OP_LN_BWD, OP_ATTN_BWD, OP_ZERO_UP };
+enum OpKind { OP_CONV, OP_LN, OP_ATTN, OP_LN_BWD, OP_ATTN_BWD, OP_ZERO_UP, OP_SILU };
 struct Op {
   OpKind kind;
   // conv
@@ -416,8 +416,7 @@ int build_plan(c2w_handle* h, int n, bool vjp, void* base, size_t* bytes_out) {
     // forward cout is this conv's K side, forward cin its N side
     int rc = make_conv(&op, c3, gin, H, W, w.cout_pad, w.wd, h->zero_bias, w.cin_pad, mode, gout, false, 1);
     if (rc) return rc;
-    if (mode == EPI_DSILU && !conv_launch_set_aux(&op.conv, aux))
-      return fail(C2W_ERR_CUDA, "cannot encode the stash tensor map");
+    (void)aux;
     unit.push_back(op);
     return C2W_OK;
   };
@@ -477,16 +476,44 @@ int build_plan(c2w_handle* h, int n, bool vjp, void* base, size_t* bytes_out) {
       bf16* pre = vjp ? stash(e) : nullptr;
       float* inv = vjp ? stash_f(npix) : nullptr;
       add_ln(xs[l], y, inv, L.C, L.H, L.W, 0, bw.mod_off);
-      int rc = add_conv(true, y, L.H, L.W, L.C, bw.c1, EPI_BIAS_SILU, hs[l], false);
-      if (rc) return rc;
-      if (vjp && real && !conv_launch_set_out2(&P.ops.back().conv, pre))
-        return fail(C2W_ERR_CUDA, "cannot encode the pre-activation stash tensor map");
+      int rc;
+      if (vjp) {  // the pre-activation is stashed; SiLU is a separate elementwise pass
+        rc = add_conv(true, y, L.H, L.W, L.C, bw.c1, EPI_BIAS, pre, false);
+        if (rc) return rc;
+        if (real) {
+          Op op;
+          op.kind = OP_SILU;
+          op.aux = pre;
+          op.in = nullptr;
+          op.out = hs[l];
+          op.C = L.C;
+          op.H = L.H;
+          op.W = L.W;
+          op.up = 0;
+          P.ops.push_back(op);
+        }
+      } else {
+        rc = add_conv(true, y, L.H, L.W, L.C, bw.c1, EPI_BIAS_SILU, hs[l], false);
+        if (rc) return rc;
+      }
       rc = add_conv(true, hs[l], L.H, L.W, L.C, bw.c2, EPI_BIAS_RES, xs[l], false);
       if (rc) return rc;
       if (vjp) {
         units.emplace_back();
         std::vector<Op>& u = units.back();
-        if ((rc = add_dconv(u, true, gs[l], L.H, L.W, bw.c2, EPI_DSILU, gh[l], pre))) return rc;
+        if ((rc = add_dconv(u, true, gs[l], L.H, L.W, bw.c2, EPI_BIAS, gh[l], nullptr))) return rc;
+        if (real) {  // gh *= silu'(pre)
+          Op op;
+          op.kind = OP_SILU;
+          op.aux = pre;
+          op.in = gh[l];
+          op.out = gh[l];
+          op.C = L.C;
+          op.H = L.H;
+          op.W = L.W;
+          op.up = 1;
+          u.push_back(op);
+        }
         if ((rc = add_dconv(u, true, gh[l], L.H, L.W, bw.c1, EPI_BIAS, ga[l], nullptr))) return rc;
         add_ln_bwd(u, ga[l], y, inv, gs[l], gs[l], L.C, L.H, L.W, 0);
       }
@@ -687,6 +714,13 @@ int run_ops(c2w_handle* h, std::vector<Op>& ops, int nn, const FinalSpec& fs, cu
         SpanGuard sg(h, 1, st);
         int rc = launch_attention_bwd(op.aux, op.in, op.out, op.inv, nn, op.T, op.C, st);
         if (rc) return rc;
+        break;
+      }
+      case OP_SILU: {
+        SpanGuard sg(h, 1, st);
+        const long long n8 = static_cast<long long>(nn) * op.H * op.W * op.C / 8;
+        silu_elementwise_kernel<<<grid_for(n8, 256, h->sms), 256, 0, st>>>(op.aux, op.in, op.out, n8, op.up);
+        C2W_CUDA(cudaGetLastError());
         break;
       }
       case OP_ZERO_UP: {

@@ -643,6 +643,35 @@ attention_bwd_grads_kernel(const bf16* __restrict__ qkv, const bf16* __restrict_
   }
 }
 
+// SiLU and its derivative as separate elementwise passes (VJP path only: the forward stashes the pre-activation).
+//   mode 0: out = silu(pre)        mode 1: out = g * silu'(pre)   (g may alias out)
+__global__ void silu_elementwise_kernel(const bf16* __restrict__ pre, const bf16* g, bf16* out, long long n8, int mode) {
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < n8;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 pv = *reinterpret_cast<const uint4*>(pre + idx * 8);
+    uint4 gv = make_uint4(0, 0, 0, 0);
+    if (mode == 1) gv = *reinterpret_cast<const uint4*>(g + idx * 8);
+    const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 x = unpack_bf16x2(pw[j]);
+      float r0, r1;
+      const float s0 = 1.0f / (1.0f + __expf(-x.x)), s1 = 1.0f / (1.0f + __expf(-x.y));
+      if (mode == 0) {
+        r0 = x.x * s0;
+        r1 = x.y * s1;
+      } else {
+        const float2 gg = unpack_bf16x2(gw[j]);
+        r0 = gg.x * s0 * (1.0f + x.x * (1.0f - s0));
+        r1 = gg.y * s1 * (1.0f + x.y * (1.0f - s1));
+      }
+      o[j] = pack_bf16x2(r0, r1);
+    }
+    *reinterpret_cast<uint4*>(out + idx * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // Zero-insertion 2x upsample: out[n, 2h, 2w, :] = in[n, h, w, :], every other pixel zero.  The stride-2 conv's input
 // gradient is then a stride-1 conv of `out` with the flipped kernel.
 __global__ void zero_upsample_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, long long n, int H, int W,

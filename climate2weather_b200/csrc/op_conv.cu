@@ -37,6 +37,7 @@ int c2w_op_conv_ex(const c2w_conv_desc* d, void* stream) {
   L.p.bias = d->bias;
   L.p.out_f32 = d->out_f32;
   L.p.dbg_skip_loads = d->skip_loads;
+  L.p.dbg_stats = reinterpret_cast<long long*>(d->stats);
   if (d->mode != EPI_F32) {
     C2W_REQUIRE(d->out, "c2w_op_conv_ex: bf16 output modes need `out`");
     C2W_REQUIRE(d->mode != EPI_BIAS_RES || d->res == d->out, "mode 2 accumulates in place: res must equal out");

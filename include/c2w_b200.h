@@ -144,6 +144,8 @@ typedef struct c2w_conv_desc {
   void* ln_out;         /* non-NULL: fused channel LayerNorm of (bf16(out) + ln_mod) -> bf16 (bn == cout_pad)     */
   const float* ln_mod;  /* fp32 [cout_pad] or NULL                                                                */
   int32_t ln_upsample;  /* write each normalised pixel to its 2x2 block of [n_img, 2Ho, 2Wo, cout_pad]            */
+  int64_t* stats;       /* diagnostics: per-CTA cycle counters [grid][12] (producer total/wait-empty, MMA total/
+                           wait-full/wait-tmem, epilogue total/wait-accumulator); NULL = off                      */
 } c2w_conv_desc;
 int c2w_op_conv_ex(const c2w_conv_desc* d, void* stream);
 int c2w_op_conv(const void* x, int n_img, int H, int W, int cin, const void* w_packed, int cout_pad,

@@ -93,17 +93,22 @@ def test_conv3x3_vs_torch(lib, dev, n, H, W, cin, cout, mode):
 
 
 def test_gemm_mode_vs_torch(lib, dev):
+    """Plain GEMM mode (1x1 Conv1d of the attention blocks): bf16 output 2^-7; fp32 output (64-wide tiles only) 1e-4."""
     from climate2weather_b200 import _lib
     g = torch.Generator().manual_seed(7)
-    for M, K, N in [(256, 128, 128), (64, 512, 1536), (200, 576, 64)]:
+    for M, K, N in [(256, 128, 128), (64, 512, 1536), (200, 576, 64), (384, 512, 512)]:
         a = torch.randn(M, K, generator=g).to(dev).to(torch.bfloat16)
         w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev).to(torch.bfloat16)
         b = torch.randn(N, generator=g).to(dev)
-        out32 = torch.empty(M, N, device=dev)
-        _lib.check(lib.c2w_op_conv(a.data_ptr(), 1, 1, M, K, w.data_ptr(), N, b.data_ptr(), 4, None, None,
-                                   out32.data_ptr(), 0, 0, 0, stream()), "c2w_op_conv(gemm)")
+        f32 = N == 64
+        out32 = torch.empty(M, N, device=dev) if f32 else None
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        _lib.check(lib.c2w_op_conv(a.data_ptr(), 1, 1, M, K, w.data_ptr(), N, b.data_ptr(), 4 if f32 else 0, None,
+                                   None if f32 else out.data_ptr(), out32.data_ptr() if f32 else None, 0, 0, 0, stream()),
+                   "c2w_op_conv(gemm)")
         torch.cuda.synchronize()
-        assert relerr(out32, a.float() @ w.float().t() + b) < 1e-4
+        ref = a.float() @ w.float().t() + b
+        assert relerr(out32 if f32 else out.float(), ref) < (1e-4 if f32 else 2 ** -7)
 
 
 def _conv_ex(lib, xb, wp, bp, mode, n, H, W, stride=1, res=None, variant=-1, bn=0, ln_mod=None, ln=False, ln_up=0,
@@ -147,12 +152,14 @@ def _conv_problem(dev, n, H, W, cin, cout, seed):
     return g, xb, w, b, wp, bp
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 5])
 @pytest.mark.parametrize("n,H,W,cin,cout,mode", [
-    (2, 128, 128, 128, 128, 1), (3, 64, 64, 128, 128, 2), (5, 32, 32, 128, 128, 0), (1, 128, 128, 64, 128, 1)])
+    (2, 128, 128, 128, 128, 1), (3, 64, 64, 128, 128, 2), (5, 32, 32, 128, 128, 0), (1, 128, 128, 64, 128, 1),
+    (3, 16, 16, 256, 128, 2), (1, 16, 8, 64, 128, 0)])
 def test_conv3x3_kernel_variants(lib, dev, variant, n, H, W, cin, cout, mode):
-    """Single CTA (0) and CTA pair / cta_group::2 (1) compute the same conv; odd tile counts exercise the pair's
-    out-of-range half."""
+    """Single CTA (0), CTA pair / cta_group::2 (1) and CTA pair with the activation-reuse main loop (5: 16 x 8 spatial
+    tiles, one halo'd load per filter column reused by the three filter rows) compute the same conv; odd tile counts
+    exercise the pair's out-of-range half."""
     g, xb, w, b, wp, bp = _conv_problem(dev, n, H, W, cin, cout, 11 * n + cin)
     M = n * H * W
     res = torch.randn(M, wp.shape[0], generator=g).to(dev).to(torch.bfloat16)
@@ -181,6 +188,7 @@ def test_conv3x3_stride2_vs_torch(lib, dev, variant, n, H, W, cin, cout):
 
 @pytest.mark.parametrize("n,H,W,C,mode,up,use_mod,variant", [
     (2, 128, 128, 128, 2, 0, True, 1), (2, 64, 64, 128, 0, 0, True, 1), (3, 32, 32, 256, 2, 0, True, 1),
+    (2, 128, 128, 128, 2, 0, True, 5), (3, 64, 64, 128, 2, 1, False, 5), (1, 32, 32, 128, 0, 0, True, 5),
     (3, 32, 32, 256, 2, 1, False, 1), (2, 64, 64, 128, 2, 1, False, 0), (1, 16, 16, 64, 0, 0, True, 0)])
 def test_conv3x3_fused_layernorm(lib, dev, n, H, W, C, mode, up, use_mod, variant):
     """Conv epilogue that also emits LN(out + mod) (model/nn.py:154,183-184): must equal the standalone K2 semantics

@@ -90,10 +90,10 @@ def check_gemm(name, M, K, N, seed=1):
     a = torch.randn(M, K, generator=g).to(dev).to(torch.bfloat16)
     w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev).to(torch.bfloat16)
     b = torch.randn(N, generator=g).to(dev)
-    got = run_conv(a.reshape(1, 1, M, K), w, b, 4, conv3x3=False, f32=True)
+    got = run_conv(a.reshape(1, 1, M, K), w, b, 0, conv3x3=False, f32=False).float()
     ref = a.float() @ w.float().t() + b
     err = (got - ref).abs().max().item()
-    ok = err <= 2e-3 * ref.abs().max().item()
+    ok = err <= 2e-2 * ref.abs().max().item()
     print(f"{'PASS' if ok else 'FAIL'} {name}: gemm M={M} K={K} N={N} max_err={err:.3e}", flush=True)
     return ok
 
@@ -119,6 +119,8 @@ def timeit(name, n, H, W, cin, cout, iters=20, variant=-1, bn=0, skip_loads=0, l
     d.bn, d.variant, d.max_ctas, d.skip_loads = bn, variant, 0, skip_loads
     d.ln_out = ln_out.data_ptr() if ln else None
     d.ln_mod = mod.data_ptr() if ln else None
+    stats = torch.zeros(148 * 12, dtype=torch.int64, device=dev) if "--stats" in sys.argv else None
+    d.stats = stats.data_ptr() if stats is not None else None
 
     def call():
         rc = L.c2w_op_conv_ex(ctypes.byref(d), st)
@@ -134,6 +136,14 @@ def timeit(name, n, H, W, cin, cout, iters=20, variant=-1, bn=0, skip_loads=0, l
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
+    if stats is not None:
+        st = stats.reshape(148, 12).double().cpu()
+        lead = st[0::2]  # leader CTAs hold the MMA counters
+        f = lambda v: f"{v.mean().item() / 1e3:.0f}k"
+        print(f"  [{name}] cycles/launch: producer total {f(st[:, 0])} wait-empty {f(st[:, 1])} | mma total {f(lead[:, 2])} "
+              f"wait-full {f(lead[:, 3])} wait-tmem {f(lead[:, 4])} | epilogue total {f(st[:, 5])} wait-acc {f(st[:, 6])} "
+              f"wait-staging {f(st[:, 7])} pass1(incl) {f(st[:, 8])} wait-tile {f(st[:, 9])} LN(incl) {f(st[:, 10])}",
+              flush=True)
     flops = 2.0 * n * H * W * cout_pad * 9 * cin_pad
     tf = flops / ms / 1e9
     if not cudnn:
@@ -182,6 +192,11 @@ def main():
     if "--time" in sys.argv:
         timeit("G2 cg1", 32, 128, 128, 128, 128, variant=0)
         timeit("G2 cg2", 32, 128, 128, 128, 128, variant=1, cudnn=False)
+        timeit("G2 cg2+AR", 32, 128, 128, 128, 128, variant=5, cudnn=False)
+        timeit("G2 cg2+AR res", 32, 128, 128, 128, 128, variant=5, res=True, cudnn=False)
+        timeit("G2 cg2+AR res+LN", 32, 128, 128, 128, 128, variant=5, ln=True, cudnn=False)
+        timeit("G5 cg2+AR", 64, 64, 64, 128, 128, variant=5, cudnn=False)
+        timeit("G6 cg2+AR (256->128)", 64, 64, 64, 256, 128, variant=5, cudnn=False)
         timeit("G2 cg2 res", 32, 128, 128, 128, 128, variant=1, res=True, cudnn=False)
         timeit("G2 cg2+LN", 32, 128, 128, 128, 128, variant=1, ln=True, cudnn=False)
         timeit("G5 cg2", 64, 64, 64, 128, 128, variant=1, cudnn=False)
