@@ -213,6 +213,22 @@ class ScoreUNet(nn.Module):
         state["_engines"] = {}  # device handles are rebuilt lazily after unpickling / deepcopy
         return state
 
+    def __setstate__(self, state):
+        """Also accepts the pickled state of a REFERENCE `model.score.ScoreUNet` (a network snapshot,
+        training_loop.py:250-266, unpickled through `compat.install()`): the module tree keeps the reference's
+        parameter names, and the architecture description is read off their shapes."""
+        self.__dict__.update(state)
+        self._engines = {}
+        if "hidden_blocks" not in state:
+            arch = _arch_from_state_dict(self.state_dict())
+            self.channels, self.embedding_dim = arch["channels"], arch["embedding_dim"]
+            self.noise_features = NOISE_FEATURES
+            self.hidden_channels, self.hidden_blocks = arch["hidden_channels"], arch["hidden_blocks"]
+            self.attention_levels = arch["attention_levels"]
+            if getattr(self, "map_forcing", None) is not None:
+                raise NotImplementedError("snapshot has a forcing branch (forcing_dim != 0); not supported")
+            self.map_forcing = None
+
     # ---------------------------------------------------------------------------------------------- engines
     def _fingerprint(self) -> tuple:
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
@@ -288,14 +304,13 @@ class _UNetInputVJP(torch.autograd.Function):
         return gin.to(x.dtype), None, None
 
 
-def build_from_reference(module: nn.Module) -> ScoreUNet:
-    """New ScoreUNet with the architecture and weights of a reference `model.score.ScoreUNet` instance."""
-    sd = module.state_dict()
+def _arch_from_state_dict(sd) -> dict:
+    """Architecture keyword arguments of the ScoreUNet that owns this state_dict (SURVEY.md §8(b) naming)."""
     nl = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("unet.heads."))
     ch, blocks, attn = [], [], []
     for lvl in range(nl):
         wkey = "unet.heads.0.weight" if lvl == 0 else f"unet.heads.{lvl}.0.weight"
-        ch.append(sd[wkey].shape[0])
+        ch.append(int(sd[wkey].shape[0]))
         idxs = sorted({int(k.split(".")[3]) for k in sd if k.startswith(f"unet.descent.{lvl}.")})
         has_attn = any(k.startswith(f"unet.descent.{lvl}.") and ".qkv." in k for k in sd)
         if has_attn:
@@ -303,6 +318,11 @@ def build_from_reference(module: nn.Module) -> ScoreUNet:
             blocks.append(len(idxs) // 2)
         else:
             blocks.append(len(idxs))
-    net = ScoreUNet(channels=sd["unet.heads.0.weight"].shape[1], embedding_dim=sd["map_layer1.weight"].shape[0],
-                    hidden_channels=ch, hidden_blocks=blocks, attention_levels=attn)
+    return dict(channels=int(sd["unet.heads.0.weight"].shape[1]), embedding_dim=int(sd["map_layer1.weight"].shape[0]),
+                hidden_channels=ch, hidden_blocks=blocks, attention_levels=attn)
+
+
+def build_from_reference(module: nn.Module) -> ScoreUNet:
+    """New ScoreUNet with the architecture and weights of a reference `model.score.ScoreUNet` instance."""
+    net = ScoreUNet(**_arch_from_state_dict(module.state_dict()))
     return net.from_reference(module)

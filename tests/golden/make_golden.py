@@ -36,6 +36,8 @@ def _install_zuko_standin():
             var, mean = torch.var_mean(x, dim=self.dim, keepdim=True)
             return (x - mean) / (var + self.eps).sqrt()
 
+    LayerNorm.__module__ = "zuko.nn"  # picklable under the real package's name (snapshot fixture)
+    LayerNorm.__qualname__ = "LayerNorm"
     znn.LayerNorm = LayerNorm
     zuko.nn = znn
     sys.modules["zuko"] = zuko
@@ -76,8 +78,56 @@ def weight_checksums(net):
     return np.array(names), np.array(sums), np.array(asums)
 
 
+def make_snapshot(ScoreUNet):
+    """A network snapshot exactly as training_loop.py:250-266 pickles it (EasyDict with the fp16 EMA module, the
+    pipeline object and dataset_kwargs), at a tiny architecture: the fixture for the compat / unpickling test."""
+    import pickle
+
+    util = types.ModuleType("util")  # util.py imports lightning; EasyDict restated under the reference's name
+
+    class EasyDict(dict):
+        def __getattr__(self, name):
+            try:
+                return self[name]
+            except KeyError:
+                raise AttributeError(name)
+
+        def __setattr__(self, name, value):
+            self[name] = value
+
+    EasyDict.__module__ = "util"
+    EasyDict.__qualname__ = "EasyDict"
+    util.EasyDict = EasyDict
+    sys.modules["util"] = util
+    thor = types.ModuleType("thor")
+    sys.modules["thor"] = thor
+    spec = importlib.util.spec_from_file_location("thor.pipelines", REF / "src/thor/pipelines.py")
+    tp = importlib.util.module_from_spec(spec)
+    sys.modules["thor.pipelines"] = tp
+    spec.loader.exec_module(tp)
+    tiny = dict(embedding_dim=64, hidden_channels=[64, 64], hidden_blocks=[1, 1], attention_levels=[1], kernel_size=3,
+                padding_mode="zeros")
+    torch.manual_seed(11)
+    net = ScoreUNet(channels=12, spatial=2, activation=torch.nn.SiLU, **tiny)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    snap = EasyDict(dataset_kwargs=EasyDict(train=EasyDict(window=3)), pipeline=tp.SDAPipeline())
+    snap.ema = net.cpu().eval().requires_grad_(False).to(torch.float16)
+    with open(OUT / "snapshot_tiny.pkl", "wb") as f:
+        pickle.dump(snap, f)
+    x = torch.randn(2, 12, 16, 16, generator=torch.Generator().manual_seed(12))
+    net32 = ScoreUNet(channels=12, spatial=2, activation=torch.nn.SiLU, **tiny)
+    net32.load_state_dict({k: v.half().float() for k, v in sd.items()})  # what the fp16 snapshot holds
+    with torch.no_grad():
+        y = net32.eval()(x, torch.tensor(0.3))
+    names = np.array(list(sd.keys()))
+    np.savez_compressed(OUT / "snapshot_tiny_expect.npz", names=names,
+                        sums=np.array([sd[k].half().double().sum().item() for k in sd]), x=x.numpy(), t=0.3, y=y.numpy())
+    print("wrote snapshot_tiny.pkl", (OUT / "snapshot_tiny.pkl").stat().st_size, "bytes")
+
+
 def main():
     ScoreUNet, score, pipelines = load_reference()
+    make_snapshot(ScoreUNet)
     torch.set_num_threads(8)
 
     # ---------------------------------------------------------------- 1. full architecture (sda_unet.yml)

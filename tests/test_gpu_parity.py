@@ -515,6 +515,24 @@ def test_sampler_vs_reference_golden(dev, golden_dir):
     assert relerr(s2, torch.from_numpy(g["sample_one_window"])) < 5e-2
 
 
+def test_reference_snapshot_forward(dev, golden_dir):
+    """The unpickled reference snapshot (fp16 EMA module) runs through the CUDA path and reproduces the reference's
+    own forward on the same weights (fixture from tests/golden/make_golden.py)."""
+    import pickle
+
+    import climate2weather_b200.compat as compat
+    compat.install()
+    with open(golden_dir / "snapshot_tiny.pkl", "rb") as f:
+        snap = pickle.load(f)
+    exp = np.load(golden_dir / "snapshot_tiny_expect.npz")
+    net = snap["ema"].to(dev).eval()
+    with torch.no_grad():
+        y = net(torch.from_numpy(exp["x"]).to(dev), torch.tensor(float(exp["t"])))
+    e = relerr(y, torch.from_numpy(exp["y"]))
+    print(f"\nsnapshot forward rel-err vs reference: {e:.3e}")
+    assert e < 3e-2
+
+
 # ------------------------------------------------------------------------------------------------ VJP (exact_grad)
 @pytest.mark.parametrize("C", [64, 128, 384, 512])
 @pytest.mark.parametrize("down", [0, 1])

@@ -57,6 +57,37 @@ def test_package_never_imports_oracle():
         assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
 
 
+# ------------------------------------------------------------------------------------------------ snapshots
+def test_reference_snapshot_unpickles_through_compat():
+    """A network snapshot pickled by the REFERENCE's own classes (tests/golden/make_golden.py: util.EasyDict with the
+    fp16 model.score.ScoreUNet, thor.pipelines.SDAPipeline, dataset_kwargs — training_loop.py:250-266) loads through
+    compat.install() into this package's classes with every parameter intact (exp/downscaling.py:110-126)."""
+    import pickle
+
+    import climate2weather_b200 as c2w
+    import climate2weather_b200.compat as compat
+
+    compat.install()
+    with open(ROOT / "tests" / "golden" / "snapshot_tiny.pkl", "rb") as f:
+        snap = pickle.load(f)
+    exp = np.load(ROOT / "tests" / "golden" / "snapshot_tiny_expect.npz")
+    assert snap["dataset_kwargs"]["train"]["window"] == 3 and snap.dataset_kwargs.train.window == 3
+    assert isinstance(snap["pipeline"], c2w.SDAPipeline) and snap["pipeline"].eta == 1e-3
+    net = snap["ema"]
+    assert isinstance(net, c2w.ScoreUNet)
+    assert (net.channels, net.embedding_dim) == (12, 64)
+    assert net.hidden_channels == [64, 64] and net.hidden_blocks == [1, 1] and net.attention_levels == [1]
+    sd = net.state_dict()
+    assert list(sd.keys()) == [str(k) for k in exp["names"]]
+    for k, want in zip(exp["names"], exp["sums"]):
+        assert sd[str(k)].dtype == torch.float16
+        assert abs(sd[str(k)].double().sum().item() - want) <= 1e-9 + 1e-12 * abs(want)
+    net.eval()  # the calls exp/downscaling.py makes on it before sampling
+    # a natively constructed net with the same architecture has the same parameter names
+    native = c2w.ScoreUNet(12, 64, hidden_channels=[64, 64], hidden_blocks=[1, 1], attention_levels=[1])
+    assert sorted(native.state_dict().keys()) == sorted(sd.keys())
+
+
 # ------------------------------------------------------------------------------------------------ shard plan
 @pytest.mark.parametrize("L,k,world", [(168, 6, 1), (168, 6, 2), (720, 6, 8), (25, 6, 2), (30, 2, 4), (8760, 6, 8),
                                        (13, 6, 1), (181, 6, 7)])
