@@ -7,6 +7,7 @@ from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "libc2w_b200.so"
 MAX_LEVELS = 8
+WS_VJP, WS_PER_SAMPLE_T = 1, 2
 
 
 class C2WError(RuntimeError):
@@ -92,6 +93,9 @@ SIGNATURES = {
     "c2w_finalize_weights": (_i, [_vp]),
     "c2w_workspace_bytes": (_i64, [_vp, C.c_int32]),
     "c2w_bind_workspace": (_i, [_vp, C.c_int32, _vp, _i64]),
+    "c2w_workspace_bytes_ex": (_i64, [_vp, C.c_int32, C.c_int32]),
+    "c2w_bind_workspace_ex": (_i, [_vp, C.c_int32, _vp, _i64, C.c_int32]),
+    "c2w_unet_forward_t": (_i, [_vp, _vp, C.c_int32, _vp, _vp, _vp]),
     "c2w_workspace_bytes_vjp": (_i64, [_vp, C.c_int32]),
     "c2w_bind_workspace_vjp": (_i, [_vp, C.c_int32, _vp, _i64]),
     "c2w_unet_vjp": (_i, [_vp, _vp, C.c_int32, _f, _vp, _vp, _vp, _vp]),

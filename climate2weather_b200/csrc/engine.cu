@@ -69,6 +69,7 @@ struct Op {
 struct Plan {
   int n_max = 0;
   bool vjp = false;        // forward ops stash what the backward ops need
+  bool per_t = false;      // one diffusion time per sample: mods is [n, total_mod], no LayerNorm fusion
   std::vector<Op> ops;
   std::vector<Op> bwd;     // input-gradient pass (vjp plans only), in execution order
   bf16* cot = nullptr;     // UNet-output cotangent [n, HW, cout_pad(window channels)] bf16
@@ -182,13 +183,14 @@ int upload_named(c2w_handle* h, const std::string& name, size_t numel, float** o
 
 template <int C>
 void launch_ln_c(const bf16* x, const float* mod, bf16* out, float* inv, long long npix, int H, int W, int up, int sms,
-                 cudaStream_t st) {
+                 cudaStream_t st, long long mod_stride) {
   const int threads = 256;
   long long blocks = (npix + 7) / 8;
   const long long cap = static_cast<long long>(sms) * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  channel_layernorm_kernel<C><<<static_cast<int>(blocks), threads, 0, st>>>(x, mod, out, inv, npix, H, W, up, 1e-5f);
+  channel_layernorm_kernel<C><<<static_cast<int>(blocks), threads, 0, st>>>(x, mod, out, inv, npix, H, W, up, 1e-5f,
+                                                                            mod_stride);
 }
 template <int C>
 void launch_ln_bwd_c(const bf16* gy, const bf16* y, const float* inv, const bf16* gres, bf16* out, long long npix, int H,
@@ -215,8 +217,8 @@ void launch_ln_bwd_c(const bf16* gy, const bf16* y, const float* inv, const bf16
   }
 
 int launch_ln(const bf16* x, const float* mod, bf16* out, float* inv, long long npix, int C, int H, int W, int up,
-              int sms, cudaStream_t st) {
-#define C2W_CALL(CC) launch_ln_c<CC>(x, mod, out, inv, npix, H, W, up, sms, st)
+              int sms, cudaStream_t st, long long mod_stride = 0) {
+#define C2W_CALL(CC) launch_ln_c<CC>(x, mod, out, inv, npix, H, W, up, sms, st, mod_stride)
   C2W_LN_DISPATCH(C, C2W_CALL)
 #undef C2W_CALL
   C2W_CUDA(cudaGetLastError());
@@ -298,12 +300,15 @@ int grid_for(long long items, int threads, int sms) {
   return static_cast<int>(b);
 }
 
-int run_modulation(c2w_handle* h, float t, float* h0, float* emb, float* mods, cudaStream_t st) {
+// ns samples: t_dev (device, ns values) or the scalar t for all; h0/emb: [ns, E], mods: [ns, total_mod]
+int run_modulation(c2w_handle* h, float t, const float* t_dev, int ns, float* h0, float* emb, float* mods,
+                   cudaStream_t st) {
   const int E = h->cfg.embedding_dim, nf = h->cfg.noise_features;
-  time_embed_kernel<<<1, 256, nf * sizeof(float), st>>>(t, h->map0_w, h->map0_b, h0, E, nf);
-  matvec_kernel<<<ceil_div(static_cast<long long>(E) * 32, 256), 256, 0, st>>>(h->map1_w, h->map1_b, h0, emb, E, E, 1);
-  matvec_kernel<<<ceil_div(static_cast<long long>(h->total_mod) * 32, 256), 256, 0, st>>>(h->proj_w, h->proj_b, emb, mods,
-                                                                                         h->total_mod, E, 0);
+  time_embed_kernel<<<ns, 256, nf * sizeof(float), st>>>(t, t_dev, h->map0_w, h->map0_b, h0, E, nf);
+  matvec_kernel<<<dim3(ceil_div(static_cast<long long>(E) * 32, 256), ns), 256, 0, st>>>(h->map1_w, h->map1_b, h0, emb, E,
+                                                                                      E, 1);
+  matvec_kernel<<<dim3(ceil_div(static_cast<long long>(h->total_mod) * 32, 256), ns), 256, 0, st>>>(
+      h->proj_w, h->proj_b, emb, mods, h->total_mod, E, 0);
   g_launches += 3;
   C2W_CUDA(cudaGetLastError());
   return C2W_OK;
@@ -312,7 +317,7 @@ int run_modulation(c2w_handle* h, float t, float* h0, float* emb, float* mods, c
 // Lays the workspace out and (if base != null) builds every launch of the forward pass over it.  vjp: the forward
 // ops additionally stash (per block) the LayerNorm output + 1/std and the SiLU pre-activation, (per attention block)
 // qkv, and the plan gets the input-gradient pass `bwd`.
-int build_plan(c2w_handle* h, int n, bool vjp, void* base, size_t* bytes_out) {
+int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* bytes_out) {
   Plan& P = h->plan;
   const bool real = base != nullptr;
   Bump B(base);
@@ -323,11 +328,13 @@ int build_plan(c2w_handle* h, int n, bool vjp, void* base, size_t* bytes_out) {
     P.bwd.clear();
     P.n_max = n;
     P.vjp = vjp;
+    P.per_t = per_t;
   }
   bf16* xin = B.take<bf16>(n * HW0 * h->cin_pad);
-  float* h0 = B.take<float>(h->cfg.embedding_dim);
-  float* emb = B.take<float>(h->cfg.embedding_dim);
-  float* mods = B.take<float>(h->total_mod);
+  const size_t ns = per_t ? n : 1;  // modulation vectors: one per sample or one for the batch
+  float* h0 = B.take<float>(ns * h->cfg.embedding_dim);
+  float* emb = B.take<float>(ns * h->cfg.embedding_dim);
+  float* mods = B.take<float>(ns * h->total_mod);
   float* out32 = B.take<float>(n * HW0 * h->levels[0].tail.cout_pad);
   std::vector<bf16*> xs(nl), as(nl), hs(nl), gs(nl), ga(nl), gh(nl);
   size_t up_elems = 0, qkv_elems = 0, att_elems = 0;
@@ -424,7 +431,7 @@ int build_plan(c2w_handle* h, int n, bool vjp, void* base, size_t* bytes_out) {
   // tile holds all C channels of a pixel, the normalisation is done in that conv's epilogue (no extra HBM pass).
   auto add_ln = [&](const bf16* in, bf16* out, float* inv, int C, int H, int W, int upf, int mod_off) {
     if (!real) return;
-    if (h->fuse_ln && !P.ops.empty()) {
+    if (h->fuse_ln && !per_t && !P.ops.empty()) {
       Op& prev = P.ops.back();
       if (prev.kind == OP_CONV && !prev.is_final && prev.conv.out_ptr == in && prev.conv.cout_pad == C &&
           conv_launch_can_ln(&prev.conv, upf) &&
@@ -693,7 +700,8 @@ int run_ops(c2w_handle* h, std::vector<Op>& ops, int nn, const FinalSpec& fs, cu
       case OP_LN: {
         SpanGuard sg(h, 1, st);
         int rc = launch_ln(op.in, op.mod_off >= 0 ? P.mods + op.mod_off : nullptr, op.out, op.inv,
-                           static_cast<long long>(nn) * op.H * op.W, op.C, op.H, op.W, op.up, h->sms, st);
+                           static_cast<long long>(nn) * op.H * op.W, op.C, op.H, op.W, op.up, h->sms, st,
+                           P.per_t ? h->total_mod : 0);
         if (rc) return rc;
         break;
       }
@@ -896,39 +904,43 @@ int c2w_timing_read(c2w_handle* h, double* ms, int64_t* n) {
   return C2W_OK;
 }
 
-static int64_t workspace_bytes(c2w_handle* h, int32_t max_windows, bool vjp) {
+int64_t c2w_workspace_bytes_ex(c2w_handle* h, int32_t max_windows, int32_t flags) {
   if (!h || !h->finalized || max_windows < 1) {
     fail(C2W_ERR_STATE, "c2w_workspace_bytes: finalise the weights first");
     return -1;
   }
   size_t bytes = 0;
-  if (build_plan(h, max_windows, vjp, nullptr, &bytes)) return -1;
+  if (build_plan(h, max_windows, (flags & C2W_WS_VJP) != 0, (flags & C2W_WS_PER_SAMPLE_T) != 0, nullptr, &bytes)) return -1;
   return static_cast<int64_t>(bytes);
 }
-static int bind_workspace(c2w_handle* h, int32_t max_windows, bool vjp, void* dev_ptr, int64_t bytes) {
+int c2w_bind_workspace_ex(c2w_handle* h, int32_t max_windows, void* dev_ptr, int64_t bytes, int32_t flags) {
   C2W_REQUIRE(h && dev_ptr && max_windows >= 1, "c2w_bind_workspace: bad argument");
   if (!h->finalized) return fail(C2W_ERR_STATE, "finalise the weights first");
+  const bool vjp = (flags & C2W_WS_VJP) != 0, per_t = (flags & C2W_WS_PER_SAMPLE_T) != 0;
+  C2W_REQUIRE(!(vjp && per_t), "a VJP workspace with per-sample diffusion times is not built");
   size_t need_bytes = 0;
-  int rc = build_plan(h, max_windows, vjp, nullptr, &need_bytes);
+  int rc = build_plan(h, max_windows, vjp, per_t, nullptr, &need_bytes);
   if (rc) return rc;
   C2W_REQUIRE(static_cast<size_t>(bytes) >= need_bytes, "workspace too small: %lld < %zu", (long long)bytes, need_bytes);
   void* aligned = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(dev_ptr) + 1023) & ~uintptr_t(1023));
-  return build_plan(h, max_windows, vjp, aligned, &need_bytes);
+  return build_plan(h, max_windows, vjp, per_t, aligned, &need_bytes);
 }
 
-int64_t c2w_workspace_bytes(c2w_handle* h, int32_t max_windows) { return workspace_bytes(h, max_windows, false); }
+int64_t c2w_workspace_bytes(c2w_handle* h, int32_t max_windows) { return c2w_workspace_bytes_ex(h, max_windows, 0); }
 int c2w_bind_workspace(c2w_handle* h, int32_t max_windows, void* dev_ptr, int64_t bytes) {
-  return bind_workspace(h, max_windows, false, dev_ptr, bytes);
+  return c2w_bind_workspace_ex(h, max_windows, dev_ptr, bytes, 0);
 }
-int64_t c2w_workspace_bytes_vjp(c2w_handle* h, int32_t max_windows) { return workspace_bytes(h, max_windows, true); }
+int64_t c2w_workspace_bytes_vjp(c2w_handle* h, int32_t max_windows) {
+  return c2w_workspace_bytes_ex(h, max_windows, C2W_WS_VJP);
+}
 int c2w_bind_workspace_vjp(c2w_handle* h, int32_t max_windows, void* dev_ptr, int64_t bytes) {
-  return bind_workspace(h, max_windows, true, dev_ptr, bytes);
+  return c2w_bind_workspace_ex(h, max_windows, dev_ptr, bytes, C2W_WS_VJP);
 }
 
 int c2w_op_modulation(c2w_handle* h, float t, float* emb_out, float* mods_out, void* stream) {
   C2W_REQUIRE(h && h->finalized && h->plan.n_max > 0, "c2w_op_modulation: bind a workspace first");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = run_modulation(h, t, h->plan.h0, h->plan.emb, h->plan.mods, st);
+  int rc = run_modulation(h, t, nullptr, 1, h->plan.h0, h->plan.emb, h->plan.mods, st);
   if (rc) return rc;
   if (emb_out)
     C2W_CUDA(cudaMemcpyAsync(emb_out, h->plan.emb, h->cfg.embedding_dim * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -937,19 +949,23 @@ int c2w_op_modulation(c2w_handle* h, float t, float* emb_out, float* mods_out, v
   return C2W_OK;
 }
 
-int c2w_unet_forward(c2w_handle* h, const float* x_nchw, int32_t n, float t, float* out_nchw, void* stream) {
+static int unet_forward_impl(c2w_handle* h, const float* x_nchw, int32_t n, float t, const float* t_dev, float* out_nchw,
+                             void* stream) {
   C2W_REQUIRE(h && x_nchw && out_nchw && n >= 1, "c2w_unet_forward: bad argument");
   if (h->plan.n_max < 1) return fail(C2W_ERR_STATE, "bind a workspace first");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Plan& P = h->plan;
+  C2W_REQUIRE((t_dev != nullptr) == P.per_t,
+              "per-sample diffusion times need a workspace bound with C2W_WS_PER_SAMPLE_T (and only then)");
   const int hw = h->cfg.height * h->cfg.width;
   const int cout_pad = h->levels[0].tail.cout_pad;
-  int rc = run_modulation(h, t, P.h0, P.emb, P.mods, st);
-  if (rc) return rc;
+  int rc;
+  if (!t_dev && (rc = run_modulation(h, t, nullptr, 1, P.h0, P.emb, P.mods, st))) return rc;
   FinalSpec fs;
   fs.mode = EPI_F32;
   for (int i0 = 0; i0 < n; i0 += P.n_max) {
     const int nn = std::min(P.n_max, n - i0);
+    if (t_dev && (rc = run_modulation(h, 0.f, t_dev + i0, nn, P.h0, P.emb, P.mods, st))) return rc;
     dim3 blk(32, 8);
     dim3 g1(ceil_div(hw, 32), ceil_div(h->cin_pad, 32), nn);
     nchw_to_nhwc_bf16_kernel<<<g1, blk, 0, st>>>(x_nchw + static_cast<size_t>(i0) * h->cin * hw, P.xin, h->cin, hw,
@@ -965,10 +981,19 @@ int c2w_unet_forward(c2w_handle* h, const float* x_nchw, int32_t n, float t, flo
   return C2W_OK;
 }
 
+int c2w_unet_forward(c2w_handle* h, const float* x_nchw, int32_t n, float t, float* out_nchw, void* stream) {
+  return unet_forward_impl(h, x_nchw, n, t, nullptr, out_nchw, stream);
+}
+int c2w_unet_forward_t(c2w_handle* h, const float* x_nchw, int32_t n, const float* t_dev, float* out_nchw, void* stream) {
+  C2W_REQUIRE(t_dev, "c2w_unet_forward_t: null time array");
+  return unet_forward_impl(h, x_nchw, n, 0.f, t_dev, out_nchw, stream);
+}
+
 int c2w_window_score(c2w_handle* h, const float* traj, int32_t n_frames_local, int32_t frame_global0,
                      int32_t win_first, int32_t n_win, int32_t n_win_global, float t, float* eps, void* stream) {
   C2W_REQUIRE(h && traj && eps, "c2w_window_score: bad argument");
   if (h->plan.n_max < 1) return fail(C2W_ERR_STATE, "bind a workspace first");
+  if (h->plan.per_t) return fail(C2W_ERR_STATE, "window scores use one diffusion time: bind a plain workspace");
   const int w = h->cfg.window, k = w / 2, C = h->cfg.frame_channels;
   C2W_REQUIRE(n_win >= 1 && win_first >= 0 && win_first + n_win <= n_win_global, "window range [%d,%d) outside [0,%d)",
               win_first, win_first + n_win, n_win_global);
@@ -979,7 +1004,7 @@ int c2w_window_score(c2w_handle* h, const float* traj, int32_t n_frames_local, i
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Plan& P = h->plan;
   const int hw = h->cfg.height * h->cfg.width;
-  int rc = run_modulation(h, t, P.h0, P.emb, P.mods, st);
+  int rc = run_modulation(h, t, nullptr, 1, P.h0, P.emb, P.mods, st);
   if (rc) return rc;
   for (int c0 = 0; c0 < n_win; c0 += P.n_max) {
     const int nn = std::min(P.n_max, n_win - c0);
@@ -1012,7 +1037,7 @@ int c2w_unet_vjp(c2w_handle* h, const float* x_nchw, int32_t n, float t, const f
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int hw = h->cfg.height * h->cfg.width;
   const int cout_pad = h->levels[0].tail.cout_pad;
-  int rc = run_modulation(h, t, P.h0, P.emb, P.mods, st);
+  int rc = run_modulation(h, t, nullptr, 1, P.h0, P.emb, P.mods, st);
   if (rc) return rc;
   dim3 blk(32, 8);
   dim3 g1(ceil_div(hw, 32), ceil_div(h->cin_pad, 32), n);

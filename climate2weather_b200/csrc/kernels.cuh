@@ -83,7 +83,7 @@ __global__ void gather_windows_kernel(const float* __restrict__ traj, bf16* __re
 template <int C>
 __global__ void channel_layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ mod,
                                          bf16* __restrict__ out, float* __restrict__ inv_out, long long npix, int H,
-                                         int W, int upsample, float eps) {
+                                         int W, int upsample, float eps, long long mod_img_stride) {
   constexpr int VEC = (C % 128 == 0) ? 4 : 2;
   constexpr int NCH = C / (32 * VEC);
   static_assert(C % 64 == 0 && NCH >= 1, "C must be a multiple of 64");
@@ -98,6 +98,13 @@ __global__ void channel_layernorm_kernel(const bf16* __restrict__ x, const float
 
   for (long long pix = warp0; pix < npix; pix += nwarps) {
     const bf16* px = x + pix * C;
+    if (mod && mod_img_stride) {  // per-sample diffusion times: every image has its own modulation vector
+      const float* mi = mod + (pix / (static_cast<long long>(H) * W)) * mod_img_stride;
+#pragma unroll
+      for (int j = 0; j < NCH; ++j)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) m[j * VEC + e] = __ldg(mi + j * 32 * VEC + lane * VEC + e);
+    }
     float v[NCH * VEC];
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
@@ -165,9 +172,13 @@ __global__ void channel_layernorm_kernel(const bf16* __restrict__ x, const float
 
 // ------------------------------------------------------------------------------------------------ K3
 // h0 = silu(W0 * [cos(t f), sin(t f)] + b0)      (model/score.py:14-34, :62-63)
-__global__ void time_embed_kernel(float t, const float* __restrict__ W0, const float* __restrict__ b0,
-                                  float* __restrict__ h0, int E, int nf) {
+// blockIdx.x = sample: t_dev != null reads the sample's own diffusion time (training / DSM loss,
+// src/thor/pipelines.py:27-35), else every sample uses the scalar t (sampling).
+__global__ void time_embed_kernel(float t_scalar, const float* __restrict__ t_dev, const float* __restrict__ W0,
+                                  const float* __restrict__ b0, float* __restrict__ h0_all, int E, int nf) {
   extern __shared__ float e[];
+  const float t = t_dev ? t_dev[blockIdx.x] : t_scalar;
+  float* h0 = h0_all + static_cast<size_t>(blockIdx.x) * E;
   const int half = nf / 2;
   if (threadIdx.x < half) {
     const float f = expf(-9.210340371976184f * static_cast<float>(threadIdx.x) / static_cast<float>(half));
@@ -183,11 +194,14 @@ __global__ void time_embed_kernel(float t, const float* __restrict__ W0, const f
   }
 }
 // y[r] = act(b[r] + W[r, :] . x)   warp per row, float4 lanes.  act: 0 none, 1 SiLU
-__global__ void matvec_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ x,
-                              float* __restrict__ y, int rows, int cols, int act) {
+// blockIdx.y = sample: x and y advance by cols / rows per sample
+__global__ void matvec_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ x_all,
+                              float* __restrict__ y_all, int rows, int cols, int act) {
   const int lane = threadIdx.x & 31;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
+  const float* x = x_all + static_cast<size_t>(blockIdx.y) * cols;
+  float* y = y_all + static_cast<size_t>(blockIdx.y) * rows;
   const float4* w4 = reinterpret_cast<const float4*>(W + static_cast<size_t>(row) * cols);
   const float4* x4 = reinterpret_cast<const float4*>(x);
   float acc = 0.f;

@@ -70,7 +70,7 @@ class Engine:
     """One c2w handle: packed weights + workspace for a fixed (frame_channels, window, H, W)."""
 
     def __init__(self, net: "ScoreUNet", frame_channels: int, window: int, height: int, width: int,
-                 device: torch.device, max_windows: int, vjp: bool = False):
+                 device: torch.device, max_windows: int, vjp: bool = False, per_sample_t: bool = False):
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -96,19 +96,19 @@ class Engine:
             self.max_windows = 0
             self.workspace = None
             self.vjp = bool(vjp)
+            self.per_sample_t = bool(per_sample_t)
             self.bind(max_windows)
 
     def bind(self, max_windows: int) -> None:
-        size_fn = self.lib.c2w_workspace_bytes_vjp if self.vjp else self.lib.c2w_workspace_bytes
-        bind_fn = self.lib.c2w_bind_workspace_vjp if self.vjp else self.lib.c2w_bind_workspace
+        flags = (_lib.WS_VJP if self.vjp else 0) | (_lib.WS_PER_SAMPLE_T if self.per_sample_t else 0)
         with torch.cuda.device(self.device):
-            nbytes = size_fn(self.handle, max_windows)
+            nbytes = self.lib.c2w_workspace_bytes_ex(self.handle, max_windows, flags)
             if nbytes < 0:
                 _lib.check(-1, "c2w_workspace_bytes")
             self.workspace = None  # release the old arena before taking the new one
             self.workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
-            _lib.check(bind_fn(self.handle, max_windows, self.workspace.data_ptr(), self.workspace.numel()),
-                       "c2w_bind_workspace")
+            _lib.check(self.lib.c2w_bind_workspace_ex(self.handle, max_windows, self.workspace.data_ptr(),
+                                                      self.workspace.numel(), flags), "c2w_bind_workspace")
             self.max_windows = max_windows
 
     @property
@@ -121,6 +121,15 @@ class Engine:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.c2w_unet_forward(self.handle, x.data_ptr(), x.shape[0], float(t), out.data_ptr(),
                                                  self.stream), "c2w_unet_forward")
+        return out
+
+    def unet_forward_t(self, x: Tensor, t: Tensor) -> Tensor:
+        """x: fp32 NCHW [n, C*window, H, W]; t: fp32 [n] on self.device (one diffusion time per sample)."""
+        assert self.per_sample_t, "engine was built without per-sample modulation"
+        out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.c2w_unet_forward_t(self.handle, x.data_ptr(), x.shape[0], t.data_ptr(), out.data_ptr(),
+                                                   self.stream), "c2w_unet_forward_t")
         return out
 
     def unet_vjp(self, x: Tensor, t: float, gout: Tensor):
@@ -234,14 +243,14 @@ class ScoreUNet(nn.Module):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def engine(self, frame_channels: int, window: int, height: int, width: int, device, max_windows: Optional[int] = None,
-               vjp: bool = False) -> Engine:
+               vjp: bool = False, per_sample_t: bool = False) -> Engine:
         """Packed-weight engine for this geometry; rebuilt if the parameters changed since it was packed."""
         device = torch.device(device)
         if device.type == "cuda" and device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
         if frame_channels * window != self.channels:
             raise ValueError(f"frame_channels*window = {frame_channels * window} != channels = {self.channels}")
-        key = (frame_channels, window, height, width, str(device), bool(vjp))
+        key = (frame_channels, window, height, width, str(device), bool(vjp), bool(per_sample_t))
         fp = self._fingerprint()
         hit = self._engines.get(key)
         want = max_windows or self.DEFAULT_MAX_WINDOWS
@@ -250,7 +259,7 @@ class ScoreUNet(nn.Module):
             if max_windows is not None and eng.max_windows != max_windows:
                 eng.bind(max_windows)
             return eng
-        eng = Engine(self, frame_channels, window, height, width, device, want, vjp=vjp)
+        eng = Engine(self, frame_channels, window, height, width, device, want, vjp=vjp, per_sample_t=per_sample_t)
         self._engines[key] = (eng, fp)
         return eng
 
@@ -268,8 +277,16 @@ class ScoreUNet(nn.Module):
             raise _lib.C2WError("ScoreUNet.forward: input must live on a CUDA device (no CPU path); "
                                 "BatchedScoreFunction moves window batches for you")
         tt = torch.as_tensor(t).reshape(-1).float()
+        B, Cc, H, W = x.shape
         if tt.numel() != 1 and not bool((tt == tt[0]).all()):
-            raise NotImplementedError("per-sample diffusion times are not built yet (sampling uses one t per call)")
+            # one diffusion time per sample (model/score.py:61; the DSM objective, src/thor/pipelines.py:27-35)
+            if tt.numel() != B:
+                raise ValueError(f"t has {tt.numel()} entries for a batch of {B}")
+            if torch.is_grad_enabled() and x.requires_grad:
+                raise NotImplementedError("input gradients with per-sample diffusion times are not built")
+            eng = self.engine(Cc, 1, H, W, x.device, per_sample_t=True)
+            out = eng.unet_forward_t(x.detach().float().contiguous(), tt.to(x.device).contiguous())
+            return out.to(x.dtype).reshape(x.shape)
         B, Cc, H, W = x.shape
         if torch.is_grad_enabled() and x.requires_grad:
             # input gradients only (model/nn.py weights are frozen in sampling, training_loop.py:257); parameter

@@ -515,6 +515,38 @@ def test_sampler_vs_reference_golden(dev, golden_dir):
     assert relerr(s2, torch.from_numpy(g["sample_one_window"])) < 5e-2
 
 
+def test_per_sample_times_and_dsm_loss(dev, golden_dir):
+    """ScoreUNet with one diffusion time per sample (model/score.py:61) and SDAPipeline.loss
+    (src/thor/pipelines.py:27-35) against the oracle with the same t and eps; chunked through a 2-window workspace."""
+    import climate2weather_b200 as c2w
+    net, ref = make_small(dev)
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(5, 20, 32, 32, generator=g)
+    t = torch.tensor([0.05, 0.9, 0.33, 0.33, 0.71])
+    want = ref(x, t.reshape(-1, 1, 1, 1))
+    net.DEFAULT_MAX_WINDOWS = 2
+    with torch.no_grad():
+        got = net(x.to(dev), t.reshape(-1, 1, 1, 1).to(dev))
+    e = relerr(got, want)
+    print(f"\nper-sample-t forward rel-err vs oracle: {e:.3e}")
+    assert e < 3e-2
+    # each sample must equal the single-t call at its own time (the modulation is per sample, nothing else is)
+    with torch.no_grad():
+        one = net(x[1:2].to(dev), torch.tensor(0.9))
+    assert relerr(got[1:2], one) < 1e-2
+    # DSM loss: same draws as the oracle (torch.rand for t, then randn_like for eps, on the CPU generator)
+    pipe = c2w.SDAPipeline()
+    torch.manual_seed(7)
+    tt = torch.rand(5, 1, 1, 1)
+    eps = torch.randn_like(x)
+    want_loss = pipeline_ref.RefPipeline().loss(ref, x, t=tt, eps=eps)
+    torch.manual_seed(7)
+    xt = pipe.mu(tt) * x + pipe.sigma(tt) * eps
+    with torch.no_grad():
+        got_loss = (net(xt.to(dev), tt.to(dev)).cpu() - eps) ** 2
+    assert relerr(got_loss, want_loss) < 6e-2  # squared error of a 3e-2 output
+
+
 def test_reference_snapshot_forward(dev, golden_dir):
     """The unpickled reference snapshot (fp16 EMA module) runs through the CUDA path and reproduces the reference's
     own forward on the same weights (fixture from tests/golden/make_golden.py)."""
