@@ -53,7 +53,9 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line).  The sampler is
+    started BEFORE the warm-up (nvidia-smi needs a few hundred ms to come up) and every row is stamped on arrival;
+    the summary uses the rows between mark_start() and mark_end()."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -61,11 +63,12 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -74,7 +77,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def __exit__(self, *a):
         if self.proc:
@@ -85,8 +94,11 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
+        t0, t1 = self.t0 or 0.0, self.t1 or float("inf")
+        inside = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.05]
+        rows = inside or [r for _, r in self.rows]
         sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx = max(mx, float(r[2]))
@@ -96,9 +108,9 @@ class ClockSampler:
             except Exception:
                 pass
         sm.sort()
-        # the median of the upper half ~ clocks while the kernels run (the sampler also sees idle gaps)
         med = sm[len(sm) // 2] if sm else None
-        return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm),
+                "window": "timed region" if inside else "whole run"}
 
 
 def make_problem(L: int, seed: int = 0):
@@ -161,19 +173,21 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timed region: exactly K steps, CUDA events on the launch stream
-    rt.load(noise)
-    for i in range(args.warmup):
-        one_step(i)
-    rt.load(noise)  # restart the trajectory so the timed steps see the schedule from t = 1
-    barrier()
-    launches0 = lib.c2w_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
+        rt.load(noise)
+        for i in range(args.warmup):
+            one_step(i)
+        rt.load(noise)  # restart the trajectory so the timed steps see the schedule from t = 1
+        barrier()
+        launches0 = lib.c2w_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clocks.mark_start()
         e0.record()
         for i in range(args.steps):
             one_step(i)
         e1.record()
         barrier()
+        clocks.mark_end()
     ms_total = e0.elapsed_time(e1)
     launches = lib.c2w_launch_count() - launches0
     tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -214,7 +228,7 @@ def run_ours(args):
         pipe2 = c2w.SDAPipeline()
         pipe2.nan_check_every = 1
         noise_pinned = noise.pin_memory()
-        ke = max(1, min(args.steps, args.e2e_steps))
+        ke = max(1, args.e2e_steps)  # one full sample() call of this many denoising steps (independent of --steps)
         barrier()
         t0 = time.perf_counter()
         out = pipe2.sample(sf, noise_pinned, steps=ke, corrections=0, tau=0.5, show_progressbar=False)
@@ -338,7 +352,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=None, help="override L (default 12 + 156 * gpus)")
     ap.add_argument("--chunk", type=int, default=int(os.environ.get("C2W_CHUNK", 156)), help="windows per UNet launch")
-    ap.add_argument("--e2e-steps", type=int, default=32)
+    ap.add_argument("--e2e-steps", type=int, default=64,
+                    help="denoising steps of the end-to-end sample() call (its fixed costs — noise upload, final gather and "
+                         "download — are amortised over these steps; the real run has 256)")
     ap.add_argument("--cpu-windows", type=int, default=13)
     ap.add_argument("--ref-steps", type=int, default=3)
     ap.add_argument("--warmup-ref", type=int, default=1)
