@@ -264,32 +264,43 @@ int launch_attention_bwd(const bf16* qkv, const bf16* go, bf16* gqkv, float* scr
   return C2W_OK;
 }
 
-int launch_attention(const bf16* qkv, bf16* out, int n, int T, int C, cudaStream_t st) {
-  C2W_REQUIRE(T % 4 == 0 && C % 8 == 0, "attention: T %% 4 and C %% 8 must be 0 (T=%d C=%d)", T, C);
-  // 64-query CTAs when they already fill the machine twice over, else 16-query CTAs (4x the parallelism)
-  const int sms = c2w_num_sms();
-  const bool big = static_cast<long long>(n) * ((T + 63) / 64) >= 2LL * sms;
-  const int qb = big ? 64 : 16;
-  const size_t smem = attention_smem_bytes(T, C, qb);
+template <int QB>
+int launch_attention_qb(const bf16* qkv, bf16* out, int n, int T, int C, cudaStream_t st) {
+  const size_t smem = attention_smem_bytes(T, C, QB);
   C2W_REQUIRE(smem <= static_cast<size_t>(kSmemLimit), "attention: T=%d C=%d needs %zu B of shared memory", T, C, smem);
-  static size_t configured[2] = {0, 0};
-  const float scale2 = 1.0f / sqrtf(static_cast<float>(C));
-  dim3 grid((T + qb - 1) / qb, n);
-  if (big) {
-    if (smem > configured[0]) {
-      C2W_CUDA(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      configured[0] = smem;
-    }
-    attention_kernel<64><<<grid, kAttnThreads, smem, st>>>(qkv, out, T, C, scale2);
-  } else {
-    if (smem > configured[1]) {
-      C2W_CUDA(cudaFuncSetAttribute(attention_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      configured[1] = smem;
-    }
-    attention_kernel<16><<<grid, kAttnThreads, smem, st>>>(qkv, out, T, C, scale2);
+  static size_t configured = 0;
+  if (smem > configured) {
+    C2W_CUDA(cudaFuncSetAttribute(attention_kernel<QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
   }
+  dim3 grid((T + QB - 1) / QB, n);
+  attention_kernel<QB><<<grid, kAttnThreads, smem, st>>>(qkv, out, T, C, 1.0f / sqrtf(static_cast<float>(C)));
   C2W_CUDA(cudaGetLastError());
   return C2W_OK;
+}
+
+int launch_attention(const bf16* qkv, bf16* out, int n, int T, int C, cudaStream_t st) {
+  C2W_REQUIRE(T % 4 == 0 && C % 8 == 0, "attention: T %% 4 and C %% 8 must be 0 (T=%d C=%d)", T, C);
+  // Queries per CTA: the largest block that still gives every SM two CTAs' worth of work (K and V are re-read from L2
+  // by every query block of a window, so bigger blocks move less data; smaller ones fill the machine).
+  const int sms = c2w_num_sms();
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("C2W_ATTN_QB");
+    forced = e ? atoi(e) : 0;
+  }
+  int qb = 16;
+  for (int cand : {64, 32})
+    if (static_cast<long long>(n) * ((T + cand - 1) / cand) >= 2LL * sms) {
+      qb = cand;
+      break;
+    }
+  if (forced == 16 || forced == 32 || forced == 64) qb = forced;
+  switch (qb) {
+    case 64: return launch_attention_qb<64>(qkv, out, n, T, C, st);
+    case 32: return launch_attention_qb<32>(qkv, out, n, T, C, st);
+    default: return launch_attention_qb<16>(qkv, out, n, T, C, st);
+  }
 }
 
 int grid_for(long long items, int threads, int sms) {
