@@ -918,14 +918,14 @@ inline bool conv_launch_init(ConvLaunch* L, bool is_conv3x3, const __nv_bfloat16
     p.tile_h = th;
     p.tile_n = tn;
     p.tiles_per_img = Ho / th;
-    // activation reuse: stride-1 convs with one 128-wide N tile per CTA pair on images that tile into 16 x 8 blocks
+    // activation reuse: stride-1 convs with 64- or 128-wide N tiles per CTA pair on images that tile into 16 x 8 blocks
     static int ar_ok = -1;
     if (ar_ok < 0) {
       const char* e = getenv("C2W_NO_AR");
       ar_ok = (e && e[0] == '1') ? 0 : 1;
     }
     const bool want_ar = (variant < 0) ? ar_ok != 0 : (variant & 4) != 0;
-    if (want_ar && stride == 1 && bn == 128 && L->cg == 2 && H % 16 == 0 && W % 8 == 0) {
+    if (want_ar && stride == 1 && (bn == 128 || bn == 64) && L->cg == 2 && H % 16 == 0 && W % 8 == 0) {
       L->ar = 1;
       p.tiles_w = W / 8;
       p.tiles_per_img = (H / 16) * p.tiles_w;
@@ -1034,7 +1034,7 @@ inline cudaError_t conv_launch_variant(const ConvLaunch& L, cudaStream_t stream)
 template <int BN, bool LN>
 inline cudaError_t conv_launch_bn_ln(const ConvLaunch& L, cudaStream_t stream) {
   if (L.cg == 2) {
-    if constexpr (BN == 128) {
+    if constexpr (BN == 128 || BN == 64) {
       if (L.ar) return conv_launch_variant<BN, 2, LN, true>(L, stream);
     }
     return conv_launch_variant<BN, 2, LN, false>(L, stream);
