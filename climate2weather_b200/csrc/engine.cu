@@ -279,8 +279,34 @@ int launch_attention_qb(const bf16* qkv, bf16* out, int n, int T, int C, cudaStr
   return C2W_OK;
 }
 
+template <int C>
+int launch_attention_mma(const bf16* qkv, bf16* out, int n, cudaStream_t st) {
+  const size_t smem = attention_mma_smem_bytes(C);
+  static bool configured = false;
+  if (!configured) {
+    C2W_CUDA(cudaFuncSetAttribute(attention_mma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    configured = true;
+  }
+  attention_mma_kernel<C><<<n, 256, smem, st>>>(qkv, out, 1.0f / sqrtf(static_cast<float>(C)));
+  C2W_CUDA(cudaGetLastError());
+  return C2W_OK;
+}
+
 int launch_attention(const bf16* qkv, bf16* out, int n, int T, int C, cudaStream_t st) {
   C2W_REQUIRE(T % 4 == 0 && C % 8 == 0, "attention: T %% 4 and C %% 8 must be 0 (T=%d C=%d)", T, C);
+  {  // 64 tokens (8 x 8 attention level): tensor-core kernel; C2W_ATTN_MMA=0 keeps the CUDA-core kernel (A/B runs)
+    static int use_mma = -1;
+    if (use_mma < 0) {
+      const char* e = getenv("C2W_ATTN_MMA");
+      use_mma = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (use_mma && T == 64) {
+      if (C == 512) return launch_attention_mma<512>(qkv, out, n, st);
+      if (C == 256) return launch_attention_mma<256>(qkv, out, n, st);
+      if (C == 128) return launch_attention_mma<128>(qkv, out, n, st);
+    }
+  }
   // Queries per CTA: the largest block that still gives every SM two CTAs' worth of work (K and V are re-read from L2
   // by every query block of a window, so bigger blocks move less data; smaller ones fill the machine).
   const int sms = c2w_num_sms();

@@ -398,6 +398,148 @@ __global__ void nhwc_f32_to_nchw_kernel(const float* __restrict__ in, float* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------ K4 (tensor cores)
+// Attention core for T = 64 tokens (the reference's 8 x 8 attention level) on warp-level tensor-core MMAs
+// (mma.sync m16n8k16, bf16 in, fp32 accumulate): 0.04 % of the UNet's FLOPs, so the legacy warp MMA is plenty — the
+// point is to get it off the CUDA cores, where it cost 5 % of a step.  One CTA per window:
+//   cp.async q, k, v [64, C] -> shared (16 B chunks XOR-swizzled by row for conflict-free ldmatrix)
+//   warps 0-3: S = scale2 q k^T for 16 query rows each, fp32 softmax in registers, P -> shared (bf16)
+//   warps 0-7: O = P v for 16 rows x C/2 channels each, bf16 -> global
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+inline size_t attention_mma_smem_bytes(int C) { return static_cast<size_t>(3) * 64 * C * 2 + 64 * 64 * 2; }
+template <int C>
+__global__ void __launch_bounds__(256) attention_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                                                            float scale2) {
+  constexpr int T = 64, CH = C / 8, PITCH = C * 2;  // CH: 16 B chunks per row
+  extern __shared__ __align__(128) uint8_t smraw[];
+  const uint32_t sQ = static_cast<uint32_t>(__cvta_generic_to_shared(smraw));
+  const uint32_t sK = sQ + T * PITCH, sV = sK + T * PITCH, sP = sV + T * PITCH;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bf16* src = qkv + static_cast<size_t>(blockIdx.x) * T * 3 * C;
+  for (int idx = tid; idx < 3 * T * CH; idx += 256) {
+    const int which = idx / (T * CH), rem = idx - which * (T * CH);
+    const int r = rem / CH, cc = rem - r * CH;
+    const uint32_t dst = sQ + which * (T * PITCH) + r * PITCH + ((cc ^ (r & 7)) << 4);
+    const bf16* g = src + static_cast<size_t>(r) * 3 * C + which * C + cc * 8;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const int mat = lane >> 3, rr = lane & 7;  // ldmatrix: lane -> (8x8 matrix, row)
+  const int g = lane >> 2, tq = lane & 3;    // mma fragments: row group, column pair
+  if (warp < 4) {
+    const int r0 = 16 * warp;
+    float acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+    const int arow = r0 + rr + (mat & 1) * 8;
+#pragma unroll 4
+    for (int ks = 0; ks < C / 16; ++ks) {
+      uint32_t a[4];
+      ldmatrix_x4(a, sQ + arow * PITCH + (((2 * ks + (mat >> 1)) ^ (arow & 7)) << 4));
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {  // key tiles 2 jp, 2 jp + 1
+        const int key = 16 * jp + rr + (mat >> 1) * 8;
+        uint32_t b[4];
+        ldmatrix_x4(b, sK + key * PITCH + (((2 * ks + (mat & 1)) ^ (key & 7)) << 4));
+        mma_bf16_16816(acc[2 * jp], a, b[0], b[1]);
+        mma_bf16_16816(acc[2 * jp + 1], a, b[2], b[3]);
+      }
+    }
+    // fp32 softmax over the 64 keys of rows g and g + 8 (model/nn.py:82); a row lives in the 4 lanes of a quad
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] *= scale2;
+      m0 = fmaxf(m0, fmaxf(acc[j][0], acc[j][1]));
+      m1 = fmaxf(m1, fmaxf(acc[j][2], acc[j][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[j][0] = expf(acc[j][0] - m0);
+      acc[j][1] = expf(acc[j][1] - m0);
+      acc[j][2] = expf(acc[j][2] - m1);
+      acc[j][3] = expf(acc[j][3] - m1);
+      s0 += acc[j][0] + acc[j][1];
+      s1 += acc[j][2] + acc[j][3];
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    const float i0 = 1.0f / s0, i1 = 1.0f / s1;
+    const int row0 = r0 + g, row1 = r0 + g + 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {  // P[row][8 j + 2 tq, +1] (bf16): chunk j of the 128 B row, swizzled
+      const uint32_t p0 = pack_bf16x2(acc[j][0] * i0, acc[j][1] * i0), p1 = pack_bf16x2(acc[j][2] * i1, acc[j][3] * i1);
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(sP + row0 * 128 + ((j ^ (row0 & 7)) << 4) + tq * 4), "r"(p0) : "memory");
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(sP + row1 * 128 + ((j ^ (row1 & 7)) << 4) + tq * 4), "r"(p1) : "memory");
+    }
+  }
+  __syncthreads();
+  {
+    const int r0 = 16 * (warp & 3), cbase = (warp >> 2) * (C / 2);
+    const int arow = r0 + rr + (mat & 1) * 8;
+    uint32_t pa[4][4];  // P fragments of the 4 k-steps over the 64 keys
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(pa[ks], sP + arow * 128 + (((2 * ks + (mat >> 1)) ^ (arow & 7)) << 4));
+    bf16* orow0 = out + (static_cast<size_t>(blockIdx.x) * T + r0 + g) * C;
+    bf16* orow1 = orow0 + static_cast<size_t>(8) * C;
+#pragma unroll 1
+    for (int grp = 0; grp < C / 128; ++grp) {  // 64 channels at a time
+      const int c0 = cbase + 64 * grp;
+      float acc[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const int key = 16 * ks + rr + (mat & 1) * 8;
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {  // channel tiles 2 jp, 2 jp + 1
+          const int chunk = (c0 >> 3) + 2 * jp + (mat >> 1);
+          uint32_t b[4];
+          ldmatrix_x4_trans(b, sV + key * PITCH + ((chunk ^ (key & 7)) << 4));
+          mma_bf16_16816(acc[2 * jp], pa[ks], b[0], b[1]);
+          mma_bf16_16816(acc[2 * jp + 1], pa[ks], b[2], b[3]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int col = c0 + 8 * j + 2 * tq;
+        *reinterpret_cast<uint32_t*>(orow0 + col) = pack_bf16x2(acc[j][0], acc[j][1]);
+        *reinterpret_cast<uint32_t*>(orow1 + col) = pack_bf16x2(acc[j][2], acc[j][3]);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ VJP kernels
 // Backward of the channel LayerNorm (model/nn.py:154,183; zuko LayerNorm, unbiased variance):
 //   g_v = inv * (g_y - mean_C(g_y) - y * sum_C(g_y y) / (C - 1)),   out = gres + g_v

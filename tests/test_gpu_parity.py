@@ -233,7 +233,7 @@ def test_channel_layernorm(lib, dev, C, up):
     assert relerr(out.float().cpu().permute(0, 3, 1, 2), ref) < 2 ** -8
 
 
-@pytest.mark.parametrize("T,C", [(64, 512), (256, 128), (16, 64)])
+@pytest.mark.parametrize("T,C", [(64, 512), (256, 128), (16, 64), (64, 128), (64, 256)])
 def test_attention_core(lib, dev, T, C):
     """K4 vs model/nn.py:74-85 semantics in fp32 on the same bf16 q, k, v: bf16 output rounding only."""
     from climate2weather_b200 import _lib
