@@ -303,7 +303,7 @@ class AbstractScoreFunction:
     #: (profiles/r01_chunk_sweep.log).  The workspace is ~24 MiB per window.
     DEFAULT_WINDOWS = 192
     #: windows per forward+backward chunk with exact_grad=True
-    VJP_WINDOWS = 64
+    VJP_WINDOWS = 192
 
     def _default_windows(self, n_win: int) -> int:
         return min(n_win, self.DEFAULT_WINDOWS)
