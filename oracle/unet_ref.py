@@ -87,7 +87,7 @@ def init_state_dict(cfg: dict, seed: int = 0) -> Dict[str, Tensor]:
 def timestep_embedding(t: Tensor, dim: int = NOISE_FEATURES, max_period: float = 10000.0) -> Tensor:
     """model/score.py:14-34 — [cos(t f_j), sin(t f_j)], f_j = exp(-ln(max_period) j / half)."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     args = t.reshape(-1, 1).float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
