@@ -53,7 +53,7 @@ class SDAPipeline:
         return score_fn(x, t)
 
     def _sample_step(self, score_fn, x, t, dt, proc_x0=None):
-        """:41-46 (generic form, used only for foreign score functions)."""
+        """:41-46, the reference's formula kept for API completeness (`sample` itself runs the fused kernels)."""
         eps_pred = self.pred_eps(score_fn, x, t)
         pred_x0 = (x - self.sigma(t) * eps_pred) / self.mu(t)
         if proc_x0 is not None:
@@ -63,9 +63,13 @@ class SDAPipeline:
     # ---------------------------------------------------------------- sampler (:48-97)
     def sample(self, score_fn, noise, steps: int = 64, corrections: int = 0, tau: float = 1.0, proc_x0=None,
                device=None, show_progressbar=True, seed: Optional[int] = None):
-        if isinstance(score_fn, AbstractScoreFunction) and proc_x0 is None:
-            return self._sample_resident(score_fn, noise, steps, corrections, tau, device, show_progressbar, seed)
-        return self._sample_generic(score_fn, noise, steps, corrections, tau, proc_x0, device, show_progressbar)
+        if not isinstance(score_fn, AbstractScoreFunction):
+            raise TypeError("SDAPipeline.sample drives this package's score functions (Default/BatchedScoreFunction); "
+                            f"got {type(score_fn).__name__}.  There is no generic torch-op sampling loop here.")
+        if proc_x0 is not None:
+            raise NotImplementedError("proc_x0 hooks are not supported: the predictor update is one fused kernel over the "
+                                      "resident trajectory (no reference experiment config uses the hook)")
+        return self._sample_resident(score_fn, noise, steps, corrections, tau, device, show_progressbar, seed)
 
     def _sample_resident(self, sf: AbstractScoreFunction, noise: Tensor, steps: int, corrections: int, tau: float,
                          device, show_progressbar: bool, seed: Optional[int]) -> Tensor:
@@ -123,24 +127,3 @@ class SDAPipeline:
         print(f"Total sampling time: {total_time:.2f} s  = {total_time / 60:.3f} min = {total_time / 3600:.4f} h")
         target = noise.device if device is None else torch.device(device)
         return out.to(device=target, dtype=noise.dtype).reshape(noise.shape)
-
-    def _sample_generic(self, score_fn, noise, steps, corrections, tau, proc_x0, device, show_progressbar):
-        """The reference loop for score functions this package does not own (plain callables, proc_x0 hooks)."""
-        if device is None:
-            device = torch.device("cpu")
-        x = noise.to(device=device)
-        dims = tuple(range(-len(noise.shape), 0))
-        time_steps = torch.linspace(1, 0, steps + 1).to(dtype=x.dtype, device=device)
-        dt = 1 / steps
-        z = torch.empty_like(x) if corrections > 0 else None
-        with torch.no_grad():
-            for t in time_steps[:-1]:
-                x = self._sample_step(score_fn, x, t, dt, proc_x0=proc_x0)
-                for _ in range(corrections):
-                    z.normal_()
-                    eps = score_fn(x, t - dt)
-                    delta = tau / eps.square().mean(dim=dims, keepdim=True)
-                    x = x - (delta * eps + torch.sqrt(2 * delta) * z) * self.sigma(t - dt)
-                if torch.isnan(x).any():
-                    raise ValueError("NaN detected in sample")
-        return x.reshape(noise.shape)

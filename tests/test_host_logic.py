@@ -50,6 +50,23 @@ def test_no_cpu_path():
         sf(torch.zeros(8, 4, 16, 16), torch.tensor(0.5))
 
 
+def test_sampler_has_no_generic_torch_loop():
+    """SDAPipeline.sample must not quietly run a torch-op loop for foreign score functions or proc_x0 hooks."""
+    import climate2weather_b200 as c2w
+
+    pipe = c2w.SDAPipeline()
+    with pytest.raises(TypeError):
+        pipe.sample(lambda x, t: x, torch.zeros(3, 4, 8, 8), steps=1)
+    net = c2w.ScoreUNet(channels=20, embedding_dim=64, hidden_channels=(64,), hidden_blocks=(1,), attention_levels=())
+    sf = c2w.DefaultScoreFunction(net, markov_order=2, noise_process=pipe)
+    with pytest.raises(NotImplementedError):
+        pipe.sample(sf, torch.zeros(8, 4, 16, 16), steps=1, proc_x0=lambda v: v)
+    # the schedule is the reference's (src/thor/pipelines.py:13-20): mu(0) = 1, sigma(0) = eta, mu(1) = eta
+    t0, t1 = torch.tensor(0.0), torch.tensor(1.0)
+    assert abs(float(pipe.mu(t0)) - 1.0) < 1e-6 and abs(float(pipe.sigma(t0)) - 1e-3) < 1e-6
+    assert abs(float(pipe.mu(t1)) - 1e-3) < 1e-6 and abs(float(pipe.sigma(t1)) - 1.0) < 1e-5
+
+
 def test_package_never_imports_oracle():
     """oracle/ is test infrastructure: nothing under climate2weather_b200/ may import it."""
     for f in (ROOT / "climate2weather_b200").rglob("*.py"):
