@@ -80,7 +80,9 @@ constexpr int kBlockK = 64;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kEpiWarps = 8;                        // two warps per TMEM lane quarter, each half of the columns
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kConvThreads = 128 + kEpiThreads;
+constexpr int kConvThreads = 128 + kEpiThreads;  // + kLnThreads in kernels with the fused LayerNorm
+constexpr int kLnWarps = 4;                      // LayerNorm warps (one warpgroup) of those kernels
+constexpr int kLnThreads = kLnWarps * 32;
 constexpr int kSmemLimit = 232448;  // 227 KB
 constexpr int kEpiBarrier = 1;      // named barrier of the epilogue warps
 
@@ -242,7 +244,7 @@ __device__ __forceinline__ void epilogue_chunk_staged(const ConvParams& p, const
 }
 
 template <int BN, int CG, bool LN, bool AR>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kConvThreads + (LN ? kLnThreads : 0), 1)
 conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmOut, const ConvParams p) {
   using Cfg = ConvCfg<BN, CG>;
@@ -296,7 +298,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       mbar_init(&res_full[b], 1);
       mbar_init(&stg_full[b], kEpiWarps);
       mbar_init(&stg_free[b], 1);
-      mbar_init(&ln_done[b], kEpiWarps);
+      mbar_init(&ln_done[b], kLnWarps);
     }
     fence_mbar_init();
   }
@@ -313,474 +315,501 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   // Producer and MMA warps run CONVERGED (all 32 lanes wait on the barriers) and issue under elect_one():
   // operands stay warp-uniform, so ptxas keeps descriptors/coordinates in uniform registers instead of wrapping
   // every tcgen05/TMA instruction in an R2UR waterfall.
-  if (warp_idx == 0) {
-    // ------------------------------------------------------------ TMA producer (every CTA loads its own rows)
-    int stage = 0;
-    uint32_t phase = 0;
-    int issued = 0;
-    long long w_empty = 0;
-    const long long t_begin = clock64();
-    for (int tile = group_id; AR && tile < num_tiles; tile += num_groups) {
-      const int nt = tile % p.num_n_tiles;
-      const int mt = (tile / p.num_n_tiles) * CG + rank;
-      const int img = mt / p.tiles_per_img, tt = mt % p.tiles_per_img;
-      const int h0 = (tt / p.tiles_w) * Cfg::kARTileH, w0 = (tt % p.tiles_w) * Cfg::kARTileW;
-      for (int kb = 0; kb < 3 * p.cin_blocks; ++kb) {  // kb = cb * 3 + s
-        const int cb = kb / 3, s3 = kb - cb * 3;
-        {
-          const long long t0 = clock64();
-          mbar_wait(&empty[stage], phase ^ 1);
-          w_empty += clock64() - t0;
-        }
-        if (elect_one()) {
-          const uint32_t full_bar = (CG == 2) ? mapa_shared(smem_u32(&full[stage]), 0) : smem_u32(&full[stage]);
-          uint8_t* sbase = smem + stage * Cfg::kARStageBytes;
-          if (p.dbg_skip_loads && issued >= num_stages) {
-            if (rank == 0) mbar_arrive(&full[stage]);
-          } else {
-            if (rank == 0) mbar_arrive_expect_tx(&full[stage], CG * Cfg::kARStageBytes);
-            if (CG == 2) tma_load_4d_pair(&tmA, full_bar, sbase, cb * kBlockK, w0 + s3 - 1, h0 - 1, img);
-            else tma_load_4d(&tmA, &full[stage], sbase, cb * kBlockK, w0 + s3 - 1, h0 - 1, img);
-            for (int r = 0; r < 3; ++r) {
-              const int kk = (r * 3 + s3) * p.cin_blocks + cb;  // K block of tap (r, s) in the packed weights
-              uint8_t* bdst = sbase + Cfg::kARUnitBytes + r * Cfg::kBTileBytes;
-              if (CG == 2) tma_load_2d_pair(&tmB, full_bar, bdst, kk * kBlockK, nt * BN + rank * Cfg::kBRows);
-              else tma_load_2d(&tmB, &full[stage], bdst, kk * kBlockK, nt * BN);
-            }
-          }
-        }
-        __syncwarp();
-        ++issued;
-        if (++stage == num_stages) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-    }
-    for (int tile = group_id; !AR && tile < num_tiles; tile += num_groups) {
-      const int nt = tile % p.num_n_tiles;
-      const int mt = (tile / p.num_n_tiles) * CG + rank;
-      int b1, b2, b3;
-      if (p.taps == 9) {
-        b1 = 0;
-        b2 = (mt % p.tiles_per_img) * p.tile_h * p.stride;
-        b3 = (mt / p.tiles_per_img) * p.tile_n;
-      } else {
-        b1 = mt * kBlockM;
-        b2 = 0;
-        b3 = 0;
-      }
-      for (int kb = 0; kb < num_kb; kb += Cfg::kSub) {
-        const int nsub = (num_kb - kb) < Cfg::kSub ? (num_kb - kb) : Cfg::kSub;
-        {
-          const long long t0 = clock64();
-          mbar_wait(&empty[stage], phase ^ 1);
-          w_empty += clock64() - t0;
-        }
-        if (elect_one()) {
-          const uint32_t full_bar = (CG == 2) ? mapa_shared(smem_u32(&full[stage]), 0) : smem_u32(&full[stage]);
-          if (p.dbg_skip_loads && issued >= num_stages) {
-            if (rank == 0) mbar_arrive(&full[stage]);
-          } else {
-            if (rank == 0) mbar_arrive_expect_tx(&full[stage], CG * nsub * Cfg::kSubBytes);
-            for (int sub = 0; sub < nsub; ++sub) {
-              const int kk = kb + sub;
-              const int tap = kk / p.cin_blocks;
-              const int cb = kk - tap * p.cin_blocks;
-              const int dr = (p.taps == 9) ? tap / 3 - 1 : 0;
-              const int ds = (p.taps == 9) ? tap % 3 - 1 : 0;
-              const int slot = stage * Cfg::kSub + sub;
-              if (CG == 2) {
-                tma_load_4d_pair(&tmA, full_bar, smA + slot * kATileBytes, cb * kBlockK, b1 + ds, b2 + dr, b3);
-                tma_load_2d_pair(&tmB, full_bar, smB + slot * Cfg::kBTileBytes, kk * kBlockK,
-                                 nt * BN + rank * Cfg::kBRows);
-              } else {
-                tma_load_4d(&tmA, &full[stage], smA + slot * kATileBytes, cb * kBlockK, b1 + ds, b2 + dr, b3);
-                tma_load_2d(&tmB, &full[stage], smB + slot * Cfg::kBTileBytes, kk * kBlockK, nt * BN);
-              }
-            }
-          }
-        }
-        __syncwarp();
-        ++issued;
-        if (++stage == num_stages) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-    }
-    if (p.dbg_stats && lane == 0) {
-      p.dbg_stats[blockIdx.x * 12 + 0] = clock64() - t_begin;
-      p.dbg_stats[blockIdx.x * 12 + 1] = w_empty;
-    }
-  } else if (warp_idx == 1 && rank == 0) {
-    // ------------------------------------------------------------ MMA issuer (leader CTA, one elected lane issues)
-    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * CG, BN);
-    const uint64_t adesc0 = umma_desc_kmajor_sw128(smem_u32(smA));
-    const uint64_t bdesc0 = umma_desc_kmajor_sw128(smem_u32(smB));
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    long long w_full = 0, w_tmem = 0;
-    const long long t_begin = clock64();
-    for (int tile = group_id; tile < num_tiles; tile += num_groups) {
-      {
-        const long long t0 = clock64();
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        w_tmem += clock64() - t0;
-      }
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * BN;
-      for (int kb = 0; AR && kb < 3 * p.cin_blocks; ++kb) {
-        {
-          const long long t0 = clock64();
-          mbar_wait(&full[stage], phase);
-          w_full += clock64() - t0;
-        }
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (Cfg::kARStageBytes >> 4));
-          const uint64_t bdesc = adesc + static_cast<uint64_t>(Cfg::kARUnitBytes >> 4);
-#pragma unroll
-          for (int r = 0; r < 3; ++r) {
-#pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              // filter row r = the unit from its r-th pixel row on: + r * 8 rows * 128 B (keeps the swizzle phase)
-              const uint64_t a = adesc + r * ((Cfg::kARTileW * 128) >> 4) + 2 * k;
-              const uint64_t b = bdesc + r * (Cfg::kBTileBytes >> 4) + 2 * k;
-              if (CG == 2) umma_bf16_pair(tmem_d, a, b, idesc, (kb | r | k) != 0);
-              else umma_bf16(tmem_d, a, b, idesc, (kb | r | k) != 0);
-            }
-          }
-          if (CG == 2) {
-            umma_commit_pair(&empty[stage]);
-            if (kb + 1 >= 3 * p.cin_blocks) umma_commit_pair(&tmem_full[acc]);
-          } else {
-            umma_commit(&empty[stage]);
-            if (kb + 1 >= 3 * p.cin_blocks) umma_commit(&tmem_full[acc]);
-          }
-        }
-        __syncwarp();
-        if (++stage == num_stages) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-      for (int kb = 0; !AR && kb < num_kb; kb += Cfg::kSub) {
-        const int nsub = (num_kb - kb) < Cfg::kSub ? (num_kb - kb) : Cfg::kSub;
-        {
-          const long long t0 = clock64();
-          mbar_wait(&full[stage], phase);
-          w_full += clock64() - t0;
-        }
-        tc_fence_after();
-        if (elect_one()) {
-          // descriptor start-address field is (addr >> 4): slot stride and the 32 B K-advance are plain adds
-          const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * Cfg::kSub * (kATileBytes >> 4));
-          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * Cfg::kSub * (Cfg::kBTileBytes >> 4));
-#pragma unroll
-          for (int sub = 0; sub < Cfg::kSub; ++sub) {
-            if (sub < nsub) {
-#pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k) {
-                const uint64_t a = adesc + sub * (kATileBytes >> 4) + 2 * k;
-                const uint64_t b = bdesc + sub * (Cfg::kBTileBytes >> 4) + 2 * k;
-                if (CG == 2) umma_bf16_pair(tmem_d, a, b, idesc, (kb | sub | k) != 0);
-                else umma_bf16(tmem_d, a, b, idesc, (kb | sub | k) != 0);
-              }
-            }
-          }
-          if (CG == 2) {
-            umma_commit_pair(&empty[stage]);
-            if (kb + Cfg::kSub >= num_kb) umma_commit_pair(&tmem_full[acc]);
-          } else {
-            umma_commit(&empty[stage]);
-            if (kb + Cfg::kSub >= num_kb) umma_commit(&tmem_full[acc]);
-          }
-        }
-        __syncwarp();
-        if (++stage == num_stages) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
-    if (p.dbg_stats && lane == 0) {
-      p.dbg_stats[blockIdx.x * 12 + 2] = clock64() - t_begin;
-      p.dbg_stats[blockIdx.x * 12 + 3] = w_full;
-      p.dbg_stats[blockIdx.x * 12 + 4] = w_tmem;
-    }
-  } else if (warp_idx >= 4) {
-    // ------------------------------------------------------------ epilogue: 8 warps = 128 rows x 2 column halves
-    // TMEM -> registers -> (accumulator released) -> bias / SiLU / residual -> bf16 -> staging tile -> stg_full.
-    // The stores, the LayerNorm pass and the auxiliary-tile prefetch belong to warps 2-3 (below): these warps never
-    // wait for a TMA transfer they issued.
-    const int ew = warp_idx - 4;
-    const int q = ew & 3;       // TMEM lane quarter this warp may access (warp_idx % 4)
-    const int half = ew >> 2;   // column half
-    const int row = q * 32 + lane;
-    constexpr int kHalfCols = BN / 2;
-    constexpr int kChunks = kHalfCols / 32;  // 32-column chunks per warp (BN = 64: 1 ... BN = 256: 4)
-    const int col_base = half * kHalfCols;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    int it_local = 0;  // tiles processed by this CTA: staging tile it_local % 2 when double-buffered
-    long long w_tfull = 0, w_stg = 0, c_pass1 = 0, w_lnfull = 0, c_ln = 0;
-    const long long t_epi_begin = clock64();
-    // fused LayerNorm: warp `ew` normalises rows [16 ew, 16 ew + 16) of the staged tile
-    constexpr int kLPR = BN / 8;                  // lanes per row (8 channels = 16 B each)
-    constexpr int kRPI = (kLPR >= 32) ? 1 : 32 / kLPR;  // rows per warp iteration
-    static_assert(!LN || (kLPR == 8 || kLPR == 16 || kLPR == 32), "fused LayerNorm needs BN in {64, 128, 256}");
-    const int ln_chunk = lane % kLPR;             // 16 B chunk of the row this lane owns (channels 8 ln_chunk .. +8)
-    float ln_m[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) ln_m[e] = (LN && p.ln_mod) ? __ldg(p.ln_mod + (ln_chunk * 8 + e) % BN) : 0.f;
-
-
-    for (int tile = group_id; tile < num_tiles; tile += num_groups) {
-      const int nt = tile % p.num_n_tiles;
-      const int mt = (tile / p.num_n_tiles) * CG + rank;
-      int m = mt * kBlockM + row;
-      if (AR) {
+  // Roles by warpgroup.  Kernels with the fused LayerNorm run 16 warps (512 threads x 128 registers at launch) and
+  // re-split the register file per warpgroup (setmaxnreg at the top of each warpgroup's code region): producer /
+  // MMA / store warps 56, epilogue warps 168, LayerNorm warps 96.
+  if (warp_idx < 4) {
+    if constexpr (LN) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp_idx == 0) {
+      // ------------------------------------------------------------ TMA producer (every CTA loads its own rows)
+      int stage = 0;
+      uint32_t phase = 0;
+      int issued = 0;
+      long long w_empty = 0;
+      const long long t_begin = clock64();
+      for (int tile = group_id; AR && tile < num_tiles; tile += num_groups) {
+        const int nt = tile % p.num_n_tiles;
+        const int mt = (tile / p.num_n_tiles) * CG + rank;
         const int img = mt / p.tiles_per_img, tt = mt % p.tiles_per_img;
-        m = (img * p.img_h + (tt / p.tiles_w) * Cfg::kARTileH + (row >> 3)) * p.img_w + (tt % p.tiles_w) * Cfg::kARTileW +
-            (row & 7);
-      }
-      const bool valid = m < p.m_total;
-      {
-        const long long t0 = clock64();
-        mbar_wait(&tmem_full[acc], acc_phase);
-        w_tfull += clock64() - t0;
-      }
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col_base;
-      const int buf = two_bufs ? (it_local & 1) : 0;
-      const int use = two_bufs ? (it_local >> 1) : it_local;  // how often this staging tile has been used before
-      uint8_t* stg = stg0 + buf * Cfg::kStagingBytes;
-      uint8_t* stg_row = stg + row * 128;
-      // The accumulator is handed back to the MMA warp as soon as its last tcgen05.ld has landed in registers, before
-      // the epilogue math: the MMAs of the next tile but one only ever wait for TMEM reads.
-      auto release_acc = [&]() {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (CG == 2 && rank != 0) mbar_arrive_remote(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
-          else mbar_arrive(&tmem_empty[acc]);
-        }
-      };
-      // staging tile ready to be written: its auxiliary tile has landed, or its previous store has read it
-      auto wait_staging = [&]() {
-        if (!staged) return;
-        const long long t0 = clock64();
-        if (has_aux) mbar_wait(&res_full[buf], use & 1);
-        else mbar_wait(&stg_free[buf], (use & 1) ^ 1);
-        w_stg += clock64() - t0;
-      };
-      const long long t_p1 = clock64();
-      float s1 = 0.f, s2 = 0.f;
-      uint32_t va[32], vb[32];
-      if constexpr (kChunks <= 2) {
-        tmem_ld_32x32(taddr, va);
-        if (kChunks == 2) tmem_ld_32x32(taddr + 32, vb);
-        tmem_ld_wait();
-        release_acc();
-        wait_staging();
-        if (staged) epilogue_chunk_staged<LN>(p, va, nt * BN + col_base, col_base, stg_row, row, s1, s2);
-        else if constexpr (BN == 64) epilogue_chunk_direct(p, va, nt * BN + col_base, m, valid);
-        if (kChunks == 2) {
-          if (staged) epilogue_chunk_staged<LN>(p, vb, nt * BN + col_base + 32, col_base + 32, stg_row, row, s1, s2);
-          else if constexpr (BN == 64) epilogue_chunk_direct(p, vb, nt * BN + col_base + 32, m, valid);
-        }
-      } else {
-        // two register buffers: the tcgen05.ld of chunk i+1 is in flight while chunk i is processed
-        tmem_ld_32x32(taddr, va);
-        wait_staging();
-#pragma unroll
-        for (int c = 0; c < kChunks; ++c) {
-          tmem_ld_wait();
-          if (c + 1 < kChunks) tmem_ld_32x32(taddr + 32 * (c + 1), (c & 1) ? va : vb);
-          else release_acc();
-          const int col = col_base + 32 * c;
-          if (staged) epilogue_chunk_staged<LN>(p, (c & 1) ? vb : va, nt * BN + col, col, stg_row, row, s1, s2);
-        }
-      }
-      if (staged) {
-        if (LN) ln_stats[(buf * 2 + half) * kBlockM + row] = make_float2(s1, s2);
-        fence_proxy_async();  // generic-proxy writes of the tile -> visible to the TMA store
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&stg_full[buf]);
-      }
-      c_pass1 += clock64() - t_p1;
-      const long long t_ln0 = clock64();
-      if (LN) {
-        mbar_wait(&stg_full[buf], use & 1);  // every warp's columns of the tile and the row statistics are in place
-        w_lnfull += clock64() - t_ln0;
-        // ---- channel LayerNorm of the staged rows: y = (x + mod - mean) * inv with the row statistics the epilogue
-        //      warps summed (unbiased variance, model/nn.py:154,183); kLPR lanes write a row's C channels as one
-        //      contiguous segment (x4 when the output is 2x nearest-upsampled, model/nn.py:184)
-        const float2* st0 = ln_stats + (buf * 2 + 0) * kBlockM;
-        const float2* st1 = ln_stats + (buf * 2 + 1) * kBlockM;
-        int img = 0, th0 = 0, tw0 = 0;
-        if (AR) {
-          const int tt = mt % p.tiles_per_img;
-          img = mt / p.tiles_per_img;
-          th0 = (tt / p.tiles_w) * Cfg::kARTileH;
-          tw0 = (tt % p.tiles_w) * Cfg::kARTileW;
-        }
-        constexpr int kIters = 16 / kRPI;
-        constexpr int kBatch = kIters < 4 ? kIters : 4;
-#pragma unroll 1
-        for (int it0 = 0; it0 < kIters; it0 += kBatch) {
-          // loads of the whole batch, then the math, then the stores: the global stores alias the shared-memory
-          // loads as far as the compiler can tell and would otherwise serialise the rows
-          uint4 xr[kBatch];
-          float2 sa[kBatch], sb[kBatch];
-#pragma unroll
-          for (int bb = 0; bb < kBatch; ++bb) {
-            const int r = ew * 16 + (it0 + bb) * kRPI + lane / kLPR;
-            xr[bb] = ld_shared_v4(stg, static_cast<uint32_t>(ln_chunk >> 3) * kATileBytes + static_cast<uint32_t>(r) * 128u +
-                                           (static_cast<uint32_t>((ln_chunk & 7) ^ (r & 7)) << 4));
-            sa[bb] = st0[r];
-            sb[bb] = st1[r];
+        const int h0 = (tt / p.tiles_w) * Cfg::kARTileH, w0 = (tt % p.tiles_w) * Cfg::kARTileW;
+        for (int kb = 0; kb < 3 * p.cin_blocks; ++kb) {  // kb = cb * 3 + s
+          const int cb = kb / 3, s3 = kb - cb * 3;
+          {
+            const long long t0 = clock64();
+            mbar_wait(&empty[stage], phase ^ 1);
+            w_empty += clock64() - t0;
           }
-          uint4 yv[kBatch];
-          float invv[kBatch];
-#pragma unroll
-          for (int bb = 0; bb < kBatch; ++bb) {
-            const float sum = sa[bb].x + sb[bb].x, sq = sa[bb].y + sb[bb].y;
-            const float mean = sum * (1.0f / BN);
-            const float var = fmaxf(sq - sum * mean, 0.f) * (1.0f / (BN - 1));
-            const float inv = rsqrtf(var + p.ln_eps);
-            const float nmi = -mean * inv;
-            const uint32_t w[4] = {xr[bb].x, xr[bb].y, xr[bb].z, xr[bb].w};
-            uint32_t o4[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
-              const float y0 = fmaf(__low2float(h), inv, fmaf(ln_m[2 * j], inv, nmi));
-              const float y1 = fmaf(__high2float(h), inv, fmaf(ln_m[2 * j + 1], inv, nmi));
-              __nv_bfloat162 y = __floats2bfloat162_rn(y0, y1);
-              o4[j] = *reinterpret_cast<uint32_t*>(&y);
-            }
-            yv[bb] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
-            invv[bb] = inv;
-          }
-#pragma unroll
-          for (int bb = 0; bb < kBatch; ++bb) {
-            const int r = ew * 16 + (it0 + bb) * kRPI + lane / kLPR;
-            int hh, ww, nimg;  // output pixel of this row
-            if (AR) {
-              hh = th0 + (r >> 3);
-              ww = tw0 + (r & 7);
-              nimg = img;
+          if (elect_one()) {
+            const uint32_t full_bar = (CG == 2) ? mapa_shared(smem_u32(&full[stage]), 0) : smem_u32(&full[stage]);
+            uint8_t* sbase = smem + stage * Cfg::kARStageBytes;
+            if (p.dbg_skip_loads && issued >= num_stages) {
+              if (rank == 0) mbar_arrive(&full[stage]);
             } else {
-              const int mr = mt * kBlockM + r;
-              ww = mr % p.ln_W;
-              const int t = mr / p.ln_W;
-              hh = t % p.ln_H;
-              nimg = t / p.ln_H;
-            }
-            const long long pix = (static_cast<long long>(nimg) * p.ln_H + hh) * p.ln_W + ww;
-            if (pix < p.m_total) {
-              if (p.ln_inv != nullptr && ln_chunk == 0) p.ln_inv[pix] = invv[bb];
-              if (p.ln_up) {
-                const long long o00 = (static_cast<long long>(nimg) * 2 * p.ln_H + 2 * hh) * 2 * p.ln_W + 2 * ww;
-                __nv_bfloat16* dst = p.ln_out + o00 * BN + ln_chunk * 8;
-                *reinterpret_cast<uint4*>(dst) = yv[bb];
-                *reinterpret_cast<uint4*>(dst + BN) = yv[bb];
-                *reinterpret_cast<uint4*>(dst + 2ll * p.ln_W * BN) = yv[bb];
-                *reinterpret_cast<uint4*>(dst + (2ll * p.ln_W + 1) * BN) = yv[bb];
-              } else {
-                *reinterpret_cast<uint4*>(p.ln_out + pix * BN + ln_chunk * 8) = yv[bb];
+              if (rank == 0) mbar_arrive_expect_tx(&full[stage], CG * Cfg::kARStageBytes);
+              if (CG == 2) tma_load_4d_pair(&tmA, full_bar, sbase, cb * kBlockK, w0 + s3 - 1, h0 - 1, img);
+              else tma_load_4d(&tmA, &full[stage], sbase, cb * kBlockK, w0 + s3 - 1, h0 - 1, img);
+              for (int r = 0; r < 3; ++r) {
+                const int kk = (r * 3 + s3) * p.cin_blocks + cb;  // K block of tap (r, s) in the packed weights
+                uint8_t* bdst = sbase + Cfg::kARUnitBytes + r * Cfg::kBTileBytes;
+                if (CG == 2) tma_load_2d_pair(&tmB, full_bar, bdst, kk * kBlockK, nt * BN + rank * Cfg::kBRows);
+                else tma_load_2d(&tmB, &full[stage], bdst, kk * kBlockK, nt * BN);
               }
             }
           }
+          __syncwarp();
+          ++issued;
+          if (++stage == num_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ln_done[buf]);
-        c_ln += clock64() - t_ln0;
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-      ++it_local;
-    }
-    if (p.dbg_stats && threadIdx.x == 128) {
-      p.dbg_stats[blockIdx.x * 12 + 5] = clock64() - t_epi_begin;
-      p.dbg_stats[blockIdx.x * 12 + 6] = w_tfull;
-      p.dbg_stats[blockIdx.x * 12 + 7] = w_stg;
-      p.dbg_stats[blockIdx.x * 12 + 8] = c_pass1;
-      p.dbg_stats[blockIdx.x * 12 + 9] = w_lnfull;
-      p.dbg_stats[blockIdx.x * 12 + 10] = c_ln;
-    }
-  } else if (staged && warp_idx == 2) {
-    // ------------------------------------------------------------ warp 2: staging tile -> global
-    // TMA store of the finished tile and the prefetch of the auxiliary tile of the staging tile's next user; the
-    // epilogue warps never wait for a TMA transfer.
-    const bool leader = lane == 0;                // owns every bulk async-group of this CTA
-    auto box_coords = [&](int mt, int& c1, int& c2, int& c3) {
-      const int img = mt / p.tiles_per_img, tt = mt % p.tiles_per_img;
-      c1 = (tt % p.tiles_w) * Cfg::kARTileW;
-      c2 = (tt / p.tiles_w) * Cfg::kARTileH;
-      c3 = img;
-    };
-    auto prefetch_aux = [&](int tile, int buf) {  // leader only: staging[buf] <- aux[tile]
-      const int nt = tile % p.num_n_tiles;
-      const int mt = (tile / p.num_n_tiles) * CG + rank;
-      uint8_t* dst = stg0 + buf * Cfg::kStagingBytes;
-      mbar_arrive_expect_tx(&res_full[buf], Cfg::kStagingBytes);
-#pragma unroll
-      for (int b = 0; b < BN / 64; ++b) {
-        if (AR) {
-          int c1, c2, c3;
-          box_coords(mt, c1, c2, c3);
-          tma_load_4d(&tmOut, &res_full[buf], dst + b * kATileBytes, nt * BN + b * 64, c1, c2, c3);
+      for (int tile = group_id; !AR && tile < num_tiles; tile += num_groups) {
+        const int nt = tile % p.num_n_tiles;
+        const int mt = (tile / p.num_n_tiles) * CG + rank;
+        int b1, b2, b3;
+        if (p.taps == 9) {
+          b1 = 0;
+          b2 = (mt % p.tiles_per_img) * p.tile_h * p.stride;
+          b3 = (mt / p.tiles_per_img) * p.tile_n;
         } else {
-          tma_load_2d(&tmOut, &res_full[buf], dst + b * kATileBytes, nt * BN + b * 64, mt * kBlockM);
+          b1 = mt * kBlockM;
+          b2 = 0;
+          b3 = 0;
+        }
+        for (int kb = 0; kb < num_kb; kb += Cfg::kSub) {
+          const int nsub = (num_kb - kb) < Cfg::kSub ? (num_kb - kb) : Cfg::kSub;
+          {
+            const long long t0 = clock64();
+            mbar_wait(&empty[stage], phase ^ 1);
+            w_empty += clock64() - t0;
+          }
+          if (elect_one()) {
+            const uint32_t full_bar = (CG == 2) ? mapa_shared(smem_u32(&full[stage]), 0) : smem_u32(&full[stage]);
+            if (p.dbg_skip_loads && issued >= num_stages) {
+              if (rank == 0) mbar_arrive(&full[stage]);
+            } else {
+              if (rank == 0) mbar_arrive_expect_tx(&full[stage], CG * nsub * Cfg::kSubBytes);
+              for (int sub = 0; sub < nsub; ++sub) {
+                const int kk = kb + sub;
+                const int tap = kk / p.cin_blocks;
+                const int cb = kk - tap * p.cin_blocks;
+                const int dr = (p.taps == 9) ? tap / 3 - 1 : 0;
+                const int ds = (p.taps == 9) ? tap % 3 - 1 : 0;
+                const int slot = stage * Cfg::kSub + sub;
+                if (CG == 2) {
+                  tma_load_4d_pair(&tmA, full_bar, smA + slot * kATileBytes, cb * kBlockK, b1 + ds, b2 + dr, b3);
+                  tma_load_2d_pair(&tmB, full_bar, smB + slot * Cfg::kBTileBytes, kk * kBlockK,
+                                   nt * BN + rank * Cfg::kBRows);
+                } else {
+                  tma_load_4d(&tmA, &full[stage], smA + slot * kATileBytes, cb * kBlockK, b1 + ds, b2 + dr, b3);
+                  tma_load_2d(&tmB, &full[stage], smB + slot * Cfg::kBTileBytes, kk * kBlockK, nt * BN);
+                }
+              }
+            }
+          }
+          __syncwarp();
+          ++issued;
+          if (++stage == num_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
-    };
-    if (has_aux && leader) {  // two staging tiles: the auxiliary tile is prefetched two tiles ahead
-      if (group_id < num_tiles) prefetch_aux(group_id, 0);
-      if (group_id + num_groups < num_tiles) prefetch_aux(group_id + num_groups, 1);
-    }
-    int it_local = 0;
-    for (int tile = group_id; tile < num_tiles; tile += num_groups) {
-      const int nt = tile % p.num_n_tiles;
-      const int mt = (tile / p.num_n_tiles) * CG + rank;
-      const int buf = two_bufs ? (it_local & 1) : 0;
-      const int use = two_bufs ? (it_local >> 1) : it_local;
-      uint8_t* stg = stg0 + buf * Cfg::kStagingBytes;
-      mbar_wait(&stg_full[buf], use & 1);
-      if (leader) {
-#pragma unroll
+      if (p.dbg_stats && lane == 0) {
+        p.dbg_stats[blockIdx.x * 12 + 0] = clock64() - t_begin;
+        p.dbg_stats[blockIdx.x * 12 + 1] = w_empty;
+      }
+    } else if (warp_idx == 1 && rank == 0) {
+      // ------------------------------------------------------------ MMA issuer (leader CTA, one elected lane issues)
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * CG, BN);
+      const uint64_t adesc0 = umma_desc_kmajor_sw128(smem_u32(smA));
+      const uint64_t bdesc0 = umma_desc_kmajor_sw128(smem_u32(smB));
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      long long w_full = 0, w_tmem = 0;
+      const long long t_begin = clock64();
+      for (int tile = group_id; tile < num_tiles; tile += num_groups) {
+        {
+          const long long t0 = clock64();
+          mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+          w_tmem += clock64() - t0;
+        }
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; AR && kb < 3 * p.cin_blocks; ++kb) {
+          {
+            const long long t0 = clock64();
+            mbar_wait(&full[stage], phase);
+            w_full += clock64() - t0;
+          }
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (Cfg::kARStageBytes >> 4));
+            const uint64_t bdesc = adesc + static_cast<uint64_t>(Cfg::kARUnitBytes >> 4);
+  #pragma unroll
+            for (int r = 0; r < 3; ++r) {
+  #pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                // filter row r = the unit from its r-th pixel row on: + r * 8 rows * 128 B (keeps the swizzle phase)
+                const uint64_t a = adesc + r * ((Cfg::kARTileW * 128) >> 4) + 2 * k;
+                const uint64_t b = bdesc + r * (Cfg::kBTileBytes >> 4) + 2 * k;
+                if (CG == 2) umma_bf16_pair(tmem_d, a, b, idesc, (kb | r | k) != 0);
+                else umma_bf16(tmem_d, a, b, idesc, (kb | r | k) != 0);
+              }
+            }
+            if (CG == 2) {
+              umma_commit_pair(&empty[stage]);
+              if (kb + 1 >= 3 * p.cin_blocks) umma_commit_pair(&tmem_full[acc]);
+            } else {
+              umma_commit(&empty[stage]);
+              if (kb + 1 >= 3 * p.cin_blocks) umma_commit(&tmem_full[acc]);
+            }
+          }
+          __syncwarp();
+          if (++stage == num_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        for (int kb = 0; !AR && kb < num_kb; kb += Cfg::kSub) {
+          const int nsub = (num_kb - kb) < Cfg::kSub ? (num_kb - kb) : Cfg::kSub;
+          {
+            const long long t0 = clock64();
+            mbar_wait(&full[stage], phase);
+            w_full += clock64() - t0;
+          }
+          tc_fence_after();
+          if (elect_one()) {
+            // descriptor start-address field is (addr >> 4): slot stride and the 32 B K-advance are plain adds
+            const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * Cfg::kSub * (kATileBytes >> 4));
+            const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * Cfg::kSub * (Cfg::kBTileBytes >> 4));
+  #pragma unroll
+            for (int sub = 0; sub < Cfg::kSub; ++sub) {
+              if (sub < nsub) {
+  #pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  const uint64_t a = adesc + sub * (kATileBytes >> 4) + 2 * k;
+                  const uint64_t b = bdesc + sub * (Cfg::kBTileBytes >> 4) + 2 * k;
+                  if (CG == 2) umma_bf16_pair(tmem_d, a, b, idesc, (kb | sub | k) != 0);
+                  else umma_bf16(tmem_d, a, b, idesc, (kb | sub | k) != 0);
+                }
+              }
+            }
+            if (CG == 2) {
+              umma_commit_pair(&empty[stage]);
+              if (kb + Cfg::kSub >= num_kb) umma_commit_pair(&tmem_full[acc]);
+            } else {
+              umma_commit(&empty[stage]);
+              if (kb + Cfg::kSub >= num_kb) umma_commit(&tmem_full[acc]);
+            }
+          }
+          __syncwarp();
+          if (++stage == num_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      if (p.dbg_stats && lane == 0) {
+        p.dbg_stats[blockIdx.x * 12 + 2] = clock64() - t_begin;
+        p.dbg_stats[blockIdx.x * 12 + 3] = w_full;
+        p.dbg_stats[blockIdx.x * 12 + 4] = w_tmem;
+      }
+    } else if (staged && warp_idx == 2) {
+      // ------------------------------------------------------------ warp 2: staging tile -> global
+      // TMA store of the finished tile and the prefetch of the auxiliary tile of the staging tile's next user; the
+      // epilogue warps never wait for a TMA transfer.
+      const bool leader = lane == 0;                // owns every bulk async-group of this CTA
+      auto box_coords = [&](int mt, int& c1, int& c2, int& c3) {
+        const int img = mt / p.tiles_per_img, tt = mt % p.tiles_per_img;
+        c1 = (tt % p.tiles_w) * Cfg::kARTileW;
+        c2 = (tt / p.tiles_w) * Cfg::kARTileH;
+        c3 = img;
+      };
+      auto prefetch_aux = [&](int tile, int buf) {  // leader only: staging[buf] <- aux[tile]
+        const int nt = tile % p.num_n_tiles;
+        const int mt = (tile / p.num_n_tiles) * CG + rank;
+        uint8_t* dst = stg0 + buf * Cfg::kStagingBytes;
+        mbar_arrive_expect_tx(&res_full[buf], Cfg::kStagingBytes);
+  #pragma unroll
         for (int b = 0; b < BN / 64; ++b) {
           if (AR) {
             int c1, c2, c3;
             box_coords(mt, c1, c2, c3);
-            tma_store_4d(&tmOut, stg + b * kATileBytes, nt * BN + b * 64, c1, c2, c3);
+            tma_load_4d(&tmOut, &res_full[buf], dst + b * kATileBytes, nt * BN + b * 64, c1, c2, c3);
           } else {
-            tma_store_2d(&tmOut, stg + b * kATileBytes, nt * BN + b * 64, mt * kBlockM);
+            tma_load_2d(&tmOut, &res_full[buf], dst + b * kATileBytes, nt * BN + b * 64, mt * kBlockM);
           }
         }
-        bulk_commit();
+      };
+      if (has_aux && leader) {  // two staging tiles: the auxiliary tile is prefetched two tiles ahead
+        if (group_id < num_tiles) prefetch_aux(group_id, 0);
+        if (group_id + num_groups < num_tiles) prefetch_aux(group_id + num_groups, 1);
       }
-      // ---- the staging tile is free once the store has read it and every epilogue warp is done with its LayerNorm rows
-      if (LN) mbar_wait(&ln_done[buf], use & 1);
-      if (leader) {
-        bulk_wait_read_all();
-        const int next = tile + (two_bufs ? 2 : 1) * num_groups;  // this staging tile's next user
-        if (has_aux) {
-          if (next < num_tiles) prefetch_aux(next, buf);
-        } else {
-          mbar_arrive(&stg_free[buf]);
+      int it_local = 0;
+      for (int tile = group_id; tile < num_tiles; tile += num_groups) {
+        const int nt = tile % p.num_n_tiles;
+        const int mt = (tile / p.num_n_tiles) * CG + rank;
+        const int buf = two_bufs ? (it_local & 1) : 0;
+        const int use = two_bufs ? (it_local >> 1) : it_local;
+        uint8_t* stg = stg0 + buf * Cfg::kStagingBytes;
+        mbar_wait(&stg_full[buf], use & 1);
+        if (leader) {
+  #pragma unroll
+          for (int b = 0; b < BN / 64; ++b) {
+            if (AR) {
+              int c1, c2, c3;
+              box_coords(mt, c1, c2, c3);
+              tma_store_4d(&tmOut, stg + b * kATileBytes, nt * BN + b * 64, c1, c2, c3);
+            } else {
+              tma_store_2d(&tmOut, stg + b * kATileBytes, nt * BN + b * 64, mt * kBlockM);
+            }
+          }
+          bulk_commit();
         }
+        // ---- the staging tile is free once the store has read it and every epilogue warp is done with its LayerNorm rows
+        if (LN) mbar_wait(&ln_done[buf], use & 1);
+        if (leader) {
+          bulk_wait_read_all();
+          const int next = tile + (two_bufs ? 2 : 1) * num_groups;  // this staging tile's next user
+          if (has_aux) {
+            if (next < num_tiles) prefetch_aux(next, buf);
+          } else {
+            mbar_arrive(&stg_free[buf]);
+          }
+        }
+        ++it_local;
       }
-      ++it_local;
+      if (leader) bulk_wait_all();  // global writes of the last stores are complete before the CTA retires
     }
-    if (leader) bulk_wait_all();  // global writes of the last stores are complete before the CTA retires
+  } else if (warp_idx < 4 + kEpiWarps) {
+    if constexpr (LN) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    {
+      // ------------------------------------------------------------ epilogue: 8 warps = 128 rows x 2 column halves
+      // TMEM -> registers -> (accumulator released) -> bias / SiLU / residual -> bf16 -> staging tile -> stg_full.
+      // The stores, the LayerNorm pass and the auxiliary-tile prefetch belong to warps 2-3 (below): these warps never
+      // wait for a TMA transfer they issued.
+      const int ew = warp_idx - 4;
+      const int q = ew & 3;       // TMEM lane quarter this warp may access (warp_idx % 4)
+      const int half = ew >> 2;   // column half
+      const int row = q * 32 + lane;
+      constexpr int kHalfCols = BN / 2;
+      constexpr int kChunks = kHalfCols / 32;  // 32-column chunks per warp (BN = 64: 1 ... BN = 256: 4)
+      const int col_base = half * kHalfCols;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      int it_local = 0;  // tiles processed by this CTA: staging tile it_local % 2 when double-buffered
+      long long w_tfull = 0, w_stg = 0, c_pass1 = 0;
+      const long long t_epi_begin = clock64();
+      for (int tile = group_id; tile < num_tiles; tile += num_groups) {
+        const int nt = tile % p.num_n_tiles;
+        const int mt = (tile / p.num_n_tiles) * CG + rank;
+        int m = mt * kBlockM + row;
+        if (AR) {
+          const int img = mt / p.tiles_per_img, tt = mt % p.tiles_per_img;
+          m = (img * p.img_h + (tt / p.tiles_w) * Cfg::kARTileH + (row >> 3)) * p.img_w + (tt % p.tiles_w) * Cfg::kARTileW +
+              (row & 7);
+        }
+        const bool valid = m < p.m_total;
+        {
+          const long long t0 = clock64();
+          mbar_wait(&tmem_full[acc], acc_phase);
+          w_tfull += clock64() - t0;
+        }
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col_base;
+        const int buf = two_bufs ? (it_local & 1) : 0;
+        const int use = two_bufs ? (it_local >> 1) : it_local;  // how often this staging tile has been used before
+        uint8_t* stg = stg0 + buf * Cfg::kStagingBytes;
+        uint8_t* stg_row = stg + row * 128;
+        // The accumulator is handed back to the MMA warp as soon as its last tcgen05.ld has landed in registers, before
+        // the epilogue math: the MMAs of the next tile but one only ever wait for TMEM reads.
+        auto release_acc = [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 2 && rank != 0) mbar_arrive_remote(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+            else mbar_arrive(&tmem_empty[acc]);
+          }
+        };
+        // staging tile ready to be written: its auxiliary tile has landed, or its previous store has read it
+        auto wait_staging = [&]() {
+          if (!staged) return;
+          const long long t0 = clock64();
+          if (has_aux) mbar_wait(&res_full[buf], use & 1);
+          else mbar_wait(&stg_free[buf], (use & 1) ^ 1);
+          w_stg += clock64() - t0;
+        };
+        const long long t_p1 = clock64();
+        float s1 = 0.f, s2 = 0.f;
+        uint32_t va[32], vb[32];
+        if constexpr (kChunks <= 2) {
+          tmem_ld_32x32(taddr, va);
+          if (kChunks == 2) tmem_ld_32x32(taddr + 32, vb);
+          tmem_ld_wait();
+          release_acc();
+          wait_staging();
+          if (staged) epilogue_chunk_staged<LN>(p, va, nt * BN + col_base, col_base, stg_row, row, s1, s2);
+          else if constexpr (BN == 64) epilogue_chunk_direct(p, va, nt * BN + col_base, m, valid);
+          if (kChunks == 2) {
+            if (staged) epilogue_chunk_staged<LN>(p, vb, nt * BN + col_base + 32, col_base + 32, stg_row, row, s1, s2);
+            else if constexpr (BN == 64) epilogue_chunk_direct(p, vb, nt * BN + col_base + 32, m, valid);
+          }
+        } else {
+          // two register buffers: the tcgen05.ld of chunk i+1 is in flight while chunk i is processed
+          tmem_ld_32x32(taddr, va);
+          wait_staging();
+  #pragma unroll
+          for (int c = 0; c < kChunks; ++c) {
+            tmem_ld_wait();
+            if (c + 1 < kChunks) tmem_ld_32x32(taddr + 32 * (c + 1), (c & 1) ? va : vb);
+            else release_acc();
+            const int col = col_base + 32 * c;
+            if (staged) epilogue_chunk_staged<LN>(p, (c & 1) ? vb : va, nt * BN + col, col, stg_row, row, s1, s2);
+          }
+        }
+        if (staged) {
+          if (LN) ln_stats[(buf * 2 + half) * kBlockM + row] = make_float2(s1, s2);
+          fence_proxy_async();  // generic-proxy writes of the tile -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&stg_full[buf]);
+        }
+        c_pass1 += clock64() - t_p1;
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        ++it_local;
+      }
+      if (p.dbg_stats && threadIdx.x == 128) {
+        p.dbg_stats[blockIdx.x * 12 + 5] = clock64() - t_epi_begin;
+        p.dbg_stats[blockIdx.x * 12 + 6] = w_tfull;
+        p.dbg_stats[blockIdx.x * 12 + 7] = w_stg;
+        p.dbg_stats[blockIdx.x * 12 + 8] = c_pass1;
+      }
+    }
+  } else {
+    if constexpr (LN) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    if (LN && staged) {
+      // ------------------------------------------------------------ warps 12-15: fused channel LayerNorm
+      // Warp lw normalises rows [32 lw, 32 lw + 32) of every staged tile with the row statistics the epilogue warps
+      // summed, while those warps are already working on the next tile.
+      const int lw = warp_idx - (4 + kEpiWarps);
+      constexpr int kLPR = BN / 8;                  // lanes per row (8 channels = 16 B each)
+      constexpr int kRPI = (kLPR >= 32) ? 1 : 32 / kLPR;  // rows per warp iteration
+      static_assert(!LN || (kLPR == 8 || kLPR == 16 || kLPR == 32), "fused LayerNorm needs BN in {64, 128, 256}");
+      const int ln_chunk = lane % kLPR;             // 16 B chunk of the row this lane owns (channels 8 ln_chunk .. +8)
+      float ln_m[8];
+  #pragma unroll
+      for (int e = 0; e < 8; ++e) ln_m[e] = (LN && p.ln_mod) ? __ldg(p.ln_mod + (ln_chunk * 8 + e) % BN) : 0.f;
+
+
+      long long w_lnfull = 0, c_ln = 0;
+      int it_local = 0;
+      for (int tile = group_id; tile < num_tiles; tile += num_groups) {
+        const int mt = (tile / p.num_n_tiles) * CG + rank;
+        const int buf = two_bufs ? (it_local & 1) : 0;
+        const int use = two_bufs ? (it_local >> 1) : it_local;
+        uint8_t* stg = stg0 + buf * Cfg::kStagingBytes;
+        const long long t_ln0 = clock64();
+        if (LN) {
+          mbar_wait(&stg_full[buf], use & 1);  // every warp's columns of the tile and the row statistics are in place
+          w_lnfull += clock64() - t_ln0;
+          // ---- channel LayerNorm of the staged rows: y = (x + mod - mean) * inv with the row statistics the epilogue
+          //      warps summed (unbiased variance, model/nn.py:154,183); kLPR lanes write a row's C channels as one
+          //      contiguous segment (x4 when the output is 2x nearest-upsampled, model/nn.py:184)
+          const float2* st0 = ln_stats + (buf * 2 + 0) * kBlockM;
+          const float2* st1 = ln_stats + (buf * 2 + 1) * kBlockM;
+          int img = 0, th0 = 0, tw0 = 0;
+          if (AR) {
+            const int tt = mt % p.tiles_per_img;
+            img = mt / p.tiles_per_img;
+            th0 = (tt / p.tiles_w) * Cfg::kARTileH;
+            tw0 = (tt % p.tiles_w) * Cfg::kARTileW;
+          }
+          constexpr int kIters = 32 / kRPI;
+          constexpr int kBatch = kIters < 4 ? kIters : 4;
+  #pragma unroll 1
+          for (int it0 = 0; it0 < kIters; it0 += kBatch) {
+            // loads of the whole batch, then the math, then the stores: the global stores alias the shared-memory
+            // loads as far as the compiler can tell and would otherwise serialise the rows
+            uint4 xr[kBatch];
+            float2 sa[kBatch], sb[kBatch];
+  #pragma unroll
+            for (int bb = 0; bb < kBatch; ++bb) {
+              const int r = lw * 32 + (it0 + bb) * kRPI + lane / kLPR;
+              xr[bb] = ld_shared_v4(stg, static_cast<uint32_t>(ln_chunk >> 3) * kATileBytes + static_cast<uint32_t>(r) * 128u +
+                                             (static_cast<uint32_t>((ln_chunk & 7) ^ (r & 7)) << 4));
+              sa[bb] = st0[r];
+              sb[bb] = st1[r];
+            }
+            uint4 yv[kBatch];
+            float invv[kBatch];
+  #pragma unroll
+            for (int bb = 0; bb < kBatch; ++bb) {
+              const float sum = sa[bb].x + sb[bb].x, sq = sa[bb].y + sb[bb].y;
+              const float mean = sum * (1.0f / BN);
+              const float var = fmaxf(sq - sum * mean, 0.f) * (1.0f / (BN - 1));
+              const float inv = rsqrtf(var + p.ln_eps);
+              const float nmi = -mean * inv;
+              const uint32_t w[4] = {xr[bb].x, xr[bb].y, xr[bb].z, xr[bb].w};
+              uint32_t o4[4];
+  #pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+                const float y0 = fmaf(__low2float(h), inv, fmaf(ln_m[2 * j], inv, nmi));
+                const float y1 = fmaf(__high2float(h), inv, fmaf(ln_m[2 * j + 1], inv, nmi));
+                __nv_bfloat162 y = __floats2bfloat162_rn(y0, y1);
+                o4[j] = *reinterpret_cast<uint32_t*>(&y);
+              }
+              yv[bb] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+              invv[bb] = inv;
+            }
+  #pragma unroll
+            for (int bb = 0; bb < kBatch; ++bb) {
+              const int r = lw * 32 + (it0 + bb) * kRPI + lane / kLPR;
+              int hh, ww, nimg;  // output pixel of this row
+              if (AR) {
+                hh = th0 + (r >> 3);
+                ww = tw0 + (r & 7);
+                nimg = img;
+              } else {
+                const int mr = mt * kBlockM + r;
+                ww = mr % p.ln_W;
+                const int t = mr / p.ln_W;
+                hh = t % p.ln_H;
+                nimg = t / p.ln_H;
+              }
+              const long long pix = (static_cast<long long>(nimg) * p.ln_H + hh) * p.ln_W + ww;
+              if (pix < p.m_total) {
+                if (p.ln_inv != nullptr && ln_chunk == 0) p.ln_inv[pix] = invv[bb];
+                if (p.ln_up) {
+                  const long long o00 = (static_cast<long long>(nimg) * 2 * p.ln_H + 2 * hh) * 2 * p.ln_W + 2 * ww;
+                  __nv_bfloat16* dst = p.ln_out + o00 * BN + ln_chunk * 8;
+                  *reinterpret_cast<uint4*>(dst) = yv[bb];
+                  *reinterpret_cast<uint4*>(dst + BN) = yv[bb];
+                  *reinterpret_cast<uint4*>(dst + 2ll * p.ln_W * BN) = yv[bb];
+                  *reinterpret_cast<uint4*>(dst + (2ll * p.ln_W + 1) * BN) = yv[bb];
+                } else {
+                  *reinterpret_cast<uint4*>(p.ln_out + pix * BN + ln_chunk * 8) = yv[bb];
+                }
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ln_done[buf]);
+          c_ln += clock64() - t_ln0;
+        }
+        ++it_local;
+      }
+      if (p.dbg_stats && lane == 0 && lw == 0) {
+        p.dbg_stats[blockIdx.x * 12 + 9] = w_lnfull;
+        p.dbg_stats[blockIdx.x * 12 + 10] = c_ln;
+      }
+    }
   }
 
   tc_fence_before();
@@ -1018,7 +1047,7 @@ inline cudaError_t conv_launch_variant(const ConvLaunch& L, cudaStream_t stream)
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(L.grid);
-  cfg.blockDim = dim3(kConvThreads);
+  cfg.blockDim = dim3(kConvThreads + (LN ? kLnThreads : 0));
   cfg.dynamicSmemBytes = AR ? Cfg::ar_smem_bytes(p.num_staging) : Cfg::smem_bytes(p.num_staging);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
