@@ -276,8 +276,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   // direct (fp32 / compose) epilogues exist for the 64-wide tile only: the last conv of the UNet
   const bool staged = BN != 64 || (p.mode != EPI_COMPOSE && p.mode != EPI_F32);
   const bool has_aux = p.mode == EPI_BIAS_RES;  // TMA-prefetched residual tile, double-buffered
-  // two staging tiles used alternately (always with a residual tile; for narrow tiles also to take the TMA store's
-  // read of tile i off the critical path of tile i+1)
+  // two staging tiles used alternately (residual convs: the residual tile is prefetched two tiles ahead)
   const bool two_bufs = p.num_staging == 2;
 
   if (warp_idx == 0 && lane == 0) {
@@ -549,7 +548,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       };
       if (has_aux && leader) {  // two staging tiles: the auxiliary tile is prefetched two tiles ahead
         if (group_id < num_tiles) prefetch_aux(group_id, 0);
-        if (group_id + num_groups < num_tiles) prefetch_aux(group_id + num_groups, 1);
+        if (two_bufs && group_id + num_groups < num_tiles) prefetch_aux(group_id + num_groups, 1);
       }
       int it_local = 0;
       for (int tile = group_id; tile < num_tiles; tile += num_groups) {
@@ -1042,7 +1041,10 @@ inline cudaError_t conv_launch_variant(const ConvLaunch& L, cudaStream_t stream)
   ConvParams p = L.p;
   const bool staged = p.mode != EPI_COMPOSE && p.mode != EPI_F32;
   if (!staged && BN != 64) return cudaErrorInvalidValue;  // fp32 / compose epilogues: 64-wide tiles only
-  p.num_staging = (p.mode == EPI_BIAS_RES || (staged && BN <= 128)) ? 2 : 1;
+  // Two staging tiles only for residual convs with narrow tiles (the residual tile is prefetched two tiles ahead; wide
+  // tiles take long enough to prefetch one ahead into the single tile); everywhere else the shared memory is worth
+  // more as ring stages (G2: 1239 -> 1345 TFLOP/s with 4 instead of 3 activation-reuse stages).
+  p.num_staging = (p.mode == EPI_BIAS_RES && BN <= 128) ? 2 : 1;
   p.num_stages = AR ? Cfg::ar_stages_for(p.num_staging) : Cfg::stages_for(p.num_staging);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
