@@ -5,24 +5,31 @@
 //   M = pixels (n, h, w flattened, NHWC activations, bf16),
 //   N = output channels, K = taps * Cin  (k index = (r*3 + s) * Cin + c).
 //
-// Feeding:   A is never materialised.  For filter tap (r, s) the 128-pixel A tile (whole output rows)
+// Feeding:   A is never materialised.  Generic path: for filter tap (r, s) the 128-pixel A tile (whole output rows)
 //            is a SHIFTED BOX of the NHWC input: one 4-D TMA load {64 ch, W, tile_h, tile_n} at
-//            (c0, s-1, h0+r-1, n0); out-of-bounds rows/columns are zero-filled by the TMA unit,
-//            which is exactly padding=1 / padding_mode=zeros (configs/sda_unet.yml:16).  Stride-2 convs use
-//            the same box with element strides {1, 2, 2, 1}.
+//            (c0, s-1, h0+r-1, n0); out-of-bounds rows/columns are zero-filled by the TMA unit, which is exactly
+//            padding=1 / padding_mode=zeros (configs/sda_unet.yml:16).  Stride-2 convs use the same box with element
+//            strides {1, 2, 2, 1}.  Activation-reuse path (AR; stride-1 convs with 64/128-wide N tiles): the M tile is
+//            a 16 x 8 spatial block and ONE halo'd box [18 x 8 px][64 ch] per (channel block, filter column) serves
+//            the three filter rows as sub-views r * 8 rows into it.
 //            B (packed weights [Cout, 9*Cin], K-major) is a 2-D TMA load {64, BN}.
 //            Both land in 128B-swizzled K-major tiles that tcgen05.mma consumes directly.
-// Pipeline:  warp 0 = TMA producer, warp 1 = MMA issuer (single thread), warp 2 = TMEM allocator,
-//            warps 4..11 = epilogue.  STAGES-deep smem ring (full/empty mbarriers) and a
-//            double-buffered TMEM accumulator (tmem_full/tmem_empty) so the epilogue of tile i
-//            overlaps the main loop of tile i+1.  Persistent: grid = #SMs, static round-robin tiles.
-//            Optionally two CTAs (a cluster) share one MMA (cta_group::2, 256 x BN tile).
+// Roles:     warp 0 = TMA producer, warp 1 = MMA issuer (single thread), warp 2 = TMEM allocator + TMA stores of the
+//            finished tiles + residual prefetch, warps 4..11 = epilogue, warps 12..15 (fused-LayerNorm kernels only)
+//            = LayerNorm pass; the register file is re-split per warpgroup with setmaxnreg in those kernels.
+//            Persistent CTAs (grid = #SMs, static round-robin tiles), a ring of operand stages (full/empty
+//            mbarriers), two TMEM accumulators (tmem_full/tmem_empty; released as soon as the epilogue's tcgen05.ld
+//            have landed), staging tiles handed between epilogue, LayerNorm and store warps by mbarriers only.
+//            Two CTAs (a cluster) share one MMA (cta_group::2, 256 x BN tile) whenever there are two M tiles.
 // Epilogue:  TMEM -> registers (tcgen05.ld 32x32b.x32) -> +bias [-> SiLU | + residual] -> bf16 -> 128B-swizzled
-//            staging tile in shared memory -> TMA store (the L1 data pipe is what bounds this kernel: per-thread
-//            row stores cost 8x the wavefronts of the staged path, profiles/r01a_ncu_conv_G2.csv).  The residual
-//            tile is prefetched into the staging tile by TMA; the fused channel LayerNorm re-reads the staged
-//            row, normalises in place and stores a second tensor.  The last conv of the UNet writes fp32 /
-//            the fused window compose (src/thor/score.py:76-88,111-141) straight from registers.
+//            staging tile in shared memory -> TMA store (per-thread row stores cost 8x the L1 wavefronts of the
+//            staged path, profiles/r01a_ncu_conv_G2.csv).  The residual tile is TMA-prefetched into the staging tile;
+//            the fused channel LayerNorm re-reads the staged rows and writes a second tensor with coalesced stores.
+//            The last conv of the UNet (64-wide tile) writes fp32 / the fused window compose
+//            (src/thor/score.py:76-88,111-141) straight from registers.
+// What bounds it (profiles/r01d_k1_role_cycles.log, r01e_ncu_conv_G2.csv): L2 -> SM TMA throughput with streamed
+//            operands; with activation reuse the operand-ring depth (TMA latency) and the SM's L1/shared-memory
+//            data pipe (tensor-core operand reads + TMA writes + epilogue traffic).
 #pragma once
 #include <cuda_bf16.h>
 #include <stdio.h>
@@ -84,7 +91,6 @@ constexpr int kConvThreads = 128 + kEpiThreads;  // + kLnThreads in kernels with
 constexpr int kLnWarps = 4;                      // LayerNorm warps (one warpgroup) of those kernels
 constexpr int kLnThreads = kLnWarps * 32;
 constexpr int kSmemLimit = 232448;  // 227 KB
-constexpr int kEpiBarrier = 1;      // named barrier of the epilogue warps
 
 // BN   : N tile (output channels per tile).
 // CG   : CTAs per MMA (tcgen05 cta_group).  CG == 2: a cluster of two CTAs computes a 256 x BN tile, each CTA

@@ -565,6 +565,59 @@ def test_reference_snapshot_forward(dev, golden_dir):
     assert e < 3e-2
 
 
+def test_driver_flow_from_snapshot(dev, golden_dir):
+    """The hot-path lines of exp/downscaling.py:_run_impl, in order, on the reference-pickled snapshot fixture:
+    pickle.load -> markov order from dataset_kwargs (:110-118) -> net.eval() (:125) -> A = AvgPool2d(s)(x[::t]) closure
+    (:129-132) -> BatchedScoreFunction(...) (:208-214) -> condition_on(A=, y=, std=[1,C,1,1], gamma=, exact_grad=False)
+    (:236-242) -> pipeline.sample(score_fn, noise (CPU), steps=, corrections=, tau=) (:254-261) -> .float().cpu().numpy().
+    The same flow through the oracle on the snapshot's (fp16) weights is the ground truth."""
+    import pickle
+
+    import climate2weather_b200.compat as compat
+    compat.install()
+    from thor.score import BatchedScoreFunction  # resolves to this package, as in the driver
+
+    with open(golden_dir / "snapshot_tiny.pkl", "rb") as f:
+        snapshot_data = pickle.load(f)
+    markov_window = snapshot_data["dataset_kwargs"]["train"]["window"]
+    markov_order = markov_window // 2
+    pipeline = snapshot_data["pipeline"]
+    net = snapshot_data["ema"].to(dev)
+    net.eval()
+    t_step, s_step = 2, 4
+    pool = torch.nn.AvgPool2d(s_step, stride=s_step, padding=0)
+
+    def A(x):
+        return pool(x[..., ::t_step, :, :, :])
+
+    g = torch.Generator().manual_seed(17)
+    L, C, H, W = 9, 4, 16, 16
+    truth = torch.randn(L, C, H, W, generator=g)
+    y = A(truth)
+    std = torch.tensor(STD).reshape(1, C, 1, 1)
+    score_function = BatchedScoreFunction(net, markov_order=markov_order, noise_process=pipeline, batch_size=4,
+                                          device=dev)
+    score_function.condition_on(A=A, y=y, std=std, gamma=GAMMA, exact_grad=False)
+    noise = torch.randn(L, C, H, W, generator=g)
+    out = pipeline.sample(score_function, noise, steps=5, corrections=0, tau=0.5, show_progressbar=False)
+    out_np = out.to(torch.float32).cpu().numpy()
+    assert out_np.shape == (L, C, H, W) and np.isfinite(out_np).all()
+    # ground truth: oracle network on the snapshot's weights, oracle guidance and sampler
+    cfg = dict(channels=12, embedding_dim=64, hidden_channels=(64, 64), hidden_blocks=(1, 1), attention_levels=(1,),
+               kernel_size=3)
+    ref = unet_ref.RefNet({k: v.float().cpu() for k, v in net.state_dict().items()}, cfg)
+
+    def guided(xx, tt):
+        with torch.no_grad():
+            eps = score_ref.window_score(ref, xx, tt, markov_order, batch_size=4)
+        return score_ref.guided_score_closed_form(eps, xx, tt, y, std, GAMMA, t_step, s_step)
+
+    want = pipeline_ref.RefPipeline().sample(guided, noise, steps=5, corrections=0, tau=0.5)
+    e = relerr(out, want)
+    print(f"\ndriver flow (snapshot -> guided sampling) rel-err vs oracle: {e:.3e}")
+    assert e < 5e-2
+
+
 # ------------------------------------------------------------------------------------------------ VJP (exact_grad)
 @pytest.mark.parametrize("C", [64, 128, 384, 512])
 @pytest.mark.parametrize("down", [0, 1])
