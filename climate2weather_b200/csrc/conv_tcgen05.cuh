@@ -1037,12 +1037,15 @@ inline bool conv_launch_set_ln(ConvLaunch* L, __nv_bfloat16* ln_out, const float
 template <int BN, int CG, bool LN, bool AR>
 inline cudaError_t conv_launch_variant(const ConvLaunch& L, cudaStream_t stream) {
   using Cfg = ConvCfg<BN, CG>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  // the attribute is per device: remember which devices of this process have it
+  static unsigned long long attr_done = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_done >> (dev & 63)) & 1ull)) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<BN, CG, LN, AR>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    attr_done |= 1ull << (dev & 63);
   }
   ConvParams p = L.p;
   const bool staged = p.mode != EPI_COMPOSE && p.mode != EPI_F32;

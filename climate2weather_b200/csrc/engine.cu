@@ -235,6 +235,19 @@ int launch_ln_bwd(const bf16* gy, const bf16* y, const float* inv, const bf16* g
 }
 
 // scratch: fp32 [2][n][T][T] (P and gS)
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: set it once per (kernel, device) of this process
+template <typename K>
+int ensure_smem(K kernel, size_t smem, unsigned long long* done) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((*done >> (dev & 63)) & 1ull)) {
+    C2W_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    *done |= 1ull << (dev & 63);
+  }
+  (void)smem;
+  return C2W_OK;
+}
+
 int launch_attention_bwd(const bf16* qkv, const bf16* go, bf16* gqkv, float* scratch, int n, int T, int C,
                          cudaStream_t st) {
   C2W_REQUIRE(T % 8 == 0 && C % 8 == 0 && scratch, "attention backward: T %% 8 and C %% 8 must be 0 (T=%d C=%d)", T, C);
@@ -242,17 +255,10 @@ int launch_attention_bwd(const bf16* qkv, const bf16* go, bf16* gqkv, float* scr
   const size_t smem1 = attention_bwd_scores_smem(T, C, QB), smem2 = attention_bwd_grads_smem(T, C, QB);
   C2W_REQUIRE(std::max(smem1, smem2) <= static_cast<size_t>(kSmemLimit),
               "attention backward: T=%d C=%d needs %zu B of shared memory", T, C, std::max(smem1, smem2));
-  static size_t conf1 = 0, conf2 = 0;
-  if (smem1 > conf1) {
-    C2W_CUDA(cudaFuncSetAttribute(attention_bwd_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem1)));
-    conf1 = smem1;
-  }
-  if (smem2 > conf2) {
-    C2W_CUDA(cudaFuncSetAttribute(attention_bwd_grads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem2)));
-    conf2 = smem2;
-  }
+  static unsigned long long done1 = 0, done2 = 0;
+  int rc = ensure_smem(attention_bwd_scores_kernel, smem1, &done1);
+  if (rc) return rc;
+  if ((rc = ensure_smem(attention_bwd_grads_kernel, smem2, &done2))) return rc;
   float* Pm = scratch;
   float* gSm = scratch + static_cast<size_t>(n) * T * T;
   const float scale2 = 1.0f / sqrtf(static_cast<float>(C));
@@ -268,11 +274,9 @@ template <int QB>
 int launch_attention_qb(const bf16* qkv, bf16* out, int n, int T, int C, cudaStream_t st) {
   const size_t smem = attention_smem_bytes(T, C, QB);
   C2W_REQUIRE(smem <= static_cast<size_t>(kSmemLimit), "attention: T=%d C=%d needs %zu B of shared memory", T, C, smem);
-  static size_t configured = 0;
-  if (smem > configured) {
-    C2W_CUDA(cudaFuncSetAttribute(attention_kernel<QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
-  }
+  static unsigned long long done = 0;
+  int rc = ensure_smem(attention_kernel<QB>, smem, &done);
+  if (rc) return rc;
   dim3 grid((T + QB - 1) / QB, n);
   attention_kernel<QB><<<grid, kAttnThreads, smem, st>>>(qkv, out, T, C, 1.0f / sqrtf(static_cast<float>(C)));
   C2W_CUDA(cudaGetLastError());
@@ -282,12 +286,9 @@ int launch_attention_qb(const bf16* qkv, bf16* out, int n, int T, int C, cudaStr
 template <int C>
 int launch_attention_mma(const bf16* qkv, bf16* out, int n, cudaStream_t st) {
   const size_t smem = attention_mma_smem_bytes(C);
-  static bool configured = false;
-  if (!configured) {
-    C2W_CUDA(cudaFuncSetAttribute(attention_mma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem)));
-    configured = true;
-  }
+  static unsigned long long done = 0;
+  int rc = ensure_smem(attention_mma_kernel<C>, smem, &done);
+  if (rc) return rc;
   attention_mma_kernel<C><<<n, 256, smem, st>>>(qkv, out, 1.0f / sqrtf(static_cast<float>(C)));
   C2W_CUDA(cudaGetLastError());
   return C2W_OK;
