@@ -304,6 +304,37 @@ def test_unet_forward_small_vs_oracle(dev):
     assert e < 3e-2
 
 
+@pytest.mark.parametrize("cfg,H,W,n", [
+    (dict(channels=12, embedding_dim=64, hidden_channels=(64, 192), hidden_blocks=(2, 1), attention_levels=()), 32, 64, 3),
+    (dict(channels=36, embedding_dim=128, hidden_channels=(128, 256, 320), hidden_blocks=(1, 1, 2), attention_levels=(2,)),
+     32, 32, 2),
+    (dict(channels=52, embedding_dim=64, hidden_channels=(64, 64, 64, 128), hidden_blocks=(1, 1, 1, 1),
+          attention_levels=(3,)), 64, 64, 5),
+    (dict(channels=20, embedding_dim=64, hidden_channels=(128,), hidden_blocks=(3,), attention_levels=()), 16, 128, 7),
+])
+def test_unet_forward_other_architectures(dev, cfg, H, W, n):
+    """Architectures and patch shapes other than the two fixtures (non-square patches, channel counts that map to
+    the 64/128/192/256-wide tiles, attention at different depths, odd window counts): forward and input-VJP against
+    the fp32 oracle."""
+    import climate2weather_b200 as c2w
+    cfg = dict(cfg, kernel_size=3)
+    torch.manual_seed(H + W + n)
+    net = c2w.ScoreUNet(**cfg)
+    ref = unet_ref.RefNet({k: v.detach().clone() for k, v in net.state_dict().items()}, cfg)
+    net = net.to(dev)
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, cfg["channels"], H, W, generator=g)
+    gout = torch.randn(n, cfg["channels"], H, W, generator=g)
+    t = torch.tensor(0.45)
+    want_out, want_gin = _autograd_vjp(ref, x, t, gout)
+    with torch.no_grad():
+        got = net(x.to(dev), t)
+    assert relerr(got, want_out) < 3e-2
+    eng = net.engine(cfg["channels"], 1, H, W, dev, max_windows=n, vjp=True)
+    out, gin = eng.unet_vjp(x.to(dev), 0.45, gout.to(dev))
+    assert relerr(out, want_out) < 3e-2 and relerr(gin, want_gin) < 5e-2
+
+
 def test_unet_forward_full_vs_golden(dev, golden_dir):
     """configs/sda_unet.yml architecture, seed-0 weights, one window: against the REFERENCE's own output slice."""
     import climate2weather_b200 as c2w
