@@ -56,6 +56,12 @@ struct ConvParams {
   int tile_h, tile_n, tiles_per_img;
   int tiles_w;      // AR: 16 x 8 spatial tiles per image row (W / 8); tiles_per_img = (H / 16) * tiles_w
   int img_h, img_w; // AR: output image size
+  // AR on 8-row images (ar2): the 16 x 8 M tile is two images stacked row-interleaved — tile row = (image row, image,
+  // pixel) — so that filter row r is still one contiguous sub-view of the halo'd unit ([10 rows][2 img][8 px][64 ch],
+  // 20 KB): the tensor maps list the image dimension BEFORE the row dimension.  tiles_per_img = tiles per image pair.
+  int ar2;
+  int ar_row_step16;  // (bytes >> 4) from filter row r to r + 1 inside the unit: 64 (ar2: 128)
+  int ar_tx_bytes;    // bytes one CTA's loads of a stage deliver
   int num_stages;   // depth of the A/B ring
   int num_staging;  // epilogue staging tiles (2: used alternately)
   // epilogue
@@ -117,7 +123,8 @@ struct ConvCfg {
   // K block instead of 16 KB.  (K1 with streamed operands is bound by the chip-wide L2 -> SM TMA throughput,
   // ~12 TB/s: profiles/r01c_*.)
   static constexpr int kARTileH = 16, kARTileW = 8;
-  static constexpr int kARUnitBytes = (kARTileH + 2) * kARTileW * kBlockK * 2;  // 18 KB
+  // unit slot: 18 KB; 20 KB for 128-wide tiles, which also run the two-image form (ConvParams::ar2)
+  static constexpr int kARUnitBytes = (BN == 128 ? 20 : 18) * kARTileW * kBlockK * 2;
   static constexpr int kARStageBytes = kARUnitBytes + 3 * kBTileBytes;
   static constexpr int ar_stages_for(int num_staging) {
     const int n = (kSmemLimit - 1024 - kBarrierBytes - num_staging * kStagingBytes) / kARStageBytes;
@@ -350,9 +357,10 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             if (p.dbg_skip_loads && issued >= num_stages) {
               if (rank == 0) mbar_arrive(&full[stage]);
             } else {
-              if (rank == 0) mbar_arrive_expect_tx(&full[stage], CG * Cfg::kARStageBytes);
-              if (CG == 2) tma_load_4d_pair(&tmA, full_bar, sbase, cb * kBlockK, w0 + s3 - 1, h0 - 1, img);
-              else tma_load_4d(&tmA, &full[stage], sbase, cb * kBlockK, w0 + s3 - 1, h0 - 1, img);
+              if (rank == 0) mbar_arrive_expect_tx(&full[stage], CG * p.ar_tx_bytes);
+              const int a2 = p.ar2 ? 2 * img : h0 - 1, a3 = p.ar2 ? -1 : img;
+              if (CG == 2) tma_load_4d_pair(&tmA, full_bar, sbase, cb * kBlockK, w0 + s3 - 1, a2, a3);
+              else tma_load_4d(&tmA, &full[stage], sbase, cb * kBlockK, w0 + s3 - 1, a2, a3);
               for (int r = 0; r < 3; ++r) {
                 const int kk = (r * 3 + s3) * p.cin_blocks + cb;  // K block of tap (r, s) in the packed weights
                 uint8_t* bdst = sbase + Cfg::kARUnitBytes + r * Cfg::kBTileBytes;
@@ -444,6 +452,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
+        const uint32_t ar_row_step = static_cast<uint32_t>(p.ar_row_step16);
         for (int kb = 0; AR && kb < 3 * p.cin_blocks; ++kb) {
           {
             const long long t0 = clock64();
@@ -459,7 +468,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   #pragma unroll
               for (int k = 0; k < kBlockK / 16; ++k) {
                 // filter row r = the unit from its r-th pixel row on: + r * 8 rows * 128 B (keeps the swizzle phase)
-                const uint64_t a = adesc + r * ((Cfg::kARTileW * 128) >> 4) + 2 * k;
+                const uint64_t a = adesc + r * ar_row_step + 2 * k;
                 const uint64_t b = bdesc + r * (Cfg::kBTileBytes >> 4) + 2 * k;
                 if (CG == 2) umma_bf16_pair(tmem_d, a, b, idesc, (kb | r | k) != 0);
                 else umma_bf16(tmem_d, a, b, idesc, (kb | r | k) != 0);
@@ -533,8 +542,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       auto box_coords = [&](int mt, int& c1, int& c2, int& c3) {
         const int img = mt / p.tiles_per_img, tt = mt % p.tiles_per_img;
         c1 = (tt % p.tiles_w) * Cfg::kARTileW;
-        c2 = (tt / p.tiles_w) * Cfg::kARTileH;
-        c3 = img;
+        c2 = (tt / p.tiles_w) * Cfg::kARTileH;  // ar2: 0
+        c3 = p.ar2 ? 2 * img : img;             // ar2: first of the tile's two images
       };
       auto prefetch_aux = [&](int tile, int buf) {  // leader only: staging[buf] <- aux[tile]
         const int nt = tile % p.num_n_tiles;
@@ -546,7 +555,12 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           if (AR) {
             int c1, c2, c3;
             box_coords(mt, c1, c2, c3);
-            tma_load_4d(&tmOut, &res_full[buf], dst + b * kATileBytes, nt * BN + b * 64, c1, c2, c3);
+            if (p.ar2) {
+              tma_load_4d(&tmOut, &res_full[buf], dst + b * kATileBytes, nt * BN + b * 64, c1, c2, c3);
+              tma_load_4d(&tmOut, &res_full[buf], dst + b * kATileBytes + kATileBytes / 2, nt * BN + b * 64, c1, c2, c3 + 1);
+            } else {
+              tma_load_4d(&tmOut, &res_full[buf], dst + b * kATileBytes, nt * BN + b * 64, c1, c2, c3);
+            }
           } else {
             tma_load_2d(&tmOut, &res_full[buf], dst + b * kATileBytes, nt * BN + b * 64, mt * kBlockM);
           }
@@ -571,6 +585,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               int c1, c2, c3;
               box_coords(mt, c1, c2, c3);
               tma_store_4d(&tmOut, stg + b * kATileBytes, nt * BN + b * 64, c1, c2, c3);
+              if (p.ar2) tma_store_4d(&tmOut, stg + b * kATileBytes + kATileBytes / 2, nt * BN + b * 64, c1, c2, c3 + 1);
             } else {
               tma_store_2d(&tmOut, stg + b * kATileBytes, nt * BN + b * 64, mt * kBlockM);
             }
@@ -619,6 +634,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           const int img = mt / p.tiles_per_img, tt = mt % p.tiles_per_img;
           m = (img * p.img_h + (tt / p.tiles_w) * Cfg::kARTileH + (row >> 3)) * p.img_w + (tt % p.tiles_w) * Cfg::kARTileW +
               (row & 7);
+          if (p.ar2)
+            m = ((2 * img + ((row >> 3) & 1)) * p.img_h + (row >> 4)) * p.img_w + tt * Cfg::kARTileW + (row & 7);
         }
         const bool valid = m < p.m_total;
         {
@@ -631,7 +648,9 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int buf = two_bufs ? (it_local & 1) : 0;
         const int use = two_bufs ? (it_local >> 1) : it_local;  // how often this staging tile has been used before
         uint8_t* stg = stg0 + buf * Cfg::kStagingBytes;
-        uint8_t* stg_row = stg + row * 128;
+        // ar2: the staging tile is kept image-major ([img][row][px]) so that each image is one plain TMA box
+        const int srow = (AR && p.ar2) ? (((row >> 3) & 1) << 6) + ((row >> 4) << 3) + (row & 7) : row;
+        uint8_t* stg_row = stg + srow * 128;
         // The accumulator is handed back to the MMA warp as soon as its last tcgen05.ld has landed in registers, before
         // the epilogue math: the MMAs of the next tile but one only ever wait for TMEM reads.
         auto release_acc = [&]() {
@@ -916,6 +935,9 @@ inline void conv_set_grid(ConvLaunch* L, int num_sms) {
 //  conv3x3: x is NHWC [n_img, H, W, cin] bf16 (cin % 64 == 0); stride 1: output [n_img, H, W], stride 2: output
 //           [n_img, H/2, W/2] (pad 1 either way)
 //  gemm   : x is [m, k] bf16 row-major (k % 64 == 0) with m = n_img * H * W
+// Images the activation-reuse main loop can tile: 16 x 8 pixel blocks.
+inline bool conv_ar_geometry_ok(int H, int W) { return (H % 16 == 0 || H == 8) && W % 8 == 0; }
+
 // variant: -1 = pick; else bit 0 = CTA pair (cta_group::2), bit 2 = activation-reuse main loop
 inline bool conv_launch_init(ConvLaunch* L, bool is_conv3x3, const __nv_bfloat16* x, int n_img, int H, int W, int cin,
                              const __nv_bfloat16* w_packed, int cout_pad, int bn, int num_sms, int stride = 1,
@@ -965,9 +987,28 @@ inline bool conv_launch_init(ConvLaunch* L, bool is_conv3x3, const __nv_bfloat16
       p.tiles_per_img = (H / 16) * p.tiles_w;
       p.img_h = H;
       p.img_w = W;
+      p.ar_row_step16 = (8 * 128) >> 4;
+      const int b_bytes = 3 * (bn / L->cg) * kBlockK * 2;
+      p.ar_tx_bytes = 18 * 8 * kBlockK * 2 + b_bytes;
       const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)n_img};
       const uint32_t box[4] = {(uint32_t)kBlockK, 8u, 18u, 1u};
       if (!make_tmap_bf16(&L->tmA, x, 4, dims, box)) return false;
+    } else if (want_ar && stride == 1 && bn == 128 && L->cg == 2 && H == 8 && W % 8 == 0 && n_img >= 2) {
+      // two 8-row images per M tile, image dimension inside the row dimension (see ConvParams::ar2)
+      L->ar = 1;
+      p.ar2 = 1;
+      p.tiles_w = W / 8;
+      p.tiles_per_img = p.tiles_w;
+      p.num_m_tiles = ((n_img + 1) / 2) * p.tiles_w;
+      p.img_h = H;
+      p.img_w = W;
+      p.ar_row_step16 = (2 * 8 * 128) >> 4;
+      p.ar_tx_bytes = 10 * 2 * 8 * kBlockK * 2 + 3 * (bn / L->cg) * kBlockK * 2;
+      const uint64_t row_b = (uint64_t)W * cin * 2;
+      const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)n_img, (uint64_t)H};
+      const uint64_t strides[3] = {(uint64_t)cin * 2, row_b * H, row_b};
+      const uint32_t box[4] = {(uint32_t)kBlockK, 8u, 2u, 10u};
+      if (!make_tmap_bf16(&L->tmA, x, 4, dims, box, nullptr, strides)) return false;
     } else {
       if (variant >= 0 && (variant & 4)) return false;  // AR was requested explicitly but does not apply
       const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)n_img};
@@ -997,9 +1038,9 @@ inline bool conv_launch_init(ConvLaunch* L, bool is_conv3x3, const __nv_bfloat16
 // Tensor map of a bf16 [M, cout_pad] epilogue tensor: rows of 128 pixels, or (AR) 16 x 8 spatial blocks of the
 // [n, H, W, cout_pad] view of the same memory.
 inline bool conv_make_epi_map(const ConvLaunch* L, CUtensorMap* m, const void* ptr) {
-  if (L->ar) {
+  if (L->ar) {  // ar2: one 8 x 8 box per image (the staging tile is image-major)
     const uint64_t dims[4] = {(uint64_t)L->cout_pad, (uint64_t)L->Wo, (uint64_t)L->Ho, (uint64_t)L->n_img};
-    const uint32_t box[4] = {64u, 8u, 16u, 1u};
+    const uint32_t box[4] = {64u, 8u, L->p.ar2 ? 8u : 16u, 1u};
     return make_tmap_bf16(m, ptr, 4, dims, box);
   }
   const uint64_t dims[2] = {(uint64_t)L->cout_pad, (uint64_t)L->p.m_total};
@@ -1015,7 +1056,7 @@ inline bool conv_launch_set_out(ConvLaunch* L, __nv_bfloat16* out) {
 // Whether this launch can also emit the channel LayerNorm of its output (one N tile = all channels of a pixel).
 inline bool conv_launch_can_ln(const ConvLaunch* L, int upsample) {
   const ConvParams& p = L->p;
-  if (L->ln || p.num_n_tiles != 1 || !(L->bn == 64 || L->bn == 128 || L->bn == 256)) return false;
+  if (L->ln || p.ar2 || p.num_n_tiles != 1 || !(L->bn == 64 || L->bn == 128 || L->bn == 256)) return false;
   if (!(p.mode == EPI_BIAS || p.mode == EPI_BIAS_RES)) return false;
   if (upsample && p.taps != 9) return false;
   return true;
@@ -1106,6 +1147,42 @@ inline int conv_pick_bn(int cout_pad) {
   if (cout_pad % 192 == 0) return 192;
   if (cout_pad % 128 == 0) return 128;
   return 64;
+}
+
+// N-tile width for one conv of the UNet.  Below 256 output channels one tile holds a whole pixel.  From 256 up the
+// choice is made on the number of WAVES the persistent grid needs — ceil(pair tiles / CTA pairs) * BN, weighted by
+// the measured per-flop cost of each main loop with a full grid (tools/bringup_conv.py --tiles, 156 windows:
+// activation reuse with 128-wide tiles ~1540 TFLOP/s, 256-wide streamed ~1470, 192-wide streamed ~1340, 128-wide
+// streamed ~1110).  E.g. 16x16x384: 5 waves of 192 (94 us) -> 7 waves of 128 with activation reuse (69 us); 8x8x512:
+// 2 waves of 256 (55 us) -> 3 waves of 128 in the two-image form (41 us).  A 256-channel conv whose output feeds a
+// LayerNorm is rebuilt with one 256-wide tile by the engine (the fused normalisation needs the whole pixel).
+inline int conv_pick_bn_tiled(int cout_pad, bool is_conv3x3, int n_img, int H, int W, int stride, int num_sms) {
+  static int policy = -1;
+  if (policy < 0) {
+    const char* e = getenv("C2W_BN_POLICY");
+    policy = e ? atoi(e) : 1;
+  }
+  if (policy == 0 || cout_pad < 256) return conv_pick_bn(cout_pad);
+  const long long m_tiles = (static_cast<long long>(n_img) * (H / stride) * (W / stride) + kBlockM - 1) / kBlockM;
+  if (m_tiles < 2) return conv_pick_bn(cout_pad);
+  const bool ar = is_conv3x3 && stride == 1 && conv_ar_geometry_ok(H, W);
+  const long long pairs = num_sms / 2 > 0 ? num_sms / 2 : 1;
+  int best = 0;
+  double best_cost = 0.0;
+  const int cand[4] = {256, 192, 128, 64};
+  for (int bn : cand) {
+    if (cout_pad % bn != 0) continue;
+    const bool bn_ar = ar && (bn == 128 || (bn == 64 && H != 8));
+    const double per_flop = bn_ar ? (bn == 128 ? 1.0 : 1.35) : (bn == 256 ? 1.05 : bn == 192 ? 1.15 : bn == 128 ? 1.39 : 1.9);
+    const long long groups = ((m_tiles + 1) / 2) * (cout_pad / bn);
+    const long long waves = (groups + pairs - 1) / pairs;
+    const double cost = static_cast<double>(waves) * bn * per_flop;
+    if (best == 0 || cost < best_cost - 1e-9) {
+      best = bn;
+      best_cost = cost;
+    }
+  }
+  return best ? best : conv_pick_bn(cout_pad);
 }
 
 }  // namespace c2w

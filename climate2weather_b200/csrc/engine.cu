@@ -55,6 +55,17 @@ struct Op {
   ConvLaunch conv;
   int pix_per_img = 0;
   bool is_final = false;
+  // what the launch was built from (the LayerNorm fusion may rebuild it with one N tile per pixel)
+  struct ConvSpec {
+    bool c3 = false;
+    const bf16* in = nullptr;
+    int H = 0, W = 0, cin = 0;
+    const bf16* wts = nullptr;
+    const float* bias = nullptr;
+    int cout_pad = 0, mode = 0;
+    bf16* out = nullptr;
+    int stride = 1;
+  } spec;
   // layernorm (forward: in -> out [+ inv]; backward: in = g_y, aux = y stash, res = incoming gradient or null)
   const bf16* in = nullptr;
   bf16* out = nullptr;
@@ -431,9 +442,20 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
 
   // H, W: INPUT image size; stride 2 halves it (heads of levels > 0, model/nn.py:169-176)
   auto make_conv = [&](Op* op, bool c3, const bf16* in, int H, int W, int cin, const bf16* wts, const float* bias,
-                       int cout_pad, int mode, bf16* out, bool is_final, int stride) -> int {
+                       int cout_pad, int mode, bf16* out, bool is_final, int stride, int bn_force = 0) -> int {
     op->kind = OP_CONV;
-    const int bn = conv_pick_bn(cout_pad);
+    op->spec.c3 = c3;
+    op->spec.in = in;
+    op->spec.H = H;
+    op->spec.W = W;
+    op->spec.cin = cin;
+    op->spec.wts = wts;
+    op->spec.bias = bias;
+    op->spec.cout_pad = cout_pad;
+    op->spec.mode = mode;
+    op->spec.out = out;
+    op->spec.stride = stride;
+    const int bn = bn_force ? bn_force : conv_pick_bn_tiled(cout_pad, c3, n, H, W, stride, h->sms);
     if (!conv_launch_init(&op->conv, c3, in, n, H, W, cin, wts, cout_pad, bn, h->sms, stride))
       return fail(C2W_ERR_INVALID, "cannot build conv launch (n=%d H=%d W=%d cin=%d cout=%d stride=%d) %s", n, H, W, cin,
                   cout_pad, stride, tmap_error_slot());
@@ -471,6 +493,15 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
     if (!real) return;
     if (h->fuse_ln && !per_t && !P.ops.empty()) {
       Op& prev = P.ops.back();
+      if (prev.kind == OP_CONV && !prev.is_final && prev.conv.out_ptr == in && prev.conv.cout_pad == C &&
+          prev.conv.p.num_n_tiles != 1 && (C == 128 || C == 256)) {
+        // the tile picker split this layer for a fuller last wave; the fused LayerNorm is worth more than that
+        Op whole;
+        const Op::ConvSpec& sp = prev.spec;
+        if (make_conv(&whole, sp.c3, sp.in, sp.H, sp.W, sp.cin, sp.wts, sp.bias, sp.cout_pad, sp.mode, sp.out, false,
+                      sp.stride, C) == C2W_OK && conv_launch_can_ln(&whole.conv, upf))
+          prev = whole;
+      }
       if (prev.kind == OP_CONV && !prev.is_final && prev.conv.out_ptr == in && prev.conv.cout_pad == C &&
           conv_launch_can_ln(&prev.conv, upf) &&
           conv_launch_set_ln(&prev.conv, out, mod_off >= 0 ? mods + mod_off : nullptr, upf)) {

@@ -173,6 +173,26 @@ def test_conv3x3_kernel_variants(lib, dev, variant, n, H, W, cin, cout, mode):
     assert relerr(got.float()[:, :cout], ref) < (1e-4 if mode == 4 else 2 ** -7)
 
 
+@pytest.mark.parametrize("n,H,W,cin,cout,mode", [
+    (6, 8, 8, 512, 512, 1), (5, 8, 8, 128, 256, 2), (4, 8, 16, 64, 128, 0), (3, 8, 8, 192, 384, 2),
+    (7, 16, 16, 384, 384, 1), (2, 16, 16, 512, 384, 2), (3, 32, 32, 256, 256, 1)])
+def test_conv3x3_activation_reuse_wide_and_two_image_tiles(lib, dev, n, H, W, cin, cout, mode):
+    """Activation reuse with 128-wide N tiles on layers wider than one tile (several N tiles per M tile), and its
+    two-image form on 8-row images (tile row = (image row, image, pixel); odd image counts leave half a tile out of
+    range) against the streamed single-CTA kernel's reference."""
+    g, xb, w, b, wp, bp = _conv_problem(dev, n, H, W, cin, cout, 13 * n + cout)
+    M = n * H * W
+    res = torch.randn(M, wp.shape[0], generator=g).to(dev).to(torch.bfloat16)
+    got, _ = _conv_ex(lib, xb, wp, bp, mode, n, H, W, res=res, variant=5, bn=128)
+    ref = F.conv2d(xb[..., :cin].float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), b, padding=1)
+    if mode == 1:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 3, 1).reshape(M, cout)
+    if mode == 2:
+        ref = ref + res[:, :cout].float()
+    assert relerr(got.float()[:, :cout], ref) < 2 ** -7
+
+
 @pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("n,H,W,cin,cout", [(2, 128, 128, 128, 128), (3, 64, 64, 128, 256), (3, 32, 32, 256, 384),
                                             (5, 16, 16, 384, 512), (1, 16, 32, 64, 64)])

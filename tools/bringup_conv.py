@@ -172,6 +172,20 @@ def main():
     if "--only-g2" in sys.argv:  # short run for `ncu --set full -k regex:conv_gemm`
         timeit("G2", 32, 128, 128, 128, 128, iters=5, cudnn=False)
         return 0
+    if "--tiles" in sys.argv:  # N-tile choice per level at the real window count (conv_pick_bn_tiled's cost model)
+        n = 156
+        for res in (False, True):
+            r = " res" if res else ""
+            for name, H, C, cases in (("L2 32x32x256", 32, 256, ((256, 1), (128, 5), (128, 1))),
+                                      ("L3 16x16x384", 16, 384, ((192, 1), (128, 5), (128, 1))),
+                                      ("L4 8x8x512", 8, 512, ((256, 1), (128, 5), (128, 1), (256, 0)))):
+                for bn, var in cases:
+                    timeit(f"{name} bn{bn} v{var}{r}", n, H, H, C, C, variant=var, bn=bn, res=res, cudnn=False)
+        timeit("L3 16x16 512->384 bn192 v1", n, 16, 16, 512, 384, variant=1, bn=192, cudnn=False)
+        timeit("L3 16x16 512->384 bn128 v5", n, 16, 16, 512, 384, variant=5, bn=128, cudnn=False)
+        timeit("L2 32x32 384->256 bn256 v1", n, 32, 32, 384, 256, variant=1, bn=256, cudnn=False)
+        timeit("L2 32x32 384->256 bn128 v5", n, 32, 32, 384, 256, variant=5, bn=128, cudnn=False)
+        return 0
     ok = True
     ok &= check_gemm("gemm-basic", 256, 128, 128)
     ok &= check_gemm("gemm-k512-n256", 384, 512, 256)
