@@ -354,14 +354,18 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           if (elect_one()) {
             const uint32_t full_bar = (CG == 2) ? mapa_shared(smem_u32(&full[stage]), 0) : smem_u32(&full[stage]);
             uint8_t* sbase = smem + stage * Cfg::kARStageBytes;
-            if (p.dbg_skip_loads && issued >= num_stages) {
+            if (p.dbg_skip_loads == 1 && issued >= num_stages) {
               if (rank == 0) mbar_arrive(&full[stage]);
             } else {
-              if (rank == 0) mbar_arrive_expect_tx(&full[stage], CG * p.ar_tx_bytes);
+              // timing experiment (dbg_skip_loads == 2): every other tile reuses stale weights — the operand traffic
+              // of a 256-row M tile sharing one B load, without its data flow
+              const bool skip_b = p.dbg_skip_loads == 2 && ((tile / num_groups) & 1) && issued >= num_stages;
+              if (rank == 0)
+                mbar_arrive_expect_tx(&full[stage], CG * (p.ar_tx_bytes - (skip_b ? 3 * Cfg::kBTileBytes : 0)));
               const int a2 = p.ar2 ? 2 * img : h0 - 1, a3 = p.ar2 ? -1 : img;
               if (CG == 2) tma_load_4d_pair(&tmA, full_bar, sbase, cb * kBlockK, w0 + s3 - 1, a2, a3);
               else tma_load_4d(&tmA, &full[stage], sbase, cb * kBlockK, w0 + s3 - 1, a2, a3);
-              for (int r = 0; r < 3; ++r) {
+              for (int r = 0; r < 3 && !skip_b; ++r) {
                 const int kk = (r * 3 + s3) * p.cin_blocks + cb;  // K block of tap (r, s) in the packed weights
                 uint8_t* bdst = sbase + Cfg::kARUnitBytes + r * Cfg::kBTileBytes;
                 if (CG == 2) tma_load_2d_pair(&tmB, full_bar, bdst, kk * kBlockK, nt * BN + rank * Cfg::kBRows);
@@ -399,7 +403,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
           if (elect_one()) {
             const uint32_t full_bar = (CG == 2) ? mapa_shared(smem_u32(&full[stage]), 0) : smem_u32(&full[stage]);
-            if (p.dbg_skip_loads && issued >= num_stages) {
+            if (p.dbg_skip_loads == 1 && issued >= num_stages) {
               if (rank == 0) mbar_arrive(&full[stage]);
             } else {
               if (rank == 0) mbar_arrive_expect_tx(&full[stage], CG * nsub * Cfg::kSubBytes);

@@ -172,6 +172,12 @@ def main():
     if "--only-g2" in sys.argv:  # short run for `ncu --set full -k regex:conv_gemm`
         timeit("G2", 32, 128, 128, 128, 128, iters=5, cudnn=False)
         return 0
+    if "--halfb" in sys.argv:  # what would a 256-row M tile sharing one weight load buy?  (timing only)
+        for sk in (0, 2, 0, 2):
+            timeit(f"G2 cg2+AR skip={sk}", 32, 128, 128, 128, 128, variant=5, skip_loads=sk, cudnn=False)
+            timeit(f"G2 cg2+AR res skip={sk}", 32, 128, 128, 128, 128, variant=5, skip_loads=sk, res=True, cudnn=False)
+            timeit(f"G2 cg2+AR res+LN skip={sk}", 32, 128, 128, 128, 128, variant=5, skip_loads=sk, ln=True, cudnn=False)
+        return 0
     if "--tiles" in sys.argv:  # N-tile choice per level at the real window count (conv_pick_bn_tiled's cost model)
         n = 156
         for res in (False, True):
