@@ -10,5 +10,5 @@ timeout 600 python bench.py --steps 16 --warmup 3 > $OUT/bench_$TAG.log 2>&1; ec
 timeout 600 python bench.py --steps 4 --warmup 3 --exact-grad --no-cpu > $OUT/bench_exact_$TAG.log 2>&1; echo "bench exact exit=$?"; tail -1 $OUT/bench_exact_$TAG.log | cut -c1-400
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --profile --steps 1 --warmup 1 > $OUT/ncu_launches_$TAG.log 2>&1; echo "ncu launches exit=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_gemm_tcgen05 -s 4 -c 2 -f -o $OUT/prof_conv_$TAG \
-    python tools/bringup_conv.py --only-g2 > $OUT/ncu_conv_$TAG.log 2>&1; echo "ncu conv exit=$?"
+[ -n "$SKIP_NCU_FULL" ] || { timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_gemm_tcgen05 -s 4 -c 2 -f -o $OUT/prof_conv_$TAG \
+    python tools/bringup_conv.py --only-g2 > $OUT/ncu_conv_$TAG.log 2>&1; echo "ncu conv exit=$?"; }
