@@ -1097,7 +1097,8 @@ inline cudaError_t conv_launch_variant(const ConvLaunch& L, cudaStream_t stream)
   if (!staged && BN != 64) return cudaErrorInvalidValue;  // fp32 / compose epilogues: 64-wide tiles only
   // Two staging tiles only for residual convs with narrow tiles (the residual tile is prefetched two tiles ahead; wide
   // tiles take long enough to prefetch one ahead into the single tile); everywhere else the shared memory is worth
-  // more as ring stages (G2: 1239 -> 1345 TFLOP/s with 4 instead of 3 activation-reuse stages).
+  // more as ring stages (G2: 1239 -> 1345 TFLOP/s with 4 instead of 3 activation-reuse stages).  Residual convs with
+  // ONE staging tile and a 4-deep ring were measured too: residual 1215 -> 1187, residual + LayerNorm 1050 -> 860.
   p.num_staging = (p.mode == EPI_BIAS_RES && BN <= 128) ? 2 : 1;
   p.num_stages = AR ? Cfg::ar_stages_for(p.num_staging) : Cfg::stages_for(p.num_staging);
   cudaLaunchConfig_t cfg;

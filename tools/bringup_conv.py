@@ -172,6 +172,12 @@ def main():
     if "--only-g2" in sys.argv:  # short run for `ncu --set full -k regex:conv_gemm`
         timeit("G2", 32, 128, 128, 128, 128, iters=5, cudnn=False)
         return 0
+    if "--res" in sys.argv:  # residual convs only 
+        for _ in range(2):
+            timeit("G2 cg2+AR res", 32, 128, 128, 128, 128, variant=5, res=True, cudnn=False)
+            timeit("G2 cg2+AR res+LN", 32, 128, 128, 128, 128, variant=5, ln=True, cudnn=False)
+            timeit("G5 cg2+AR res+LN", 64, 64, 64, 128, 128, variant=5, ln=True, cudnn=False)
+        return 0
     if "--halfb" in sys.argv:  # what would a 256-row M tile sharing one weight load buy?  (timing only)
         for sk in (0, 2, 0, 2):
             timeit(f"G2 cg2+AR skip={sk}", 32, 128, 128, 128, 128, variant=5, skip_loads=sk, cudnn=False)
