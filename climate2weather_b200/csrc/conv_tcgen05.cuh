@@ -193,6 +193,8 @@ __device__ __forceinline__ void epilogue_chunk_direct(const ConvParams& p, const
 // Staged epilogue of one 32-column chunk: bf16 result into the 128B-swizzled staging tile, in place over the
 // TMA-prefetched residual tile in EPI_BIAS_RES.  `stg_row` = this row in box 0 of the tile.  LN: also accumulates the
 // row's LayerNorm statistics (sums of v = out + mod and v^2 over this thread's columns).
+// (Packed fp32 pairs — FADD2 / FFMA2 via __fadd2_rn / __ffma2_rn — were tried for this function: 5 % fewer SASS
+// instructions, no measurable change: the epilogue is bound by latency, not by issue slots.)
 template <bool LN>
 __device__ __forceinline__ void epilogue_chunk_staged(const ConvParams& p, const uint32_t (&v)[32], int gcol, int col,
                                                       uint8_t* stg_row, int row, float& s1, float& s2) {
@@ -359,11 +361,16 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             } else {
               // timing experiment (dbg_skip_loads == 2): every other tile reuses stale weights — the operand traffic
               // of a 256-row M tile sharing one B load, without its data flow
-              const bool skip_b = p.dbg_skip_loads == 2 && ((tile / num_groups) & 1) && issued >= num_stages;
+              // (3: no weight loads at all, 4: no activation loads at all — which latency does the ring cover?)
+              const bool skip_b = ((p.dbg_skip_loads == 2 && ((tile / num_groups) & 1)) || p.dbg_skip_loads == 3) &&
+                                  issued >= num_stages;
+              const bool skip_a = p.dbg_skip_loads == 4 && issued >= num_stages;
               if (rank == 0)
-                mbar_arrive_expect_tx(&full[stage], CG * (p.ar_tx_bytes - (skip_b ? 3 * Cfg::kBTileBytes : 0)));
+                mbar_arrive_expect_tx(&full[stage], CG * (p.ar_tx_bytes - (skip_b ? 3 * Cfg::kBTileBytes : 0) -
+                                                          (skip_a ? p.ar_tx_bytes - 3 * Cfg::kBTileBytes : 0)));
               const int a2 = p.ar2 ? 2 * img : h0 - 1, a3 = p.ar2 ? -1 : img;
-              if (CG == 2) tma_load_4d_pair(&tmA, full_bar, sbase, cb * kBlockK, w0 + s3 - 1, a2, a3);
+              if (skip_a) {
+              } else if (CG == 2) tma_load_4d_pair(&tmA, full_bar, sbase, cb * kBlockK, w0 + s3 - 1, a2, a3);
               else tma_load_4d(&tmA, &full[stage], sbase, cb * kBlockK, w0 + s3 - 1, a2, a3);
               for (int r = 0; r < 3 && !skip_b; ++r) {
                 const int kk = (r * 3 + s3) * p.cin_blocks + cb;  // K block of tap (r, s) in the packed weights

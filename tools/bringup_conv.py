@@ -178,6 +178,12 @@ def main():
             timeit("G2 cg2+AR res+LN", 32, 128, 128, 128, 128, variant=5, ln=True, cudnn=False)
             timeit("G5 cg2+AR res+LN", 64, 64, 64, 128, 128, variant=5, ln=True, cudnn=False)
         return 0
+    if "--which" in sys.argv:  # residual convs (3-deep ring): drop the weight loads (3) or the activation loads (4)
+        for sk in (0, 3, 4, 1):
+            timeit(f"G2 cg2+AR res skip={sk}", 32, 128, 128, 128, 128, variant=5, skip_loads=sk, res=True, cudnn=False)
+            timeit(f"G2 cg2+AR res+LN skip={sk}", 32, 128, 128, 128, 128, variant=5, skip_loads=sk, ln=True, cudnn=False)
+            timeit(f"G2 cg2+AR skip={sk}", 32, 128, 128, 128, 128, variant=5, skip_loads=sk, cudnn=False)
+        return 0
     if "--halfb" in sys.argv:  # what would a 256-row M tile sharing one weight load buy?  (timing only)
         for sk in (0, 2, 0, 2):
             timeit(f"G2 cg2+AR skip={sk}", 32, 128, 128, 128, 128, variant=5, skip_loads=sk, cudnn=False)
