@@ -264,7 +264,9 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                          const __grid_constant__ CUtensorMap tmOut, const ConvParams p) {
   using Cfg = ConvCfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024 B alignment by POINTER arithmetic (an integer round trip hides the address space from the compiler and
+  // every staging-tile access becomes a generic LD/ST with 64-bit address math instead of LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int num_stages = p.num_stages;
   uint8_t* smA = smem;
   uint8_t* smB = smem + num_stages * Cfg::kSub * kATileBytes;  // (AR: stages are [A unit][B r0][B r1][B r2])
@@ -758,15 +760,37 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           //      contiguous segment (x4 when the output is 2x nearest-upsampled, model/nn.py:184)
           const float2* st0 = ln_stats + (buf * 2 + 0) * kBlockM;
           const float2* st1 = ln_stats + (buf * 2 + 1) * kBlockM;
-          int img = 0, th0 = 0, tw0 = 0;
+          // Output addressing, strength-reduced (this warp shares an issue port with two epilogue warps: every
+          // instruction here is taken from them).  Row r of the tile -> element offset from a per-tile base:
+          //   AR    : 16 x 8 block: ((r >> 3) * W' + (r & 7) * px) * BN     (W', px doubled when upsampled)
+          //   rows  : plain [M, C] rows: r * BN  (the upsampled form of these tiles keeps the general path below)
+          const bool fast = AR || !p.ln_up;
+          __nv_bfloat16* tile_out = p.ln_out + ln_chunk * 8;
+          long long tile_pix = 0;   // pixel index of tile row 0 (ln_inv, validity)
+          int row_pitch = 0, px_pitch = BN;  // elements per image row / per pixel inside the tile
+          bool tile_valid = true;
           if (AR) {
-            const int tt = mt % p.tiles_per_img;
-            img = mt / p.tiles_per_img;
-            th0 = (tt / p.tiles_w) * Cfg::kARTileH;
-            tw0 = (tt % p.tiles_w) * Cfg::kARTileW;
+            const int tt = mt % p.tiles_per_img, img = mt / p.tiles_per_img;
+            const int th0 = (tt / p.tiles_w) * Cfg::kARTileH, tw0 = (tt % p.tiles_w) * Cfg::kARTileW;
+            tile_pix = (static_cast<long long>(img) * p.ln_H + th0) * p.ln_W + tw0;
+            tile_valid = tile_pix < p.m_total;
+            if (p.ln_up) {
+              tile_out += ((static_cast<long long>(img) * 2 * p.ln_H + 2 * th0) * 2 * p.ln_W + 2 * tw0) * BN;
+              row_pitch = 4 * p.ln_W * BN;
+              px_pitch = 2 * BN;
+            } else {
+              tile_out += tile_pix * BN;
+              row_pitch = p.ln_W * BN;
+            }
+          } else {
+            tile_pix = static_cast<long long>(mt) * kBlockM;
+            tile_out += tile_pix * BN;
           }
+          const int up_row = 2 * p.ln_W * BN;  // upsampled output: one output row further down
           constexpr int kIters = 32 / kRPI;
           constexpr int kBatch = kIters < 4 ? kIters : 4;
+          const int rlane = lw * 32 + lane / kLPR;
+          const uint32_t cbox = static_cast<uint32_t>(ln_chunk >> 3) * kATileBytes;
   #pragma unroll 1
           for (int it0 = 0; it0 < kIters; it0 += kBatch) {
             // loads of the whole batch, then the math, then the stores: the global stores alias the shared-memory
@@ -775,9 +799,9 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             float2 sa[kBatch], sb[kBatch];
   #pragma unroll
             for (int bb = 0; bb < kBatch; ++bb) {
-              const int r = lw * 32 + (it0 + bb) * kRPI + lane / kLPR;
-              xr[bb] = ld_shared_v4(stg, static_cast<uint32_t>(ln_chunk >> 3) * kATileBytes + static_cast<uint32_t>(r) * 128u +
-                                             (static_cast<uint32_t>((ln_chunk & 7) ^ (r & 7)) << 4));
+              const int r = rlane + (it0 + bb) * kRPI;
+              xr[bb] = ld_shared_v4(stg, cbox + static_cast<uint32_t>(r) * 128u +
+                                             (static_cast<uint32_t>((ln_chunk ^ r) & 7) << 4));
               sa[bb] = st0[r];
               sb[bb] = st1[r];
             }
@@ -794,42 +818,50 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               uint32_t o4[4];
   #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
-                const float y0 = fmaf(__low2float(h), inv, fmaf(ln_m[2 * j], inv, nmi));
-                const float y1 = fmaf(__high2float(h), inv, fmaf(ln_m[2 * j + 1], inv, nmi));
+                // bf16 pair -> fp32: low half shifted up, high half masked
+                const float x0 = __uint_as_float(w[j] << 16), x1 = __uint_as_float(w[j] & 0xffff0000u);
+                const float y0 = fmaf(x0, inv, fmaf(ln_m[2 * j], inv, nmi));
+                const float y1 = fmaf(x1, inv, fmaf(ln_m[2 * j + 1], inv, nmi));
                 __nv_bfloat162 y = __floats2bfloat162_rn(y0, y1);
                 o4[j] = *reinterpret_cast<uint32_t*>(&y);
               }
               yv[bb] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
               invv[bb] = inv;
             }
+            if (fast) {
   #pragma unroll
-            for (int bb = 0; bb < kBatch; ++bb) {
-              const int r = lw * 32 + (it0 + bb) * kRPI + lane / kLPR;
-              int hh, ww, nimg;  // output pixel of this row
-              if (AR) {
-                hh = th0 + (r >> 3);
-                ww = tw0 + (r & 7);
-                nimg = img;
-              } else {
-                const int mr = mt * kBlockM + r;
-                ww = mr % p.ln_W;
-                const int t = mr / p.ln_W;
-                hh = t % p.ln_H;
-                nimg = t / p.ln_H;
+              for (int bb = 0; bb < kBatch; ++bb) {
+                const int r = rlane + (it0 + bb) * kRPI;
+                const int eo = AR ? (r >> 3) * row_pitch + (r & 7) * px_pitch : r * BN;
+                const bool ok = AR ? tile_valid : (tile_pix + r < p.m_total);
+                if (ok) {
+                  if (p.ln_inv != nullptr && ln_chunk == 0)
+                    p.ln_inv[tile_pix + (AR ? (r >> 3) * p.ln_W + (r & 7) : r)] = invv[bb];
+                  __nv_bfloat16* dst = tile_out + eo;
+                  *reinterpret_cast<uint4*>(dst) = yv[bb];
+                  if (AR && p.ln_up) {
+                    *reinterpret_cast<uint4*>(dst + BN) = yv[bb];
+                    *reinterpret_cast<uint4*>(dst + up_row) = yv[bb];
+                    *reinterpret_cast<uint4*>(dst + up_row + BN) = yv[bb];
+                  }
+                }
               }
-              const long long pix = (static_cast<long long>(nimg) * p.ln_H + hh) * p.ln_W + ww;
-              if (pix < p.m_total) {
-                if (p.ln_inv != nullptr && ln_chunk == 0) p.ln_inv[pix] = invv[bb];
-                if (p.ln_up) {
+            } else {
+  #pragma unroll
+              for (int bb = 0; bb < kBatch; ++bb) {  // upsampled output of a row tile: pixel coordinates by division
+                const int r = rlane + (it0 + bb) * kRPI;
+                const int mr = mt * kBlockM + r;
+                const int ww = mr % p.ln_W;
+                const int t = mr / p.ln_W;
+                const int hh = t % p.ln_H, nimg = t / p.ln_H;
+                if (mr < p.m_total) {
+                  if (p.ln_inv != nullptr && ln_chunk == 0) p.ln_inv[mr] = invv[bb];
                   const long long o00 = (static_cast<long long>(nimg) * 2 * p.ln_H + 2 * hh) * 2 * p.ln_W + 2 * ww;
                   __nv_bfloat16* dst = p.ln_out + o00 * BN + ln_chunk * 8;
                   *reinterpret_cast<uint4*>(dst) = yv[bb];
                   *reinterpret_cast<uint4*>(dst + BN) = yv[bb];
-                  *reinterpret_cast<uint4*>(dst + 2ll * p.ln_W * BN) = yv[bb];
-                  *reinterpret_cast<uint4*>(dst + (2ll * p.ln_W + 1) * BN) = yv[bb];
-                } else {
-                  *reinterpret_cast<uint4*>(p.ln_out + pix * BN + ln_chunk * 8) = yv[bb];
+                  *reinterpret_cast<uint4*>(dst + up_row) = yv[bb];
+                  *reinterpret_cast<uint4*>(dst + up_row + BN) = yv[bb];
                 }
               }
             }

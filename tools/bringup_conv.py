@@ -178,6 +178,11 @@ def main():
             timeit("G2 cg2+AR res+LN", 32, 128, 128, 128, 128, variant=5, ln=True, cudnn=False)
             timeit("G5 cg2+AR res+LN", 64, 64, 64, 128, 128, variant=5, ln=True, cudnn=False)
         return 0
+    if "--lnfloor" in sys.argv:  # role counters of the LayerNorm conv with and without operand loads (use --stats)
+        for sk in (0, 1):
+            timeit(f"G2 cg2+AR res skip={sk}", 32, 128, 128, 128, 128, variant=5, skip_loads=sk, res=True, cudnn=False)
+            timeit(f"G2 cg2+AR res+LN skip={sk}", 32, 128, 128, 128, 128, variant=5, skip_loads=sk, ln=True, cudnn=False)
+        return 0
     if "--which" in sys.argv:  # residual convs (3-deep ring): drop the weight loads (3) or the activation loads (4)
         for sk in (0, 3, 4, 1):
             timeit(f"G2 cg2+AR res skip={sk}", 32, 128, 128, 128, 128, variant=5, skip_loads=sk, res=True, cudnn=False)
