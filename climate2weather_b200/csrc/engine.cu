@@ -1178,6 +1178,37 @@ int c2w_traj_unpack(const float* fhwc, float* nchw, int64_t frames, int32_t C, i
   return C2W_OK;
 }
 
+int c2w_normalize_pack(const float* src, float* fhwc, int64_t frames, int32_t C, int32_t hw, int32_t clhw,
+                       const float* shift, const float* scale, int32_t field, void* stream) {
+  C2W_REQUIRE(src && fhwc && shift && scale && frames >= 1 && C >= 1 && hw >= 1, "c2w_normalize_pack: bad argument");
+  const int grid = grid_for(frames * hw, 256, c2w_num_sms());
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool vec = C == 4 && hw % 4 == 0 && (reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(fhwc) |
+                                             reinterpret_cast<uintptr_t>(shift) | reinterpret_cast<uintptr_t>(scale)) % 16 == 0;
+  if (vec)
+    normalize_pack4_kernel<<<grid_for(frames * hw / 4, 256, c2w_num_sms()), 256, 0, st>>>(src, fhwc, frames, hw, clhw,
+                                                                                          shift, scale, field);
+  else if (C == 4) normalize_pack_kernel<4><<<grid, 256, 0, st>>>(src, fhwc, frames, C, hw, clhw, shift, scale, field);
+  else normalize_pack_kernel<0><<<grid, 256, 0, st>>>(src, fhwc, frames, C, hw, clhw, shift, scale, field);
+  C2W_CUDA(cudaGetLastError());
+  return C2W_OK;
+}
+int c2w_unpack_unnormalize(const float* fhwc, float* dst, int64_t frames, int32_t C, int32_t hw, int32_t clhw,
+                           const float* shift, const float* scale, int32_t field, void* stream) {
+  C2W_REQUIRE(dst && fhwc && shift && scale && frames >= 1 && C >= 1 && hw >= 1, "c2w_unpack_unnormalize: bad argument");
+  const int grid = grid_for(frames * hw, 256, c2w_num_sms());
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool vec = C == 4 && hw % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(fhwc) |
+                                             reinterpret_cast<uintptr_t>(shift) | reinterpret_cast<uintptr_t>(scale)) % 16 == 0;
+  if (vec)
+    unpack_unnormalize4_kernel<<<grid_for(frames * hw / 4, 256, c2w_num_sms()), 256, 0, st>>>(fhwc, dst, frames, hw, clhw,
+                                                                                              shift, scale, field);
+  else if (C == 4) unpack_unnormalize_kernel<4><<<grid, 256, 0, st>>>(fhwc, dst, frames, C, hw, clhw, shift, scale, field);
+  else unpack_unnormalize_kernel<0><<<grid, 256, 0, st>>>(fhwc, dst, frames, C, hw, clhw, shift, scale, field);
+  C2W_CUDA(cudaGetLastError());
+  return C2W_OK;
+}
+
 int c2w_guided_step(const c2w_guide* g, void* stream) {
   C2W_REQUIRE(g && g->x && g->eps && g->nan_flag, "c2w_guided_step: bad argument");
   C2W_REQUIRE(g->s_step >= 1 && g->H % g->s_step == 0 && g->W % g->s_step == 0 && g->W / g->s_step <= 32,

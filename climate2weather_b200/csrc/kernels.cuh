@@ -367,6 +367,126 @@ __global__ void fhwc_to_nchw_kernel(const float* __restrict__ in, float* __restr
     for (int c = 0; c < C; ++c) out[(f * C + c) * hw + pix] = in[idx * C + c];
   }
 }
+// N4: the step either side of the path, data/pipeline.py:183-272 — per-variable normalisation
+// (normalize_ds: (x - shift) / scale, the five modes differ only in which quantiles shift and scale are) fused with the
+// layout change ds_to_sorted_np + trajectory packing: per-variable arrays [C][F][hw] (clhw != 0; what xarray holds,
+// concatenated) or the sorted-numpy order [F][C][hw] -> device trajectory [F, hw, C].  shift / scale: [C], or [C][hw]
+// per-grid-point fields (field != 0).  One thread per pixel: C strided coalesced reads, one contiguous C-vector write.
+template <int CT>
+__global__ void normalize_pack_kernel(const float* __restrict__ in, float* __restrict__ out, long long F, int C, int hw,
+                                      int clhw, const float* __restrict__ shift, const float* __restrict__ scale,
+                                      int field) {
+  const long long total = F * hw;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long f = idx / hw;
+    const int pix = static_cast<int>(idx - f * hw);
+    float v[CT > 0 ? CT : 1];
+    const int cc = CT > 0 ? CT : C;
+#pragma unroll
+    for (int c = 0; c < cc; ++c) {
+      const float x = in[clhw ? (static_cast<long long>(c) * F + f) * hw + pix : (f * cc + c) * hw + pix];
+      const int q = field ? c * hw + pix : c;
+      const float y = (x - __ldg(shift + q)) / __ldg(scale + q);  // IEEE division, as the reference divides
+      if (CT > 0) v[c] = y;
+      else out[idx * cc + c] = y;
+    }
+    if (CT == 4) *reinterpret_cast<float4*>(out + idx * 4) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+// C = 4, hw % 4 == 0: four pixels per thread — one 16 B load per variable, a register transpose, four 16 B stores
+// (64 contiguous bytes per thread): enough bytes in flight to approach the HBM copy rate.
+__global__ void normalize_pack4_kernel(const float* __restrict__ in, float* __restrict__ out, long long F, int hw,
+                                       int clhw, const float* __restrict__ shift, const float* __restrict__ scale,
+                                       int field) {
+  const long long total4 = F * hw / 4;
+  const int hw4 = hw / 4;
+  for (long long i4 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i4 < total4;
+       i4 += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long f = i4 / hw4;
+    const int pix = static_cast<int>(i4 - f * hw4) * 4;
+    float v[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float4 x = *reinterpret_cast<const float4*>(in + (clhw ? (static_cast<long long>(c) * F + f) * hw + pix
+                                                                    : (f * 4 + c) * hw + pix));
+      float4 sh, sc;
+      if (field) {
+        sh = __ldg(reinterpret_cast<const float4*>(shift + c * hw + pix));
+        sc = __ldg(reinterpret_cast<const float4*>(scale + c * hw + pix));
+      } else {
+        const float a = __ldg(shift + c), b = __ldg(scale + c);
+        sh = make_float4(a, a, a, a);
+        sc = make_float4(b, b, b, b);
+      }
+      v[0][c] = (x.x - sh.x) / sc.x;
+      v[1][c] = (x.y - sh.y) / sc.y;
+      v[2][c] = (x.z - sh.z) / sc.z;
+      v[3][c] = (x.w - sh.w) / sc.w;
+    }
+    float4* o = reinterpret_cast<float4*>(out + (f * hw + pix) * 4);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q] = make_float4(v[q][0], v[q][1], v[q][2], v[q][3]);
+  }
+}
+__global__ void unpack_unnormalize4_kernel(const float* __restrict__ in, float* __restrict__ out, long long F, int hw,
+                                           int clhw, const float* __restrict__ shift, const float* __restrict__ scale,
+                                           int field) {
+  const long long total4 = F * hw / 4;
+  const int hw4 = hw / 4;
+  for (long long i4 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i4 < total4;
+       i4 += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long f = i4 / hw4;
+    const int pix = static_cast<int>(i4 - f * hw4) * 4;
+    const float4* x = reinterpret_cast<const float4*>(in + (f * hw + pix) * 4);
+    float v[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 t = x[q];
+      v[q][0] = t.x, v[q][1] = t.y, v[q][2] = t.z, v[q][3] = t.w;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float4 sh, sc;
+      if (field) {
+        sh = __ldg(reinterpret_cast<const float4*>(shift + c * hw + pix));
+        sc = __ldg(reinterpret_cast<const float4*>(scale + c * hw + pix));
+      } else {
+        const float a = __ldg(shift + c), b = __ldg(scale + c);
+        sh = make_float4(a, a, a, a);
+        sc = make_float4(b, b, b, b);
+      }
+      const float4 y = make_float4(__fadd_rn(__fmul_rn(v[0][c], sc.x), sh.x), __fadd_rn(__fmul_rn(v[1][c], sc.y), sh.y),
+                                   __fadd_rn(__fmul_rn(v[2][c], sc.z), sh.z), __fadd_rn(__fmul_rn(v[3][c], sc.w), sh.w));
+      *reinterpret_cast<float4*>(out + (clhw ? (static_cast<long long>(c) * F + f) * hw + pix : (f * 4 + c) * hw + pix)) = y;
+    }
+  }
+}
+// unnormalize_ds + np_to_ds: device trajectory [F, hw, C] -> x * scale + shift in per-variable / sorted-numpy order
+template <int CT>
+__global__ void unpack_unnormalize_kernel(const float* __restrict__ in, float* __restrict__ out, long long F, int C,
+                                          int hw, int clhw, const float* __restrict__ shift,
+                                          const float* __restrict__ scale, int field) {
+  const long long total = F * hw;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long f = idx / hw;
+    const int pix = static_cast<int>(idx - f * hw);
+    const int cc = CT > 0 ? CT : C;
+    float v[CT > 0 ? CT : 1];
+    if (CT == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(in + idx * 4);
+      v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+    }
+#pragma unroll
+    for (int c = 0; c < cc; ++c) {
+      const float x = CT == 4 ? v[c] : in[idx * cc + c];
+      const int q = field ? c * hw + pix : c;
+      out[clhw ? (static_cast<long long>(c) * F + f) * hw + pix : (f * cc + c) * hw + pix] =
+          __fadd_rn(__fmul_rn(x, __ldg(scale + q)), __ldg(shift + q));  // two roundings, as `ds * range + lo`
+    }
+  }
+}
 // fp32 NCHW [n, C, HW] -> bf16 [n, HW, cpad] (zero padded channels); smem transpose keeps both sides coalesced
 __global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int C, int hw, int cpad) {
   __shared__ float tile[32][33];

@@ -121,6 +121,17 @@ int c2w_window_score_backward(c2w_handle* h, const float* cot, int32_t n_frames_
 int c2w_traj_pack(const float* nchw, float* fhwc, int64_t frames, int32_t C, int32_t hw, void* stream);
 int c2w_traj_unpack(const float* fhwc, float* nchw, int64_t frames, int32_t C, int32_t hw, void* stream);
 
+/* ---- N4: normalisation fused with the layout change (data/pipeline.py:183-272) -------------------------------
+ * normalize_ds + ds_to_sorted_np + packing:  fhwc[f, pix, c] = (src - shift[c]) / scale[c]
+ * unnormalize_ds + np_to_ds               :  dst = fhwc[f, pix, c] * scale[c] + shift[c]
+ * src / dst: fp32 per-variable arrays [C][frames][hw] (clhw != 0) or sorted-numpy order [frames][C][hw] (clhw == 0);
+ * shift / scale: device fp32 [C], or per-grid-point fields [C][hw] (field != 0).  Which quantiles they are is the
+ * normalisation mode (minmax / robust / robust95 / quant95 / quant99), resolved by the host. */
+int c2w_normalize_pack(const float* src, float* fhwc, int64_t frames, int32_t C, int32_t hw, int32_t clhw,
+                       const float* shift, const float* scale, int32_t field, void* stream);
+int c2w_unpack_unnormalize(const float* fhwc, float* dst, int64_t frames, int32_t C, int32_t hw, int32_t clhw,
+                           const float* shift, const float* scale, int32_t field, void* stream);
+
 /* ---- guided predictor / corrector (see c2w_guide) --------------------------------------------------------- */
 int c2w_guided_step(const c2w_guide* g, void* stream);
 int c2w_reduce_partials(const float* partials, int32_t n, double* sumsq, void* stream);
