@@ -19,6 +19,12 @@ int c2w_num_sms() {
 
 extern "C" {
 
+int c2w_conv_tile_width(int cout_pad, int conv3x3, int n_img, int H, int W, int stride, int num_sms) {
+  if (cout_pad < 64 || cout_pad % 64 != 0 || n_img < 1 || H < 1 || W < 1 || (stride != 1 && stride != 2) || num_sms < 2)
+    return fail(C2W_ERR_INVALID, "c2w_conv_tile_width: bad argument");
+  return conv_pick_bn_tiled(cout_pad, conv3x3 != 0, n_img, H, W, stride, num_sms);
+}
+
 int c2w_op_conv_ex(const c2w_conv_desc* d, void* stream) {
   C2W_REQUIRE(d && d->x && d->w_packed && d->bias, "c2w_op_conv_ex: null argument");
   C2W_REQUIRE(d->mode == EPI_BIAS || d->mode == EPI_BIAS_SILU || d->mode == EPI_BIAS_RES || d->mode == EPI_F32,

@@ -168,6 +168,9 @@ typedef struct c2w_conv_desc {
                            wait-full/wait-tmem, epilogue total/wait-accumulator); NULL = off                      */
 } c2w_conv_desc;
 int c2w_op_conv_ex(const c2w_conv_desc* d, void* stream);
+/* Planning query (host only, no device call): the N-tile width the engine picks for one conv of `n_img` images on a
+ * GPU with `num_sms` SMs — the wave-aware choice described in DESIGN.md (conv_pick_bn_tiled). */
+int c2w_conv_tile_width(int cout_pad, int conv3x3, int n_img, int H, int W, int stride, int num_sms);
 int c2w_op_conv(const void* x, int n_img, int H, int W, int cin, const void* w_packed, int cout_pad,
                 const float* bias, int mode, const void* res, void* out, float* out_f32, int conv3x3, int bn,
                 int max_ctas, void* stream);

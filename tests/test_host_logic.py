@@ -232,3 +232,23 @@ def test_halo_exchange_and_gather_gloo_world2(tmp_path, L, k):
     mp.spawn(_worker, args=(world, port, L, k, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert (tmp_path / f"ok{r}").read_text() == "11111"
+
+
+# ------------------------------------------------------------------------------------------------ tile planning
+def test_conv_tile_width_is_wave_aware():
+    """Host-only planning query of the C ABI (no device call): the N-tile width per UNet level for the 156 windows of
+    a one-week trajectory on 148 SMs — 128-wide activation-reuse tiles wherever a wider tile would leave the last wave
+    of the persistent grid mostly empty."""
+    from climate2weather_b200 import _lib
+
+    lib = _lib.load()
+    pick = lambda cout, H, W, n=156, c3=1, stride=1, sms=148: lib.c2w_conv_tile_width(cout, c3, n, H, W, stride, sms)
+    assert pick(128, 128, 128) == 128 and pick(128, 64, 64) == 128 and pick(64, 128, 128) == 64
+    assert pick(256, 32, 32) == 128   # 9 waves of 256 -> 17 waves of 128 with activation reuse
+    assert pick(384, 16, 16) == 128   # 5 waves of 192 -> 7 waves of 128
+    assert pick(512, 8, 8) == 128     # 2 waves of 256 -> 3 waves of 128 (two-image tiles)
+    assert pick(384, 32, 32, stride=2) == 192 and pick(256, 64, 64, stride=2) == 256   # strided heads: streamed loop
+    assert pick(1536, 8, 8, c3=0) == 256 and pick(512, 8, 8, c3=0) == 256              # attention GEMMs
+    assert pick(384, 12, 12) == 192   # images the 16 x 8 blocks do not tile
+    assert pick(512, 8, 8, n=1) == 256  # a single M tile: nothing to balance
+    assert lib.c2w_conv_tile_width(100, 1, 4, 8, 8, 1, 148) < 0
