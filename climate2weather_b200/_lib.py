@@ -29,6 +29,12 @@ class Config(C.Structure):
     ]
 
 
+class AdamW(C.Structure):
+    """include/c2w_b200.h: c2w_adamw"""
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("weight_decay", C.c_float), ("ema_rate", C.c_float), ("grad_scale", C.c_float), ("step", C.c_int32)]
+
+
 class Guide(C.Structure):
     _fields_ = [
         ("x", C.c_void_p),
@@ -104,6 +110,7 @@ SIGNATURES = {
     "c2w_window_score": (_i, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f, _vp, _vp]),
     "c2w_traj_pack": (_i, [_vp, _vp, _i64, C.c_int32, C.c_int32, _vp]),
     "c2w_traj_unpack": (_i, [_vp, _vp, _i64, C.c_int32, C.c_int32, _vp]),
+    "c2w_adamw_ema_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(AdamW), _vp]),
     "c2w_normalize_pack": (_i, [_vp, _vp, _i64, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, C.c_int32, _vp]),
     "c2w_unpack_unnormalize": (_i, [_vp, _vp, _i64, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, C.c_int32, _vp]),
     "c2w_guided_step": (_i, [C.POINTER(Guide), _vp]),

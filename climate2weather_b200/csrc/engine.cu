@@ -1209,6 +1209,30 @@ int c2w_unpack_unnormalize(const float* fhwc, float* dst, int64_t frames, int32_
   return C2W_OK;
 }
 
+int c2w_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, int64_t n, const c2w_adamw* hp,
+                       void* stream) {
+  C2W_REQUIRE(p && g && m && v && hp && n >= 1, "c2w_adamw_ema_step: bad argument");
+  C2W_REQUIRE(hp->step >= 1 && hp->beta1 >= 0.f && hp->beta1 < 1.f && hp->beta2 >= 0.f && hp->beta2 < 1.f,
+              "c2w_adamw_ema_step: step must be >= 1 and betas in [0, 1)");
+  C2W_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(ema)) & 15) == 0,
+              "c2w_adamw_ema_step: buffers must be 16-byte aligned");
+  AdamWParams h;
+  h.lr = hp->lr;
+  h.beta1 = hp->beta1;
+  h.beta2 = hp->beta2;
+  h.eps = hp->eps;
+  h.weight_decay = hp->weight_decay;
+  h.bias1 = static_cast<float>(1.0 - pow(static_cast<double>(hp->beta1), static_cast<double>(hp->step)));
+  h.bias2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(hp->beta2), static_cast<double>(hp->step))));
+  h.ema_rate = hp->ema_rate;
+  h.grad_scale = hp->grad_scale;
+  adamw_ema_kernel<<<grid_for((n + 3) / 4, 256, c2w_num_sms()), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      p, g, m, v, ema, n, h);
+  C2W_CUDA(cudaGetLastError());
+  return C2W_OK;
+}
+
 int c2w_guided_step(const c2w_guide* g, void* stream) {
   C2W_REQUIRE(g && g->x && g->eps && g->nan_flag, "c2w_guided_step: bad argument");
   C2W_REQUIRE(g->s_step >= 1 && g->H % g->s_step == 0 && g->W % g->s_step == 0 && g->W / g->s_step <= 32,

@@ -132,6 +132,20 @@ int c2w_normalize_pack(const float* src, float* fhwc, int64_t frames, int32_t C,
 int c2w_unpack_unnormalize(const float* fhwc, float* dst, int64_t frames, int32_t C, int32_t hw, int32_t clhw,
                            const float* shift, const float* scale, int32_t field, void* stream);
 
+/* ---- N2 (optimiser half): torch.optim.AdamW.step() + StandardEMA.update() in one pass --------------------------
+ * training_loop.py:381-390 (optimizer.step(); ema.update()), src/thor/ema.py:24-27.  All buffers: device fp32 [n]
+ * (the flat parameter buffer, its gradient, the two moments, the EMA copy), 16-byte aligned; ema may be NULL.
+ *   g' = g * grad_scale;  p *= 1 - lr * weight_decay;  m += (1 - beta1)(g' - m);  v = beta2 v + (1 - beta2) g'^2
+ *   p -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps);  ema = ema * ema_rate + p * (1 - ema_rate) */
+typedef struct c2w_adamw {
+  float lr, beta1, beta2, eps, weight_decay;
+  float ema_rate;    /* StandardEMA rate (0.9999); ignored when ema == NULL */
+  float grad_scale;  /* 1 / loss_scaling */
+  int32_t step;      /* 1-based optimiser step count (bias correction) */
+} c2w_adamw;
+int c2w_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, int64_t n, const c2w_adamw* hp,
+                       void* stream);
+
 /* ---- guided predictor / corrector (see c2w_guide) --------------------------------------------------------- */
 int c2w_guided_step(const c2w_guide* g, void* stream);
 int c2w_reduce_partials(const float* partials, int32_t n, double* sumsq, void* stream);

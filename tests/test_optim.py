@@ -1,0 +1,147 @@
+"""N2, optimiser half: `optimizer.step()` + `ema.update()` of training_loop.py:381-390 as one fused
+pass (`c2w_adamw_ema_step`, climate2weather_b200/optim.py).
+
+CPU: the oracle (oracle/optim_ref.py) is pinned against torch.optim.AdamW itself and, where the reference checkout is
+present, against the reference's own thor/ema.py.  GPU (`-m gpu`): the fused kernel against the oracle over several
+steps with a changing learning rate, gradients set directly and through autograd, and its HBM rate at the reference
+model's 72.1 M parameters.
+"""
+import importlib.util
+import pathlib
+
+import pytest
+import torch
+
+from oracle import optim_ref
+
+REF_EMA = pathlib.Path("/root/reference/src/thor/ema.py")
+HP = dict(lr=3e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-3)  # train.py:176-181
+
+
+def _tiny_net(seed=0):
+    torch.manual_seed(seed)
+    return torch.nn.Sequential(torch.nn.Conv2d(3, 5, 3, padding=1), torch.nn.SiLU(), torch.nn.Flatten(),
+                               torch.nn.Linear(5 * 4 * 4, 7), torch.nn.Linear(7, 1, bias=False))
+
+
+def _grads(params, step):
+    g = torch.Generator().manual_seed(100 + step)
+    return [torch.randn(p.shape, generator=g, dtype=torch.float64) * (0.1 + 0.05 * step) for p in params]
+
+
+# ---------------------------------------------------------------------------------------------------- CPU
+def test_oracle_matches_torch_adamw():
+    net = _tiny_net().double()
+    params = list(net.parameters())
+    ref = optim_ref.AdamWEMARef(params, **HP)
+    opt = torch.optim.AdamW(params, **HP)
+    for step in range(6):
+        lr = HP["lr"] * (1.0 - step / 10.0)  # linear schedule, re-set every step like training_loop.py:380-382
+        for g in opt.param_groups:
+            g["lr"] = lr
+        ref.lr = lr
+        grads = _grads(params, step)
+        for p, g in zip(params, grads):
+            p.grad = g.clone()
+        opt.step()
+        ref.step(grads)
+        for p, q in zip(params, ref.p):
+            assert torch.allclose(p.detach(), q, rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.skipif(not REF_EMA.exists(), reason="reference checkout not present")
+def test_oracle_ema_matches_reference_ema():
+    spec = importlib.util.spec_from_file_location("_ref_ema", REF_EMA)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)  # the reference's own StandardEMA
+    net = _tiny_net().double()
+    params = list(net.parameters())
+    ema = mod.StandardEMA(net, rates=[0.99])
+    ref = optim_ref.AdamWEMARef(params, ema_rate=0.99, **HP)
+    opt = torch.optim.AdamW(params, **HP)
+    for step in range(5):
+        grads = _grads(params, step)
+        for p, g in zip(params, grads):
+            p.grad = g.clone()
+        opt.step()
+        ema.update(cur_ndata=0, batch_size=1)
+        ref.step(grads)
+    for p, q in zip(ema.emas[0].parameters(), ref.ema):
+        assert torch.allclose(p.detach(), q, rtol=1e-12, atol=1e-14)
+
+
+def test_optimizer_has_no_cpu_path():
+    from climate2weather_b200 import _lib, optim
+
+    with pytest.raises((_lib.C2WError, OSError)):
+        optim.AdamW(_tiny_net().parameters(), **HP)
+
+
+# ---------------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("fused_ema", [True, False])
+def test_fused_adamw_ema_vs_oracle(fused_ema):
+    from climate2weather_b200 import optim
+
+    dev = torch.device("cuda:0")
+    net = _tiny_net(1).to(dev)
+    cpu_params = [p.detach().cpu() for p in net.parameters()]
+    ref = optim_ref.AdamWEMARef(cpu_params, ema_rate=0.99, **HP)
+    opt = optim.AdamW(net.parameters(), loss_scaling=4.0, **HP)
+    ema = optim.StandardEMA(net, rates=[0.99])
+    if fused_ema:
+        opt.fuse_ema(ema)
+    x = torch.randn(2, 3, 4, 4, generator=torch.Generator().manual_seed(9)).to(dev)
+    for step in range(6):
+        lr = HP["lr"] * (1.0 - step / 10.0)
+        for g in opt.param_groups:
+            g["lr"] = lr
+        ref.lr = lr
+        opt.zero_grad()
+        if step < 4:  # gradients written into the flat views directly
+            grads = _grads(cpu_params, step)
+            for p, g in zip(net.parameters(), grads):
+                p.grad.copy_(g.to(dev).float())
+        else:         # gradients accumulated by autograd (two backward passes, like gradient accumulation rounds)
+            for _ in range(2):
+                (net(x) ** 2).mean().mul(4.0).backward()
+            grads = [p.grad.detach().cpu().double() for p in net.parameters()]
+        opt.step()
+        ema.update(cur_ndata=0, batch_size=1)
+        ref.step(grads, grad_scale=0.25)
+        for p, q in zip(net.parameters(), ref.p):
+            assert torch.allclose(p.detach().cpu().double(), q, rtol=2e-5, atol=2e-7), step
+    for p, q in zip(ema.emas[0].parameters(), ref.ema):
+        assert torch.allclose(p.detach().cpu().double(), q, rtol=2e-5, atol=2e-7)
+    out = net(x)  # the module still runs on its (flat-buffer) parameters
+    assert torch.isfinite(out).all()
+
+
+@pytest.mark.gpu
+def test_fused_adamw_ema_rate():
+    import ctypes
+
+    from climate2weather_b200 import _lib
+
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    n = 72_100_000  # parameters of the reference ScoreUNet (sda_unet.yml)
+    bufs = [torch.randn(n, device=dev) * 0.01 for _ in range(2)] + [torch.zeros(n, device=dev) for _ in range(2)]
+    p, g, m, v = bufs
+    ema = p.clone()
+    hp = _lib.AdamW(3e-4, 0.9, 0.999, 1e-8, 1e-3, 0.9999, 1.0, 1)
+    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    call = lambda: lib.c2w_adamw_ema_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), ema.data_ptr(), n,
+                                          ctypes.byref(hp), st)
+    for _ in range(2):
+        assert call() == 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        call()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    gbs = 36.0 * n / ms / 1e6
+    print(f"\nc2w_adamw_ema_step: {n / 1e6:.1f} M parameters, {ms:.3f} ms, {gbs:.0f} GB/s (36 B per parameter)")
+    assert torch.isfinite(p).all() and gbs > 2000
