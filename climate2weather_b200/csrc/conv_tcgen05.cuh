@@ -44,6 +44,7 @@ enum EpiMode : int {
   EPI_BIAS_RES = 2,   // out += acc + bias                      -> bf16   (in place)
   EPI_COMPOSE = 3,    // centre-pick / edge-fill compose        -> fp32 eps [L, H, W, 4]
   EPI_F32 = 4,        // out = acc + bias                       -> fp32 [M, ldc]
+  EPI_MUL_DSILU = 5,  // out = (acc + bias) * silu'(out)        -> bf16   (in place: `out` holds the pre-activation)
 };
 
 struct ConvParams {
@@ -228,6 +229,24 @@ __device__ __forceinline__ void epilogue_chunk_staged(const ConvParams& p, const
         f[8 * i + 2 * j + 1] += __high2float(h);
       }
     }
+  } else if (p.mode == EPI_MUL_DSILU) {
+    // input-gradient pass: the staging tile holds the forward pre-activation x; g *= silu'(x) with
+    // silu'(x) = s (1 + x (1 - s)), s = sigmoid(x) = 1/2 + 1/2 tanh(x / 2)
+    uint4 aux[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) aux[i] = ld_shared_v4(stg_row, boff + (static_cast<uint32_t>((j0 + i) ^ (row & 7)) << 4));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t w[4] = {aux[i].x, aux[i].y, aux[i].z, aux[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+        const float x0 = __low2float(h), x1 = __high2float(h);
+        const float s0 = fmaf(0.5f, tanh_approx(0.5f * x0), 0.5f), s1 = fmaf(0.5f, tanh_approx(0.5f * x1), 0.5f);
+        f[8 * i + 2 * j] *= s0 * fmaf(x0, 1.0f - s0, 1.0f);
+        f[8 * i + 2 * j + 1] *= s1 * fmaf(x1, 1.0f - s1, 1.0f);
+      }
+    }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -292,7 +311,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int num_kb = p.taps * p.cin_blocks;
   // direct (fp32 / compose) epilogues exist for the 64-wide tile only: the last conv of the UNet
   const bool staged = BN != 64 || (p.mode != EPI_COMPOSE && p.mode != EPI_F32);
-  const bool has_aux = p.mode == EPI_BIAS_RES;  // TMA-prefetched residual tile, double-buffered
+  // TMA-prefetched auxiliary tile (the residual / the pre-activation the gradient is multiplied with), overwritten in place
+  const bool has_aux = p.mode == EPI_BIAS_RES || p.mode == EPI_MUL_DSILU;
   // two staging tiles used alternately (residual convs: the residual tile is prefetched two tiles ahead)
   const bool two_bufs = p.num_staging == 2;
 
@@ -1138,7 +1158,7 @@ inline cudaError_t conv_launch_variant(const ConvLaunch& L, cudaStream_t stream)
   // tiles take long enough to prefetch one ahead into the single tile); everywhere else the shared memory is worth
   // more as ring stages (G2: 1239 -> 1345 TFLOP/s with 4 instead of 3 activation-reuse stages).  Residual convs with
   // ONE staging tile and a 4-deep ring were measured too: residual 1215 -> 1187, residual + LayerNorm 1050 -> 860.
-  p.num_staging = (p.mode == EPI_BIAS_RES && BN <= 128) ? 2 : 1;
+  p.num_staging = ((p.mode == EPI_BIAS_RES || p.mode == EPI_MUL_DSILU) && BN <= 128) ? 2 : 1;
   p.num_stages = AR ? Cfg::ar_stages_for(p.num_staging) : Cfg::stages_for(p.num_staging);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

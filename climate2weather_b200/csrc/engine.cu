@@ -112,6 +112,7 @@ struct c2w_handle {
   int sms = 0;
   bool timing = false;
   bool fuse_ln = true;  // C2W_NO_FUSE_LN=1 keeps every LayerNorm a separate kernel (A/B runs)
+  bool fuse_dsilu = true;  // C2W_NO_FUSE_DSILU=1: silu' of the input-gradient pass as a separate elementwise kernel
   std::vector<TimedSpan> spans;
   size_t spans_used = 0;
 };
@@ -577,20 +578,27 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
       if (vjp) {
         units.emplace_back();
         std::vector<Op>& u = units.back();
-        if ((rc = add_dconv(u, true, gs[l], L.H, L.W, bw.c2, EPI_BIAS, gh[l], nullptr))) return rc;
-        if (real) {  // gh *= silu'(pre)
-          Op op;
-          op.kind = OP_SILU;
-          op.aux = pre;
-          op.in = gh[l];
-          op.out = gh[l];
-          op.C = L.C;
-          op.H = L.H;
-          op.W = L.W;
-          op.up = 1;
-          u.push_back(op);
+        if (h->fuse_dsilu) {
+          // conv2's input gradient times silu'(pre), written in place over the stashed pre-activation (the epilogue
+          // prefetches `pre` like a residual tile), then conv1's input gradient from it
+          if ((rc = add_dconv(u, true, gs[l], L.H, L.W, bw.c2, EPI_MUL_DSILU, pre, nullptr))) return rc;
+          if ((rc = add_dconv(u, true, pre, L.H, L.W, bw.c1, EPI_BIAS, ga[l], nullptr))) return rc;
+        } else {
+          if ((rc = add_dconv(u, true, gs[l], L.H, L.W, bw.c2, EPI_BIAS, gh[l], nullptr))) return rc;
+          if (real) {  // gh *= silu'(pre)
+            Op op;
+            op.kind = OP_SILU;
+            op.aux = pre;
+            op.in = gh[l];
+            op.out = gh[l];
+            op.C = L.C;
+            op.H = L.H;
+            op.W = L.W;
+            op.up = 1;
+            u.push_back(op);
+          }
+          if ((rc = add_dconv(u, true, gh[l], L.H, L.W, bw.c1, EPI_BIAS, ga[l], nullptr))) return rc;
         }
-        if ((rc = add_dconv(u, true, gh[l], L.H, L.W, bw.c1, EPI_BIAS, ga[l], nullptr))) return rc;
         add_ln_bwd(u, ga[l], y, inv, gs[l], gs[l], L.C, L.H, L.W, 0);
       }
       if (L.attn) {
@@ -852,6 +860,8 @@ int c2w_create(const c2w_config* cfg, c2w_handle** out) {
   {
     const char* e = getenv("C2W_NO_FUSE_LN");
     h->fuse_ln = !(e && e[0] == '1');
+    const char* e2 = getenv("C2W_NO_FUSE_DSILU");
+    h->fuse_dsilu = !(e2 && e2[0] == '1');
   }
   *out = h;
   return C2W_OK;

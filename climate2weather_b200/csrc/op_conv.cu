@@ -27,7 +27,8 @@ int c2w_conv_tile_width(int cout_pad, int conv3x3, int n_img, int H, int W, int 
 
 int c2w_op_conv_ex(const c2w_conv_desc* d, void* stream) {
   C2W_REQUIRE(d && d->x && d->w_packed && d->bias, "c2w_op_conv_ex: null argument");
-  C2W_REQUIRE(d->mode == EPI_BIAS || d->mode == EPI_BIAS_SILU || d->mode == EPI_BIAS_RES || d->mode == EPI_F32,
+  C2W_REQUIRE(d->mode == EPI_BIAS || d->mode == EPI_BIAS_SILU || d->mode == EPI_BIAS_RES || d->mode == EPI_F32 ||
+                  d->mode == EPI_MUL_DSILU,
               "c2w_op_conv_ex: unsupported mode %d", d->mode);
   const int sms = c2w_num_sms();
   C2W_REQUIRE(sms > 0, "c2w_op_conv_ex: no CUDA device");
@@ -46,7 +47,8 @@ int c2w_op_conv_ex(const c2w_conv_desc* d, void* stream) {
   L.p.dbg_stats = reinterpret_cast<long long*>(d->stats);
   if (d->mode != EPI_F32) {
     C2W_REQUIRE(d->out, "c2w_op_conv_ex: bf16 output modes need `out`");
-    C2W_REQUIRE(d->mode != EPI_BIAS_RES || d->res == d->out, "mode 2 accumulates in place: res must equal out");
+    C2W_REQUIRE((d->mode != EPI_BIAS_RES && d->mode != EPI_MUL_DSILU) || d->res == d->out,
+                "modes 2 and 5 work in place: res must equal out");
     if (!conv_launch_set_out(&L, static_cast<__nv_bfloat16*>(d->out)))
       return fail(C2W_ERR_CUDA, "c2w_op_conv_ex: cannot encode the output tensor map");
   }

@@ -73,7 +73,7 @@ def test_conv3x3_vs_torch(lib, dev, n, H, W, cin, cout, mode):
     bp[:cout] = b
     M = n * H * W
     res = torch.randn(M, cout_pad, generator=g).to(dev).to(torch.bfloat16)
-    out = res.clone() if mode == 2 else torch.empty(M, cout_pad, device=dev, dtype=torch.bfloat16)
+    out = res.clone() if mode in (2, 5) else torch.empty(M, cout_pad, device=dev, dtype=torch.bfloat16)
     out32 = torch.empty(M, cout_pad, device=dev) if mode == 4 else None
     _lib.check(lib.c2w_op_conv(xb.data_ptr(), n, H, W, cin_pad, wp.data_ptr(), cout_pad, bp.data_ptr(), mode,
                                out.data_ptr() if mode == 2 else None, out.data_ptr(),
@@ -119,14 +119,14 @@ def _conv_ex(lib, xb, wp, bp, mode, n, H, W, stride=1, res=None, variant=-1, bn=
     cout_pad = wp.shape[0]
     Ho, Wo = H // stride, W // stride
     M = n * Ho * Wo
-    out = res.clone() if mode == 2 else torch.empty(M, cout_pad, device=dev, dtype=torch.bfloat16)
+    out = res.clone() if mode in (2, 5) else torch.empty(M, cout_pad, device=dev, dtype=torch.bfloat16)
     out32 = torch.empty(M, cout_pad, device=dev) if f32 else None
     up = 2 if ln_up else 1
     ln_out = torch.full((n, Ho * up, Wo * up, cout_pad), 7.0, device=dev, dtype=torch.bfloat16) if ln else None
     d = _lib.ConvDesc()
     d.x, d.n_img, d.H, d.W, d.cin, d.stride, d.conv3x3 = xb.data_ptr(), n, H, W, xb.shape[-1], stride, 1
     d.w_packed, d.cout_pad, d.bias, d.mode = wp.data_ptr(), cout_pad, bp.data_ptr(), mode
-    d.res = out.data_ptr() if mode == 2 else None
+    d.res = out.data_ptr() if mode in (2, 5) else None
     d.out = out.data_ptr()
     d.out_f32 = out32.data_ptr() if f32 else None
     d.bn, d.variant, d.max_ctas, d.skip_loads = bn, variant, max_ctas, 0
@@ -190,6 +190,24 @@ def test_conv3x3_activation_reuse_wide_and_two_image_tiles(lib, dev, n, H, W, ci
     ref = ref.permute(0, 2, 3, 1).reshape(M, cout)
     if mode == 2:
         ref = ref + res[:, :cout].float()
+    assert relerr(got.float()[:, :cout], ref) < 2 ** -7
+
+
+@pytest.mark.parametrize("n,H,W,cin,cout,variant,bn", [
+    (2, 128, 128, 128, 128, 5, 0), (3, 32, 32, 256, 256, 1, 256), (3, 32, 32, 256, 256, 5, 128), (5, 8, 8, 512, 512, 5, 128),
+    (2, 16, 16, 384, 384, 1, 192)])
+def test_conv3x3_times_dsilu_in_place(lib, dev, n, H, W, cin, cout, variant, bn):
+    """Epilogue mode 5 of the input-gradient pass: out <- conv(x) * silu'(out), the pre-activation prefetched into the
+    staging tile like a residual and overwritten in place."""
+    g, xb, w, b, wp, bp = _conv_problem(dev, n, H, W, cin, cout, 17 * n + cout)
+    M = n * H * W
+    pre = (2.0 * torch.randn(M, wp.shape[0], generator=g)).to(dev).to(torch.bfloat16)
+    got, _ = _conv_ex(lib, xb, wp, bp, 5, n, H, W, res=pre, variant=variant, bn=bn)
+    ref = F.conv2d(xb[..., :cin].float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), b, padding=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(M, cout)
+    x = pre[:, :cout].float()
+    sg = torch.sigmoid(x)
+    ref = ref * (sg * (1 + x * (1 - sg)))
     assert relerr(got.float()[:, :cout], ref) < 2 ** -7
 
 
