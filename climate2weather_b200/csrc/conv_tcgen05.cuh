@@ -1226,7 +1226,7 @@ inline int conv_pick_bn_tiled(int cout_pad, bool is_conv3x3, int n_img, int H, i
     const char* e = getenv("C2W_BN_POLICY");
     policy = e ? atoi(e) : 1;
   }
-  if (policy == 0 || cout_pad < 256 || !is_conv3x3) return conv_pick_bn(cout_pad);  // costs below: 3x3 convs
+  if (policy == 0 || cout_pad < 256) return conv_pick_bn(cout_pad);
   const long long m_tiles = (static_cast<long long>(n_img) * (H / stride) * (W / stride) + kBlockM - 1) / kBlockM;
   if (m_tiles < 2) return conv_pick_bn(cout_pad);
   const bool ar = is_conv3x3 && stride == 1 && conv_ar_geometry_ok(H, W);
