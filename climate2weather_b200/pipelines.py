@@ -23,7 +23,8 @@ class SDAPipeline:
     #: corrector noise: "device" = on-chip Philox keyed by the global pixel index (default, sharding-invariant);
     #: "reference" = z.normal_() from the global CPU generator exactly like src/thor/pipelines.py:82 (parity runs).
     rng: str = "device"
-    #: check the device NaN flag every this many steps (0 = only at the end); the reference syncs every step (:90)
+    #: read the device NaN flag every this many steps (0 = only at the end); the reference syncs every step (:90).
+    #: The per-step read is asynchronous and inspected one check later, so a NaN raises one step after it appeared.
     nan_check_every: int = 0
 
     def __init__(self, eta=1e-3):
@@ -77,7 +78,7 @@ class SDAPipeline:
             sf.device = torch.device(device)
         rt = sf.runtime(noise)
         group = sf.shard[2] if sf.shard else None
-        rt.nan_flag.zero_()
+        rt.reset_finite_check()
         rt.load(noise)
         time_steps = torch.linspace(1, 0, steps + 1).to(dtype=torch.float32)
         dt = 1 / steps
@@ -118,7 +119,7 @@ class SDAPipeline:
                 rt.corrector(tau, sigma_n, z_dev, seed, istep * max(corrections, 1) + ic, group)
                 rt.halo(group)
             if self.nan_check_every and (istep + 1) % self.nan_check_every == 0:
-                rt.check_finite()
+                rt.check_finite_lagged()  # reads the flag every check, one check behind: no launch-queue stall
         rt.check_finite()
         out = rt.owned(rt.x)
         if sf.shard:

@@ -217,6 +217,30 @@ class _Runtime:
         if int(self.nan_flag.item()) != 0:
             raise ValueError("NaN detected in sample")  # same error as src/thor/pipelines.py:90-91
 
+    def reset_finite_check(self) -> None:
+        self.nan_flag.zero_()
+        self._flag_n = 0
+
+    def check_finite_lagged(self) -> None:
+        """Per-step NaN check without stalling the launch queue: the flag is copied to pinned host memory every step
+        (asynchronously, with an event) and the copy made ONE step earlier is inspected — by then it has long
+        completed, so the host never waits for the step it has just enqueued.  A NaN raises the same error one step
+        later than `check_finite()` would; the last step is covered by the final `check_finite()`."""
+        if getattr(self, "_flag_host", None) is None:
+            self._flag_host = [torch.zeros(1, dtype=self.nan_flag.dtype).pin_memory() for _ in range(2)]
+            self._flag_event = [torch.cuda.Event() for _ in range(2)]
+            self._flag_n = 0
+        i = self._flag_n & 1
+        if self._flag_n >= 1:
+            j = (self._flag_n - 1) & 1
+            self._flag_event[j].synchronize()
+            if int(self._flag_host[j][0]) != 0:
+                raise ValueError("NaN detected in sample")
+        with torch.cuda.device(self.device):
+            self._flag_host[i].copy_(self.nan_flag.reshape(-1)[:1], non_blocking=True)
+            self._flag_event[i].record(torch.cuda.current_stream(self.device))
+        self._flag_n += 1
+
 
 class AbstractScoreFunction:
     """src/thor/score.py:7-60."""

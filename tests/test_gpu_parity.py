@@ -634,6 +634,32 @@ def test_reference_snapshot_forward(dev, golden_dir):
     assert e < 3e-2
 
 
+@pytest.mark.parametrize("every", [0, 1])
+def test_sampler_raises_on_nan_like_the_reference(dev, every):
+    """src/thor/pipelines.py:90-91: `raise ValueError("NaN detected in sample")`.  With a per-step check the flag is
+    read asynchronously and inspected one step later; without it, at the end — both raise the reference's error, and a
+    clean run with the per-step check returns the same trajectory as one without."""
+    import climate2weather_b200 as c2w
+
+    torch.manual_seed(5)
+    net = c2w.ScoreUNet(**SMALL).to(dev)
+    pipe = c2w.SDAPipeline()
+    pipe.nan_check_every = every
+    sf = c2w.BatchedScoreFunction(net, markov_order=2, noise_process=pipe, batch_size=4, device=dev)
+    g = torch.Generator().manual_seed(6)
+    noise = torch.randn(9, 4, 32, 32, generator=g)
+    clean = pipe.sample(sf, noise, steps=4, show_progressbar=False)
+    assert torch.isfinite(clean).all()
+    pipe0 = c2w.SDAPipeline()
+    assert torch.equal(clean, pipe0.sample(sf, noise, steps=4, show_progressbar=False))
+    bad = noise.clone()
+    bad[4, 1, 7, 9] = float("nan")
+    with pytest.raises(ValueError, match="NaN detected in sample"):
+        pipe.sample(sf, bad, steps=4, show_progressbar=False)
+    # and the runtime recovers for the next trajectory
+    assert torch.equal(clean, pipe.sample(sf, noise, steps=4, show_progressbar=False))
+
+
 def test_driver_flow_from_snapshot(dev, golden_dir):
     """The hot-path lines of exp/downscaling.py:_run_impl, in order, on the reference-pickled snapshot fixture:
     pickle.load -> markov order from dataset_kwargs (:110-118) -> net.eval() (:125) -> A = AvgPool2d(s)(x[::t]) closure
