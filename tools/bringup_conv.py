@@ -178,6 +178,11 @@ def main():
             timeit("G2 cg2+AR res+LN", 32, 128, 128, 128, 128, variant=5, ln=True, cudnn=False)
             timeit("G5 cg2+AR res+LN", 64, 64, 64, 128, 128, variant=5, ln=True, cudnn=False)
         return 0
+    if "--noaux" in sys.argv:  # residual convs with the residual prefetch disabled (does it delay the operand loads?)
+        for sk in (0, 5, 0, 5):
+            timeit(f"G2 cg2+AR res skip={sk}", 32, 128, 128, 128, 128, variant=5, skip_loads=sk, res=True, cudnn=False)
+            timeit(f"G2 cg2+AR res+LN skip={sk}", 32, 128, 128, 128, 128, variant=5, skip_loads=sk, ln=True, cudnn=False)
+        return 0
     if "--lnfloor" in sys.argv:  # role counters of the LayerNorm conv with and without operand loads (use --stats)
         for sk in (0, 1):
             timeit(f"G2 cg2+AR res skip={sk}", 32, 128, 128, 128, 128, variant=5, skip_loads=sk, res=True, cudnn=False)
