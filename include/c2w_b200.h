@@ -204,6 +204,15 @@ int c2w_op_gather_windows(const float* traj, void* out_bf16, int n, int hw, int 
 int c2w_op_modulation(c2w_handle* h, float t, float* emb_out, float* mods_out, void* stream);
 int c2w_total_mod_channels(c2w_handle* h);
 
+/* ---- EXPERIMENTAL (round-2 groundwork; c2w_op_wgrad does NOT work yet — see csrc/wgrad_tcgen05.cuh; no parity claim;
+ * c2w_op_transpose_bf16 passes its opt-in test): weight gradient of a 3x3 stride-1
+ * conv as a split-K tcgen05 GEMM over the TRANSPOSED activations (training_loop.py:378, the wgrad half of N2).
+ *   x_t [cin][n*H*W], dy_t [cout][n*H*W] bf16 (c2w_op_transpose_bf16 of the NHWC tensors);
+ *   dw fp32 [cout][9*cin], k = (r*3+s)*cin + ci like the packed forward weights, ACCUMULATED (zero it first). */
+int c2w_op_transpose_bf16(const void* in_rows_cols, void* out_cols_rows, int64_t rows, int32_t cols, void* stream);
+int c2w_op_wgrad(const void* x_t, const void* dy_t, int32_t n_img, int32_t H, int32_t W, int32_t cin, int32_t cout,
+                 float* dw, void* stream);
+
 /* ---- measurement hooks (bench.py): kernel launches issued by this library so far; optional CUDA-event timing of
  * every forward-pass launch on its own stream, summed per class: [0] K1 conv/GEMM (tensor cores), [1] the rest --- */
 int64_t c2w_launch_count(void);
