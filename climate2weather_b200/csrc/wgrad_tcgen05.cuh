@@ -183,8 +183,21 @@ inline cudaError_t wgrad_launch_bn(const CUtensorMap& tmA, const CUtensorMap& tm
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  wgrad_tcgen05_kernel<BN><<<grid, kWgThreads, smem, stream>>>(tmA, tmB, p);
-  return cudaGetLastError();
+  // launched like K1 (explicit 1-CTA cluster): the tcgen05.commit / TMA forms address shared::cluster
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kWgThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, wgrad_tcgen05_kernel<BN>, tmA, tmB, p);
 }
 
 inline int wgrad_launch(const __nv_bfloat16* xt, const __nv_bfloat16* dyt, int n_img, int H, int W, int cin, int cout,
