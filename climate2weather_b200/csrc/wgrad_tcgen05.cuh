@@ -1,7 +1,9 @@
 // EXPERIMENTAL — weight-gradient GEMM of a 3x3 stride-1 conv (the wgrad half of SURVEY 8(f) N2).
 // Written at the end of round 1, compiled for sm_100a, NOT WORKING YET: its first (and, for lack of GPU budget, only)
-// hardware run ended in cudaErrorIllegalInstruction inside wgrad_tcgen05_kernel (transpose_bf16_kernel passes its
-// test); to be located with compute-sanitizer next round.  No product path calls it, no parity claim covers it, and
+// hardware runs ended in cudaErrorIllegalInstruction after ~4 s in every case (transpose_bf16_kernel passes its test).
+// That is mbar_wait's watchdog (BPT.TRAP after 4e9 cycles), i.e. the kernel DEADLOCKS: by the SASS the first wait to
+// time out is the MMA warp's on full[stage] — the stage's TMA bytes never complete.  Launch style (plain vs 1-CTA
+// cluster) makes no difference.  Next step: compute-sanitizer + a single-K-block run dumping the barrier state.  No product path calls it, no parity claim covers it, and
 // its GPU test is opt-in (C2W_EXPERIMENTAL=1).  Ground truth for it: tests/golden/train_step.npz.
 //
 //   dW[co, (r*3+s)*Cin + ci] += sum over pixels  dY[pix, co] * X[pix + (r-1, s-1), ci]        (zero padding)
