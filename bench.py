@@ -1,20 +1,27 @@
 #!/usr/bin/env python
 """bench.py — guided-sampling frames/sec of the Climate2Weather hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-Workload (config.workload): BASELINE.json configs[1] at N=1 — guided predictor-corrector sampling of a 1-week hourly
-trajectory, L = 168 frames of 4 x 128 x 128, ScoreUNet of configs/sda_unet.yml (random init), Markov order k = 6
-(156 windows), 256 denoising steps, 0 corrections, tau 0.5, exact_grad False, observation = every 6th frame 16x16
-tile means (exp/configs/000_on-model-eval/s16_t6.yml).  For N > 1 the trajectory is time-sharded with 156 windows
-per GPU (L = 12 + 156 N frames: weak scaling) and the k boundary frames are exchanged after every update.
+Workloads (config.workload), all on the ScoreUNet of configs/sda_unet.yml (random init), 4 x 128 x 128 frames, Markov
+order k = 6, 256 denoising steps, 0 corrections, tau 0.5, closed-form guidance (exact_grad False), observation = every
+6th frame's 16x16 tile means (exp/configs/000_on-model-eval/s16_t6.yml):
 
-A "step" is one denoising step over the whole trajectory: window score (156 UNet windows per GPU) + fused guidance
-and predictor update (+ halo exchange).  `value` = frames / (256 * mean step time): frames per second of a full
-256-step sampling run, state resident in HBM, timed with CUDA events over exactly K steps.  `e2e` = the same metric
-through the public API (SDAPipeline.sample) with pinned HOST noise in, HOST result out and the per-step NaN-flag
-read the reference does (src/thor/pipelines.py:90), all inside the timed region.
+  N = 1 (default)  BASELINE.json configs[1]: a 1-week hourly trajectory, L = 168 frames (156 windows), one GPU.
+  N > 1 (default)  BASELINE.json configs[2]: a 1-month trajectory, L = 720 frames (708 windows) TIME-SHARDED over the
+                   N GPUs with the k boundary frames exchanged after every update — strong scaling.  Rank 0 also times
+                   the same 720-frame trajectory on ONE GPU in the same run (`strong_scaling` in the line).
+  --config 4       BASELINE.json configs[3]: a 16-member ensemble of a synthetic year (L = 8760) over the N GPUs,
+                   members as independent replicas (16 / N per GPU, exp/downscaling.py:96-99,248-261), windows chunked.
+  --weak           the round-1 weak-scaling workload (L = 12 + 156 N).
+
+A "step" is one denoising step over the whole trajectory: window score (UNet on every window of this rank) + fused
+guidance and predictor update (+ halo exchange).  `value` = frames / (256 * mean step time): frames per second of a
+full 256-step sampling run, state resident in HBM, timed with CUDA events over exactly K steps, max over ranks.
+`e2e` = the same metric through the public API (SDAPipeline.sample) with pinned HOST noise in, HOST result out and
+the per-step NaN-flag read the reference does (src/thor/pipelines.py:90), all inside the timed region.
+`--impl reference` times the reference's CPU path (the oracle port, all host threads) on the same config.
 """
 from __future__ import annotations
 
@@ -35,11 +42,13 @@ SAMPLER_STEPS = 256
 K_ORDER = 6
 C, H, W = 4, 128, 128
 WINDOWS_PER_GPU = 156
+L_WEEK, L_MONTH, L_YEAR, MEMBERS = 168, 720, 8760, 16
 T_STEP, S_STEP = 6, 16
 STD = [0.1692666615037876, 0.0425178630338289, 0.3268027589410125, 0.3268027589410125]
 GAMMA = 0.0007196856730011522
 F_WIN_CONV = 115.134e9  # Conv2d FLOPs per window forward
 F_WIN = 116.0e9
+FRAME_BYTES = C * H * W * 4
 ARCH = dict(channels=52, embedding_dim=512, hidden_channels=[128, 128, 256, 384, 512], hidden_blocks=[3, 3, 3, 3, 3],
             attention_levels=[4])
 
@@ -50,6 +59,16 @@ def measured_peaks():
         d = json.loads(p.read_text())
         return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
     return 1400.0, 6650.0, "fallback"
+
+
+def k1_traffic():
+    """DRAM bytes per K1 launch from the committed ncu capture of one step (profiles/k1_traffic.json, written by
+    tools/ncu_traffic.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over bench.py --profile)."""
+    p = ROOT / "profiles" / "k1_traffic.json"
+    if not p.exists():
+        return None, None
+    d = json.loads(p.read_text())
+    return d.get("dram_bytes_per_launch"), d
 
 
 class ClockSampler:
@@ -113,13 +132,20 @@ class ClockSampler:
                 "window": "timed region" if inside else "whole run"}
 
 
-def make_problem(L: int, seed: int = 0):
+def member_seed(seed: int, rank: int) -> int:
+    """util.set_random_seed (util.py:27-29): hash((seed, rank)) % 2**31 — Python's tuple-of-ints hash is deterministic."""
+    return hash((seed, rank)) % (1 << 31)
+
+
+def make_problem(L: int, seed: int = 0, with_net: bool = True):
     import torch
 
     import climate2weather_b200 as c2w
 
-    torch.manual_seed(seed)
-    net = c2w.ScoreUNet(**ARCH)
+    net = None
+    if with_net:
+        torch.manual_seed(0)
+        net = c2w.ScoreUNet(activation=torch.nn.SiLU, **ARCH).requires_grad_(False)
     g = torch.Generator().manual_seed(seed + 1)
     noise = torch.randn(L, C, H, W, generator=g)
     truth = torch.randn(L, C, H, W, generator=g)
@@ -128,14 +154,123 @@ def make_problem(L: int, seed: int = 0):
     return net, noise, y, cg
 
 
+def pick_workload(args, world: int):
+    """(name, L, scaling, members_per_gpu)."""
+    if args.config == 4:
+        if MEMBERS % world:
+            raise SystemExit(f"config 4: {MEMBERS} members do not divide over {world} GPUs")
+        return "config4", args.frames or L_YEAR, "weak", MEMBERS // world
+    if args.weak:
+        return "config2-weak", args.frames or (2 * K_ORDER + WINDOWS_PER_GPU * world), "weak", 0
+    if world == 1 and args.config in (None, 2):
+        return "config2", args.frames or L_WEEK, "weak", 0
+    return "config3", args.frames or L_MONTH, "strong", 0
+
+
 # ====================================================================================================== ours
+class Stepper:
+    """One resident trajectory (or this rank's shard of it) and its denoising step."""
+
+    def __init__(self, net, noise, y, cg, dev, chunk, exact, shard):
+        import torch
+
+        import climate2weather_b200 as c2w
+        from climate2weather_b200.score import _mu_sigma
+
+        self.torch, self._mu_sigma = torch, _mu_sigma
+        self.pipe = c2w.SDAPipeline()
+        self.sf = c2w.BatchedScoreFunction(net, markov_order=K_ORDER, noise_process=self.pipe, batch_size=chunk, device=dev)
+        self.sf.max_windows = chunk
+        self.sf.condition_on(A=cg, y=y, std=torch.tensor(STD).reshape(1, C, 1, 1), gamma=GAMMA, exact_grad=exact)
+        if shard:
+            self.sf.enable_time_sharding()
+        self.rt = self.sf.runtime(noise)
+        self.group = None
+        self.times = torch.linspace(1, 0, SAMPLER_STEPS + 1)
+        self.noise = noise
+
+    def load(self):
+        self.rt.load(self.noise)
+
+    def step(self, i: int):
+        t = self.times[i % SAMPLER_STEPS]
+        dt = 1 / SAMPLER_STEPS
+        mu, sigma = self._mu_sigma(self.pipe, t)
+        mu_n, sigma_n = self._mu_sigma(self.pipe, t - dt)
+        self.rt.score(float(t), self.group)
+        self.rt.predictor(mu, sigma, mu_n, sigma_n)
+        self.rt.halo(self.group)
+
+    def timed(self, steps: int, warmup: int, barrier, clocks=None):
+        """ms for exactly `steps` steps (CUDA events on the launch stream), after `warmup` untimed steps."""
+        torch = self.torch
+        self.load()
+        for i in range(warmup):
+            self.step(i)
+        self.load()  # restart the trajectory so the timed steps see the schedule from t = 1
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if clocks:
+            clocks.mark_start()
+        e0.record()
+        for i in range(steps):
+            self.step(i)
+        e1.record()
+        barrier()
+        if clocks:
+            clocks.mark_end()
+        return e0.elapsed_time(e1)
+
+
+def hbm_kernel_rates(lib, rt, dev, peak_gbs):
+    """Achieved GB/s of the two HBM-bound kernels of a step, each timed alone with CUDA events over 20 launches.
+    K6 guided predictor: algorithmic 3 x 4 x H x W x 4 B per owned frame (read x, read eps, write x).
+    K0 window gather: algorithmic DRAM bytes = the local trajectory read once + the bf16 window batch written once
+    (the 13x re-reads of a frame by neighbouring windows are L2 hits).
+    Working sets (x, eps, the window batch) are re-touched every launch; at L = 168 x and eps (44 MB each) fit the
+    126 MB L2, so K6's figure there is an L2-assisted upper bound — stated with the number (`l2_resident`)."""
+    import torch
+
+    from climate2weather_b200 import _lib as L_
+
+    out = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    n = 20
+    rt.score(0.5)  # eps valid
+    e0, e1 = ev(), ev()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        rt.predictor(0.9, 0.4, 0.9, 0.4)  # mu == mu_next, sigma == sigma_next: x is a fixed point, values stay finite
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    by = 3 * FRAME_BYTES * rt.plan.own_n
+    out["K6_guided_predictor"] = {"GBps": round(by / ms / 1e6, 1), "frac": round(by / ms / 1e6 / peak_gbs, 4),
+                                  "bytes_per_launch": by, "ms": round(ms, 5), "l2_resident": bool(by < 126e6)}
+    nw = min(rt.engine.max_windows, rt.plan.win_hi - rt.plan.win_lo)
+    xin = torch.empty(nw, H * W, 64, dtype=torch.bfloat16, device=dev)
+    e0, e1 = ev(), ev()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        L_.check(lib.c2w_op_gather_windows(rt.x.data_ptr(), xin.data_ptr(), nw, H * W, C, 2 * K_ORDER + 1, 64, 0,
+                                           torch.cuda.current_stream().cuda_stream), "gather")
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    by = (nw + 2 * K_ORDER) * FRAME_BYTES + nw * H * W * 64 * 2
+    out["K0_gather_windows"] = {"GBps": round(by / ms / 1e6, 1), "frac": round(by / ms / 1e6 / peak_gbs, 4),
+                                "bytes_per_launch": by, "ms": round(ms, 5), "l2_resident": bool(by < 126e6)}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     import climate2weather_b200 as c2w
     from climate2weather_b200 import _lib
-    from climate2weather_b200.score import _mu_sigma
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -145,56 +280,53 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    L = 2 * K_ORDER + WINDOWS_PER_GPU * world if args.frames is None else args.frames
-    net, noise, y, cg = make_problem(L)
-    net = net.to(dev)
-    pipe = c2w.SDAPipeline()
-    sf = c2w.BatchedScoreFunction(net, markov_order=K_ORDER, noise_process=pipe, batch_size=args.chunk, device=dev)
-    sf.condition_on(A=cg, y=y, std=torch.tensor(STD).reshape(1, C, 1, 1), gamma=GAMMA, exact_grad=args.exact_grad)
-    if world > 1:
-        sf.enable_time_sharding()
-    rt = sf.runtime(noise)
-    group = None
+    name, L, scaling, members_per_gpu = pick_workload(args, world)
     lib = _lib.load()
-    times = torch.linspace(1, 0, SAMPLER_STEPS + 1)
-    dt = 1 / SAMPLER_STEPS
-
-    def one_step(i: int):
-        t = times[i % SAMPLER_STEPS]
-        mu, sigma = _mu_sigma(pipe, t)
-        mu_n, sigma_n = _mu_sigma(pipe, t - dt)
-        rt.score(float(t), group)
-        rt.predictor(mu, sigma, mu_n, sigma_n)
-        rt.halo(group)
+    peak_tf, peak_gbs, peak_src = measured_peaks()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(v: float) -> float:
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    ensemble = name == "config4"
+    seed = member_seed(0, rank) if ensemble else 0  # exp/downscaling.py:103: every rank seeds its own members
+    net, noise, y, cg = make_problem(L, seed=seed)
+    net = net.to(dev)
+
+    # ---- strong scaling: the same trajectory on ONE GPU (rank 0), before the sharded run
+    single = None
+    if name == "config3" and world > 1 and not args.no_single:
+        if rank == 0:
+            s1 = Stepper(net, noise, y, cg, dev, args.chunk, args.exact_grad, shard=False)
+            ks = max(2, min(args.steps, 6))
+            ms1 = s1.timed(ks, 3, lambda: torch.cuda.synchronize()) / ks
+            single = {"ms_per_step": round(ms1, 4), "value": round(L / (SAMPLER_STEPS * ms1 / 1e3), 3),
+                      "windows": L - 2 * K_ORDER, "steps": ks}
+            del s1
+            torch.cuda.empty_cache()
+        barrier()
+
+    st = Stepper(net, noise, y, cg, dev, args.chunk, args.exact_grad, shard=(world > 1 and not ensemble))
+    rt = st.rt
+    n_win_local = rt.plan.win_hi - rt.plan.win_lo
+
     # ---- device-resident timed region: exactly K steps, CUDA events on the launch stream
     with ClockSampler(local_rank) as clocks:
-        rt.load(noise)
-        for i in range(args.warmup):
-            one_step(i)
-        rt.load(noise)  # restart the trajectory so the timed steps see the schedule from t = 1
-        barrier()
         launches0 = lib.c2w_launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        clocks.mark_start()
-        e0.record()
-        for i in range(args.steps):
-            one_step(i)
-        e1.record()
-        barrier()
-        clocks.mark_end()
-    ms_total = e0.elapsed_time(e1)
-    launches = lib.c2w_launch_count() - launches0
-    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_step = tmax.item() / args.steps
-    value = L / (SAMPLER_STEPS * ms_step / 1e3)
+        ms_total = st.timed(args.steps, args.warmup, barrier, clocks)
+        launches = lib.c2w_launch_count() - launches0
+    launches = launches * args.steps // (args.steps + args.warmup)  # the counter also saw the warm-up steps
+    ms_step = allmax(ms_total) / args.steps
+    frames_total = L * (MEMBERS if ensemble else 1)
+    # ensemble: each GPU runs its members one after the other -> a GPU-step of the job costs members_per_gpu steps
+    value = frames_total / (SAMPLER_STEPS * ms_step * (members_per_gpu if ensemble else 1) / 1e3)
     rt.check_finite()
 
     # ---- roofline pass: event-time every forward-pass launch of a few steps (same process, right after)
@@ -202,25 +334,34 @@ def run_ours(args):
     _lib.check(lib.c2w_set_timing(eng.handle, 1), "c2w_set_timing")
     ms2 = (ctypes.c_double * 2)()
     n2 = (ctypes.c_int64 * 2)()
-    nprof = 0 if args.profile else min(args.steps, 4)
+    nprof = 0 if args.profile else min(args.steps, 4 if not ensemble else 1)
     for i in range(nprof):
-        one_step(i)
+        st.step(i)
     _lib.check(lib.c2w_timing_read(eng.handle, ms2, n2), "c2w_timing_read")
     _lib.check(lib.c2w_set_timing(eng.handle, 0), "c2w_set_timing")
-    n_win_local = rt.plan.win_hi - rt.plan.win_lo
     conv_ms_step = ms2[0] / max(nprof, 1)
     other_ms_step = ms2[1] / max(nprof, 1)
-    peak_tf, peak_gbs, peak_src = measured_peaks()
-    conv_tf = F_WIN_CONV * n_win_local / (conv_ms_step * 1e-3) / 1e12 if conv_ms_step > 0 else 0.0
+    # K1 work per step: every conv / 1x1 GEMM of the forward pass; exact-grad adds the input-gradient conv of each
+    # (same FLOPs with Cin and Cout swapped), src/thor/score.py:28-33,51-52
+    k1_flops_step = F_WIN_CONV * n_win_local * (2 if args.exact_grad else 1)
+    conv_tf = k1_flops_step / (conv_ms_step * 1e-3) / 1e12 if conv_ms_step > 0 else 0.0
+    traffic, traffic_src = k1_traffic()
+    k1_per_step = n2[0] // max(nprof, 1)
     roofline = {
-        "kernel": "conv_gemm_tcgen05_kernel (K1, all %d conv/GEMM launches of a step)" % (n2[0] // max(nprof, 1)),
+        "kernel": "conv_gemm_tcgen05_kernel (K1, all %d conv/GEMM launches of a step)" % k1_per_step,
         "bound": "tensor", "achieved": round(conv_tf, 1), "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": round(conv_tf / peak_tf, 4), "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": None,
-        "algorithmic_flops_per_step": F_WIN_CONV * n_win_local,
+        "frac": round(conv_tf / peak_tf, 4), "peak_source": f"{peak_src} bf16_tflops_sustained",
+        "traffic": traffic, "traffic_source": (traffic_src or {}).get("source"),
+        "algorithmic_flops_per_launch": k1_flops_step / max(k1_per_step, 1),
+        "algorithmic_flops_per_step": k1_flops_step,
         "avg_launch_ms": round(ms2[0] / max(1, n2[0]), 5), "k1_ms_per_step": round(conv_ms_step, 3),
         "other_fwd_kernels_ms_per_step": round(other_ms_step, 3),
         "k1_share_of_step": round(conv_ms_step / ms_step, 4),
+        "whole_step_frac": round(k1_flops_step / (ms_step * 1e-3) / 1e12 / peak_tf, 4),
     }
+    hbm = None
+    if not args.profile and not ensemble and not args.exact_grad:
+        hbm = hbm_kernel_rates(lib, rt, dev, peak_gbs)
 
     # ---- end to end through the public API: pinned host noise in, host result out, per-step NaN-flag read
     e2e = None
@@ -231,42 +372,59 @@ def run_ours(args):
         ke = max(1, args.e2e_steps)  # one full sample() call of this many denoising steps (independent of --steps)
         barrier()
         t0 = time.perf_counter()
-        out = pipe2.sample(sf, noise_pinned, steps=ke, corrections=0, tau=0.5, show_progressbar=False)
+        out = pipe2.sample(st.sf, noise_pinned, steps=ke, corrections=0, tau=0.5, show_progressbar=False)
         barrier()
-        dt_e2e = time.perf_counter() - t0
-        tm = torch.tensor([dt_e2e], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        assert out.device.type == "cpu" and bool(torch.isfinite(out).all())
-        local_frames = rt.plan.n_local
-        e2e = {"value": round(L / (SAMPLER_STEPS * tm.item() / ke), 3), "unit": "frames/s",
-               "h2d_bytes_per_step": int(local_frames * C * H * W * 4 / ke),
-               "d2h_bytes_per_step": int(rt.plan.own_n * C * H * W * 4 / ke) + 4,
-               "api": f"SDAPipeline.sample(BatchedScoreFunction, pinned host noise, steps={ke}) -> host tensor",
+        dt_e2e = allmax(time.perf_counter() - t0)
+        if out is not None:  # time-sharded: the trajectory is assembled on rank 0 only
+            assert out.device.type == "cpu" and tuple(out.shape) == (L, C, H, W) and bool(torch.isfinite(out).all())
+        sharded = world > 1 and not ensemble
+        e2e = {"value": round(frames_total / (SAMPLER_STEPS * dt_e2e * (members_per_gpu if ensemble else 1) / ke), 3),
+               "unit": "frames/s",
+               "h2d_bytes_per_step": int(rt.plan.n_local * FRAME_BYTES / ke),
+               "d2h_bytes_per_step": int((L if (sharded and rank == 0) else rt.plan.own_n) * FRAME_BYTES / ke) + 4,
+               "api": f"SDAPipeline.sample(BatchedScoreFunction, pinned host noise, steps={ke}) -> host tensor"
+                      + (" on rank 0 (gather over NVLink)" if sharded else ""),
                "steps": ke}
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_reference(sample_windows=args.cpu_windows, steps=1)
+    if rank == 0 and world == 1 and not args.no_cpu and not ensemble:
+        cpu = cpu_reference(L, sample_windows=args.cpu_windows, steps=1)
 
     if rank == 0:
+        desc = {"config2": f"config2: guided PC sampling of a 1-week trajectory, L={L} frames",
+                "config2-weak": f"config2 weak scaling: L={L} frames ({WINDOWS_PER_GPU} windows per GPU)",
+                "config3": f"config3: time-sharded guided PC sampling of a 1-month trajectory, L={L} frames over {world} GPU(s)",
+                "config4": f"config4: {MEMBERS}-member ensemble of a synthetic year, L={L} frames per member, "
+                           f"{members_per_gpu} member(s) per GPU as independent replicas"}[name]
+        x2 = 2 if args.exact_grad else 1
         line = {
             "metric": "guided-sampling frames/sec", "value": round(value, 3), "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"config2: guided PC sampling, L={L} frames ({n_win_local} windows/GPU) of "
-                                   f"{C}x{H}x{W}, sda_unet.yml ScoreUNet k={K_ORDER}, {SAMPLER_STEPS} steps, "
-                                   f"0 corrections, {'exact-grad (UNet VJP)' if args.exact_grad else 'approx-grad'} guidance "
+            "scaling": scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{desc} ({n_win_local} windows on rank 0) of {C}x{H}x{W}, sda_unet.yml ScoreUNet "
+                                   f"k={K_ORDER}, {SAMPLER_STEPS} steps, 0 corrections, "
+                                   f"{'exact-grad (UNet VJP)' if args.exact_grad else 'approx-grad'} guidance "
                                    "t_step=6 s_step=16",
-                       "frames": L, "sampler_steps": SAMPLER_STEPS, "windows_per_gpu": n_win_local,
-                       "chunk_windows": rt.engine.max_windows, "parallelism": f"time-shard x{world}",
+                       "name": name, "frames": L, "members": MEMBERS if ensemble else 1, "sampler_steps": SAMPLER_STEPS,
+                       "windows_per_gpu": n_win_local, "chunk_windows": rt.engine.max_windows,
+                       "workspace_bytes": int(rt.engine.workspace.numel()),
+                       "parallelism": (f"{members_per_gpu} replica member(s) per GPU x{world}" if ensemble
+                                       else f"time-shard x{world}"),
                        "l2": "per-step working set (activations of a chunk + 144 MB packed weights) exceeds the 126 MB "
                              "L2; no explicit flush"},
             "clocks": clocks.summary(), "gpu_launches": int(launches),
-            "roofline": roofline, "flops_per_step": F_WIN * n_win_local * world,
-            "achieved_tflops_whole_step": round(F_WIN * n_win_local / (ms_step * 1e-3) / 1e12, 1),
+            "roofline": roofline, "flops_per_step": F_WIN * n_win_local * world * x2,
+            "achieved_tflops_whole_step": round(F_WIN * n_win_local * x2 / (ms_step * 1e-3) / 1e12, 1),
         }
+        if hbm:
+            line["hbm_kernels"] = dict(hbm, peak=peak_gbs, unit="GB/s", peak_source=f"{peak_src} hbm_gbs")
+        if single:
+            speedup = single["ms_per_step"] / ms_step
+            line["strong_scaling"] = {"single_gpu": single, "speedup": round(speedup, 3),
+                                      "efficiency": round(speedup / world, 4),
+                                      "step_efficiency_window_normalised": round(
+                                          single["ms_per_step"] / single["windows"] * n_win_local / ms_step, 4)}
         if e2e:
             line["e2e"] = e2e
         if cpu:
@@ -277,70 +435,108 @@ def run_ours(args):
 
 
 # ====================================================================================================== reference arm
-def cpu_reference(sample_windows: int = 13, steps: int = 1):
-    """Times the oracle port of the reference path (fp32 torch on the host cores, all threads) on a bounded sample of
-    the same workload: `sample_windows` windows (L = sample_windows + 12 frames), `steps` guided predictor steps, and
-    scales to config 2 by the exact work ratio (cost is linear in windows, src/thor/score.py:143-185)."""
-    import torch
+class CpuReference:
+    """The oracle port of the reference path (fp32 torch on the host cores, all threads): guided predictor steps
+    (BatchedScoreFunction.score_fn, src/thor/score.py:156-185, + closed-form guidance + SDAPipeline._sample_step) on a
+    trajectory of `sample_windows` windows."""
 
-    from oracle import pipeline_ref, score_ref, unet_ref
+    def __init__(self, sample_windows: int):
+        import torch
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    Ls = sample_windows + 2 * K_ORDER
-    sd = unet_ref.init_state_dict(unet_ref.SDA_UNET, seed=0)
-    net = unet_ref.RefNet(sd, unet_ref.SDA_UNET)
-    g = torch.Generator().manual_seed(1)
-    x = torch.randn(Ls, C, H, W, generator=g)
-    y = score_ref.coarse_grain(torch.randn(Ls, C, H, W, generator=g), T_STEP, S_STEP)
-    std = torch.tensor(STD).reshape(1, C, 1, 1)
-    p = pipeline_ref.RefPipeline()
-    ts = torch.linspace(1, 0, SAMPLER_STEPS + 1)
+        from oracle import pipeline_ref, score_ref, unet_ref
 
-    def guided(xx, tt):
-        with torch.no_grad():
-            eps = score_ref.window_score(net, xx, tt, K_ORDER, batch_size=32)
-        return score_ref.guided_score_closed_form(eps, xx, tt, y, std, GAMMA, T_STEP, S_STEP)
+        self.torch, self.score_ref = torch, score_ref
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        self.sample_windows = sample_windows
+        Ls = sample_windows + 2 * K_ORDER
+        sd = unet_ref.init_state_dict(unet_ref.SDA_UNET, seed=0)
+        self.net = unet_ref.RefNet(sd, unet_ref.SDA_UNET)
+        g = torch.Generator().manual_seed(1)
+        self.x = torch.randn(Ls, C, H, W, generator=g)
+        self.y = score_ref.coarse_grain(torch.randn(Ls, C, H, W, generator=g), T_STEP, S_STEP)
+        self.std = torch.tensor(STD).reshape(1, C, 1, 1)
+        self.p = pipeline_ref.RefPipeline()
+        self.ts = torch.linspace(1, 0, SAMPLER_STEPS + 1)
+        self.i = 0
 
-    t0 = time.perf_counter()
-    for i in range(steps):
-        x = p.predictor(guided, x, ts[i], 1 / SAMPLER_STEPS)
-    dt = (time.perf_counter() - t0) / steps
+    def _guided(self, xx, tt):
+        with self.torch.no_grad():
+            eps = self.score_ref.window_score(self.net, xx, tt, K_ORDER, batch_size=32)
+        return self.score_ref.guided_score_closed_form(eps, xx, tt, self.y, self.std, GAMMA, T_STEP, S_STEP)
+
+    def step(self) -> float:
+        """One guided predictor step; returns its wall time in seconds."""
+        t0 = time.perf_counter()
+        self.x = self.p.predictor(self._guided, self.x, self.ts[self.i % SAMPLER_STEPS], 1 / SAMPLER_STEPS)
+        self.i += 1
+        return time.perf_counter() - t0
+
+
+def cpu_reference(L: int, sample_windows: int = 13, steps: int = 1):
+    """cpu_baseline of the GPU line: `steps` guided predictor steps on a bounded sample of the workload, scaled to the
+    full trajectory by the exact work ratio (cost is linear in windows, src/thor/score.py:143-185)."""
+    n_win = L - 2 * K_ORDER
+    sample_windows = min(sample_windows, n_win)
+    ref = CpuReference(sample_windows)
+    ref.step()  # untimed: thread pool, allocator and oneDNN primitive caches
+    dt = sum(ref.step() for _ in range(steps)) / steps
     sec_per_window = dt / sample_windows
-    L = 2 * K_ORDER + WINDOWS_PER_GPU
-    value = L / (SAMPLER_STEPS * sec_per_window * WINDOWS_PER_GPU)
-    return {"value": round(value, 6), "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} guided predictor step(s) on L={Ls} ({sample_windows} windows), scaled x"
-                      f"{WINDOWS_PER_GPU}/{sample_windows} windows to config 2 (cost linear in windows)",
-            "sec_per_window_eval": round(sec_per_window, 4), "threads": torch.get_num_threads()}
+    value = L / (SAMPLER_STEPS * sec_per_window * n_win)
+    return {"value": round(value, 6), "unit": "frames/s", "cores": ref.cores, "kind": "port",
+            "sample": f"{steps} guided predictor step(s) on {sample_windows} of the {n_win} windows (L={sample_windows + 12} "
+                      f"frames) after one untimed step, scaled x{n_win}/{sample_windows} (cost linear in windows)",
+            "sec_per_window_eval": round(sec_per_window, 4), "threads": ref.cores}
 
 
 def run_reference(args):
+    """The reference arm: exactly --warmup untimed and --steps timed guided predictor steps of the oracle port on the
+    host cores.  A step processes ALL windows of the config when that fits the time budget (--ref-budget-s for the whole
+    run), otherwise a bounded sample of them — the same windows-per-step for every step, stated in `config`;
+    `ms_per_step` is the MEASURED time of such a step and `value` scales it to the full trajectory by the window ratio."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    world = args.gpus
+    name, L, scaling, _ = pick_workload(args, world)
+    n_win = L - 2 * K_ORDER
+    t_start = time.perf_counter()
+    probe = CpuReference(13)
+    probe.step()                        # first-touch / thread-pool warm-up of the probe itself
+    sec_per_window = probe.step() / 13  # one probe step prices a window
+    del probe
+    total_steps = args.steps + args.warmup
+    budget = max(30.0, args.ref_budget_s - (time.perf_counter() - t_start))
+    fit = int(budget / (total_steps * sec_per_window))
+    ws = max(13, min(n_win, fit))
+    if args.cpu_windows_ref:
+        ws = min(n_win, args.cpu_windows_ref)
+    ref = CpuReference(ws)
+    for _ in range(args.warmup):
+        ref.step()
     t0 = time.perf_counter()
-    per = []
-    for _ in range(args.warmup_ref):
-        cpu_reference(sample_windows=args.cpu_windows, steps=1)
-    steps = max(1, min(args.steps, args.ref_steps))
-    for _ in range(steps):
-        per.append(cpu_reference(sample_windows=args.cpu_windows, steps=1))
-    vals = [p["value"] for p in per]
-    value = len(vals) / sum(1.0 / v for v in vals)  # harmonic mean == total work / total time
-    cpu = dict(per[-1])
-    cpu["value"] = round(value, 6)
-    L = 2 * K_ORDER + WINDOWS_PER_GPU
+    per = [ref.step() for _ in range(args.steps)]
+    wall_timed = time.perf_counter() - t0
+    ms_step_sample = 1e3 * wall_timed / args.steps
+    sec_full_step = (wall_timed / args.steps) * n_win / ws
+    value = L / (SAMPLER_STEPS * sec_full_step)  # one host runs one trajectory at a time: ensemble members are sequential
+    cpu = {"value": round(value, 6), "unit": "frames/s", "cores": ref.cores, "kind": "port",
+           "sample": f"{args.steps} timed guided predictor steps, each over {ws} of the {n_win} windows of the config"
+                     + ("" if ws == n_win else f" (scaled x{n_win}/{ws}: cost is linear in windows)"),
+           "sec_per_window_eval": round(wall_timed / args.steps / ws, 4), "threads": ref.cores,
+           "step_s_min_max": [round(min(per), 3), round(max(per), 3)]}
     line = {"impl": "reference", "metric": "guided-sampling frames/sec", "value": round(value, 6), "unit": "frames/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup_ref,
-            "ms_per_step": round(1e3 * L / (SAMPLER_STEPS * value), 3), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"config2: guided PC sampling, L={L} frames, sda_unet.yml ScoreUNet k={K_ORDER}, "
-                                   f"{SAMPLER_STEPS} steps, 0 corrections (CPU oracle port of the reference path; each "
-                                   f"step = bounded sample of {args.cpu_windows} windows, scaled by the window ratio)"},
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step_sample, 3),
+            "ms_per_full_step_scaled": round(1e3 * sec_full_step, 3),
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{name}: guided PC sampling, L={L} frames ({n_win} windows) of {C}x{H}x{W}, sda_unet.yml "
+                                   f"ScoreUNet k={K_ORDER}, {SAMPLER_STEPS} steps, 0 corrections, approx-grad guidance "
+                                   f"t_step=6 s_step=16 — CPU oracle port of the reference path; every step = {ws} windows",
+                       "name": name, "frames": L, "members": MEMBERS if name == "config4" else 1, "windows_per_step": ws,
+                       "windows_full": n_win},
             "cpu_baseline": cpu,
             "e2e": {"value": round(value, 6), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "wall_s": round(time.perf_counter() - t0, 1)}
+            "wall_s": round(time.perf_counter() - t_start, 1)}
     print(json.dumps(line), flush=True)
 
 
@@ -350,26 +546,32 @@ def main():
     ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=None, help="override L (default 12 + 156 * gpus)")
-    ap.add_argument("--chunk", type=int, default=int(os.environ.get("C2W_CHUNK", 156)), help="windows per UNet launch")
-    ap.add_argument("--e2e-steps", type=int, default=64,
-                    help="denoising steps of the end-to-end sample() call (its fixed costs — noise upload, final gather and "
-                         "download — are amortised over these steps; the real run has 256)")
-    ap.add_argument("--cpu-windows", type=int, default=13)
-    ap.add_argument("--ref-steps", type=int, default=3)
-    ap.add_argument("--warmup-ref", type=int, default=1)
+    ap.add_argument("--config", type=int, default=None, choices=[2, 3, 4],
+                    help="BASELINE.json workload: 2 = 1 week on one GPU (default at N=1), 3 = 1 month time-sharded "
+                         "(default at N>1), 4 = 16-member ensemble of a year as replicas")
+    ap.add_argument("--weak", action="store_true", help="weak-scaling workload: L = 12 + 156 N frames")
+    ap.add_argument("--frames", type=int, default=None, help="override the trajectory length L")
+    ap.add_argument("--chunk", type=int, default=int(os.environ.get("C2W_CHUNK", 192)), help="windows per UNet launch")
+    ap.add_argument("--e2e-steps", type=int, default=None,
+                    help="denoising steps of the end-to-end sample() call (default: the real run's 256; 8 for config 4)")
+    ap.add_argument("--cpu-windows", type=int, default=52, help="cpu_baseline sample of the GPU line")
+    ap.add_argument("--cpu-windows-ref", type=int, default=0, help="reference arm: force this many windows per step")
+    ap.add_argument("--ref-budget-s", type=float, default=420.0, help="reference arm: wall-time budget of the whole run")
     ap.add_argument("--exact-grad", action="store_true",
                     help="guidance through the UNet vector-Jacobian product (condition_on(exact_grad=True)); the shipped "
                          "experiment configs and the default bench line use the closed-form guidance")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-single", action="store_true", help="config 3: skip the one-GPU run of the same trajectory")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: no warm-up floor, no roofline/e2e/cpu legs")
     args = ap.parse_args()
+    if args.e2e_steps is None:
+        args.e2e_steps = 8 if args.config == 4 else SAMPLER_STEPS
     if args.impl == "reference":
         run_reference(args)
     else:
         if args.profile:
-            args.no_e2e = args.no_cpu = True
+            args.no_e2e = args.no_cpu = args.no_single = True
         else:
             args.warmup = max(args.warmup, 3)
         run_ours(args)

@@ -3,9 +3,11 @@ missing or a call fails, this raises."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libc2w_b200.so"
+# C2W_LIB selects another build of the same ABI (tools/: the -DC2W_DIAG library with K1's cycle counters)
+LIB_PATH = Path(os.environ.get("C2W_LIB") or Path(__file__).resolve().parent / "libc2w_b200.so")
 MAX_LEVELS = 8
 WS_VJP, WS_PER_SAMPLE_T = 1, 2
 

@@ -47,19 +47,24 @@ def _fingerprint() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every csrc/*.cu and link libc2w_b200.so.  Returns the library path."""
-    stamp = OBJ_DIR / "fingerprint.txt"
+def build(force: bool = False, verbose: bool = False, diag: bool = False) -> Path:
+    """Compile every csrc/*.cu and link libc2w_b200.so.  Returns the library path.
+    diag=True builds libc2w_b200_diag.so with -DC2W_DIAG instead: K1 with its per-role cycle counters and the
+    load-skipping timing experiments (tools/bringup_conv.py); the shipped library has none of that code."""
+    lib_path = PKG_DIR / "libc2w_b200_diag.so" if diag else LIB_PATH
+    obj_dir = PKG_DIR / "build" / "diag" if diag else OBJ_DIR
+    stamp = obj_dir / "fingerprint.txt"
     fp = _fingerprint()
-    if not force and LIB_PATH.exists() and stamp.exists() and stamp.read_text() == fp:
-        return LIB_PATH
+    if not force and lib_path.exists() and stamp.exists() and stamp.read_text() == fp:
+        return lib_path
     nvcc = _nvcc()
-    OBJ_DIR.mkdir(exist_ok=True)
+    obj_dir.mkdir(parents=True, exist_ok=True)
     inc = ["-I", str(CSRC), "-I", str(PKG_DIR.parent / "include")]
+    extra = ["-DC2W_DIAG"] if diag else []
 
     def compile_one(src: Path) -> Path:
-        obj = OBJ_DIR / (src.stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, *inc, "-c", str(src), "-o", str(obj)]
+        obj = obj_dir / (src.stem + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *extra, *inc, "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -71,13 +76,13 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *map(str, objs)]
+    cmd = [nvcc, "-shared", "-o", str(lib_path), *map(str, objs)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     stamp.write_text(fp)
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, diag="--diag" in sys.argv))

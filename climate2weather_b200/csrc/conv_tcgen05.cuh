@@ -38,6 +38,22 @@
 
 namespace c2w {
 
+// Diagnostics (per-role cycle counters, load-skipping timing experiments) exist only in builds with -DC2W_DIAG
+// (`python -m climate2weather_b200.build --diag` -> libc2w_b200_diag.so, used by tools/bringup_conv.py).  The shipped
+// library carries none of it: no clock64() around the barrier waits, no dbg_* branches in the producer.
+#ifdef C2W_DIAG
+#define C2W_TIMED_WAIT(ACC, BAR, PARITY) \
+  do {                                   \
+    const long long t0_ = clock64();     \
+    mbar_wait(BAR, PARITY);              \
+    (ACC) += clock64() - t0_;            \
+  } while (0)
+#define C2W_DIAG_CLOCK() clock64()
+#else
+#define C2W_TIMED_WAIT(ACC, BAR, PARITY) mbar_wait(BAR, PARITY)
+#define C2W_DIAG_CLOCK() 0ll
+#endif
+
 enum EpiMode : int {
   EPI_BIAS = 0,       // out = acc + bias                       -> bf16
   EPI_BIAS_SILU = 1,  // out = silu(acc + bias)                 -> bf16
@@ -348,6 +364,14 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map prefetch) touched only
+  // this CTA's shared memory / TMEM and may run while the PREVIOUS kernel of the stream is still draining its last
+  // tiles on other SMs.  launch_dependents lets the next kernel's CTAs be scheduled as SMs free up; wait blocks until
+  // the previous grid has completed and its global writes are visible — every global read below comes after it.
+  // (No-ops when the kernel was launched without the programmatic-serialization attribute.)
+  griddep_launch_dependents();
+  griddep_wait();
+
   // Producer and MMA warps run CONVERGED (all 32 lanes wait on the barriers) and issue under elect_one():
   // operands stay warp-uniform, so ptxas keeps descriptors/coordinates in uniform registers instead of wrapping
   // every tcgen05/TMA instruction in an R2UR waterfall.
@@ -361,8 +385,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       int issued = 0;
-      long long w_empty = 0;
-      const long long t_begin = clock64();
+      [[maybe_unused]] long long w_empty = 0;
+      [[maybe_unused]] const long long t_begin = C2W_DIAG_CLOCK();
       for (int tile = group_id; AR && tile < num_tiles; tile += num_groups) {
         const int nt = tile % p.num_n_tiles;
         const int mt = (tile / p.num_n_tiles) * CG + rank;
@@ -370,23 +394,26 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int h0 = (tt / p.tiles_w) * Cfg::kARTileH, w0 = (tt % p.tiles_w) * Cfg::kARTileW;
         for (int kb = 0; kb < 3 * p.cin_blocks; ++kb) {  // kb = cb * 3 + s
           const int cb = kb / 3, s3 = kb - cb * 3;
-          {
-            const long long t0 = clock64();
-            mbar_wait(&empty[stage], phase ^ 1);
-            w_empty += clock64() - t0;
-          }
+          C2W_TIMED_WAIT(w_empty, &empty[stage], phase ^ 1);
           if (elect_one()) {
             const uint32_t full_bar = (CG == 2) ? mapa_shared(smem_u32(&full[stage]), 0) : smem_u32(&full[stage]);
             uint8_t* sbase = smem + stage * Cfg::kARStageBytes;
+#ifdef C2W_DIAG
             if (p.dbg_skip_loads == 1 && issued >= num_stages) {
               if (rank == 0) mbar_arrive(&full[stage]);
-            } else {
+            } else
+#endif
+            {
+#ifdef C2W_DIAG
               // timing experiment (dbg_skip_loads == 2): every other tile reuses stale weights — the operand traffic
               // of a 256-row M tile sharing one B load, without its data flow
               // (3: no weight loads at all, 4: no activation loads at all — which latency does the ring cover?)
               const bool skip_b = ((p.dbg_skip_loads == 2 && ((tile / num_groups) & 1)) || p.dbg_skip_loads == 3) &&
                                   issued >= num_stages;
               const bool skip_a = p.dbg_skip_loads == 4 && issued >= num_stages;
+#else
+              constexpr bool skip_b = false, skip_a = false;
+#endif
               if (rank == 0)
                 mbar_arrive_expect_tx(&full[stage], CG * (p.ar_tx_bytes - (skip_b ? 3 * Cfg::kBTileBytes : 0) -
                                                           (skip_a ? p.ar_tx_bytes - 3 * Cfg::kBTileBytes : 0)));
@@ -425,16 +452,15 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         for (int kb = 0; kb < num_kb; kb += Cfg::kSub) {
           const int nsub = (num_kb - kb) < Cfg::kSub ? (num_kb - kb) : Cfg::kSub;
-          {
-            const long long t0 = clock64();
-            mbar_wait(&empty[stage], phase ^ 1);
-            w_empty += clock64() - t0;
-          }
+          C2W_TIMED_WAIT(w_empty, &empty[stage], phase ^ 1);
           if (elect_one()) {
             const uint32_t full_bar = (CG == 2) ? mapa_shared(smem_u32(&full[stage]), 0) : smem_u32(&full[stage]);
+#ifdef C2W_DIAG
             if (p.dbg_skip_loads == 1 && issued >= num_stages) {
               if (rank == 0) mbar_arrive(&full[stage]);
-            } else {
+            } else
+#endif
+            {
               if (rank == 0) mbar_arrive_expect_tx(&full[stage], CG * nsub * Cfg::kSubBytes);
               for (int sub = 0; sub < nsub; ++sub) {
                 const int kk = kb + sub;
@@ -462,10 +488,12 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
         }
       }
+#ifdef C2W_DIAG
       if (p.dbg_stats && lane == 0) {
         p.dbg_stats[blockIdx.x * 12 + 0] = clock64() - t_begin;
         p.dbg_stats[blockIdx.x * 12 + 1] = w_empty;
       }
+#endif
     } else if (warp_idx == 1 && rank == 0) {
       // ------------------------------------------------------------ MMA issuer (leader CTA, one elected lane issues)
       constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * CG, BN);
@@ -475,23 +503,15 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      long long w_full = 0, w_tmem = 0;
-      const long long t_begin = clock64();
+      [[maybe_unused]] long long w_full = 0, w_tmem = 0;
+      [[maybe_unused]] const long long t_begin = C2W_DIAG_CLOCK();
       for (int tile = group_id; tile < num_tiles; tile += num_groups) {
-        {
-          const long long t0 = clock64();
-          mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-          w_tmem += clock64() - t0;
-        }
+        C2W_TIMED_WAIT(w_tmem, &tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         const uint32_t ar_row_step = static_cast<uint32_t>(p.ar_row_step16);
         for (int kb = 0; AR && kb < 3 * p.cin_blocks; ++kb) {
-          {
-            const long long t0 = clock64();
-            mbar_wait(&full[stage], phase);
-            w_full += clock64() - t0;
-          }
+          C2W_TIMED_WAIT(w_full, &full[stage], phase);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (Cfg::kARStageBytes >> 4));
@@ -523,11 +543,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         for (int kb = 0; !AR && kb < num_kb; kb += Cfg::kSub) {
           const int nsub = (num_kb - kb) < Cfg::kSub ? (num_kb - kb) : Cfg::kSub;
-          {
-            const long long t0 = clock64();
-            mbar_wait(&full[stage], phase);
-            w_full += clock64() - t0;
-          }
+          C2W_TIMED_WAIT(w_full, &full[stage], phase);
           tc_fence_after();
           if (elect_one()) {
             // descriptor start-address field is (addr >> 4): slot stride and the 32 B K-advance are plain adds
@@ -562,11 +578,13 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
+#ifdef C2W_DIAG
       if (p.dbg_stats && lane == 0) {
         p.dbg_stats[blockIdx.x * 12 + 2] = clock64() - t_begin;
         p.dbg_stats[blockIdx.x * 12 + 3] = w_full;
         p.dbg_stats[blockIdx.x * 12 + 4] = w_tmem;
       }
+#endif
     } else if (staged && warp_idx == 2) {
       // ------------------------------------------------------------ warp 2: staging tile -> global
       // TMA store of the finished tile and the prefetch of the auxiliary tile of the staging tile's next user; the
@@ -582,10 +600,12 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int nt = tile % p.num_n_tiles;
         const int mt = (tile / p.num_n_tiles) * CG + rank;
         uint8_t* dst = stg0 + buf * Cfg::kStagingBytes;
+#ifdef C2W_DIAG
         if (p.dbg_skip_loads == 5) {  // timing experiment: no residual traffic (stale staging contents are used)
           mbar_arrive(&res_full[buf]);
           return;
         }
+#endif
         mbar_arrive_expect_tx(&res_full[buf], Cfg::kStagingBytes);
   #pragma unroll
         for (int b = 0; b < BN / 64; ++b) {
@@ -661,8 +681,8 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       int acc = 0;
       uint32_t acc_phase = 0;
       int it_local = 0;  // tiles processed by this CTA: staging tile it_local % 2 when double-buffered
-      long long w_tfull = 0, w_stg = 0, c_pass1 = 0;
-      const long long t_epi_begin = clock64();
+      [[maybe_unused]] long long w_tfull = 0, w_stg = 0, c_pass1 = 0;
+      [[maybe_unused]] const long long t_epi_begin = C2W_DIAG_CLOCK();
       for (int tile = group_id; tile < num_tiles; tile += num_groups) {
         const int nt = tile % p.num_n_tiles;
         const int mt = (tile / p.num_n_tiles) * CG + rank;
@@ -675,11 +695,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             m = ((2 * img + ((row >> 3) & 1)) * p.img_h + (row >> 4)) * p.img_w + tt * Cfg::kARTileW + (row & 7);
         }
         const bool valid = m < p.m_total;
-        {
-          const long long t0 = clock64();
-          mbar_wait(&tmem_full[acc], acc_phase);
-          w_tfull += clock64() - t0;
-        }
+        C2W_TIMED_WAIT(w_tfull, &tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col_base;
         const int buf = two_bufs ? (it_local & 1) : 0;
@@ -701,12 +717,10 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // staging tile ready to be written: its auxiliary tile has landed, or its previous store has read it
         auto wait_staging = [&]() {
           if (!staged) return;
-          const long long t0 = clock64();
-          if (has_aux) mbar_wait(&res_full[buf], use & 1);
-          else mbar_wait(&stg_free[buf], (use & 1) ^ 1);
-          w_stg += clock64() - t0;
+          if (has_aux) C2W_TIMED_WAIT(w_stg, &res_full[buf], use & 1);
+          else C2W_TIMED_WAIT(w_stg, &stg_free[buf], (use & 1) ^ 1);
         };
-        const long long t_p1 = clock64();
+        [[maybe_unused]] const long long t_p1 = C2W_DIAG_CLOCK();
         float s1 = 0.f, s2 = 0.f;
         uint32_t va[32], vb[32];
         if constexpr (kChunks <= 2) {
@@ -740,17 +754,21 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           __syncwarp();
           if (lane == 0) mbar_arrive(&stg_full[buf]);
         }
+#ifdef C2W_DIAG
         c_pass1 += clock64() - t_p1;
+#endif
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
         ++it_local;
       }
+#ifdef C2W_DIAG
       if (p.dbg_stats && threadIdx.x == 128) {
         p.dbg_stats[blockIdx.x * 12 + 5] = clock64() - t_epi_begin;
         p.dbg_stats[blockIdx.x * 12 + 6] = w_tfull;
         p.dbg_stats[blockIdx.x * 12 + 7] = w_stg;
         p.dbg_stats[blockIdx.x * 12 + 8] = c_pass1;
       }
+#endif
     }
   } else {
     if constexpr (LN) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
@@ -768,17 +786,16 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       for (int e = 0; e < 8; ++e) ln_m[e] = (LN && p.ln_mod) ? __ldg(p.ln_mod + (ln_chunk * 8 + e) % BN) : 0.f;
 
 
-      long long w_lnfull = 0, c_ln = 0;
+      [[maybe_unused]] long long w_lnfull = 0, c_ln = 0;
       int it_local = 0;
       for (int tile = group_id; tile < num_tiles; tile += num_groups) {
         const int mt = (tile / p.num_n_tiles) * CG + rank;
         const int buf = two_bufs ? (it_local & 1) : 0;
         const int use = two_bufs ? (it_local >> 1) : it_local;
         uint8_t* stg = stg0 + buf * Cfg::kStagingBytes;
-        const long long t_ln0 = clock64();
+        [[maybe_unused]] const long long t_ln0 = C2W_DIAG_CLOCK();
         if (LN) {
-          mbar_wait(&stg_full[buf], use & 1);  // every warp's columns of the tile and the row statistics are in place
-          w_lnfull += clock64() - t_ln0;
+          C2W_TIMED_WAIT(w_lnfull, &stg_full[buf], use & 1);  // every warp's columns of the tile and the row statistics are in place
           // ---- channel LayerNorm of the staged rows: y = (x + mod - mean) * inv with the row statistics the epilogue
           //      warps summed (unbiased variance, model/nn.py:154,183); kLPR lanes write a row's C channels as one
           //      contiguous segment (x4 when the output is 2x nearest-upsampled, model/nn.py:184)
@@ -892,14 +909,18 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&ln_done[buf]);
+#ifdef C2W_DIAG
           c_ln += clock64() - t_ln0;
+#endif
         }
         ++it_local;
       }
+#ifdef C2W_DIAG
       if (p.dbg_stats && lane == 0 && lw == 0) {
         p.dbg_stats[blockIdx.x * 12 + 9] = w_lnfull;
         p.dbg_stats[blockIdx.x * 12 + 10] = c_ln;
       }
+#endif
     }
   }
 
@@ -1142,6 +1163,16 @@ inline bool conv_launch_set_ln(ConvLaunch* L, __nv_bfloat16* ln_out, const float
   return true;
 }
 
+// C2W_PDL=0 launches K1 fully stream-serialised (A/B runs); default: programmatic dependent launch.
+inline bool conv_use_pdl() {
+  static int pdl = -1;
+  if (pdl < 0) {
+    const char* e = getenv("C2W_PDL");
+    pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return pdl != 0;
+}
+
 template <int BN, int CG, bool LN, bool AR>
 inline cudaError_t conv_launch_variant(const ConvLaunch& L, cudaStream_t stream) {
   using Cfg = ConvCfg<BN, CG>;
@@ -1170,13 +1201,18 @@ inline cudaError_t conv_launch_variant(const ConvLaunch& L, cudaStream_t stream)
   cfg.blockDim = dim3(kConvThreads + (LN ? kLnThreads : 0));
   cfg.dynamicSmemBytes = AR ? Cfg::ar_smem_bytes(p.num_staging) : Cfg::smem_bytes(p.num_staging);
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (conv_use_pdl()) {  // overlap this kernel's prologue with the previous kernel's tail (griddepcontrol in the kernel)
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   return cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<BN, CG, LN, AR>, L.tmA, L.tmB, L.tmOut, p);
 }
 

@@ -357,9 +357,10 @@ int run_modulation(c2w_handle* h, float t, const float* t_dev, int ns, float* h0
   time_embed_kernel<<<ns, 256, nf * sizeof(float), st>>>(t, t_dev, h->map0_w, h->map0_b, h0, E, nf);
   matvec_kernel<<<dim3(ceil_div(static_cast<long long>(E) * 32, 256), ns), 256, 0, st>>>(h->map1_w, h->map1_b, h0, emb, E,
                                                                                       E, 1);
-  matvec_kernel<<<dim3(ceil_div(static_cast<long long>(h->total_mod) * 32, 256), ns), 256, 0, st>>>(
-      h->proj_w, h->proj_b, emb, mods, h->total_mod, E, 0);
-  g_launches += 3;
+  if (h->total_mod > 0)  // a network without residual blocks has no modulation projections
+    matvec_kernel<<<dim3(ceil_div(static_cast<long long>(h->total_mod) * 32, 256), ns), 256, 0, st>>>(
+        h->proj_w, h->proj_b, emb, mods, h->total_mod, E, 0);
+  g_launches += h->total_mod > 0 ? 3 : 2;
   C2W_CUDA(cudaGetLastError());
   return C2W_OK;
 }

@@ -43,8 +43,14 @@ int c2w_op_conv_ex(const c2w_conv_desc* d, void* stream) {
   L.p.mode = d->mode;
   L.p.bias = d->bias;
   L.p.out_f32 = d->out_f32;
+#ifdef C2W_DIAG
   L.p.dbg_skip_loads = d->skip_loads;
   L.p.dbg_stats = reinterpret_cast<long long*>(d->stats);
+#else
+  C2W_REQUIRE(d->skip_loads == 0 && d->stats == nullptr,
+              "c2w_op_conv_ex: skip_loads / stats are diagnostics of the -DC2W_DIAG build (libc2w_b200_diag.so); the "
+              "shipped kernels carry no instrumentation");
+#endif
   if (d->mode != EPI_F32) {
     C2W_REQUIRE(d->out, "c2w_op_conv_ex: bf16 output modes need `out`");
     C2W_REQUIRE((d->mode != EPI_BIAS_RES && d->mode != EPI_MUL_DSILU) || d->res == d->out,

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import weakref
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -50,6 +51,15 @@ def _layer_specs(channels: int, embedding_dim: int, hidden_channels: Sequence[in
     specs.append(("map_layer0", (embedding_dim, NOISE_FEATURES)))
     specs.append(("map_layer1", (embedding_dim, embedding_dim)))
     return specs
+
+
+#: id(parameter) -> (weakref(parameter), weakref(ScoreUNet that owns it))
+_PARAM_OWNER: Dict[int, tuple] = {}
+
+
+def owner_of(p: nn.Parameter):
+    hit = _PARAM_OWNER.get(id(p))
+    return hit[1]() if hit is not None and hit[0]() is p else None
 
 
 class _Node(nn.Module):
@@ -180,9 +190,14 @@ class ScoreUNet(nn.Module):
 
     def __init__(self, channels: int, embedding_dim: int, forcing_dim: int = 0,
                  hidden_channels: Sequence[int] = (32, 64, 128), hidden_blocks: Sequence[int] = (2, 3, 5),
-                 attention_levels: Sequence[int] = (), kernel_size=3, stride=2, activation=nn.SiLU, spatial: int = 2,
+                 attention_levels: Sequence[int] = (), kernel_size=3, stride=2, activation=None, spatial: int = 2,
                  padding_mode: str = "zeros", **kwargs):
         super().__init__()
+        if activation is None:
+            # the reference's own default is torch.nn.ReLU (model/nn.py:118); every config passes SiLU (train.py:171).
+            # Falling back to either silently would build a different network than the caller may expect.
+            raise NotImplementedError("climate2weather_b200.ScoreUNet: pass activation=torch.nn.SiLU explicitly (the "
+                                      "reference default, ReLU, is not built; train.py:171 configures SiLU)")
         ks = kernel_size if isinstance(kernel_size, int) else kernel_size[0]
         st = stride if isinstance(stride, int) else stride[0]
         unsupported = []
@@ -216,6 +231,20 @@ class ScoreUNet(nn.Module):
             _register(self, prefix + ".weight", nn.Parameter(w))
             _register(self, prefix + ".bias", nn.Parameter(b))
         self._engines: Dict[tuple, Engine] = {}
+        self._weights_epoch = 0
+        self._tag_parameters()
+
+    def _tag_parameters(self) -> None:
+        """Lets an optimiser built from `net.parameters()` alone find the module whose engines it must invalidate."""
+        ref = weakref.ref(self)
+        for p in self.parameters():
+            # a side table keyed by identity, not an attribute: parameters must stay picklable
+            _PARAM_OWNER[id(p)] = (weakref.ref(p, lambda _, k=id(p): _PARAM_OWNER.pop(k, None)), ref)
+
+    def invalidate_engines(self) -> None:
+        """Declare the parameters changed behind autograd's back (raw-pointer optimiser / EMA updates do not bump
+        `Tensor._version`): the next forward re-packs the weights instead of serving the cached engine."""
+        self._weights_epoch = getattr(self, "_weights_epoch", 0) + 1
 
     def __getstate__(self):
         state = self.__dict__.copy()
@@ -226,9 +255,12 @@ class ScoreUNet(nn.Module):
         """Also accepts the pickled state of a REFERENCE `model.score.ScoreUNet` (a network snapshot,
         training_loop.py:250-266, unpickled through `compat.install()`): the module tree keeps the reference's
         parameter names, and the architecture description is read off their shapes."""
-        self.__dict__.update(state)
+        super().__setstate__(state)  # also restores the hook dictionaries older pickles lack
         self._engines = {}
+        self._weights_epoch = 0
+        self._tag_parameters()
         if "hidden_blocks" not in state:
+            _validate_reference_tree(self)
             arch = _arch_from_state_dict(self.state_dict())
             self.channels, self.embedding_dim = arch["channels"], arch["embedding_dim"]
             self.noise_features = NOISE_FEATURES
@@ -240,7 +272,7 @@ class ScoreUNet(nn.Module):
 
     # ---------------------------------------------------------------------------------------------- engines
     def _fingerprint(self) -> tuple:
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return (getattr(self, "_weights_epoch", 0),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def engine(self, frame_channels: int, window: int, height: int, width: int, device, max_windows: Optional[int] = None,
                vjp: bool = False, per_sample_t: bool = False) -> Engine:
@@ -288,9 +320,13 @@ class ScoreUNet(nn.Module):
             out = eng.unet_forward_t(x.detach().float().contiguous(), tt.to(x.device).contiguous())
             return out.to(x.dtype).reshape(x.shape)
         B, Cc, H, W = x.shape
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "ScoreUNet.forward under autograd with trainable parameters: parameter gradients come from "
+                "climate2weather_b200.training.TrainStep (fused forward + backward), not from torch autograd; "
+                "freeze the parameters (requires_grad_(False), as snapshots are: training_loop.py:257) for sampling")
         if torch.is_grad_enabled() and x.requires_grad:
-            # input gradients only (model/nn.py weights are frozen in sampling, training_loop.py:257); parameter
-            # gradients (training) are not built
+            # input gradients only (the weights are frozen in sampling, training_loop.py:257)
             return _UNetInputVJP.apply(x, self, float(tt[0]))
         eng = self.engine(Cc, 1, H, W, x.device)
         out = eng.unet_forward(x.detach().float().contiguous(), float(tt[0]))
@@ -339,7 +375,23 @@ def _arch_from_state_dict(sd) -> dict:
                 hidden_channels=ch, hidden_blocks=blocks, attention_levels=attn)
 
 
+def _validate_reference_tree(module: nn.Module) -> None:
+    """A reference module tree (a snapshot's `ema`, or a live model.score.ScoreUNet) must be the network this package
+    builds: SiLU activations (model/nn.py:156 `residue.2`) and zero padding; anything else would run silently wrong."""
+    for name, m in module.named_modules():
+        leaf = name.rsplit(".", 1)[-1]
+        if ".residue" in name and leaf == "2" and not list(m.children()):
+            if type(m).__name__ != "SiLU":
+                raise NotImplementedError(f"{name} is {type(m).__name__}: only SiLU activations are built")
+        pm = getattr(m, "padding_mode", None)
+        if pm is not None and pm != "zeros":
+            raise NotImplementedError(f"{name} has padding_mode={pm!r}: only zero padding is built")
+    if getattr(module, "map_forcing", None) is not None:
+        raise NotImplementedError("the network has a forcing branch (forcing_dim != 0); not supported")
+
+
 def build_from_reference(module: nn.Module) -> ScoreUNet:
     """New ScoreUNet with the architecture and weights of a reference `model.score.ScoreUNet` instance."""
-    net = ScoreUNet(**_arch_from_state_dict(module.state_dict()))
+    _validate_reference_tree(module)
+    net = ScoreUNet(activation=nn.SiLU, **_arch_from_state_dict(module.state_dict()))
     return net.from_reference(module)

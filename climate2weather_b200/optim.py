@@ -56,6 +56,70 @@ class AdamW:
             p.grad = self.grad[o:o + p.numel()].view_as(p)
         self.step_count = 0
         self._ema: Optional["StandardEMA"] = None
+        self._owners: List[torch.nn.Module] = []  # modules whose packed-weight engines go stale when we step
+        from .model import owner_of
+        for p in ps:
+            owner = owner_of(p)
+            if owner is not None:
+                self.track(owner)
+
+    def track(self, *modules: torch.nn.Module) -> "AdamW":
+        """Modules holding these parameters (ScoreUNet instances): `step()` updates the flat buffer through raw
+        pointers, which does not bump `Tensor._version`, so their cached packed-weight engines are invalidated
+        explicitly (`ScoreUNet.invalidate_engines`)."""
+        for m in modules:
+            if hasattr(m, "invalidate_engines") and all(m is not o for o in self._owners):
+                self._owners.append(m)
+        return self
+
+    def _bind_views(self) -> None:
+        """Parameters must alias the flat buffer (a later `.to()`, `load_state_dict(assign=True)` or manual `p.data =`
+        detaches them): re-adopt the current values and rebind, so a step never updates memory nobody reads."""
+        for p, o in zip(self.params, self.offsets):
+            if p.data_ptr() != self.flat.data_ptr() + 4 * o:
+                if p.device != self.flat.device or p.dtype != torch.float32:
+                    raise _lib.C2WError("a parameter left the optimizer's device/dtype; rebuild the optimizer")
+                self.flat[o:o + p.numel()].view_as(p).copy_(p.data)
+                p.data = self.flat[o:o + p.numel()].view_as(p)
+
+    # ---- checkpointing (training_loop.py:131-138 saves/restores the optimiser through CheckpointIO): torch.optim layout
+    def state_dict(self) -> dict:
+        state = {}
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+            sl = slice(o, o + p.numel())
+            state[i] = dict(step=torch.tensor(float(self.step_count)),
+                            exp_avg=self.exp_avg[sl].view_as(p).clone(), exp_avg_sq=self.exp_avg_sq[sl].view_as(p).clone())
+        groups = [{k: v for k, v in g.items() if k != "params"} | {"params": list(range(len(self.params)))}
+                  for g in self.param_groups]
+        return dict(state=state if self.step_count > 0 else {}, param_groups=groups, loss_scaling=self.loss_scaling)
+
+    def load_state_dict(self, sd: dict) -> None:
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.params):
+            raise ValueError("optimizer state does not match this parameter list")
+        for k, v in groups[0].items():
+            if k != "params":
+                self.param_groups[0][k] = tuple(v) if k == "betas" else v
+        self.loss_scaling = sd.get("loss_scaling", self.loss_scaling)
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        self.step_count = 0
+        for i, st in sd.get("state", {}).items():
+            i = int(i)
+            p, o = self.params[i], self.offsets[i]
+            sl = slice(o, o + p.numel())
+            self.exp_avg[sl].view_as(p).copy_(st["exp_avg"])
+            self.exp_avg_sq[sl].view_as(p).copy_(st["exp_avg_sq"])
+            self.step_count = max(self.step_count, int(float(st["step"])))
+
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d.pop("lib", None)  # a ctypes.CDLL cannot be pickled; reloaded on demand
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self.lib = _lib.load()
 
     def fuse_ema(self, ema: "StandardEMA") -> None:
         """Update `ema`'s first rate in the same pass as the parameters."""
@@ -63,6 +127,7 @@ class AdamW:
             raise ValueError("the EMA tracks a different parameter list than this optimizer")
         ema._bind(self)
         self._ema = ema
+        self.track(ema.net)
 
     def zero_grad(self, set_to_none: bool = False) -> None:
         self.grad.zero_()
@@ -72,6 +137,7 @@ class AdamW:
 
     @torch.no_grad()
     def step(self) -> None:
+        self._bind_views()
         for p, o in zip(self.params, self.offsets):
             if p.grad is None:
                 raise RuntimeError("a parameter has no gradient; call backward() before step()")
@@ -92,6 +158,10 @@ class AdamW:
             _lib.check(self.lib.c2w_adamw_ema_step(self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
                                                    self.exp_avg_sq.data_ptr(), ema_ptr, self.flat.numel(),
                                                    ctypes.byref(hp), st), "c2w_adamw_ema_step")
+        for m in self._owners:
+            m.invalidate_engines()
+        if self._ema is not None:
+            self._ema._invalidate(0)
 
 
 class StandardEMA:
@@ -117,12 +187,20 @@ class StandardEMA:
                 flat[o:o + p.numel()].view_as(p).copy_(p.data)
                 p.data = flat[o:o + p.numel()].view_as(p)
             self._flat.append(flat)
+            self._invalidate(len(self._flat) - 1)
+
+    def _invalidate(self, i: int) -> None:
+        """EMA copy i changed through its flat buffer: its cached packed-weight engine (validation sampling runs on
+        the EMA network, training_loop.py:277-313) must be rebuilt."""
+        if hasattr(self.emas[i], "invalidate_engines"):
+            self.emas[i].invalidate_engines()
 
     @torch.no_grad()
     def reset(self):
-        for ema in self.emas:
+        for i, ema in enumerate(self.emas):
             for p_net, p_ema in zip(self.net.parameters(), ema.parameters()):
                 p_ema.copy_(p_net)
+            self._invalidate(i)
 
     @torch.no_grad()
     def update(self, **kwargs):
@@ -137,6 +215,7 @@ class StandardEMA:
             else:
                 for p_net, p_ema in zip(self.net.parameters(), ema.parameters()):
                     p_ema.detach().mul_(rate).add_(p_net, alpha=1 - rate)
+            self._invalidate(i)
 
     @torch.no_grad()
     def get(self):

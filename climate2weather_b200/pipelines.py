@@ -15,8 +15,9 @@ from typing import Optional
 import torch
 from torch import Tensor
 
+from . import _lib
 from .score import AbstractScoreFunction, _mu_sigma
-from .sharding import all_gather_frames
+from .sharding import all_gather_frames, gather_frames
 
 
 class SDAPipeline:
@@ -26,9 +27,13 @@ class SDAPipeline:
     #: read the device NaN flag every this many steps (0 = only at the end); the reference syncs every step (:90).
     #: The per-step read is asynchronous and inspected one check later, so a NaN raises one step after it appeared.
     nan_check_every: int = 0
+    #: optional debugging / parity hook: sampler steps (1-based) after which the trajectory is copied out; the copies
+    #: land in `self.traces[step]` (NCHW, host).  None = off (no copies, no synchronisation).
+    trace_at = None
 
     def __init__(self, eta=1e-3):
         self.eta = eta  # src/thor/pipelines.py:9-11
+        self.traces = {}
 
     # ---------------------------------------------------------------- schedule (src/thor/pipelines.py:13-20)
     def alpha(self, t):
@@ -67,13 +72,10 @@ class SDAPipeline:
         if not isinstance(score_fn, AbstractScoreFunction):
             raise TypeError("SDAPipeline.sample drives this package's score functions (Default/BatchedScoreFunction); "
                             f"got {type(score_fn).__name__}.  There is no generic torch-op sampling loop here.")
-        if proc_x0 is not None:
-            raise NotImplementedError("proc_x0 hooks are not supported: the predictor update is one fused kernel over the "
-                                      "resident trajectory (no reference experiment config uses the hook)")
-        return self._sample_resident(score_fn, noise, steps, corrections, tau, device, show_progressbar, seed)
+        return self._sample_resident(score_fn, noise, steps, corrections, tau, device, show_progressbar, seed, proc_x0)
 
     def _sample_resident(self, sf: AbstractScoreFunction, noise: Tensor, steps: int, corrections: int, tau: float,
-                         device, show_progressbar: bool, seed: Optional[int]) -> Tensor:
+                         device, show_progressbar: bool, seed: Optional[int], proc_x0=None) -> Optional[Tensor]:
         if device is not None and torch.device(device).type == "cuda":
             sf.device = torch.device(device)
         rt = sf.runtime(noise)
@@ -85,6 +87,15 @@ class SDAPipeline:
         z_dev = None
         if seed is None:
             seed = int(torch.empty((), dtype=torch.int64).random_().item()) if corrections > 0 else 0
+            if sf.shard and corrections > 0 and self.rng != "reference":
+                # the on-chip Philox stream is keyed by (seed, step, GLOBAL pixel): every rank must use rank 0's draw,
+                # otherwise the result would depend on the sharding
+                s_t = torch.tensor([seed], dtype=torch.int64, device=rt.device)
+                torch.distributed.broadcast(s_t, src=torch.distributed.get_global_rank(group, 0) if group else 0,
+                                            group=group)
+                seed = int(s_t.item())
+        self.traces = {}
+        trace_at = set(int(v) for v in self.trace_at) if self.trace_at else ()
         iterator = time_steps[:-1]
         if show_progressbar:
             try:
@@ -100,7 +111,10 @@ class SDAPipeline:
             mu_n, sigma_n = _mu_sigma(self, t_next)
             # predictor
             rt.score(float(t), group)
-            rt.predictor(mu, sigma, mu_n, sigma_n)
+            if proc_x0 is None:
+                rt.predictor(mu, sigma, mu_n, sigma_n)
+            else:
+                rt.predictor_with_hook(mu, sigma, mu_n, sigma_n, proc_x0)
             rt.halo(group)
             # corrector
             for ic in range(corrections):
@@ -110,7 +124,6 @@ class SDAPipeline:
                     if z_dev is None:
                         z_dev = torch.empty_like(rt.x)
                     src = z_host[p.frame_lo:p.frame_hi].to(rt.device, non_blocking=False).contiguous()
-                    from . import _lib
                     with torch.cuda.device(rt.device):
                         _lib.check(rt.lib.c2w_traj_pack(src.data_ptr(), z_dev.data_ptr(), p.n_local, rt.C, rt.H * rt.W,
                                                         rt.stream), "c2w_traj_pack")
@@ -120,11 +133,29 @@ class SDAPipeline:
                 rt.halo(group)
             if self.nan_check_every and (istep + 1) % self.nan_check_every == 0:
                 rt.check_finite_lagged()  # reads the flag every check, one check behind: no launch-queue stall
+            if (istep + 1) in trace_at:
+                tr = rt.owned(rt.x)
+                if sf.shard:
+                    tr = all_gather_frames(tr, rt.plan, group)
+                self.traces[istep + 1] = tr.cpu()
         rt.check_finite()
         out = rt.owned(rt.x)
         if sf.shard:
-            out = all_gather_frames(out, rt.plan, group)
+            # time-sharded: the trajectory is assembled on the ranks that asked for it (default: rank 0 of the group;
+            # `enable_time_sharding(gather="all")` for every rank) — the others return None
+            if sf.shard_gather == "all":
+                out = all_gather_frames(out, rt.plan, group)
+            else:
+                out = gather_frames(out, rt.plan, group, dst=int(sf.shard_gather))
         total_time = time.time() - total_start_time
         print(f"Total sampling time: {total_time:.2f} s  = {total_time / 60:.3f} min = {total_time / 3600:.4f} h")
+        if out is None:
+            return None
         target = noise.device if device is None else torch.device(device)
+        if target.type == "cpu":
+            # one asynchronous copy into pinned memory (a pageable destination makes the driver stage it in chunks)
+            host = rt.host_result(out.shape, noise.dtype)
+            host.copy_(out.to(noise.dtype), non_blocking=True)
+            torch.cuda.current_stream(rt.device).synchronize()
+            return host.reshape(noise.shape)
         return out.to(device=target, dtype=noise.dtype).reshape(noise.shape)

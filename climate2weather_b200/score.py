@@ -17,7 +17,7 @@ from torch import Tensor
 
 from . import _lib
 from .model import ScoreUNet, build_from_reference
-from .sharding import ShardPlan, all_gather_frames, exchange_halos, exchange_halos_adjoint, make_plan
+from .sharding import ShardPlan, exchange_halos, exchange_halos_adjoint, make_plan
 
 
 class CoarseGrain:
@@ -79,8 +79,11 @@ class _Runtime:
         self.lib = _lib.load()
         k = sf.markov_order
         self.exact = bool(exact)  # exact_grad=True: guidance through the UNet VJP (src/thor/score.py:28-33,51-52)
-        self.engine = sf.unet.engine(C, 2 * k + 1, H, W, device, max_windows=min(max_windows, plan.win_hi - plan.win_lo),
-                                     vjp=self.exact)
+        self._engine_args = (C, 2 * k + 1, H, W, device)
+        self._engine_windows = min(max_windows, plan.win_hi - plan.win_lo)
+        self._engine = None
+        self._engine_epoch = None
+        self.refresh_engine()
         f32 = dict(dtype=torch.float32, device=device)
         self.x = torch.zeros(plan.n_local, H, W, C, **f32)
         self.eps = torch.zeros_like(self.x)
@@ -92,6 +95,19 @@ class _Runtime:
         self.partials: Optional[Tensor] = None
         self.cond = None
         self.s_tile = next(s for s in (16, 8, 32, 4, 64, 2, 128, 1) if H % s == 0 and W % s == 0 and W // s <= 32)
+
+    # ------------------------------------------------------------------------------------------------ engine
+    def refresh_engine(self) -> None:
+        """(Re)binds the packed-weight engine; `ScoreUNet.engine` re-packs if the parameters changed since (full
+        fingerprint: data pointers, autograd versions, and the explicit epoch raw-pointer optimisers bump)."""
+        self._engine = self.sf.unet.engine(*self._engine_args, max_windows=self._engine_windows, vjp=self.exact)
+        self._engine_epoch = getattr(self.sf.unet, "_weights_epoch", 0)
+
+    @property
+    def engine(self):
+        if getattr(self.sf.unet, "_weights_epoch", 0) != self._engine_epoch:  # optimiser / EMA step since the last call
+            self.refresh_engine()
+        return self._engine
 
     # ------------------------------------------------------------------------------------------------ state io
     @property
@@ -185,6 +201,29 @@ class _Runtime:
         """x <- mu' (x - sigma eps_g)/mu + sigma' eps_g on the owned frames (src/thor/pipelines.py:41-46)."""
         self._guide(0, mu, sigma, mu_next, sigma_next)
 
+    def predictor_with_hook(self, mu: float, sigma: float, mu_next: float, sigma_next: float, proc_x0) -> None:
+        """The predictor with a user `proc_x0` callable (src/thor/pipelines.py:43-45).  The fused update is split around
+        the hook: the guided score comes from the kernel (mode 1); x0 = (x - sigma eps)/mu is handed to the callable as
+        an NCHW device tensor and `mu' proc(x0) + sigma' eps` written back — elementwise torch ops on the resident
+        tensors, because the hook itself is an arbitrary torch callable (no shipped config passes one)."""
+        p = self.plan
+        self._guide(1, mu, sigma, 0.0, 0.0)
+        lo = p.own_lo - p.frame_lo
+        x_own, e_own = self.x[lo:lo + p.own_n], self.eps_g[lo:lo + p.own_n]
+        x0 = proc_x0(((x_own - sigma * e_own) / mu).permute(0, 3, 1, 2))
+        if tuple(x0.shape) != (p.own_n, self.C, self.H, self.W):
+            raise ValueError(f"proc_x0 returned shape {tuple(x0.shape)}")
+        x_own.copy_(mu_next * x0.permute(0, 2, 3, 1) + sigma_next * e_own)
+        self.nan_flag |= (~torch.isfinite(x_own)).any().to(torch.int32)
+
+    def host_result(self, shape, dtype) -> Tensor:
+        """Pinned host buffer for the sampler's result (reused across sample() calls of this geometry)."""
+        buf = getattr(self, "_host_result", None)
+        if buf is None or tuple(buf.shape) != tuple(shape) or buf.dtype != dtype:
+            buf = torch.empty(tuple(shape), dtype=dtype).pin_memory()
+            self._host_result = buf
+        return buf
+
     def guided_eps(self, mu: float, sigma: float) -> None:
         """eps_g <- eps - sigma * grad_x log p(y | x) (src/thor/score.py:24-35) and the partial sums of eps_g^2."""
         self._guide(1, mu, sigma, 0.0, 0.0)
@@ -258,6 +297,7 @@ class AbstractScoreFunction:
         self.likelihood = None
         self.device: Optional[torch.device] = None
         self.shard = None  # (rank, world, group) once enable_time_sharding() was called
+        self.shard_gather = 0  # rank that receives the sampled trajectory ("all": every rank)
         self._runtimes = {}
         self.unet.eval()
 
@@ -302,11 +342,13 @@ class AbstractScoreFunction:
         return rt.owned(rt.eps).to(device=x.device, dtype=x.dtype)
 
     # ------------------------------------------------------------------------------------------------ runtime
-    def enable_time_sharding(self, group=None) -> "AbstractScoreFunction":
-        """Partition trajectories along time over the ranks of `group` (default: the world group)."""
+    def enable_time_sharding(self, group=None, gather=0) -> "AbstractScoreFunction":
+        """Partition trajectories along time over the ranks of `group` (default: the world group).  `gather`: the
+        group rank on which `SDAPipeline.sample` assembles the result (the other ranks return None), or "all"."""
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self.shard = (dist.get_rank(group), dist.get_world_size(group), group)
+        self.shard_gather = gather
         self._runtimes.clear()
         return self
 
@@ -353,6 +395,8 @@ class AbstractScoreFunction:
                     lk["gamma_c"] = _per_channel(lk["gamma"], C, "gamma")
                 rt.set_condition(dict(op=lk["op"], y=lk["y"], std=lk["std_c"], gamma=lk["gamma_c"]))
             self._runtimes = {key: rt}  # one live trajectory geometry at a time
+        else:
+            rt.refresh_engine()  # once per score call / sampling run: catches in-place parameter updates
         return rt
 
 
@@ -361,12 +405,47 @@ def _mu_sigma(noise_process, t) -> tuple:
     return float(noise_process.mu(tt)), float(noise_process.sigma(tt))
 
 
+def _window_view(x: Tensor, w: int) -> Tensor:
+    """[L, C, H, W] -> [L-w+1, w*C, H, W] with U[j, tau*C + c] = x[j + tau, c]: the zero-copy strided view the
+    reference builds with unfold/movedim/flatten (src/thor/score.py:68-74, :143-152).  Layout helper only — the
+    sampling path never materialises it (K0 gathers windows straight from the resident trajectory)."""
+    L, C, H, W = x.shape
+    if L < w:
+        raise ValueError(f"trajectory of {L} frames is shorter than one window of {w}")
+    x = x.contiguous()
+    sL, sC, sH, sW = x.stride()
+    return x.as_strided((L - w + 1, w * C, H, W), (sL, sC, sH, sW))  # channel tau*C + c sits tau*sL + c*sC == (tau*C + c)*sC
+
+
+def _pick_slots(n: Tensor, k: int, head: bool, tail: bool) -> Tensor:
+    """Centre-pick / edge-fill of a window batch n[B, w*C, H, W] (src/thor/score.py:76-88, :124-141): optional head
+    slots 0..k-1 of the first window, the centre slot k of every window, optional tail slots k+1..2k of the last."""
+    w = 2 * k + 1
+    B = n.shape[0]
+    v = n.reshape(B, w, n.shape[1] // w, *n.shape[2:])
+    parts = []
+    if head:
+        parts.append(v[0, :k])
+    parts.append(v[:, k])
+    if tail:
+        parts.append(v[B - 1, k + 1:])
+    return torch.cat(parts, dim=0) if len(parts) > 1 else parts[0]
+
+
 class DefaultScoreFunction(AbstractScoreFunction):
     """src/thor/score.py:63-93."""
 
     def __init__(self, unet, markov_order, **kwargs):
         super().__init__(unet=unet, **kwargs)
         self.markov_order = markov_order
+
+    def unfold(self, x: Tensor) -> Tensor:
+        """src/thor/score.py:68-74 (index map only; see `_window_view`)."""
+        return _window_view(x, 2 * self.markov_order + 1)
+
+    def fold(self, x: Tensor) -> Tensor:
+        """src/thor/score.py:76-88 (index map only)."""
+        return _pick_slots(x, self.markov_order, True, True)
 
 
 class BatchedScoreFunction(AbstractScoreFunction):
@@ -379,6 +458,18 @@ class BatchedScoreFunction(AbstractScoreFunction):
         self.batch_size = batch_size
         self.device = device if device is not None else torch.device("cuda")
         print(f">>> Initialized batched score function to use device: {self.device}")
+
+    def _batch_noise(self, x: Tensor):
+        """src/thor/score.py:143-154: the window view split into batches of `batch_size` (views, no copies)."""
+        return _window_view(x, 2 * self.markov_order + 1).split(self.batch_size, 0)
+
+    def _window_score(self, x: Tensor, t: Tensor, is_first: bool, is_last: bool) -> Tensor:
+        """src/thor/score.py:111-141 for one explicit window batch x[B, w*C, H, W]: ScoreUNet forward on the device
+        (c2w_unet_forward), then the slot selection.  `score_fn` / `__call__` do NOT go through this method — they run
+        the fused gather -> UNet -> compose path on the resident trajectory."""
+        dev = self._compute_device(x)
+        out = self.net_forward(x.to(dev), t)
+        return _pick_slots(out, self.markov_order, is_first, is_last)
 
     def _default_windows(self, n_win: int) -> int:
         # `batch_size` bounds device memory in the reference (src/thor/score.py:143-154); results do not depend on it.

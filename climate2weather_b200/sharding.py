@@ -123,3 +123,28 @@ def all_gather_frames(x_owned: torch.Tensor, plan: ShardPlan, group: Optional[di
     bufs = [torch.empty_like(mine) for _ in counts]
     dist.all_gather(bufs, mine, group=group)  # equal-sized buffers: valid on both nccl and gloo
     return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+
+
+def gather_frames(x_owned: torch.Tensor, plan: ShardPlan, group: Optional[dist.ProcessGroup] = None,
+                  dst: int = 0) -> Optional[torch.Tensor]:
+    """Collects every rank's owned frames on rank `dst` only (end of sampling): the other ranks send their frames
+    straight into the matching slice of dst's [L, ...] tensor — no padding, no copy on the ranks that did not ask for
+    the result.  Returns the full trajectory on `dst`, None elsewhere.  (`all_gather_frames` is the every-rank form.)"""
+    if plan.world == 1:
+        return x_owned
+    x_owned = x_owned.contiguous()
+    if plan.rank != dst:
+        for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, x_owned, dst, group)]):
+            req.wait()
+        return None
+    full = torch.empty((plan.L,) + tuple(x_owned.shape[1:]), dtype=x_owned.dtype, device=x_owned.device)
+    ops: List[dist.P2POp] = []
+    for r in range(plan.world):
+        pr = make_plan(plan.L, plan.k, r, plan.world)
+        if r == dst:
+            full[pr.own_lo:pr.own_hi] = x_owned
+        else:
+            ops.append(dist.P2POp(dist.irecv, full[pr.own_lo:pr.own_hi], r, group))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    return full

@@ -1,0 +1,137 @@
+"""Full-length parity on the BASELINE network (pytest -m gpu): guided predictor-corrector sampling over 256 steps on the
+configs/sda_unet.yml ScoreUNet (random init, seed 0), L = 25 frames (13 windows, k = 6), shipped likelihood
+(exp/configs/000_on-model-eval/s16_t6.yml:13-27), against trajectories written by the REFERENCE'S OWN
+`BatchedScoreFunction.condition_on(...)` + `SDAPipeline.sample(...)` (tests/golden/make_golden_full.py ->
+tests/golden/full_sample_*.npz: state after steps 1/4/16/64/128/192/256, first guided score, checksums).
+
+How the tolerance is stated.  The sampler multiplies the state by mu(t-dt)/mu(t) every step (x1000 over the run) and a
+random-init network does not cancel that growth, so the fp32 trajectory itself reaches |x| ~ 1e4 and a per-step score
+error is carried along and amplified; 16-bit tensor-core operands therefore move the END of the trajectory far more
+than they move one score evaluation.  The fixtures include the reference's own run under bf16 autocast (the authors
+sample under Fabric "16-mixed"): its drift from the reference's fp32 run, per trace step, is the yardstick.  This path
+(bf16 operands, fp32 accumulation, bf16 residual stream, fp32 state) is held to
+
+    rel-L2(ours, reference fp32)  <=  max(FLOOR, FACTOR x rel-L2(reference bf16, reference fp32))   per trace step,
+
+plus absolute bounds on the first steps, where nothing has been amplified yet: rel-L2 <= 2e-2 / max-abs ratio <= 3e-2
+for the first guided score and the state after step 1.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+STD = [0.1692666615037876, 0.0425178630338289, 0.3268027589410125, 0.3268027589410125]
+GAMMA = 0.0007196856730011522
+L, K = 25, 6
+TRACES = (1, 4, 16, 64, 128, 192)
+FLOOR, FACTOR = 2e-2, 3.0
+
+
+def _problem():
+    g = torch.Generator().manual_seed(21)  # make_golden_full.py:problem()
+    noise = torch.randn(L, 4, 128, 128, generator=g)
+    truth = torch.randn(L, 4, 128, 128, generator=g)
+    pool = torch.nn.AvgPool2d(16, stride=16, padding=0)
+
+    def A(z):  # the driver's closure, exp/downscaling.py:129-132
+        return pool(z[..., ::6, :, :, :])
+
+    return noise, A(truth), A
+
+
+def _rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def _max_ratio(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+def _frame_rel_l2(a, b):
+    a, b = np.asarray(a, np.float64).reshape(len(a), -1), np.asarray(b, np.float64).reshape(len(b), -1)
+    return float((np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)).max())
+
+
+@pytest.fixture(scope="module")
+def net():
+    import climate2weather_b200 as c2w
+    torch.manual_seed(0)
+    n = c2w.ScoreUNet(52, 512, hidden_channels=[128, 128, 256, 384, 512], hidden_blocks=[3] * 5, attention_levels=[4],
+                      activation=torch.nn.SiLU)
+    return n.to("cuda:0").requires_grad_(False)
+
+
+def _run(net, name, golden_dir):
+    import climate2weather_b200 as c2w
+    g = np.load(golden_dir / f"full_sample_{name}.npz")
+    steps, corrections, exact = int(g["steps"]), int(g["corrections"]), bool(int(g["exact"]))
+    noise, y, A = _problem()
+    pipe = c2w.SDAPipeline()
+    pipe.rng = "reference"  # corrector noise from the global CPU generator, like src/thor/pipelines.py:82
+    pipe.trace_at = [s for s in TRACES if s < steps]
+    sf = c2w.BatchedScoreFunction(net, markov_order=K, noise_process=pipe, batch_size=13, device=torch.device("cuda:0"))
+    sf.condition_on(A=A, y=y, std=torch.tensor(STD).reshape(1, 4, 1, 1), gamma=GAMMA, exact_grad=exact)
+    first = sf(noise, torch.tensor(1.0))
+    torch.manual_seed(int(g["corr_seed"]))
+    out = pipe.sample(sf, noise, steps=steps, corrections=corrections, tau=float(g["tau"]), show_progressbar=False)
+    assert out.device.type == "cpu" and out.shape == noise.shape and bool(torch.isfinite(out).all())
+    return g, first, pipe.traces, out
+
+
+def _report(name, g, first, traces, out, yard=None):
+    rows = []
+    e_first = (_rel_l2(first[:, :, ::8, ::8], g["first_eps"]), _max_ratio(first[:, :, ::8, ::8], g["first_eps"]))
+    rows.append(("first guided score", *e_first, None))
+    for s in sorted(traces):
+        ref = g[f"x_after_{s}"]
+        got = traces[s][:, :, ::8, ::8]
+        rows.append((f"x after step {s}", _rel_l2(got, ref), _max_ratio(got, ref),
+                     None if yard is None else _rel_l2(yard[f"x_after_{s}"], ref)))
+    ref = g["final"]
+    got = out[:, :, ::4, ::4]
+    rows.append((f"final (step {int(g['steps'])})", _rel_l2(got, ref), _max_ratio(got, ref),
+                 None if yard is None else _rel_l2(yard["final"], ref)))
+    print(f"\n[{name}] vs the reference's own run (rel-L2, max-abs ratio, reference-bf16 yardstick rel-L2):")
+    for r in rows:
+        print(f"   {r[0]:<22s} {r[1]:.3e}  {r[2]:.3e}  " + ("-" if r[3] is None else f"{r[3]:.3e}"))
+    print(f"   worst frame rel-L2 of the final state: {_frame_rel_l2(got, ref):.3e}; "
+          f"energy ratio {float((out.double() ** 2).sum() / g['final_sumsq'].sum()):.4f}")
+    return rows
+
+
+def test_full_length_c0_vs_reference(net, golden_dir):
+    """The shipped configuration at its own step count: 256 steps, 0 corrections, exact_grad False."""
+    yard = np.load(golden_dir / "full_sample_c0_bf16.npz")
+    g, first, traces, out = _run(net, "c0", golden_dir)
+    rows = _report("c0: 256 steps, corrections 0", g, first, traces, out, yard)
+    assert rows[0][1] < 2e-2 and rows[0][2] < 3e-2          # one score evaluation
+    assert rows[1][1] < 2e-2 and rows[1][2] < 3e-2          # one sampler step
+    for label, l2, _, y in rows[1:]:
+        assert l2 <= max(FLOOR, FACTOR * y), (label, l2, y)
+    # the energy of the sample (a size-independent property: sum of squares over the whole tensor vs the fixture's)
+    ratio = float((out.double() ** 2).sum() / g["final_sumsq"].sum())
+    assert abs(ratio - 1) < max(2 * FLOOR, 2 * FACTOR * rows[-1][3])
+
+
+def test_full_length_c2_vs_reference(net, golden_dir):
+    """256 steps with 2 Langevin corrections each (768 score evaluations), the reference's corrector noise stream."""
+    yard = np.load(golden_dir / "full_sample_c0_bf16.npz")  # same yardstick (no bf16 run of c2 was generated)
+    g, first, traces, out = _run(net, "c2", golden_dir)
+    rows = _report("c2: 256 steps, corrections 2", g, first, traces, out)
+    assert rows[0][1] < 2e-2 and rows[1][1] < 3e-2
+    for (label, l2, _, _), key in zip(rows[1:], [f"x_after_{s}" for s in TRACES] + ["final"]):
+        y = _rel_l2(yard[key], np.load(golden_dir / "full_sample_c0.npz")[key])
+        assert l2 <= max(FLOOR, FACTOR * y), (label, l2, y)
+
+
+def test_full_length_exact_grad_vs_reference(net, golden_dir):
+    """Guidance through the UNet VJP (exact_grad=True), 16 steps: tensor-core forward AND input-gradient pass."""
+    g, first, traces, out = _run(net, "exact", golden_dir)
+    rows = _report("exact: 16 steps, exact_grad", g, first, traces, out)
+    assert rows[0][1] < 3e-2 and rows[0][2] < 5e-2
+    assert rows[1][1] < 3e-2
+    assert rows[-1][1] < 0.15, rows[-1]

@@ -30,7 +30,7 @@ def test_unet_forward_beats_cudnn_bf16_path():
     dev = torch.device("cuda:0")
     cfg = unet_ref.SDA_UNET
     torch.manual_seed(0)
-    net = c2w.ScoreUNet(52, 512, hidden_channels=[128, 128, 256, 384, 512], hidden_blocks=[3] * 5, attention_levels=[4])
+    net = c2w.ScoreUNet(52, 512, hidden_channels=[128, 128, 256, 384, 512], hidden_blocks=[3] * 5, attention_levels=[4], activation=torch.nn.SiLU)
     sd_dev = {k: v.detach().to(dev) for k, v in net.state_dict().items()}
     lib_net = unet_ref.RefNet(sd_dev, cfg)  # the oracle's torch-op forward with the weights on the GPU
     net = net.to(dev)

@@ -42,7 +42,7 @@ def test_no_cpu_path():
 
     if torch.cuda.is_available():
         pytest.skip("CUDA present")
-    net = c2w.ScoreUNet(channels=20, embedding_dim=64, hidden_channels=(64,), hidden_blocks=(1,), attention_levels=())
+    net = c2w.ScoreUNet(channels=20, embedding_dim=64, hidden_channels=(64,), hidden_blocks=(1,), attention_levels=(), activation=torch.nn.SiLU)
     with pytest.raises(_lib.C2WError):
         net(torch.zeros(1, 20, 16, 16), torch.tensor(0.5))
     sf = c2w.DefaultScoreFunction(net, markov_order=2, noise_process=c2w.SDAPipeline())
@@ -51,16 +51,18 @@ def test_no_cpu_path():
 
 
 def test_sampler_has_no_generic_torch_loop():
-    """SDAPipeline.sample must not quietly run a torch-op loop for foreign score functions or proc_x0 hooks."""
+    """SDAPipeline.sample must not quietly run a torch-op loop for foreign score functions; with one of this package's
+    score functions (proc_x0 hook or not) it needs the CUDA path and says so on a CPU box."""
     import climate2weather_b200 as c2w
 
     pipe = c2w.SDAPipeline()
     with pytest.raises(TypeError):
         pipe.sample(lambda x, t: x, torch.zeros(3, 4, 8, 8), steps=1)
-    net = c2w.ScoreUNet(channels=20, embedding_dim=64, hidden_channels=(64,), hidden_blocks=(1,), attention_levels=())
+    net = c2w.ScoreUNet(channels=20, embedding_dim=64, hidden_channels=(64,), hidden_blocks=(1,), attention_levels=(), activation=torch.nn.SiLU)
     sf = c2w.DefaultScoreFunction(net, markov_order=2, noise_process=pipe)
-    with pytest.raises(NotImplementedError):
-        pipe.sample(sf, torch.zeros(8, 4, 16, 16), steps=1, proc_x0=lambda v: v)
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.C2WError):
+            pipe.sample(sf, torch.zeros(8, 4, 16, 16), steps=1, proc_x0=lambda v: v)
     # the schedule is the reference's (src/thor/pipelines.py:13-20): mu(0) = 1, sigma(0) = eta, mu(1) = eta
     t0, t1 = torch.tensor(0.0), torch.tensor(1.0)
     assert abs(float(pipe.mu(t0)) - 1.0) < 1e-6 and abs(float(pipe.sigma(t0)) - 1e-3) < 1e-6
@@ -101,7 +103,7 @@ def test_reference_snapshot_unpickles_through_compat():
         assert abs(sd[str(k)].double().sum().item() - want) <= 1e-9 + 1e-12 * abs(want)
     net.eval()  # the calls exp/downscaling.py makes on it before sampling
     # a natively constructed net with the same architecture has the same parameter names
-    native = c2w.ScoreUNet(12, 64, hidden_channels=[64, 64], hidden_blocks=[1, 1], attention_levels=[1])
+    native = c2w.ScoreUNet(12, 64, hidden_channels=[64, 64], hidden_blocks=[1, 1], attention_levels=[1], activation=torch.nn.SiLU)
     assert sorted(native.state_dict().keys()) == sorted(sd.keys())
 
 
@@ -204,6 +206,10 @@ def _worker(rank: int, world: int, port: int, L: int, k: int, out_dir: str):
         ok_halo2 = torch.equal(loc, x[p.frame_lo:p.frame_hi] * 2 + 1)
         full = sharding.all_gather_frames(loc[lo:hi].contiguous(), p)
         ok_gather = torch.equal(full, x * 2 + 1)
+        # gather on one rank only (the sampler's default): dst gets the trajectory, the others nothing
+        for dst in (0, world - 1):
+            one = sharding.gather_frames(loc[lo:hi].contiguous(), p, dst=dst)
+            ok_gather = ok_gather and ((one is None) if rank != dst else torch.equal(one, x * 2 + 1))
         # the corrector's scalar: sum over ranks of owned-frame sums == global sum
         s = (loc[lo:hi].double() ** 2).sum().reshape(1)
         dist.all_reduce(s)
@@ -253,3 +259,58 @@ def test_conv_tile_width_is_wave_aware():
     assert pick(384, 12, 12) == 192   # images the 16 x 8 blocks do not tile
     assert pick(512, 8, 8, n=1) == 256  # a single M tile: nothing to balance
     assert lib.c2w_conv_tile_width(100, 1, 4, 8, 8, 1, 148) < 0
+
+
+# ------------------------------------------------------------------------------------------------ reference-class surface
+@pytest.mark.parametrize("L,k,C", [(13, 6, 4), (14, 6, 4), (26, 6, 4), (40, 6, 4), (5, 2, 4), (9, 2, 3), (7, 1, 1)])
+def test_unfold_fold_batch_noise_mirrors_are_the_reference_index_maps(L, k, C):
+    """DefaultScoreFunction.unfold / fold and BatchedScoreFunction._batch_noise / _window_score's slot selection
+    (src/thor/score.py:68-88, :111-154) against the REFERENCE's own outputs on index-coded tensors (index_maps.npz)."""
+    import climate2weather_b200 as c2w
+    from climate2weather_b200.score import _pick_slots
+
+    g = np.load(ROOT / "tests" / "golden" / "index_maps.npz")
+    net = c2w.ScoreUNet(channels=C * (2 * k + 1), embedding_dim=64, hidden_channels=(64,), hidden_blocks=(1,),
+                        attention_levels=(), activation=torch.nn.SiLU)
+    pipe = c2w.SDAPipeline()
+    sf = c2w.DefaultScoreFunction(net, markov_order=k, noise_process=pipe)
+    code = (torch.arange(L)[:, None, None, None] * 1000 + torch.arange(C)[None, :, None, None] * 10
+            + torch.arange(2)[None, None, :, None] * 2 + torch.arange(2)[None, None, None, :]).float()
+    u = sf.unfold(code)
+    assert np.array_equal(u.numpy().astype(np.int64), g[f"unfold_{L}_{k}_{C}"])
+    nw = L - 2 * k
+    wcode = (torch.arange(nw)[:, None, None, None] * 1000 + torch.arange((2 * k + 1) * C)[None, :, None, None]
+             ).float().expand(nw, (2 * k + 1) * C, 1, 1)
+    assert np.array_equal(sf.fold(wcode).numpy().astype(np.int64), g[f"fold_{L}_{k}_{C}"])
+    for bs in (1, 2, 3, 16):
+        bf = c2w.BatchedScoreFunction(net, markov_order=k, noise_process=pipe, batch_size=bs, device=torch.device("cpu"))
+        batches = bf._batch_noise(code)
+        assert len(batches) == -(-nw // bs) and sum(b.shape[0] for b in batches) == nw
+        # the batched compose with an identity network (slot selection only), as the reference's score_fn loops it
+        rows = [_pick_slots(b, k, i == 0, i == len(batches) - 1) for i, b in enumerate(batches)]
+        assert np.array_equal(torch.cat(rows).numpy().astype(np.int64), g[f"batched_{L}_{k}_{C}_{bs}"])
+
+
+def test_member_seeds_follow_the_reference_rule():
+    """util.set_random_seed (util.py:27-29): hash((seed, rank)) % 2**31; SURVEY.md §8(d) probes (0,0) and (0,1)."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+
+    assert bench.member_seed(0, 0) == 397586535 and bench.member_seed(0, 1) == 16979904
+
+
+def test_bench_workload_selection():
+    """bench.py: N = 1 -> BASELINE config 2 (L = 168); N > 1 -> config 3 (L = 720, strong scaling); --config 4 -> the
+    16-member ensemble of a year as replicas."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+
+    class A:
+        config, weak, frames = None, False, None
+    assert bench.pick_workload(A, 1) == ("config2", 168, "weak", 0)
+    for n in (2, 4, 8):
+        assert bench.pick_workload(A, n) == ("config3", 720, "strong", 0)
+    A.config = 4
+    assert bench.pick_workload(A, 8) == ("config4", 8760, "weak", 2)
+    A.config, A.weak = None, True
+    assert bench.pick_workload(A, 4) == ("config2-weak", 12 + 4 * 156, "weak", 0)

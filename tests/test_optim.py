@@ -145,3 +145,85 @@ def test_fused_adamw_ema_rate():
     gbs = 36.0 * n / ms / 1e6
     print(f"\nc2w_adamw_ema_step: {n / 1e6:.1f} M parameters, {ms:.3f} ms, {gbs:.0f} GB/s (36 B per parameter)")
     assert torch.isfinite(p).all() and gbs > 2000
+
+
+@pytest.mark.gpu
+def test_engine_repacks_after_optimizer_and_ema_steps():
+    """Advisor finding (round 1): the fused step updates the flat buffers through raw pointers, which does not bump
+    Tensor._version — the packed-weight engine cache must be invalidated explicitly.  forward -> step -> forward has to
+    change, and must equal a forward of a FRESH network holding the updated weights; same for the EMA copy."""
+    import climate2weather_b200 as c2w
+    from climate2weather_b200 import optim
+
+    dev = torch.device("cuda:0")
+    cfg = dict(channels=20, embedding_dim=64, hidden_channels=(64, 128), hidden_blocks=(1, 1), attention_levels=(1,))
+    torch.manual_seed(0)
+    net = c2w.ScoreUNet(activation=torch.nn.SiLU, **cfg).to(dev)
+    x = torch.randn(2, 20, 32, 32, generator=torch.Generator().manual_seed(1)).to(dev)
+    t = torch.tensor(0.4)
+    opt = optim.AdamW(net.parameters(), lr=1e-2, weight_decay=0.0)
+    ema = optim.StandardEMA(net, rates=[0.5])
+    opt.fuse_ema(ema)
+    with torch.no_grad():
+        y0 = net(x, t)
+        e0 = ema.emas[0](x, t)
+    assert torch.equal(y0, e0)
+    opt.zero_grad()
+    g = torch.Generator().manual_seed(2)
+    for p in net.parameters():
+        p.grad.copy_(torch.randn(p.shape, generator=g).to(dev))
+    opt.step()
+    ema.update()
+    with torch.no_grad():
+        y1 = net(x, t)
+        e1 = ema.emas[0](x, t)
+    assert not torch.equal(y1, y0) and not torch.equal(e1, e0) and not torch.equal(e1, y1)
+    for trained, got in ((net, y1), (ema.emas[0], e1)):
+        fresh = c2w.ScoreUNet(activation=torch.nn.SiLU, **cfg)
+        fresh.load_state_dict({k: v.detach().cpu().clone() for k, v in trained.state_dict().items()})
+        with torch.no_grad():
+            want = fresh.to(dev)(x, t)
+        assert torch.equal(got, want)
+
+
+@pytest.mark.gpu
+def test_adamw_state_dict_roundtrip_and_pickle():
+    """Checkpointing as training_loop.py:131-138 / src/thor/checkpoint.py:17-30 do it: state_dict() in torch.optim
+    layout, load_state_dict() restores the moments and the step count (bias correction continues), and the object
+    pickles (the ctypes handle is excluded)."""
+    import pickle
+
+    from climate2weather_b200 import optim
+
+    dev = torch.device("cuda:0")
+    net_a, net_b = _tiny_net(3).to(dev), _tiny_net(3).to(dev)
+    a, b = optim.AdamW(net_a.parameters(), **HP), optim.AdamW(net_b.parameters(), **HP)
+
+    def step(opt, net, s):
+        opt.zero_grad()
+        for p, g in zip(net.parameters(), _grads([q.detach().cpu() for q in net.parameters()], s)):
+            p.grad.copy_(g.to(dev).float())
+        opt.step()
+
+    for s in range(3):
+        step(a, net_a, s)
+    sd = a.state_dict()
+    assert set(sd) >= {"state", "param_groups"} and sd["param_groups"][0]["params"] == list(range(len(a.params)))
+    assert float(sd["state"][0]["step"]) == 3.0
+    # resume: fresh optimizer over a copy of the trained parameters
+    net_b.load_state_dict(net_a.state_dict())
+    b.load_state_dict(pickle.loads(pickle.dumps(sd)))
+    assert b.step_count == 3
+    step(a, net_a, 3)
+    step(b, net_b, 3)
+    for p, q in zip(net_a.parameters(), net_b.parameters()):
+        assert torch.equal(p, q)
+    # a parameter that left the flat buffer is re-adopted instead of silently ignored
+    first = next(net_b.parameters())
+    first.data = first.data.clone()
+    step(a, net_a, 4)
+    step(b, net_b, 4)
+    for p, q in zip(net_a.parameters(), net_b.parameters()):
+        assert torch.equal(p, q)
+    c = pickle.loads(pickle.dumps(b))
+    assert c.step_count == b.step_count and torch.equal(c.exp_avg, b.exp_avg)

@@ -4,6 +4,7 @@ operands, then a timing sweep of the dominant shapes.  Run on a B200 via gpurun:
 """
 import ctypes
 import json
+import os
 import sys
 import time
 from pathlib import Path
@@ -12,7 +13,7 @@ import torch
 import torch.nn.functional as F
 
 ROOT = Path(__file__).resolve().parents[1]
-lib = ctypes.CDLL(str(ROOT / "climate2weather_b200" / "libc2w_b200.so"))
+lib = ctypes.CDLL(os.environ.get("C2W_LIB") or str(ROOT / "climate2weather_b200" / "libc2w_b200.so"))
 lib.c2w_op_conv.restype = ctypes.c_int
 lib.c2w_op_conv.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                             ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
@@ -98,7 +99,8 @@ def check_gemm(name, M, K, N, seed=1):
     return ok
 
 
-def timeit(name, n, H, W, cin, cout, iters=20, variant=-1, bn=0, skip_loads=0, ln=False, res=False, cudnn=True, **kw):
+def timeit(name, n, H, W, cin, cout, iters=20, variant=-1, bn=0, skip_loads=0, ln=False, res=False, cudnn=True, warm=3,
+           **kw):
     sys.path.insert(0, str(ROOT))
     from climate2weather_b200 import _lib
     cin_pad = (cin + 63) // 64 * 64
@@ -126,7 +128,7 @@ def timeit(name, n, H, W, cin, cout, iters=20, variant=-1, bn=0, skip_loads=0, l
         rc = L.c2w_op_conv_ex(ctypes.byref(d), st)
         assert rc == 0, L.c2w_last_error()
 
-    for _ in range(3):
+    for _ in range(warm):
         call()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -171,6 +173,12 @@ def main():
     print(torch.cuda.get_device_name(0), flush=True)
     if "--only-g2" in sys.argv:  # short run for `ncu --set full -k regex:conv_gemm`
         timeit("G2", 32, 128, 128, 128, 128, iters=5, cudnn=False)
+        return 0
+    if "--ncu-variants" in sys.argv:  # `ncu --set full -k regex:conv_gemm -c 8`: 2 launches each of the four main variants
+        timeit("G2 plain AR <128,2,0,1>", 32, 128, 128, 128, 128, iters=1, warm=1, variant=5, cudnn=False)
+        timeit("G2 residual AR <128,2,0,1>", 32, 128, 128, 128, 128, iters=1, warm=1, variant=5, res=True, cudnn=False)
+        timeit("G2 residual+LN AR <128,2,1,1>", 32, 128, 128, 128, 128, iters=1, warm=1, variant=5, ln=True, cudnn=False)
+        timeit("G8 residual+LN <256,2,1,0>", 64, 32, 32, 256, 256, iters=1, warm=1, variant=1, bn=256, ln=True, cudnn=False)
         return 0
     if "--res" in sys.argv:  # residual convs only 
         for _ in range(2):
@@ -242,9 +250,9 @@ def main():
         timeit("G2 cg2 res", 32, 128, 128, 128, 128, variant=1, res=True, cudnn=False)
         timeit("G2 cg2+LN", 32, 128, 128, 128, 128, variant=1, ln=True, cudnn=False)
         timeit("G5 cg2", 64, 64, 64, 128, 128, variant=1, cudnn=False)
-        # diagnostics: no TMA traffic after priming -> MMA + smem-read + epilogue ceiling of this kernel structure
-        timeit("G2 cg1 noloads", 32, 128, 128, 128, 128, variant=0, skip_loads=1, cudnn=False)
-        timeit("G2 cg2 noloads", 32, 128, 128, 128, 128, variant=1, skip_loads=1, cudnn=False)
+        if os.environ.get("C2W_LIB"):  # diagnostics build only (-DC2W_DIAG): no TMA traffic after priming
+            timeit("G2 cg1 noloads", 32, 128, 128, 128, 128, variant=0, skip_loads=1, cudnn=False)
+            timeit("G2 cg2 noloads", 32, 128, 128, 128, 128, variant=1, skip_loads=1, cudnn=False)
         timeit("G5 cg2 (cudnn)", 64, 64, 64, 128, 128, variant=1)
         timeit("G8 cg1", 64, 32, 32, 256, 256, variant=0)
         timeit("G8 cg2", 64, 32, 32, 256, 256, variant=1, cudnn=False)

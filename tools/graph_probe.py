@@ -10,7 +10,7 @@ import climate2weather_b200 as c2w  # noqa: E402
 
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-net = c2w.ScoreUNet(52, 512, hidden_channels=[128, 128, 256, 384, 512], hidden_blocks=[3] * 5, attention_levels=[4]).to(dev)
+net = c2w.ScoreUNet(52, 512, hidden_channels=[128, 128, 256, 384, 512], hidden_blocks=[3] * 5, attention_levels=[4], activation=torch.nn.SiLU).to(dev)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 156
 eng = net.engine(4, 13, 128, 128, dev, max_windows=n)
 x = torch.randn(n, 52, 128, 128, device=dev)
