@@ -1,78 +1,122 @@
-// EXPERIMENTAL — weight-gradient GEMM of a 3x3 stride-1 conv (the wgrad half of SURVEY 8(f) N2).
-// Written at the end of round 1, compiled for sm_100a, NOT WORKING YET: its first (and, for lack of GPU budget, only)
-// hardware runs ended in cudaErrorIllegalInstruction after ~4 s in every case (transpose_bf16_kernel passes its test).
-// That is mbar_wait's watchdog (BPT.TRAP after 4e9 cycles), i.e. the kernel DEADLOCKS: by the SASS the first wait to
-// time out is the MMA warp's on full[stage] — the stage's TMA bytes never complete.  Launch style (plain vs 1-CTA
-// cluster) makes no difference.  Next step: compute-sanitizer + a single-K-block run dumping the barrier state.  No product path calls it, no parity claim covers it, and
-// its GPU test is opt-in (C2W_EXPERIMENTAL=1).  Ground truth for it: tests/golden/train_step.npz.
+// K10 — weight gradient of the UNet convolutions on tcgen05 tensor cores (the wgrad half of the training step,
+// training_loop.py:372-378: `fabric.backward(loss)` through every Conv2d / Conv1d of model/nn.py).
 //
-//   dW[co, (r*3+s)*Cin + ci] += sum over pixels  dY[pix, co] * X[pix + (r-1, s-1), ci]        (zero padding)
+//   dW[co, ci, r, s] = sum over output pixels p   dY[p, co] * X[stride * p + (r - 1, s - 1), ci]        (zero padding)
 //
-// As a GEMM per tap: M = Cout, N = Cin, K = pixels.  The reduction dimension must be contiguous for the K-major
-// shared-memory descriptors K1 uses, so the operands are the TRANSPOSED activations dY^T [Cout][pix] and
-// X^T [Cin][n][H][W] (transpose_bf16_kernel; one extra pass per tensor).  A K step is a block of 64 pixels of one image
-// (bw x bh, bw = min(W, 64)): A = a 2-D TMA box of dY^T, B = the same block of X^T shifted by the tap through the 4-D
-// box coordinates, out-of-range pixels zero-filled by the TMA unit.  Only 9 * (Cout/128) * (Cin/BN) output tiles
-// exist, so the pixel range is split over the grid (split-K): one CTA per (tap, M tile, N tile, split), fp32 partial
-// sums added to dW with red.global.add.f32.  Warp 0: TMA producer, warp 1: tcgen05.mma issuer, warps 2-5: epilogue.
+// A GEMM per filter tap with M = Cout, N = Cin and K = PIXELS.  Both operands are stored pixel-major (NHWC bf16), i.e.
+// MN-major for this product: a TMA box {64 channels, 8 x 8 pixels} lands in shared memory as 64 rows (one per pixel =
+// one K index) of 128 B (64 channels) in the 128B-swizzle pattern, which is exactly tcgen05's canonical MN-major
+// SWIZZLE_128B operand (cute: Layout_MN_SW128_Atom; descriptor: LBO = distance between 64-channel groups, SBO = 1024 B
+// between 8-pixel groups; instruction descriptor with a_major = b_major = MN).  No transposed copies of the activations.
+//
+// K blocks are 8 x 8 spatial blocks of one image.  For stride-1 3x3 convs the three taps of one filter COLUMN s share
+// one load of X: the block with a one-row halo above and below ([10 x 8 px][64 ch], shifted by s - 1 columns through
+// the box coordinates, out-of-image pixels zero-filled by the TMA unit = the conv's zero padding); filter row r is the
+// sub-view starting r * 8 pixels = r KB into it (swizzle phase preserved).  Stride-2 heads and the 1x1 GEMMs load one
+// box per tap.  A CTA owns (filter column | tap group, 128 output channels, BN input channels, one slice of the pixel
+// range): only (Cout/128) * (Cin/BN) * 3 output tiles exist per layer, so the pixel range is split over the grid
+// (split-K) and every CTA writes its three fp32 accumulators to a scratch slab; wgrad_reduce_kernel sums the slabs in
+// a fixed order (deterministic) into the fp32 OIHW gradient tensor.
+//
+// Roles: warp 0 TMA producer, warp 1 tcgen05.mma issuer (one elected lane), warp 2 TMEM allocator, warps 4-7 epilogue.
 #pragma once
 #include "conv_tcgen05.cuh"
 
 namespace c2w {
 
-constexpr int kWgStages = 5;
-constexpr int kWgThreads = 192;
+constexpr int kWgThreads = 256;
+constexpr int kWgPix = 64;  // pixels (K) per block: 8 x 8
 
 struct WgradParams {
-  int n_img, H, W;
-  int cin, cout;        // padded channel counts (multiples of 64)
-  int bw, bh;           // pixel block of one K step (bw * bh == 64)
-  int blocks_per_img;   // (H / bh) * (W / bw)
-  int k_blocks;         // n_img * blocks_per_img
+  int taps;            // 9 (3x3, pad 1) or 1 (GEMM)
+  int stride;          // 1 or 2 (3x3 only)
+  int share;           // 1: halo'd unit shared by the 3 filter rows (stride-1 3x3)
+  int blocks_w, blocks_per_img, k_blocks;  // 8x8 output-pixel blocks
   int splits, m_tiles, n_tiles;
-  float* dw;            // fp32 [cout][9 * cin], accumulated
-  int ldw;              // 9 * cin
+  int groups;          // work items per (m, n, split): 3 (filter columns, or filter rows when !share) or 1 (GEMM)
+  int cout_slab, cin_slab;  // slab dims: m_tiles * 128, n_tiles * BN
+  float* partial;      // [splits][taps][cout_slab][cin_slab]
+  int num_stages;
+};
+
+// Shared-memory descriptor of an MN-major, 128B-swizzled operand: rows of 128 B (64 channels of one pixel), 8-pixel
+// groups 1024 B apart (SBO), the next 64-channel group `lbo_bytes` further on (LBO).
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;  // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;  // SWIZZLE_128B
+  return d;
+}
+// bf16 x bf16 -> fp32, A and B both MN-major (bits 15 / 16)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+template <int BN>
+struct WgradCfg {
+  static constexpr int kABytes = 2 * kWgPix * 128;                 // dY: two 64-channel groups of 64 pixels
+  static constexpr int kBGroupShare = 80 * 128;                    // X unit: 10 x 8 pixels per 64-channel group
+  static constexpr int kBGroupTap = kWgPix * 128;                  // X box of one tap per 64-channel group
+  static constexpr int kBBytesShare = (BN / 64) * kBGroupShare;
+  static constexpr int kBBytesTaps = 3 * (BN / 64) * kBGroupTap;
+  static constexpr int kTmemCols = (3 * BN <= 256) ? 256 : 512;
+  static constexpr int stage_bytes(bool share) {
+    // stages stay 1024-B aligned (the swizzle pattern is a function of the absolute address)
+    return ((kABytes + (share ? kBBytesShare : kBBytesTaps)) + 1023) / 1024 * 1024;
+  }
+  static constexpr int kBarBytes = 512;
+  static constexpr int stages(bool share) {
+    const int n = (kSmemLimit - 1024 - kBarBytes) / stage_bytes(share);
+    return n > 8 ? 8 : n;
+  }
+  static constexpr int smem_bytes(bool share) { return stages(share) * stage_bytes(share) + kBarBytes + 1024; }
 };
 
 template <int BN>
 __global__ void __launch_bounds__(kWgThreads, 1)
-wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradParams p) {
-  constexpr int kABytes = kBlockM * kBlockK * 2;  // [128 co][64 px] bf16
-  constexpr int kBBytes = BN * kBlockK * 2;       // [BN ci][64 px] bf16
+wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
+  using Cfg = WgradCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* smA = smem;
-  uint8_t* smB = smem + kWgStages * kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + kWgStages * kBBytes);
+  const bool share = p.share != 0;
+  const int stage_bytes = Cfg::stage_bytes(share);
+  const int num_stages = p.num_stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + num_stages * stage_bytes);
   uint64_t* full = bars;
-  uint64_t* empty = bars + kWgStages;
-  uint64_t* acc_full = bars + 2 * kWgStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* empty = bars + 8;
+  uint64_t* acc_full = bars + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // work item
+  // work item: (group g, m tile, n tile, split)
   int idx = blockIdx.x;
   const int split = idx % p.splits;
   idx /= p.splits;
   const int nt = idx % p.n_tiles;
   idx /= p.n_tiles;
   const int mt = idx % p.m_tiles;
-  const int tap = idx / p.m_tiles;
-  const int r = tap / 3, s = tap - 3 * r;
+  const int g = idx / p.m_tiles;
+  const int ntap = p.taps == 1 ? 1 : 3;  // accumulators of this CTA
   const int kb0 = static_cast<int>(static_cast<long long>(p.k_blocks) * split / p.splits);
   const int kb1 = static_cast<int>(static_cast<long long>(p.k_blocks) * (split + 1) / p.splits);
 
   if (warp_idx == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    for (int i = 0; i < kWgStages; ++i) {
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < num_stages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
-  if (warp_idx == 2) tmem_alloc(tmem_slot, BN);
+  if (warp_idx == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -80,65 +124,95 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   if (warp_idx == 0) {
     // ---------------------------------------------------------------- TMA producer
-    const int blocks_w = p.W / p.bw;
+    const int tx_bytes = Cfg::kABytes + (share ? Cfg::kBBytesShare : ntap * (BN / 64) * Cfg::kBGroupTap);
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = kb0; kb < kb1; ++kb) {
       mbar_wait(&empty[stage], phase ^ 1);
       if (elect_one()) {
         const int img = kb / p.blocks_per_img, t = kb - img * p.blocks_per_img;
-        const int h0 = (t / blocks_w) * p.bh, w0 = (t - (t / blocks_w) * blocks_w) * p.bw;
-        const int pix0 = (img * p.H + h0) * p.W + w0;  // the block's pixels are contiguous (bw == W or bh == 1)
-        mbar_arrive_expect_tx(&full[stage], kABytes + kBBytes);
-        tma_load_2d(&tmA, &full[stage], smA + stage * kABytes, pix0, mt * kBlockM);
-        tma_load_4d(&tmB, &full[stage], smB + stage * kBBytes, w0 + s - 1, h0 + r - 1, img, nt * BN);
+        const int h0 = (t / p.blocks_w) * 8, w0 = (t % p.blocks_w) * 8;  // output-pixel block
+        uint8_t* sA = smem + stage * stage_bytes;
+        uint8_t* sB = sA + Cfg::kABytes;
+        mbar_arrive_expect_tx(&full[stage], tx_bytes);
+        for (int b = 0; b < 2; ++b)  // channels beyond the tensor (Cout = 64) are zero-filled by the TMA unit
+          tma_load_4d(&tmDY, &full[stage], sA + b * (kWgPix * 128), mt * 128 + b * 64, w0, h0, img);
+        if (share) {  // g = filter column s: one halo'd unit per 64-channel group, rows h0-1 .. h0+8
+          for (int b = 0; b < BN / 64; ++b)
+            tma_load_4d(&tmX, &full[stage], sB + b * Cfg::kBGroupShare, nt * BN + b * 64, w0 + g - 1, h0 - 1, img);
+        } else if (p.taps == 9) {  // g = filter row r: one box per filter column s (stride 1 or 2)
+          for (int s = 0; s < 3; ++s)
+            for (int b = 0; b < BN / 64; ++b)
+              tma_load_4d(&tmX, &full[stage], sB + (s * (BN / 64) + b) * Cfg::kBGroupTap, nt * BN + b * 64,
+                          p.stride * w0 + s - 1, p.stride * h0 + g - 1, img);
+        } else {  // GEMM: the same 64 rows of X
+          for (int b = 0; b < BN / 64; ++b)
+            tma_load_4d(&tmX, &full[stage], sB + b * Cfg::kBGroupTap, nt * BN + b * 64, w0, h0, img);
+        }
       }
       __syncwarp();
-      if (++stage == kWgStages) {
+      if (++stage == num_stages) {
         stage = 0;
         phase ^= 1;
       }
     }
   } else if (warp_idx == 1) {
     // ---------------------------------------------------------------- MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
-    const uint64_t adesc0 = umma_desc_kmajor_sw128(smem_u32(smA));
-    const uint64_t bdesc0 = umma_desc_kmajor_sw128(smem_u32(smB));
+    constexpr uint32_t idesc = umma_idesc_bf16_mn(128, BN);
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = kb0; kb < kb1; ++kb) {
       mbar_wait(&full[stage], phase);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (kABytes >> 4));
-        const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * (kBBytes >> 4));
+        const uint32_t sA = smem_u32(smem + stage * stage_bytes);
+        const uint32_t sB = sA + Cfg::kABytes;
+        const uint64_t adesc = umma_desc_mnmajor_sw128(sA, kWgPix * 128);
+        for (int a = 0; a < ntap; ++a) {
+          // accumulator a: share -> filter row r = a (sub-view a * 8 pixels into the unit); else filter column s = a
+          const uint64_t bdesc = share ? umma_desc_mnmajor_sw128(sB + a * 1024, Cfg::kBGroupShare)
+                                       : umma_desc_mnmajor_sw128(sB + a * (BN / 64) * Cfg::kBGroupTap, Cfg::kBGroupTap);
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0) || k != 0);
+          for (int k = 0; k < kWgPix / 16; ++k)  // 16 pixels = two 8-pixel groups = 2048 B further on
+            umma_bf16(tmem_d + a * BN, adesc + k * (2048 >> 4), bdesc + k * (2048 >> 4), idesc, (kb > kb0) || k != 0);
+        }
         umma_commit(&empty[stage]);
         if (kb + 1 == kb1) umma_commit(acc_full);
       }
       __syncwarp();
-      if (++stage == kWgStages) {
+      if (++stage == num_stages) {
         stage = 0;
         phase ^= 1;
       }
     }
-  } else if (kb1 > kb0) {
-    // ---------------------------------------------------------------- epilogue: TMEM -> red.global.add.f32
-    const int q = warp_idx & 3;  // TMEM lane quadrant this warp may read
+  } else if (warp_idx >= 4) {
+    // ---------------------------------------------------------------- epilogue: TMEM -> fp32 slab
+    const int q = warp_idx & 3;  // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;
-    const int co = mt * kBlockM + row;
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    float* dst = p.dw + static_cast<long long>(co) * p.ldw + tap * p.cin + nt * BN;
+    const bool any = kb1 > kb0;
+    if (any) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+    }
+    for (int a = 0; a < ntap; ++a) {
+      const int tap = p.taps == 1 ? 0 : (share ? a * 3 + g : g * 3 + a);  // tap = r * 3 + s
+      float* dst = p.partial + ((static_cast<size_t>(split) * p.taps + tap) * p.cout_slab + mt * 128 + row) * p.cin_slab +
+                   nt * BN;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
-      tmem_ld_wait();
-      if (co < p.cout) {
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        if (any) {
+          tmem_ld_32x32(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + a * BN + c * 32, v);
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(dst + c * 32 + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        float4* d4 = reinterpret_cast<float4*>(dst + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                              __uint_as_float(v[4 * j + 3]));
       }
     }
   }
@@ -146,108 +220,176 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   __syncthreads();
   if (warp_idx == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_d, BN);
+    tmem_dealloc(tmem_d, Cfg::kTmemCols);
   }
 }
 
-// bf16 [rows][cols] -> [cols][rows] (activations [pix][C] -> [C][pix]); 64 x 64 tiles through shared memory
-__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
-                                      long long rows, int cols) {
-  __shared__ __nv_bfloat16 tile[64][66];
-  const long long r0 = static_cast<long long>(blockIdx.x) * 64;
-  const int c0 = blockIdx.y * 64;
-  for (int i = threadIdx.y; i < 64; i += blockDim.y) {
-    const long long rr = r0 + i;
-    const int cc = c0 + threadIdx.x;
-    for (int h = 0; h < 2; ++h) {
-      const int c = cc + 32 * h;
-      tile[i][threadIdx.x + 32 * h] = (rr < rows && c < cols) ? in[rr * cols + c] : __float2bfloat16(0.f);
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.y; i < 64; i += blockDim.y) {
-    const int c = c0 + i;
-    for (int h = 0; h < 2; ++h) {
-      const long long rr = r0 + threadIdx.x + 32 * h;
-      if (c < cols && rr < rows) out[static_cast<long long>(c) * rows + rr] = tile[threadIdx.x + 32 * h][i];
-    }
+// dw[co][ci][tap] (fp32 OIHW / OI1, real Cout x Cin) (+)= sum over splits of partial[split][tap][co][ci]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int taps,
+                                    int cout, int cin, int cout_slab, int cin_slab, int accumulate, float scale) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(cout) * cin) return;
+  const int co = static_cast<int>(i / cin), ci = static_cast<int>(i - static_cast<long long>(co) * cin);
+  const size_t slab = static_cast<size_t>(cout_slab) * cin_slab;
+  for (int t = 0; t < taps; ++t) {
+    float acc = 0.f;
+    const float* src = partial + static_cast<size_t>(t) * slab + static_cast<size_t>(co) * cin_slab + ci;
+    for (int s = 0; s < splits; ++s) acc += src[static_cast<size_t>(s) * taps * slab];
+    float* d = dw + (static_cast<size_t>(co) * cin + ci) * taps + t;
+    *d = accumulate ? *d + acc * scale : acc * scale;
   }
 }
 
-// Host side: xt = X^T [cin][n*H*W], dyt = dY^T [cout][n*H*W] (bf16), dw fp32 [cout][9*cin] (+=)
+// Column sums of a bf16 [rows, C] matrix per group of `rows_per_group` consecutive rows (bias gradients: one group;
+// per-sample modulation gradients: one group per image):  out[group][c] (+)= scale * sum_rows x[row][c]
+// grid = (row slabs, C / 64 * ... ) — each CTA sums kColsumRows rows for 256 channel lanes and adds atomically.
+constexpr int kColsumRows = 128;
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long rows, int C,
+                                   long long rows_per_group, int out_stride, float scale) {
+  // thread -> (channel pair cp, row lane rl): C/2 channel pairs, 256 / (C/2) rows in flight (C <= 512)
+  const int pairs = C / 2;
+  const int rl_n = blockDim.x / pairs > 0 ? blockDim.x / pairs : 1;
+  const int cp = threadIdx.x % pairs, rl = threadIdx.x / pairs;
+  if (rl >= rl_n) return;
+  const long long r0 = static_cast<long long>(blockIdx.x) * kColsumRows;
+  const long long r1 = (r0 + kColsumRows < rows) ? r0 + kColsumRows : rows;
+  float a0 = 0.f, a1 = 0.f;
+  long long grp = r0 / rows_per_group;
+  for (long long r = r0 + rl; r < r1; r += rl_n) {
+    const long long gnow = r / rows_per_group;
+    if (gnow != grp) {  // a slab may straddle a group boundary
+      atomicAdd(out + grp * out_stride + 2 * cp, a0 * scale);
+      atomicAdd(out + grp * out_stride + 2 * cp + 1, a1 * scale);
+      a0 = a1 = 0.f;
+      grp = gnow;
+    }
+    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(x + r * C + 2 * cp);
+    a0 += __low2float(v);
+    a1 += __high2float(v);
+  }
+  atomicAdd(out + grp * out_stride + 2 * cp, a0 * scale);
+  atomicAdd(out + grp * out_stride + 2 * cp + 1, a1 * scale);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct WgradLaunch {
+  CUtensorMap tmDY, tmX;
+  WgradParams p;
+  int bn, grid;
+  size_t scratch_floats;
+};
+
+// bf16 NHWC tensor map with a per-dimension box / element stride, 128B swizzle (rank 4: C, W, H, N)
+inline bool wgrad_make_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, int bw, int bh, int estride) {
+  const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+  const uint32_t box[4] = {64u, (uint32_t)bw, (uint32_t)bh, 1u};
+  const uint32_t est[4] = {1u, (uint32_t)estride, (uint32_t)estride, 1u};
+  return make_tmap_bf16(m, base, 4, dims, box, est);
+}
+
+// x: bf16 NHWC [n, H, W, cin_pad] (conv input; GEMM: H = 1, W = rows); dy: bf16 NHWC [n, H/stride, W/stride, cout_pad].
+// Output-pixel blocks are 8 x 8 (GEMM: 64 consecutive rows).
+inline bool wgrad_launch_init(WgradLaunch* L, bool conv3x3, const __nv_bfloat16* x, const __nv_bfloat16* dy, int n, int H,
+                              int W, int cin_pad, int cout_pad, int stride, int num_sms, float* scratch,
+                              size_t scratch_floats) {
+  WgradParams& p = L->p;
+  memset(&p, 0, sizeof(p));
+  if (cin_pad % 64 != 0 || cout_pad % 64 != 0) return false;
+  const int bn = (cin_pad % 128 == 0) ? 128 : 64;
+  L->bn = bn;
+  p.taps = conv3x3 ? 9 : 1;
+  p.stride = conv3x3 ? stride : 1;
+  p.m_tiles = (cout_pad + 127) / 128;
+  p.n_tiles = cin_pad / bn;
+  p.cout_slab = p.m_tiles * 128;
+  p.cin_slab = cin_pad;
+  long long k_blocks;
+  if (conv3x3) {
+    const int Ho = H / stride, Wo = W / stride;
+    if (Ho % 8 != 0 || Wo % 8 != 0 || (stride != 1 && stride != 2)) return false;
+    p.share = stride == 1;
+    p.groups = 3;
+    p.blocks_w = Wo / 8;
+    p.blocks_per_img = (Ho / 8) * p.blocks_w;
+    k_blocks = static_cast<long long>(n) * p.blocks_per_img;
+    if (!wgrad_make_map(&L->tmDY, dy, cout_pad, Wo, Ho, n, 8, 8, 1)) return false;
+    if (p.share) {
+      if (!wgrad_make_map(&L->tmX, x, cin_pad, W, H, n, 8, 10, 1)) return false;
+    } else {
+      if (!wgrad_make_map(&L->tmX, x, cin_pad, W, H, n, 8 * stride, 8 * stride, stride)) return false;
+    }
+  } else {
+    const long long rows = static_cast<long long>(n) * H * W;
+    if (rows % 64 != 0) return false;
+    p.share = 0;
+    p.groups = 1;
+    p.blocks_w = 1;
+    p.blocks_per_img = static_cast<int>(rows / 64);
+    k_blocks = rows / 64;
+    // rows as the H dimension of a [rows / 8][8] image: a block of 64 rows is an 8 x 8 box
+    if (!wgrad_make_map(&L->tmDY, dy, cout_pad, 8, static_cast<int>(rows / 8), 1, 8, 8, 1)) return false;
+    if (!wgrad_make_map(&L->tmX, x, cin_pad, 8, static_cast<int>(rows / 8), 1, 8, 8, 1)) return false;
+  }
+  p.k_blocks = static_cast<int>(k_blocks);
+  const int tiles = p.groups * p.m_tiles * p.n_tiles;
+  long long splits = num_sms / tiles;
+  if (splits < 1) splits = 1;
+  if (splits > k_blocks) splits = k_blocks;
+  const size_t per_split = static_cast<size_t>(p.taps) * p.cout_slab * p.cin_slab;
+  while (splits > 1 && per_split * splits > scratch_floats) --splits;
+  if (per_split * splits > scratch_floats) return false;
+  p.splits = static_cast<int>(splits);
+  p.partial = scratch;
+  L->scratch_floats = per_split * splits;
+  L->grid = tiles * p.splits;
+  p.num_stages = bn == 128 ? WgradCfg<128>::stages(p.share != 0) : WgradCfg<64>::stages(p.share != 0);
+  return true;
+}
+
 template <int BN>
-inline cudaError_t wgrad_launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const WgradParams& p, int grid,
-                                   cudaStream_t stream) {
-  constexpr int smem = kWgStages * (kBlockM * kBlockK * 2 + BN * kBlockK * 2) + 256 + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+inline cudaError_t wgrad_launch_bn(const WgradLaunch& L, cudaStream_t stream) {
+  using Cfg = WgradCfg<BN>;
+  static unsigned long long attr_done = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_done >> (dev & 63)) & 1ull)) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    attr_done |= 1ull << (dev & 63);
   }
-  // launched like K1 (explicit 1-CTA cluster): the tcgen05.commit / TMA forms address shared::cluster
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid);
+  cfg.gridDim = dim3(L.grid);
   cfg.blockDim = dim3(kWgThreads);
-  cfg.dynamicSmemBytes = smem;
+  cfg.dynamicSmemBytes = Cfg::smem_bytes(L.p.share != 0);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].id = cudaLaunchAttributeClusterDimension;  // explicit 1-CTA cluster: the TMA / commit forms address shared::cluster
   attr[0].val.clusterDim.x = 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, wgrad_tcgen05_kernel<BN>, tmA, tmB, p);
+  return cudaLaunchKernelEx(&cfg, wgrad_tcgen05_kernel<BN>, L.tmDY, L.tmX, L.p);
 }
 
-inline int wgrad_launch(const __nv_bfloat16* xt, const __nv_bfloat16* dyt, int n_img, int H, int W, int cin, int cout,
-                        float* dw, int num_sms, cudaStream_t stream, char* err, int err_len) {
-  auto bad = [&](const char* m) {
-    snprintf(err, err_len, "%s", m);
-    return -1;
-  };
-  if (cin % 64 != 0 || cout % 64 != 0) return bad("wgrad: channel counts must be multiples of 64");
-  if (W < 8 || W > 128 || (W & (W - 1)) != 0) return bad("wgrad: W must be a power of two in 8..128");
-  WgradParams p;
-  memset(&p, 0, sizeof(p));
-  p.n_img = n_img;
-  p.H = H;
-  p.W = W;
-  p.cin = cin;
-  p.cout = cout;
-  p.bw = W < 64 ? W : 64;
-  p.bh = 64 / p.bw;
-  if (H % p.bh != 0) return bad("wgrad: H must be a multiple of 64 / min(W, 64)");
-  p.blocks_per_img = (H / p.bh) * (W / p.bw);
-  p.k_blocks = n_img * p.blocks_per_img;
-  const int bn = (cin % 128 == 0) ? 128 : 64;
-  p.m_tiles = (cout + kBlockM - 1) / kBlockM;
-  p.n_tiles = cin / bn;
-  const int tiles = 9 * p.m_tiles * p.n_tiles;
-  int splits = num_sms / tiles;
-  if (splits < 1) splits = 1;
-  if (splits > p.k_blocks) splits = p.k_blocks;
-  p.splits = splits;
-  p.dw = dw;
-  p.ldw = 9 * cin;
-  const long long pix = static_cast<long long>(n_img) * H * W;
-  CUtensorMap tmA, tmB;
-  {
-    const uint64_t dims[2] = {(uint64_t)pix, (uint64_t)cout};
-    const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)kBlockM};
-    if (!make_tmap_bf16(&tmA, dyt, 2, dims, box)) return bad(tmap_error_slot());
-  }
-  {
-    const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)n_img, (uint64_t)cin};
-    const uint32_t box[4] = {(uint32_t)p.bw, (uint32_t)p.bh, 1u, (uint32_t)bn};
-    if (!make_tmap_bf16(&tmB, xt, 4, dims, box)) return bad(tmap_error_slot());
-  }
-  const int grid = tiles * splits;
-  cudaError_t e = bn == 128 ? wgrad_launch_bn<128>(tmA, tmB, p, grid, stream) : wgrad_launch_bn<64>(tmA, tmB, p, grid, stream);
-  if (e != cudaSuccess) return bad(cudaGetErrorString(e));
-  return 0;
+// GEMM + slab reduction into dw (fp32 [cout][cin][taps], real channel counts)
+inline cudaError_t wgrad_run(const WgradLaunch& L, float* dw, int cout, int cin, int accumulate, float scale,
+                             cudaStream_t stream) {
+  cudaError_t e = L.bn == 128 ? wgrad_launch_bn<128>(L, stream) : wgrad_launch_bn<64>(L, stream);
+  if (e != cudaSuccess) return e;
+  const long long items = static_cast<long long>(cout) * cin;
+  wgrad_reduce_kernel<<<static_cast<int>((items + 255) / 256), 256, 0, stream>>>(
+      L.p.partial, dw, L.p.splits, L.p.taps, cout, cin, L.p.cout_slab, L.p.cin_slab, accumulate, scale);
+  return cudaGetLastError();
+}
+
+inline cudaError_t colsum_run(const __nv_bfloat16* x, float* out, long long rows, int C, long long rows_per_group,
+                              int out_stride, float scale, cudaStream_t stream) {
+  const int threads = 256;
+  const long long blocks = (rows + kColsumRows - 1) / kColsumRows;
+  colsum_bf16_kernel<<<static_cast<int>(blocks), threads, 0, stream>>>(x, out, rows, C, rows_per_group, out_stride, scale);
+  return cudaGetLastError();
 }
 
 }  // namespace c2w

@@ -86,8 +86,11 @@ class SDAPipeline:
         dt = 1 / steps
         z_dev = None
         if seed is None:
-            seed = int(torch.empty((), dtype=torch.int64).random_().item()) if corrections > 0 else 0
-            if sf.shard and corrections > 0 and self.rng != "reference":
+            # rng == "reference" replays the reference's draws (z.normal_() only, src/thor/pipelines.py:82): nothing else
+            # may touch the global CPU generator, or the stream is shifted by one draw
+            device_rng = corrections > 0 and self.rng != "reference"
+            seed = int(torch.empty((), dtype=torch.int64).random_().item()) if device_rng else 0
+            if sf.shard and device_rng:
                 # the on-chip Philox stream is keyed by (seed, step, GLOBAL pixel): every rank must use rank 0's draw,
                 # otherwise the result would depend on the sharding
                 s_t = torch.tensor([seed], dtype=torch.int64, device=rt.device)
@@ -154,7 +157,7 @@ class SDAPipeline:
         target = noise.device if device is None else torch.device(device)
         if target.type == "cpu":
             # one asynchronous copy into pinned memory (a pageable destination makes the driver stage it in chunks)
-            host = rt.host_result(out.shape, noise.dtype)
+            host = torch.empty(out.shape, dtype=noise.dtype, pin_memory=True)  # a fresh tensor per call: the caller owns it
             host.copy_(out.to(noise.dtype), non_blocking=True)
             torch.cuda.current_stream(rt.device).synchronize()
             return host.reshape(noise.shape)

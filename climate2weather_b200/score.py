@@ -216,14 +216,6 @@ class _Runtime:
         x_own.copy_(mu_next * x0.permute(0, 2, 3, 1) + sigma_next * e_own)
         self.nan_flag |= (~torch.isfinite(x_own)).any().to(torch.int32)
 
-    def host_result(self, shape, dtype) -> Tensor:
-        """Pinned host buffer for the sampler's result (reused across sample() calls of this geometry)."""
-        buf = getattr(self, "_host_result", None)
-        if buf is None or tuple(buf.shape) != tuple(shape) or buf.dtype != dtype:
-            buf = torch.empty(tuple(shape), dtype=dtype).pin_memory()
-            self._host_result = buf
-        return buf
-
     def guided_eps(self, mu: float, sigma: float) -> None:
         """eps_g <- eps - sigma * grad_x log p(y | x) (src/thor/score.py:24-35) and the partial sums of eps_g^2."""
         self._guide(1, mu, sigma, 0.0, 0.0)

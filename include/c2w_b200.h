@@ -204,14 +204,20 @@ int c2w_op_gather_windows(const float* traj, void* out_bf16, int n, int hw, int 
 int c2w_op_modulation(c2w_handle* h, float t, float* emb_out, float* mods_out, void* stream);
 int c2w_total_mod_channels(c2w_handle* h);
 
-/* ---- EXPERIMENTAL (round-2 groundwork; c2w_op_wgrad does NOT work yet — see csrc/wgrad_tcgen05.cuh; no parity claim;
- * c2w_op_transpose_bf16 passes its opt-in test): weight gradient of a 3x3 stride-1
- * conv as a split-K tcgen05 GEMM over the TRANSPOSED activations (training_loop.py:378, the wgrad half of N2).
- *   x_t [cin][n*H*W], dy_t [cout][n*H*W] bf16 (c2w_op_transpose_bf16 of the NHWC tensors);
- *   dw fp32 [cout][9*cin], k = (r*3+s)*cin + ci like the packed forward weights, ACCUMULATED (zero it first). */
-int c2w_op_transpose_bf16(const void* in_rows_cols, void* out_cols_rows, int64_t rows, int32_t cols, void* stream);
-int c2w_op_wgrad(const void* x_t, const void* dy_t, int32_t n_img, int32_t H, int32_t W, int32_t cin, int32_t cout,
-                 float* dw, void* stream);
+/* ---- weight-gradient kernels (op level; the training step below launches the same kernels) ---------------------
+ * c2w_op_wgrad: dW of one Conv2d 3x3 pad 1 (stride 1 or 2) or one 1x1 GEMM, the wgrad half of `fabric.backward(loss)`
+ * (training_loop.py:378) — a split-K tcgen05 GEMM with K = pixels over the NHWC tensors as they are (MN-major
+ * operands, no transposes), partial sums in `scratch`, deterministic reduction into
+ *   dw fp32 [cout][cin][taps] (= torch's OIHW / OI1 layout, REAL channel counts), overwritten or accumulated.
+ *   x  bf16 NHWC [n_img, H, W, cin_pad]  (GEMM: H = 1, W = rows per image; rows in total a multiple of 64)
+ *   dy bf16 NHWC [n_img, H/stride, W/stride, cout_pad]
+ * c2w_op_colsum: out[group][c] += scale * sum over the group's rows of x[row][c] (bias gradients: one group; the
+ * per-sample modulation gradients: one group per image), atomically accumulated — zero `out` first. */
+int c2w_op_wgrad(const void* x, const void* dy, int32_t n_img, int32_t H, int32_t W, int32_t cin_pad, int32_t cout_pad,
+                 int32_t stride, int32_t conv3x3, float* scratch, int64_t scratch_floats, float* dw, int32_t cin,
+                 int32_t cout, int32_t accumulate, void* stream);
+int c2w_op_colsum(const void* x_bf16, float* out, int64_t rows, int32_t C, int64_t rows_per_group, int32_t out_stride,
+                  float scale, void* stream);
 
 /* ---- measurement hooks (bench.py): kernel launches issued by this library so far; optional CUDA-event timing of
  * every forward-pass launch on its own stream, summed per class: [0] K1 conv/GEMM (tensor cores), [1] the rest --- */

@@ -943,14 +943,15 @@ def test_sampler_proc_x0_hook(dev, golden_dir):
     seen = []
 
     def ident(x0):
-        seen.append(tuple(x0.shape))
+        seen.append(x0.detach().clone())
         assert x0.is_cuda
         return x0
 
     same = pipe.sample(sf, x, steps=4, corrections=0, tau=0.5, show_progressbar=False, proc_x0=ident)
-    assert seen == [tuple(x.shape)] * 4
-    assert relerr(same, base) < 1e-5
-    # last step only: clamp x0 -> the final sample is mu(0) clamp(x0) + sigma(0) eps with mu(0) = 1, sigma(0) = 1e-3
+    assert [tuple(s.shape) for s in seen] == [tuple(x.shape)] * 4
+    assert relerr(same, base) < 1e-5 and rel_l2(same, base) < 1e-5
+    # clamp x0 in the LAST step only: the sample is mu(0) proc(x0) + sigma(0) eps, so it must move by exactly
+    # mu(0) (clamp(x0) - x0) with mu(0) = 1 relative to the identity-hook run
     calls = {"n": 0}
 
     def clamp_last(x0):
@@ -958,4 +959,7 @@ def test_sampler_proc_x0_hook(dev, golden_dir):
         return x0.clamp(-0.5, 0.5) if calls["n"] == 4 else x0
 
     clamped = pipe.sample(sf, x, steps=4, corrections=0, tau=0.5, show_progressbar=False, proc_x0=clamp_last)
-    assert float(clamped.abs().max()) < 0.5 + 1e-3 * 50 and not torch.equal(clamped, same)
+    x0_last = seen[3].cpu()
+    want = same + float(pipe.mu(torch.tensor(0.0))) * (x0_last.clamp(-0.5, 0.5) - x0_last)
+    assert not torch.equal(clamped, same)
+    assert rel_l2(clamped, want) < 1e-5
