@@ -13,8 +13,12 @@ sample under Fabric "16-mixed"): its drift from the reference's fp32 run, per tr
 
     rel-L2(ours, reference fp32)  <=  max(FLOOR, FACTOR x rel-L2(reference bf16, reference fp32))   per trace step,
 
-plus absolute bounds on the first steps, where nothing has been amplified yet: rel-L2 <= 2e-2 / max-abs ratio <= 3e-2
-for the first guided score and the state after step 1.
+with FLOOR = 5e-3 and FACTOR = 1.5, plus absolute bounds where nothing has been amplified yet: rel-L2 <= 2e-2 /
+max-abs ratio <= 3e-2 for the first guided score and the state after step 1.
+
+Measured on B200 (round 2, profiles/r02_full_length_parity.log): rel-L2 of the final state after 256 steps 3.97e-3
+(the reference's own bf16-autocast run: 4.09e-3), every trace below the yardstick; first guided score 8.9e-3;
+exact_grad (16 steps) final 1.4e-2.
 """
 import numpy as np
 import pytest
@@ -26,7 +30,7 @@ STD = [0.1692666615037876, 0.0425178630338289, 0.3268027589410125, 0.32680275894
 GAMMA = 0.0007196856730011522
 L, K = 25, 6
 TRACES = (1, 4, 16, 64, 128, 192)
-FLOOR, FACTOR = 2e-2, 3.0
+FLOOR, FACTOR = 5e-3, 1.5
 
 
 def _problem():
@@ -134,4 +138,4 @@ def test_full_length_exact_grad_vs_reference(net, golden_dir):
     rows = _report("exact: 16 steps, exact_grad", g, first, traces, out)
     assert rows[0][1] < 3e-2 and rows[0][2] < 5e-2
     assert rows[1][1] < 3e-2
-    assert rows[-1][1] < 0.15, rows[-1]
+    assert rows[-1][1] < 5e-2 and rows[-1][2] < 5e-2, rows[-1]
