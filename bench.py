@@ -434,6 +434,115 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ====================================================================================================== training step
+def run_train(args):
+    """BASELINE.json configs[4]: the denoising-score-matching training step at the configured batch (run_training.sh:
+    batch-gpu 128, 52 x 128 x 128 windows), the reference's own step body (training_loop.py:372-390)
+
+        loss = pipeline.loss(net, x).mean(); loss.backward(); optimizer.step(); ema.update()
+
+    on this package's ScoreUNet / AdamW / StandardEMA; DDP gradient all-reduce over NCCL for N > 1.  Metric: training
+    samples/s (whole job); roofline: algorithmic 3 x 116 GFLOP per sample (forward + input-gradient + weight-gradient
+    GEMMs) against the measured bf16 peak."""
+    import torch
+    import torch.distributed as dist
+
+    import climate2weather_b200 as c2w
+    from climate2weather_b200 import _lib, optim
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    peak_tf, _, peak_src = measured_peaks()
+    B = args.batch
+    torch.manual_seed(0)
+    net = c2w.ScoreUNet(activation=torch.nn.SiLU, **ARCH).to(dev).train()
+    model = net
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank])
+    pipe = c2w.SDAPipeline()
+    opt = optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-3, betas=(0.9, 0.999))  # train.py:176-181
+    ema = optim.StandardEMA(net, rates=[0.9999])
+    opt.fuse_ema(ema)
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    x = torch.rand(B, ARCH["channels"], H, W, generator=g, device=dev)  # quantile-normalised data lies in ~[0, 1]
+
+    def step():
+        opt.zero_grad()
+        loss = pipe.loss(net=model, x=x).mean()
+        loss.backward()
+        opt.step()
+        ema.update()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with ClockSampler(local_rank) as clocks:
+        for _ in range(args.warmup):
+            loss = step()
+        barrier()
+        launches0 = lib.c2w_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        clocks.mark_start()
+        e0.record()
+        for _ in range(args.steps):
+            loss = step()
+        e1.record()
+        barrier()
+        clocks.mark_end()
+    launches = lib.c2w_launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = ms.item()
+    assert bool(torch.isfinite(loss))
+    flops = 3 * F_WIN * B
+    # end to end: a fresh host batch every step (pinned), loss value read back
+    xh = x.cpu().pin_memory()
+    ke = max(2, min(args.steps, 8))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(ke):
+        x.copy_(xh, non_blocking=True)
+        lv = float(step().item())
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        line = {"metric": "DSM training samples/sec", "value": round(B * world / (ms_step / 1e3), 2), "unit": "samples/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"config5: DSM training step, batch {B}/GPU x{world} of 52x128x128 windows, "
+                                       "sda_unet.yml ScoreUNet (72.1 M parameters), AdamW lr 1e-4 wd 1e-3 + EMA 0.9999 "
+                                       "(fused), per-sample diffusion times" + (", DDP all-reduce over NCCL" if world > 1 else ""),
+                           "name": "config5", "batch_per_gpu": B, "global_batch": B * world,
+                           "l2": "activations of a 128-sample batch (~14 GB) exceed the 126 MB L2; no explicit flush"},
+                "clocks": clocks.summary(), "gpu_launches": int(launches),
+                "roofline": {"kernel": "K1 forward / input-gradient convs + K10 weight-gradient GEMMs (whole step)",
+                             "bound": "tensor", "achieved": round(flops / (ms_step * 1e-3) / 1e12, 1), "peak": peak_tf,
+                             "unit": "TFLOP/s", "frac": round(flops / (ms_step * 1e-3) / 1e12 / peak_tf, 4),
+                             "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": None,
+                             "algorithmic_flops_per_step": flops},
+                "loss": round(float(loss.item()), 5),
+                "e2e": {"value": round(B * world * ke / dt.item(), 2), "unit": "samples/s",
+                        "h2d_bytes_per_step": int(xh.numel() * 4), "d2h_bytes_per_step": 4, "steps": ke,
+                        "api": "pipeline.loss(net, x).mean().backward(); optimizer.step(); ema.update() with a pinned host "
+                               "batch copied in and the loss value read back every step"}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ====================================================================================================== reference arm
 class CpuReference:
     """The oracle port of the reference path (fp32 torch on the host cores, all threads): guided predictor steps
@@ -564,11 +673,17 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-single", action="store_true", help="config 3: skip the one-GPU run of the same trajectory")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: no warm-up floor, no roofline/e2e/cpu legs")
+    ap.add_argument("--mode", default="sample", choices=["sample", "train"],
+                    help="train: BASELINE config 5, the DSM training step (forward + backward + AdamW + EMA)")
+    ap.add_argument("--batch", type=int, default=128, help="--mode train: samples per GPU (run_training.sh: 128)")
     args = ap.parse_args()
     if args.e2e_steps is None:
         args.e2e_steps = 8 if args.config == 4 else SAMPLER_STEPS
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "train":
+        args.warmup = max(args.warmup, 3)
+        run_train(args)
     else:
         if args.profile:
             args.no_e2e = args.no_cpu = args.no_single = True

@@ -9,7 +9,7 @@ from pathlib import Path
 # C2W_LIB selects another build of the same ABI (tools/: the -DC2W_DIAG library with K1's cycle counters)
 LIB_PATH = Path(os.environ.get("C2W_LIB") or Path(__file__).resolve().parent / "libc2w_b200.so")
 MAX_LEVELS = 8
-WS_VJP, WS_PER_SAMPLE_T = 1, 2
+WS_VJP, WS_PER_SAMPLE_T, WS_TRAIN = 1, 2, 4
 
 
 class C2WError(RuntimeError):
@@ -132,6 +132,13 @@ SIGNATURES = {
     "c2w_op_gather_windows": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "c2w_op_modulation": (_i, [_vp, _f, _vp, _vp, _vp]),
     "c2w_total_mod_channels": (_i, [_vp]),
+    "c2w_param_total": (_i64, [_vp]),
+    "c2w_refresh_weights": (_i, [_vp, _vp, _vp]),
+    "c2w_param_layout": (_i, [_vp, C.c_char_p, C.POINTER(_i64), C.POINTER(_i64)]),
+    "c2w_train_forward": (_i, [_vp, _vp, C.c_int32, _vp, _vp, _vp]),
+    "c2w_train_backward": (_i, [_vp, _vp, C.c_int32, _vp, _vp, C.c_int32, _vp]),
+    "c2w_dsm_loss_grad": (_i, [_vp, _vp, _vp, _i64, _f, _vp, _vp, _vp]),
+    "c2w_train_step": (_i, [_vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _f, _vp, C.c_int32, _vp, _vp]),
     "c2w_launch_count": (_i64, []),
     "c2w_set_timing": (_i, [_vp, _i]),
     "c2w_timing_read": (_i, [_vp, _vp, _vp]),

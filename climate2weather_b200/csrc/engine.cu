@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "conv_tcgen05.cuh"
 #include "kernels.cuh"
+#include "wgrad_tcgen05.cuh"
 
 using namespace c2w;
 
@@ -32,9 +33,11 @@ struct ConvW {
   float* b = nullptr;  // [cout_pad]
   bf16* wd = nullptr;  // input-gradient weights [cin_pad, taps * cout_pad], k = (8 - tap) * cout_pad + o  (flipped)
   int cin = 0, cout = 0, cin_pad = 0, cout_pad = 0, taps = 0;
+  long long gw = -1, gb = -1;  // offsets of weight / bias in the flat gradient buffer (c2w_param_layout)
 };
 struct BlockW {
   int mod_off = 0;
+  long long g_pw = -1, g_pb = -1;  // project.0 weight / bias
   ConvW c1, c2;
 };
 struct AttnW {
@@ -48,7 +51,7 @@ struct LevelW {
   std::vector<AttnW> dattn, aattn;
 };
 
-enum OpKind { OP_CONV, OP_LN, OP_ATTN, OP_LN_BWD, OP_ATTN_BWD, OP_ZERO_UP, OP_SILU };
+enum OpKind { OP_CONV, OP_LN, OP_ATTN, OP_LN_BWD, OP_ATTN_BWD, OP_ZERO_UP, OP_SILU, OP_COPY, OP_WGRAD, OP_COLSUM };
 struct Op {
   OpKind kind;
   // conv
@@ -75,12 +78,27 @@ struct Op {
   int C = 0, H = 0, W = 0, up = 0, mod_off = -1;
   // attention
   int T = 0;
+  // training: OP_COPY (in -> out, C*H*W elements per image); OP_WGRAD (dW of one conv: x = spec.in, dy = in; spec.H/W/cin/
+  // cout_pad/stride/c3 as in the forward conv) and OP_COLSUM (bias gradient: column sums of `in`, C padded channels)
+  long long dst = -1;        // offset in the flat gradient buffer
+  int cin_real = 0, cout_real = 0;
+  WgradLaunch wg;            // built for `wg_n` images
+  int wg_n = -1;
 };
 
 struct Plan {
   int n_max = 0;
   bool vjp = false;        // forward ops stash what the backward ops need
   bool per_t = false;      // one diffusion time per sample: mods is [n, total_mod], no LayerNorm fusion
+  bool train = false;      // vjp + per_t + parameter gradients (wgrad / bias / modulation / time-MLP ops in `bwd`)
+  int n_last = 0;          // images of the last training forward
+  const float* t_last = nullptr;
+  float* dmods = nullptr;  // [n, total_mod] gradient w.r.t. the modulation vectors
+  float* wg_scratch = nullptr;
+  size_t wg_scratch_floats = 0;
+  float *feat = nullptr, *pre0 = nullptr, *pre1 = nullptr, *demb = nullptr, *dh0 = nullptr;  // time-MLP backward
+  float* loss_partials = nullptr;
+  float* grad = nullptr;   // flat gradient buffer of the running c2w_train_backward call
   std::vector<Op> ops;
   std::vector<Op> bwd;     // input-gradient pass (vjp plans only), in execution order
   bf16* cot = nullptr;     // UNet-output cotangent [n, HW, cout_pad(window channels)] bf16
@@ -101,6 +119,9 @@ struct c2w_handle {
   c2w_config cfg;
   int nl = 0, cin = 0, cin_pad = 0;
   std::map<std::string, std::vector<float>> raw;
+  std::vector<std::pair<std::string, long long>> params;  // (name, numel) in the order they were loaded
+  std::map<std::string, long long> param_off;              // name -> offset in the flat gradient buffer (4-float aligned)
+  long long param_total = 0;
   bool finalized = false;
   std::vector<void*> allocs;
   float *map0_w = nullptr, *map0_b = nullptr, *map1_w = nullptr, *map1_b = nullptr;
@@ -160,6 +181,8 @@ int pack_conv(c2w_handle* h, const std::string& prefix, int cout, int cin, int t
   cw->cin = cin;
   cw->cout = cout;
   cw->taps = taps;
+  cw->gw = h->param_off.count(prefix + ".weight") ? h->param_off[prefix + ".weight"] : -1;
+  cw->gb = h->param_off.count(prefix + ".bias") ? h->param_off[prefix + ".bias"] : -1;
   cw->cin_pad = pad64(cin);
   cw->cout_pad = pad64(cout);
   const size_t K = static_cast<size_t>(taps) * cw->cin_pad;
@@ -206,8 +229,16 @@ void launch_ln_c(const bf16* x, const float* mod, bf16* out, float* inv, long lo
 }
 template <int C>
 void launch_ln_bwd_c(const bf16* gy, const bf16* y, const float* inv, const bf16* gres, bf16* out, long long npix, int H,
-                     int W, int down, int sms, cudaStream_t st) {
+                     int W, int down, int sms, cudaStream_t st, float* dmod, int dmod_stride) {
   const int threads = 256;
+  if (dmod != nullptr) {  // training: contiguous per-image chunks, per-image column sums of the input gradient
+    const int pix = H * W;
+    int chunk = pix < 512 ? pix : 512;
+    while (pix % chunk != 0) --chunk;
+    channel_layernorm_bwd_kernel<C><<<static_cast<int>(npix / chunk), threads, 0, st>>>(gy, y, inv, gres, out, npix, H, W,
+                                                                                      down, dmod, dmod_stride, pix, chunk);
+    return;
+  }
   long long blocks = (npix + 7) / 8;
   const long long cap = static_cast<long long>(sms) * 8;
   if (blocks > cap) blocks = cap;
@@ -238,8 +269,8 @@ int launch_ln(const bf16* x, const float* mod, bf16* out, float* inv, long long 
 }
 
 int launch_ln_bwd(const bf16* gy, const bf16* y, const float* inv, const bf16* gres, bf16* out, long long npix, int C,
-                  int H, int W, int down, int sms, cudaStream_t st) {
-#define C2W_CALL(CC) launch_ln_bwd_c<CC>(gy, y, inv, gres, out, npix, H, W, down, sms, st)
+                  int H, int W, int down, int sms, cudaStream_t st, float* dmod = nullptr, int dmod_stride = 0) {
+#define C2W_CALL(CC) launch_ln_bwd_c<CC>(gy, y, inv, gres, out, npix, H, W, down, sms, st, dmod, dmod_stride)
   C2W_LN_DISPATCH(C, C2W_CALL)
 #undef C2W_CALL
   C2W_CUDA(cudaGetLastError());
@@ -368,7 +399,7 @@ int run_modulation(c2w_handle* h, float t, const float* t_dev, int ns, float* h0
 // Lays the workspace out and (if base != null) builds every launch of the forward pass over it.  vjp: the forward
 // ops additionally stash (per block) the LayerNorm output + 1/std and the SiLU pre-activation, (per attention block)
 // qkv, and the plan gets the input-gradient pass `bwd`.
-int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* bytes_out) {
+int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* bytes_out, bool train = false) {
   Plan& P = h->plan;
   const bool real = base != nullptr;
   Bump B(base);
@@ -380,6 +411,8 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
     P.n_max = n;
     P.vjp = vjp;
     P.per_t = per_t;
+    P.train = train;
+    P.n_last = 0;
   }
   bf16* xin = B.take<bf16>(n * HW0 * h->cin_pad);
   const size_t ns = per_t ? n : 1;  // modulation vectors: one per sample or one for the batch
@@ -427,6 +460,29 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
     gqkv = B.take<bf16>(qkv_elems);
     gatt = B.take<bf16>(att_elems);
     cot = B.take<bf16>(n * HW0 * h->levels[0].tail.cout_pad);
+  }
+  if (train) {  // parameter-gradient scratch: modulation gradients, split-K slabs, time-MLP backward
+    const size_t E = h->cfg.embedding_dim, nf = h->cfg.noise_features;
+    float* dmods = B.take<float>(static_cast<size_t>(n) * std::max(h->total_mod, 1));
+    const size_t wg_floats = 12u * 1024u * 1024u;  // 48 MB: every layer's slabs fit (wgrad_launch_init trims the splits)
+    float* wg = B.take<float>(wg_floats);
+    float* feat = B.take<float>(n * nf);
+    float* pre0 = B.take<float>(n * E);
+    float* pre1 = B.take<float>(n * E);
+    float* demb = B.take<float>(n * E);
+    float* dh0 = B.take<float>(n * E);
+    float* lp = B.take<float>(4096);
+    if (real) {
+      P.dmods = dmods;
+      P.wg_scratch = wg;
+      P.wg_scratch_floats = wg_floats;
+      P.feat = feat;
+      P.pre0 = pre0;
+      P.pre1 = pre1;
+      P.demb = demb;
+      P.dh0 = dh0;
+      P.loss_partials = lp;
+    }
   }
   // per-block stash buffers are taken on the fly below (same order in the sizing and the real pass)
   auto stash = [&](size_t elems) -> bf16* { return B.take<bf16>(elems); };
@@ -523,11 +579,44 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
     op.mod_off = mod_off;
     P.ops.push_back(op);
   };
+  // training: dW (+ bias gradient) of the conv that read `x` (input image H x W) and whose output gradient is `dy`
+  auto add_wgrad = [&](std::vector<Op>& unit, bool c3, const bf16* x, const bf16* dy, int H, int W, const ConvW& w,
+                       int stride) {
+    if (!real || !train) return;
+    if (w.gw >= 0) {
+      Op op;
+      op.kind = OP_WGRAD;
+      op.spec.c3 = c3;
+      op.spec.in = x;
+      op.in = dy;
+      op.spec.H = H;
+      op.spec.W = W;
+      op.spec.cin = w.cin_pad;
+      op.spec.cout_pad = w.cout_pad;
+      op.spec.stride = stride;
+      op.dst = w.gw;
+      op.cin_real = w.cin;
+      op.cout_real = w.cout;
+      unit.push_back(op);
+    }
+    if (w.gb >= 0) {
+      Op b;
+      b.kind = OP_COLSUM;
+      b.in = dy;
+      b.C = w.cout_pad;
+      b.H = H / stride;
+      b.W = W / stride;
+      b.dst = w.gb;
+      b.cout_real = w.cout;
+      unit.push_back(b);
+    }
+  };
   auto add_ln_bwd = [&](std::vector<Op>& unit, const bf16* gy, const bf16* y, const float* inv, const bf16* gres,
-                        bf16* out, int C, int H, int W, int down) {
+                        bf16* out, int C, int H, int W, int down, int mod_off = -1) {
     if (!real) return;
     Op op;
     op.kind = OP_LN_BWD;
+    op.mod_off = train ? mod_off : -1;
     op.in = gy;
     op.aux = y;
     op.inv = const_cast<float*>(inv);
@@ -579,10 +668,24 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
       if (vjp) {
         units.emplace_back();
         std::vector<Op>& u = units.back();
+        if (train && real) {  // conv2's input, silu(pre), lives in the level's shared buffer: recompute it for the wgrad
+          Op op;
+          op.kind = OP_SILU;
+          op.aux = pre;
+          op.in = nullptr;
+          op.out = hs[l];
+          op.C = L.C;
+          op.H = L.H;
+          op.W = L.W;
+          op.up = 0;
+          u.push_back(op);
+        }
+        add_wgrad(u, true, hs[l], gs[l], L.H, L.W, bw.c2, 1);
         if (h->fuse_dsilu) {
           // conv2's input gradient times silu'(pre), written in place over the stashed pre-activation (the epilogue
           // prefetches `pre` like a residual tile), then conv1's input gradient from it
           if ((rc = add_dconv(u, true, gs[l], L.H, L.W, bw.c2, EPI_MUL_DSILU, pre, nullptr))) return rc;
+          add_wgrad(u, true, y, pre, L.H, L.W, bw.c1, 1);
           if ((rc = add_dconv(u, true, pre, L.H, L.W, bw.c1, EPI_BIAS, ga[l], nullptr))) return rc;
         } else {
           if ((rc = add_dconv(u, true, gs[l], L.H, L.W, bw.c2, EPI_BIAS, gh[l], nullptr))) return rc;
@@ -598,9 +701,10 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
             op.up = 1;
             u.push_back(op);
           }
+          add_wgrad(u, true, y, gh[l], L.H, L.W, bw.c1, 1);
           if ((rc = add_dconv(u, true, gh[l], L.H, L.W, bw.c1, EPI_BIAS, ga[l], nullptr))) return rc;
         }
-        add_ln_bwd(u, ga[l], y, inv, gs[l], gs[l], L.C, L.H, L.W, 0);
+        add_ln_bwd(u, ga[l], y, inv, gs[l], gs[l], L.C, L.H, L.W, 0, bw.mod_off);
       }
       if (L.attn) {
         // x + proj(attn(qkv(LN(x))))    model/nn.py:50-60
@@ -609,6 +713,7 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
         bf16* ya = vjp ? stash(e) : as[l];
         float* inva = vjp ? stash_f(npix) : nullptr;
         bf16* q = vjp ? stash(3 * e) : qkv;
+        bf16* att_s = train ? stash(e) : att;  // training keeps the attention output: it is the proj conv's wgrad operand
         add_ln(xs[l], ya, inva, L.C, L.H, L.W, 0, -1);
         rc = add_conv(false, ya, L.H, L.W, L.C, aw.qkv, EPI_BIAS, q, false);
         if (rc) return rc;
@@ -616,7 +721,7 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
           Op op;
           op.kind = OP_ATTN;
           op.in = q;
-          op.out = att;
+          op.out = att_s;
           op.T = T;
           op.C = L.C;
           P.ops.push_back(op);
@@ -624,11 +729,12 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
           if (P.attn_smem > static_cast<size_t>(kSmemLimit))
             return fail(C2W_ERR_INVALID, "attention at level %d (T=%d, C=%d) exceeds shared memory", l, op.T, op.C);
         }
-        rc = add_conv(false, att, L.H, L.W, L.C, aw.proj, EPI_BIAS_RES, xs[l], false);
+        rc = add_conv(false, att_s, L.H, L.W, L.C, aw.proj, EPI_BIAS_RES, xs[l], false);
         if (rc) return rc;
         if (vjp) {
           units.emplace_back();
           std::vector<Op>& u = units.back();
+          add_wgrad(u, false, att_s, gs[l], L.H, L.W, aw.proj, 1);
           if ((rc = add_dconv(u, false, gs[l], L.H, L.W, aw.proj, EPI_BIAS, gatt, nullptr))) return rc;
           if (real) {
             Op op;
@@ -641,6 +747,7 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
             op.C = L.C;
             u.push_back(op);
           }
+          add_wgrad(u, false, ya, gqkv, L.H, L.W, aw.qkv, 1);
           if ((rc = add_dconv(u, false, gqkv, L.H, L.W, aw.qkv, EPI_BIAS, ga[l], nullptr))) return rc;
           add_ln_bwd(u, ga[l], ya, inva, gs[l], gs[l], L.C, L.H, L.W, 0);
         }
@@ -658,16 +765,30 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
       if (rc) return rc;
       if (vjp) {  // gradient w.r.t. the window batch, fp32 [n, HW, cin_pad] into out32
         units.emplace_back();
+        add_wgrad(units.back(), true, xin, gs[0], L.H, L.W, L.head, 1);
         if ((rc = add_dconv(units.back(), true, gs[0], L.H, L.W, L.head, EPI_F32, nullptr, nullptr))) return rc;
         if (real) units.back().back().conv.p.out_f32 = out32;
       }
     } else {
       const LevelW& U = h->levels[l - 1];
+      // training: the skip value xs[l-1] is the head conv's wgrad operand, but the ascent later accumulates into it
+      bf16* skip = train ? stash(static_cast<size_t>(n) * U.H * U.W * U.C) : nullptr;
+      if (train && real) {
+        Op op;
+        op.kind = OP_COPY;
+        op.in = xs[l - 1];
+        op.out = skip;
+        op.C = U.C;
+        op.H = U.H;
+        op.W = U.W;
+        P.ops.push_back(op);
+      }
       rc = add_conv(true, xs[l - 1], U.H, U.W, U.C, L.head, EPI_BIAS, xs[l], false, 2);
       if (rc) return rc;
       if (vjp) {  // g[l-1] += conv_flipped(zero-upsampled g[l])
         units.emplace_back();
         std::vector<Op>& u = units.back();
+        add_wgrad(u, true, skip, gs[l], U.H, U.W, L.head, 2);
         if (real) {
           Op op;
           op.kind = OP_ZERO_UP;
@@ -700,6 +821,7 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
       if (vjp) {  // g[l] = LN_bwd(sum_2x2 conv_flipped(g[l-1]))   (xs[l] feeds nothing else)
         units.emplace_back();
         std::vector<Op>& u = units.back();
+        add_wgrad(u, true, upl, gs[l - 1], U.H, U.W, L.tail, 1);
         if ((rc = add_dconv(u, true, gs[l - 1], U.H, U.W, L.tail, EPI_BIAS, gup, nullptr))) return rc;
         add_ln_bwd(u, gup, upl, invt, nullptr, gs[l], L.C, L.H, L.W, 1);
       }
@@ -708,6 +830,7 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
       if (rc) return rc;
       if (vjp) {
         units.emplace_back();
+        add_wgrad(units.back(), true, xs[0], cot, L.H, L.W, L.tail, 1);
         if ((rc = add_dconv(units.back(), true, cot, L.H, L.W, L.tail, EPI_BIAS, gs[0], nullptr))) return rc;
       }
     }
@@ -791,9 +914,36 @@ int run_ops(c2w_handle* h, std::vector<Op>& ops, int nn, const FinalSpec& fs, cu
       }
       case OP_LN_BWD: {
         SpanGuard sg(h, 1, st);
+        float* dmod = (P.train && op.mod_off >= 0) ? P.dmods + op.mod_off : nullptr;
         int rc = launch_ln_bwd(op.in, op.aux, op.inv, op.res, op.out, static_cast<long long>(nn) * op.H * op.W, op.C, op.H,
-                               op.W, op.up, h->sms, st);
+                               op.W, op.up, h->sms, st, dmod, h->total_mod);
         if (rc) return rc;
+        break;
+      }
+      case OP_COPY: {
+        SpanGuard sg(h, 1, st);
+        C2W_CUDA(cudaMemcpyAsync(op.out, op.in, static_cast<size_t>(nn) * op.H * op.W * op.C * sizeof(bf16),
+                                 cudaMemcpyDeviceToDevice, st));
+        break;
+      }
+      case OP_WGRAD: {
+        if (op.wg_n != nn) {
+          if (!wgrad_launch_init(&op.wg, op.spec.c3, op.spec.in, op.in, nn, op.spec.H, op.spec.W, op.spec.cin,
+                                 op.spec.cout_pad, op.spec.stride, h->sms, P.wg_scratch, P.wg_scratch_floats))
+            return fail(C2W_ERR_INVALID, "cannot build wgrad launch (n=%d H=%d W=%d cin=%d cout=%d stride=%d conv3x3=%d) %s", nn,
+                        op.spec.H, op.spec.W, op.spec.cin, op.spec.cout_pad, op.spec.stride, (int)op.spec.c3,
+                        tmap_error_slot());
+          op.wg_n = nn;
+        }
+        SpanGuard sg(h, 0, st);
+        ++g_launches;  // GEMM + slab reduction
+        C2W_CUDA(wgrad_run(op.wg, P.grad + op.dst, op.cout_real, op.cin_real, 1, 1.0f, st));
+        break;
+      }
+      case OP_COLSUM: {
+        SpanGuard sg(h, 1, st);
+        const long long rows = static_cast<long long>(nn) * op.H * op.W;
+        C2W_CUDA(colsum_run(op.in, P.grad + op.dst, rows, op.C, rows, 0, 1.0f, st, op.cout_real));
         break;
       }
       case OP_ATTN_BWD: {
@@ -877,6 +1027,7 @@ void c2w_destroy(c2w_handle* h) {
 int c2w_load_weight(c2w_handle* h, const char* name, const float* host_data, int64_t numel) {
   C2W_REQUIRE(h && name && host_data && numel > 0, "c2w_load_weight: bad argument");
   if (h->finalized) return fail(C2W_ERR_STATE, "weights already finalised");
+  if (!h->raw.count(name)) h->params.emplace_back(name, static_cast<long long>(numel));
   h->raw[name].assign(host_data, host_data + numel);
   return C2W_OK;
 }
@@ -887,6 +1038,14 @@ int c2w_finalize_weights(c2w_handle* h) {
   const c2w_config& c = h->cfg;
   const int E = c.embedding_dim, nl = h->nl;
   int rc;
+  {  // flat gradient layout: parameters in loading order (= state_dict order), each start aligned to 4 floats
+    long long off = 0;
+    for (auto& pr : h->params) {
+      h->param_off[pr.first] = off;
+      off += (pr.second + 3) / 4 * 4;
+    }
+    h->param_total = off;
+  }
   if ((rc = upload_named(h, "map_layer0.weight", static_cast<size_t>(E) * c.noise_features, &h->map0_w))) return rc;
   if ((rc = upload_named(h, "map_layer0.bias", E, &h->map0_b))) return rc;
   if ((rc = upload_named(h, "map_layer1.weight", static_cast<size_t>(E) * E, &h->map1_w))) return rc;
@@ -925,6 +1084,8 @@ int c2w_finalize_weights(c2w_handle* h) {
         if ((rc = need(h, p + ".project.0.weight", static_cast<size_t>(L.C) * E, &pw))) return rc;
         if ((rc = need(h, p + ".project.0.bias", L.C, &pb))) return rc;
         bw.mod_off = static_cast<int>(proj_b.size());
+        bw.g_pw = h->param_off.count(p + ".project.0.weight") ? h->param_off[p + ".project.0.weight"] : -1;
+        bw.g_pb = h->param_off.count(p + ".project.0.bias") ? h->param_off[p + ".project.0.bias"] : -1;
         proj_w.insert(proj_w.end(), pw->begin(), pw->end());
         proj_b.insert(proj_b.end(), pb->begin(), pb->end());
         if ((rc = pack_conv(h, p + ".residue.1", L.C, L.C, 9, &bw.c1))) return rc;
@@ -990,20 +1151,25 @@ int64_t c2w_workspace_bytes_ex(c2w_handle* h, int32_t max_windows, int32_t flags
     return -1;
   }
   size_t bytes = 0;
-  if (build_plan(h, max_windows, (flags & C2W_WS_VJP) != 0, (flags & C2W_WS_PER_SAMPLE_T) != 0, nullptr, &bytes)) return -1;
+  const bool train = (flags & C2W_WS_TRAIN) != 0;
+  if (build_plan(h, max_windows, train || (flags & C2W_WS_VJP) != 0, train || (flags & C2W_WS_PER_SAMPLE_T) != 0, nullptr,
+                 &bytes, train))
+    return -1;
   return static_cast<int64_t>(bytes);
 }
 int c2w_bind_workspace_ex(c2w_handle* h, int32_t max_windows, void* dev_ptr, int64_t bytes, int32_t flags) {
   C2W_REQUIRE(h && dev_ptr && max_windows >= 1, "c2w_bind_workspace: bad argument");
   if (!h->finalized) return fail(C2W_ERR_STATE, "finalise the weights first");
-  const bool vjp = (flags & C2W_WS_VJP) != 0, per_t = (flags & C2W_WS_PER_SAMPLE_T) != 0;
-  C2W_REQUIRE(!(vjp && per_t), "a VJP workspace with per-sample diffusion times is not built");
+  const bool train = (flags & C2W_WS_TRAIN) != 0;
+  const bool vjp = train || (flags & C2W_WS_VJP) != 0, per_t = train || (flags & C2W_WS_PER_SAMPLE_T) != 0;
+  C2W_REQUIRE(train || !(vjp && per_t),
+              "input gradients with per-sample diffusion times need the training workspace (C2W_WS_TRAIN)");
   size_t need_bytes = 0;
-  int rc = build_plan(h, max_windows, vjp, per_t, nullptr, &need_bytes);
+  int rc = build_plan(h, max_windows, vjp, per_t, nullptr, &need_bytes, train);
   if (rc) return rc;
   C2W_REQUIRE(static_cast<size_t>(bytes) >= need_bytes, "workspace too small: %lld < %zu", (long long)bytes, need_bytes);
   void* aligned = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(dev_ptr) + 1023) & ~uintptr_t(1023));
-  return build_plan(h, max_windows, vjp, per_t, aligned, &need_bytes);
+  return build_plan(h, max_windows, vjp, per_t, aligned, &need_bytes, train);
 }
 
 int64_t c2w_workspace_bytes(c2w_handle* h, int32_t max_windows) { return c2w_workspace_bytes_ex(h, max_windows, 0); }
@@ -1174,6 +1340,178 @@ int c2w_window_score_backward(c2w_handle* h, const float* cot, int32_t n_frames_
   return C2W_OK;
 }
 
+// Re-packs every weight from a DEVICE copy of the parameters in the flat layout of c2w_param_layout (after an optimiser
+// step: the buffer optim.AdamW steps on, no host round trip, no re-allocation): bf16 tensor-core operands of all convs,
+// biases, modulation projections, time MLP.
+int c2w_refresh_weights(c2w_handle* h, const float* flat_dev, void* stream) {
+  C2W_REQUIRE(h && flat_dev, "c2w_refresh_weights: bad argument");
+  if (!h->finalized) return fail(C2W_ERR_STATE, "finalise the weights first");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto conv = [&](const ConvW& w) -> int {
+    if (w.gw < 0 || w.gb < 0) return fail(C2W_ERR_MISSING, "a conv has no slot in the flat parameter layout");
+    const long long total = static_cast<long long>(w.cout) * w.cin * w.taps;
+    repack_conv_kernel<<<grid_for(total, 256, h->sms), 256, 0, st>>>(flat_dev + w.gw, flat_dev + w.gb, w.w, w.wd, w.b, w.cout,
+                                                                     w.cin, w.taps, w.cin_pad, w.cout_pad);
+    return C2W_OK;
+  };
+  const int E = h->cfg.embedding_dim;
+  int rc;
+  for (LevelW& L : h->levels) {
+    if ((rc = conv(L.head)) || (rc = conv(L.tail))) return rc;
+    for (int side = 0; side < 2; ++side) {
+      std::vector<BlockW>& blocks = side == 0 ? L.desc : L.asc;
+      std::vector<AttnW>& attns = side == 0 ? L.dattn : L.aattn;
+      for (BlockW& bw : blocks) {
+        if ((rc = conv(bw.c1)) || (rc = conv(bw.c2))) return rc;
+        C2W_REQUIRE(bw.g_pw >= 0 && bw.g_pb >= 0, "a modulation projection has no slot in the flat parameter layout");
+        C2W_CUDA(cudaMemcpyAsync(h->proj_w + static_cast<size_t>(bw.mod_off) * E, flat_dev + bw.g_pw,
+                                 static_cast<size_t>(L.C) * E * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        C2W_CUDA(cudaMemcpyAsync(h->proj_b + bw.mod_off, flat_dev + bw.g_pb, L.C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      }
+      for (AttnW& aw : attns)
+        if ((rc = conv(aw.qkv)) || (rc = conv(aw.proj))) return rc;
+    }
+  }
+  struct { const char* name; float* dst; size_t n; } mlp[4] = {
+      {"map_layer0.weight", h->map0_w, static_cast<size_t>(E) * h->cfg.noise_features}, {"map_layer0.bias", h->map0_b, (size_t)E},
+      {"map_layer1.weight", h->map1_w, static_cast<size_t>(E) * E}, {"map_layer1.bias", h->map1_b, (size_t)E}};
+  for (auto& m : mlp) {
+    auto it = h->param_off.find(m.name);
+    C2W_REQUIRE(it != h->param_off.end(), "parameter '%s' has no slot in the flat layout", m.name);
+    C2W_CUDA(cudaMemcpyAsync(m.dst, flat_dev + it->second, m.n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  C2W_CUDA(cudaGetLastError());
+  return C2W_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- training step (N2)
+int64_t c2w_param_total(c2w_handle* h) { return (h && h->finalized) ? h->param_total : -1; }
+
+int c2w_param_layout(c2w_handle* h, const char* name, int64_t* offset, int64_t* numel) {
+  C2W_REQUIRE(h && name && offset && numel, "c2w_param_layout: bad argument");
+  if (!h->finalized) return fail(C2W_ERR_STATE, "finalise the weights first");
+  auto it = h->param_off.find(name);
+  if (it == h->param_off.end()) return fail(C2W_ERR_MISSING, "no parameter named '%s'", name);
+  *offset = it->second;
+  for (auto& pr : h->params)
+    if (pr.first == name) *numel = pr.second;
+  return C2W_OK;
+}
+
+// Forward of the training step: ScoreUNet.forward with one diffusion time per sample (src/thor/pipelines.py:27-35),
+// stashing what the backward needs.  n <= max_windows of a C2W_WS_TRAIN workspace (one chunk: backward follows).
+int c2w_train_forward(c2w_handle* h, const float* x_nchw, int32_t n, const float* t_dev, float* out_nchw, void* stream) {
+  C2W_REQUIRE(h && x_nchw && t_dev && out_nchw && n >= 1, "c2w_train_forward: bad argument");
+  Plan& P = h->plan;
+  if (P.n_max < 1 || !P.train) return fail(C2W_ERR_STATE, "bind a training workspace first (C2W_WS_TRAIN)");
+  C2W_REQUIRE(n <= P.n_max, "c2w_train_forward: %d samples exceed the bound workspace (%d)", n, P.n_max);
+  int rc = unet_forward_impl(h, x_nchw, n, 0.f, t_dev, out_nchw, stream);
+  if (rc) return rc;
+  P.n_last = n;
+  P.t_last = t_dev;
+  return C2W_OK;
+}
+
+// Backward of the training step (training_loop.py:378 `fabric.backward(loss)`): gout = d loss / d output (fp32 NCHW) ->
+// input-gradient pass (K1 with flipped weights) + weight gradients (K10) + bias / modulation / time-MLP gradients,
+// written into the flat fp32 buffer grad_flat (layout: c2w_param_layout; accumulate != 0 adds to it).
+int c2w_train_backward(c2w_handle* h, const float* gout_nchw, int32_t n, float* gin_nchw, float* grad_flat,
+                       int32_t accumulate, void* stream) {
+  C2W_REQUIRE(h && gout_nchw && grad_flat && n >= 1, "c2w_train_backward: bad argument");
+  Plan& P = h->plan;
+  if (P.n_max < 1 || !P.train) return fail(C2W_ERR_STATE, "bind a training workspace first (C2W_WS_TRAIN)");
+  C2W_REQUIRE(n == P.n_last && P.t_last != nullptr, "c2w_train_backward: call c2w_train_forward on the same %d samples first", n);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int hw = h->cfg.height * h->cfg.width;
+  const int cout_pad = h->levels[0].tail.cout_pad;
+  const int E = h->cfg.embedding_dim, nf = h->cfg.noise_features, TM = h->total_mod;
+  if (!accumulate) C2W_CUDA(cudaMemsetAsync(grad_flat, 0, static_cast<size_t>(h->param_total) * sizeof(float), st));
+  if (TM > 0) C2W_CUDA(cudaMemsetAsync(P.dmods, 0, static_cast<size_t>(n) * TM * sizeof(float), st));
+  dim3 blk(32, 8);
+  dim3 g2(ceil_div(hw, 32), ceil_div(cout_pad, 32), n);
+  nchw_to_nhwc_bf16_kernel<<<g2, blk, 0, st>>>(gout_nchw, P.cot, h->cin, hw, cout_pad);
+  C2W_CUDA(cudaGetLastError());
+  P.grad = grad_flat;
+  FinalSpec fs;
+  fs.mode = EPI_F32;
+  int rc = run_ops(h, P.bwd, n, fs, st);
+  P.grad = nullptr;
+  if (rc) return rc;
+  if (gin_nchw) {
+    dim3 g3(ceil_div(hw, 32), ceil_div(h->cin_pad, 32), n);
+    nhwc_f32_to_nchw_kernel<<<g3, blk, 0, st>>>(P.out32, gin_nchw, h->cin, hw, h->cin_pad);
+    C2W_CUDA(cudaGetLastError());
+  }
+  // ---- modulation projections and the time MLP (model/nn.py:149; model/score.py:59-67): tiny fp32 products
+  auto off = [&](const char* nm) -> long long {
+    auto it = h->param_off.find(nm);
+    return it == h->param_off.end() ? -1 : it->second;
+  };
+  auto blocks1d = [](long long items) { return static_cast<int>((items + 255) / 256); };
+  if (TM > 0) {
+    for (LevelW& L : h->levels)
+      for (std::vector<BlockW>* side : {&L.desc, &L.asc})
+        for (BlockW& bw : *side) {
+          if (bw.g_pw >= 0)  // dW_p[c][e] += sum_s dmod[s][c] emb[s][e]
+            gemm_tn_f32_kernel<<<blocks1d(static_cast<long long>(L.C) * E), 256, 0, st>>>(
+                P.dmods + bw.mod_off, TM, P.emb, E, grad_flat + bw.g_pw, E, n, L.C, E, 1);
+          if (bw.g_pb >= 0)
+            colsum_f32_kernel<<<blocks1d(L.C), 256, 0, st>>>(P.dmods + bw.mod_off, TM, grad_flat + bw.g_pb, n, L.C, 1);
+        }
+    // d emb = dmods . W_proj  ([n, TM] x [TM, E]);  emb = silu(pre1), pre1 = W1 h0 + b1;  h0 = silu(pre0), pre0 = W0 feat + b0
+    gemm_nn_f32_kernel<<<blocks1d(static_cast<long long>(n) * E), 256, 0, st>>>(P.dmods, TM, h->proj_w, E, P.demb, E, n, TM, E);
+    matvec_kernel<<<dim3(ceil_div(static_cast<long long>(E) * 32, 256), n), 256, 0, st>>>(h->map1_w, h->map1_b, P.h0, P.pre1,
+                                                                                          E, E, 0);
+    dsilu_f32_kernel<<<blocks1d(static_cast<long long>(n) * E), 256, 0, st>>>(P.demb, P.pre1, static_cast<long long>(n) * E);
+    const long long o1w = off("map_layer1.weight"), o1b = off("map_layer1.bias");
+    const long long o0w = off("map_layer0.weight"), o0b = off("map_layer0.bias");
+    if (o1w >= 0)
+      gemm_tn_f32_kernel<<<blocks1d(static_cast<long long>(E) * E), 256, 0, st>>>(P.demb, E, P.h0, E, grad_flat + o1w, E, n, E,
+                                                                                  E, 1);
+    if (o1b >= 0) colsum_f32_kernel<<<blocks1d(E), 256, 0, st>>>(P.demb, E, grad_flat + o1b, n, E, 1);
+    gemm_nn_f32_kernel<<<blocks1d(static_cast<long long>(n) * E), 256, 0, st>>>(P.demb, E, h->map1_w, E, P.dh0, E, n, E, E);
+    time_features_kernel<<<n, 128, 0, st>>>(P.t_last, P.feat, nf);
+    matvec_kernel<<<dim3(ceil_div(static_cast<long long>(E) * 32, 256), n), 256, 0, st>>>(h->map0_w, h->map0_b, P.feat, P.pre0,
+                                                                                          E, nf, 0);
+    dsilu_f32_kernel<<<blocks1d(static_cast<long long>(n) * E), 256, 0, st>>>(P.dh0, P.pre0, static_cast<long long>(n) * E);
+    if (o0w >= 0)
+      gemm_tn_f32_kernel<<<blocks1d(static_cast<long long>(E) * nf), 256, 0, st>>>(P.dh0, E, P.feat, nf, grad_flat + o0w, nf, n,
+                                                                                   E, nf, 1);
+    if (o0b >= 0) colsum_f32_kernel<<<blocks1d(E), 256, 0, st>>>(P.dh0, E, grad_flat + o0b, n, E, 1);
+    C2W_CUDA(cudaGetLastError());
+  }
+  return C2W_OK;
+}
+
+// mean((out - eps)^2) * loss_scale and its cotangent (src/thor/pipelines.py:27-35 + `.mean()`, training_loop.py:377):
+// gout = 2 loss_scale (out - eps) / numel; loss_sum_dev (device double) receives sum((out - eps)^2).
+int c2w_dsm_loss_grad(const float* out, const float* eps, float* gout, int64_t numel, float loss_scale, float* partials4096,
+                      double* loss_sum_dev, void* stream) {
+  C2W_REQUIRE(out && eps && gout && partials4096 && loss_sum_dev && numel >= 1, "c2w_dsm_loss_grad: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = static_cast<int>(std::min<long long>(4096, (numel + 255) / 256));
+  dsm_loss_grad_kernel<<<grid, 256, 0, st>>>(out, eps, gout, partials4096, numel, 2.0f * loss_scale / static_cast<float>(numel));
+  reduce_partials_kernel<<<1, 256, 0, st>>>(partials4096, grid, loss_sum_dev);
+  g_launches += 2;
+  C2W_CUDA(cudaGetLastError());
+  return C2W_OK;
+}
+
+// One denoising-score-matching training step up to the gradients (training_loop.py:372-378 for one accumulation round):
+// forward on xt (already noised: xt = mu(t) x + sigma(t) eps), loss + cotangent, backward.  out_nchw / gout_nchw are
+// caller-owned work buffers of x's shape (the prediction and its cotangent).
+int c2w_train_step(c2w_handle* h, const float* xt_nchw, int32_t n, const float* t_dev, const float* eps_nchw,
+                   float* out_nchw, float* gout_nchw, float loss_scale, float* grad_flat, int32_t accumulate,
+                   double* loss_sum_dev, void* stream) {
+  C2W_REQUIRE(h && xt_nchw && t_dev && eps_nchw && out_nchw && gout_nchw && grad_flat && loss_sum_dev, "c2w_train_step: bad argument");
+  int rc = c2w_train_forward(h, xt_nchw, n, t_dev, out_nchw, stream);
+  if (rc) return rc;
+  const int64_t numel = static_cast<int64_t>(n) * h->cin * h->cfg.height * h->cfg.width;
+  if ((rc = c2w_dsm_loss_grad(out_nchw, eps_nchw, gout_nchw, numel, loss_scale, h->plan.loss_partials, loss_sum_dev, stream)))
+    return rc;
+  return c2w_train_backward(h, gout_nchw, n, nullptr, grad_flat, accumulate, stream);
+}
+
 int c2w_traj_pack(const float* nchw, float* fhwc, int64_t frames, int32_t C, int32_t hw, void* stream) {
   C2W_REQUIRE(nchw && fhwc && frames >= 1, "c2w_traj_pack: bad argument");
   nchw_to_fhwc_kernel<<<grid_for(frames * hw, 256, c2w_num_sms()), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -1337,6 +1675,33 @@ int c2w_op_gather_windows(const float* traj, void* out, int n, int hw, int C, in
   gather_windows_kernel<<<grid_for(items, 256, c2w_num_sms()), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       traj, static_cast<bf16*>(out), n, hw, C, window * C, cin_pad, frame0);
   C2W_CUDA(cudaGetLastError());
+  return C2W_OK;
+}
+
+// ---- weight-gradient kernels, op level (parity tests of single kernels; the training step launches the same kernels)
+int c2w_op_wgrad(const void* x, const void* dy, int32_t n_img, int32_t H, int32_t W, int32_t cin_pad, int32_t cout_pad,
+                 int32_t stride, int32_t conv3x3, float* scratch, int64_t scratch_floats, float* dw, int32_t cin,
+                 int32_t cout, int32_t accumulate, void* stream) {
+  C2W_REQUIRE(x && dy && dw && scratch && n_img >= 1 && cin >= 1 && cout >= 1 && cin <= cin_pad && cout <= cout_pad,
+              "c2w_op_wgrad: bad argument");
+  const int sms = c2w_num_sms();
+  C2W_REQUIRE(sms > 0, "c2w_op_wgrad: no CUDA device");
+  WgradLaunch L;
+  if (!wgrad_launch_init(&L, conv3x3 != 0, static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), n_img,
+                         H, W, cin_pad, cout_pad, stride ? stride : 1, sms, scratch, static_cast<size_t>(scratch_floats)))
+    return fail(C2W_ERR_INVALID, "c2w_op_wgrad: cannot build launch (n=%d H=%d W=%d cin=%d cout=%d stride=%d; channel "
+                "counts must be multiples of 64, output images multiples of 8 x 8, GEMM rows a multiple of 64; scratch "
+                "%lld floats) %s", n_img, H, W, cin_pad, cout_pad, stride, (long long)scratch_floats, tmap_error_slot());
+  C2W_CUDA(wgrad_run(L, dw, cout, cin, accumulate, 1.0f, static_cast<cudaStream_t>(stream)));
+  return C2W_OK;
+}
+
+int c2w_op_colsum(const void* x_bf16, float* out, int64_t rows, int32_t C, int64_t rows_per_group, int32_t out_stride,
+                  float scale, void* stream) {
+  C2W_REQUIRE(x_bf16 && out && rows >= 1 && C >= 2 && C % 2 == 0 && rows_per_group >= 1,
+              "c2w_op_colsum: bad argument");
+  C2W_CUDA(colsum_run(static_cast<const __nv_bfloat16*>(x_bf16), out, rows, C, rows_per_group, out_stride, scale,
+                      static_cast<cudaStream_t>(stream)));
   return C2W_OK;
 }
 

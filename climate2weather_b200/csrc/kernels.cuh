@@ -666,16 +666,31 @@ __global__ void __launch_bounds__(256) attention_mma_kernel(const bf16* __restri
 // y is the stashed normalised output, inv the stashed 1/sqrt(var + eps).  down != 0: the LayerNorm output had been
 // nearest-upsampled 2x (model/nn.py:184): g_y is the sum of the 2x2 block of gy [n, 2H, 2W, C] and y is read from
 // the block's first pixel.  One warp per pixel, same lane -> channel mapping as the forward kernel.
+// dmod != null (training): every CTA owns a contiguous chunk of `chunk` pixels of ONE image and also accumulates the
+// per-image column sums of g_v — the gradient w.r.t. the block's modulation vector mod = Linear(emb) (model/nn.py:27,
+// v = x + mod[:, :, None, None]) — in registers (the lane -> channel mapping is fixed), reduced over the CTA's warps in
+// shared memory and added to dmod[image * dmod_stride + c] with one atomic per channel per CTA.
 template <int C>
 __global__ void channel_layernorm_bwd_kernel(const bf16* __restrict__ gy, const bf16* __restrict__ y,
                                              const float* __restrict__ inv, const bf16* gres, bf16* out,
-                                             long long npix, int H, int W, int down) {
+                                             long long npix, int H, int W, int down, float* dmod = nullptr,
+                                             int dmod_stride = 0, int pix_per_img = 1, int chunk = 0) {
   constexpr int VEC = (C % 128 == 0) ? 4 : 2;
   constexpr int NCH = C / (32 * VEC);
   const int lane = threadIdx.x & 31;
-  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
-  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  for (long long pix = warp0; pix < npix; pix += nwarps) {
+  long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  long long pix_end = npix;
+  float macc[NCH * VEC];
+#pragma unroll
+  for (int i = 0; i < NCH * VEC; ++i) macc[i] = 0.f;
+  if (dmod != nullptr) {
+    warp0 = static_cast<long long>(blockIdx.x) * chunk + (threadIdx.x >> 5);
+    nwarps = blockDim.x >> 5;
+    pix_end = static_cast<long long>(blockIdx.x + 1) * chunk;
+    if (pix_end > npix) pix_end = npix;
+  }
+  for (long long pix = warp0; pix < pix_end; pix += nwarps) {
     long long src[4];
     int nsrc = 1;
     if (down) {
@@ -743,7 +758,10 @@ __global__ void channel_layernorm_bwd_kernel(const bf16* __restrict__ gy, const 
       const int c0 = j * 32 * VEC + lane * VEC;
       float o[VEC];
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) o[e] = iv * (g[j * VEC + e] - s - yv[j * VEC + e] * sy);
+      for (int e = 0; e < VEC; ++e) {
+        o[e] = iv * (g[j * VEC + e] - s - yv[j * VEC + e] * sy);
+        macc[j * VEC + e] += o[e];
+      }
       if (gres != nullptr) {
         if (VEC == 4) {
           const uint2 r = *reinterpret_cast<const uint2*>(gres + pix * C + c0);
@@ -763,6 +781,114 @@ __global__ void channel_layernorm_bwd_kernel(const bf16* __restrict__ gy, const 
       else
         *reinterpret_cast<uint32_t*>(out + pix * C + c0) = pack_bf16x2(o[0], o[1]);
     }
+  }
+  if (dmod != nullptr) {
+    __shared__ float red[8][C];
+    const int w = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) red[w][j * 32 * VEC + lane * VEC + e] = macc[j * VEC + e];
+    __syncthreads();
+    const long long img = (static_cast<long long>(blockIdx.x) * chunk) / pix_per_img;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float v = 0.f;
+      for (int q = 0; q < (blockDim.x >> 5); ++q) v += red[q][c];
+      atomicAdd(dmod + img * dmod_stride + c, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ training: time MLP
+// Small fp32 kernels of the modulation / time-embedding backward (model/score.py:59-67, model/nn.py:149): a few GFLOP
+// per step against ~45 TFLOP of convolutions — one thread per output element, coalesced along the output's last axis.
+//   C[m][n] (+)= sum_k A[k][m] * B[k][n]        (dW = dpre^T . input, summed over the batch)
+__global__ void gemm_tn_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                   float* __restrict__ Cm, int ldc, int K, int M, int N, int accumulate) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(M) * N) return;
+  const int m = static_cast<int>(i / N), n = static_cast<int>(i - static_cast<long long>(m) * N);
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc = fmaf(A[static_cast<size_t>(k) * lda + m], B[static_cast<size_t>(k) * ldb + n], acc);
+  float* d = Cm + static_cast<size_t>(m) * ldc + n;
+  *d = accumulate ? *d + acc : acc;
+}
+//   C[m][n] = sum_k A[m][k] * B[k][n]           (d input = dpre . W)
+__global__ void gemm_nn_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                   float* __restrict__ Cm, int ldc, int M, int K, int N) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(M) * N) return;
+  const int m = static_cast<int>(i / N), n = static_cast<int>(i - static_cast<long long>(m) * N);
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc = fmaf(A[static_cast<size_t>(m) * lda + k], B[static_cast<size_t>(k) * ldb + n], acc);
+  Cm[static_cast<size_t>(m) * ldc + n] = acc;
+}
+//   out[m] (+)= sum_k A[k][m]                    (bias gradients)
+__global__ void colsum_f32_kernel(const float* __restrict__ A, int lda, float* __restrict__ out, int K, int M, int accumulate) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc += A[static_cast<size_t>(k) * lda + m];
+  out[m] = accumulate ? out[m] + acc : acc;
+}
+//   g <- g * silu'(pre)
+__global__ void dsilu_f32_kernel(float* __restrict__ g, const float* __restrict__ pre, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = pre[i], sg = 1.0f / (1.0f + expf(-x));
+  g[i] *= sg * (1.0f + x * (1.0f - sg));
+}
+// Sinusoidal features of the diffusion times (model/score.py:14-34): feat[s] = [cos(t f_j), sin(t f_j)], f_j as in
+// time_embed_kernel (which fuses them with the first Linear and does not store them).
+__global__ void time_features_kernel(const float* __restrict__ t_dev, float* __restrict__ feat, int nf) {
+  const int half = nf / 2;
+  const float t = t_dev[blockIdx.x];
+  if (threadIdx.x < half) {
+    const float f = expf(-9.210340371976184f * static_cast<float>(threadIdx.x) / static_cast<float>(half));
+    feat[static_cast<size_t>(blockIdx.x) * nf + threadIdx.x] = cosf(t * f);
+    feat[static_cast<size_t>(blockIdx.x) * nf + half + threadIdx.x] = sinf(t * f);
+  }
+}
+// Denoising-score-matching objective and its cotangent in one pass (src/thor/pipelines.py:27-35 followed by the
+// caller's `.mean()`, training_loop.py:377):  loss = mean((out - eps)^2) * loss_scale,
+//   gout = 2 (out - eps) * loss_scale / n   (what autograd hands the network), per-CTA partial sums of (out - eps)^2.
+__global__ void dsm_loss_grad_kernel(const float* __restrict__ out, const float* __restrict__ eps, float* __restrict__ gout,
+                                     float* __restrict__ partials, long long n, float gscale) {
+  float acc = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float d = out[i] - eps[i];
+    acc = fmaf(d, d, acc);
+    gout[i] = d * gscale;
+  }
+  __shared__ float wsum[32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = (threadIdx.x < (blockDim.x >> 5)) ? wsum[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) partials[blockIdx.x] = v;
+  }
+}
+
+// Device-side re-pack of one conv's weights after an optimiser step: fp32 OIHW (torch layout, in the flat parameter
+// buffer) -> the bf16 forward operand [cout_pad][taps * cin_pad] (k = tap * cin_pad + c) and the flipped / transposed
+// input-gradient operand [cin_pad][taps * cout_pad] (k = (taps - 1 - tap) * cout_pad + o); padding entries stay zero.
+__global__ void repack_conv_kernel(const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ wp,
+                                   bf16* __restrict__ wd, float* __restrict__ bp, int cout, int cin, int taps, int cin_pad,
+                                   int cout_pad) {
+  const long long total = static_cast<long long>(cout) * cin * taps;
+  const size_t K = static_cast<size_t>(taps) * cin_pad, Kd = static_cast<size_t>(taps) * cout_pad;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int t = static_cast<int>(i % taps);
+    const long long oc = i / taps;
+    const int c = static_cast<int>(oc % cin), o = static_cast<int>(oc / cin);
+    const bf16 v = __float2bfloat16_rn(w[i]);
+    wp[o * K + static_cast<size_t>(t) * cin_pad + c] = v;
+    wd[c * Kd + static_cast<size_t>(taps - 1 - t) * cout_pad + o] = v;
+    if (i < cout) bp[i] = b[i];
   }
 }
 

@@ -245,12 +245,14 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
 // grid = (row slabs, C / 64 * ... ) — each CTA sums kColsumRows rows for 256 channel lanes and adds atomically.
 constexpr int kColsumRows = 128;
 __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long rows, int C,
-                                   long long rows_per_group, int out_stride, float scale) {
-  // thread -> (channel pair cp, row lane rl): C/2 channel pairs, 256 / (C/2) rows in flight (C <= 512)
+                                   long long rows_per_group, int out_stride, float scale, int c_valid) {
+  // thread -> (channel pair cp, row lane rl): blockIdx.y selects a group of up to 256 channel pairs, the remaining
+  // threads of the CTA take rows in parallel
   const int pairs = C / 2;
-  const int rl_n = blockDim.x / pairs > 0 ? blockDim.x / pairs : 1;
-  const int cp = threadIdx.x % pairs, rl = threadIdx.x / pairs;
-  if (rl >= rl_n) return;
+  const int pairs_cta = pairs < static_cast<int>(blockDim.x) ? pairs : static_cast<int>(blockDim.x);
+  const int rl_n = blockDim.x / pairs_cta;
+  const int cp = blockIdx.y * pairs_cta + threadIdx.x % pairs_cta, rl = threadIdx.x / pairs_cta;
+  if (rl >= rl_n || cp >= pairs) return;
   const long long r0 = static_cast<long long>(blockIdx.x) * kColsumRows;
   const long long r1 = (r0 + kColsumRows < rows) ? r0 + kColsumRows : rows;
   float a0 = 0.f, a1 = 0.f;
@@ -258,8 +260,8 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* _
   for (long long r = r0 + rl; r < r1; r += rl_n) {
     const long long gnow = r / rows_per_group;
     if (gnow != grp) {  // a slab may straddle a group boundary
-      atomicAdd(out + grp * out_stride + 2 * cp, a0 * scale);
-      atomicAdd(out + grp * out_stride + 2 * cp + 1, a1 * scale);
+      if (2 * cp < c_valid) atomicAdd(out + grp * out_stride + 2 * cp, a0 * scale);
+      if (2 * cp + 1 < c_valid) atomicAdd(out + grp * out_stride + 2 * cp + 1, a1 * scale);
       a0 = a1 = 0.f;
       grp = gnow;
     }
@@ -267,8 +269,8 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* _
     a0 += __low2float(v);
     a1 += __high2float(v);
   }
-  atomicAdd(out + grp * out_stride + 2 * cp, a0 * scale);
-  atomicAdd(out + grp * out_stride + 2 * cp + 1, a1 * scale);
+  if (2 * cp < c_valid) atomicAdd(out + grp * out_stride + 2 * cp, a0 * scale);  // channels >= c_valid are padding
+  if (2 * cp + 1 < c_valid) atomicAdd(out + grp * out_stride + 2 * cp + 1, a1 * scale);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -385,10 +387,13 @@ inline cudaError_t wgrad_run(const WgradLaunch& L, float* dw, int cout, int cin,
 }
 
 inline cudaError_t colsum_run(const __nv_bfloat16* x, float* out, long long rows, int C, long long rows_per_group,
-                              int out_stride, float scale, cudaStream_t stream) {
+                              int out_stride, float scale, cudaStream_t stream, int c_valid = -1) {
   const int threads = 256;
   const long long blocks = (rows + kColsumRows - 1) / kColsumRows;
-  colsum_bf16_kernel<<<static_cast<int>(blocks), threads, 0, stream>>>(x, out, rows, C, rows_per_group, out_stride, scale);
+  const int pairs = C / 2;
+  const dim3 grid(static_cast<unsigned>(blocks), static_cast<unsigned>((pairs + threads - 1) / threads));
+  colsum_bf16_kernel<<<grid, threads, 0, stream>>>(x, out, rows, C, rows_per_group, out_stride, scale,
+                                                                        c_valid < 0 ? C : c_valid);
   return cudaGetLastError();
 }
 

@@ -80,7 +80,8 @@ class Engine:
     """One c2w handle: packed weights + workspace for a fixed (frame_channels, window, H, W)."""
 
     def __init__(self, net: "ScoreUNet", frame_channels: int, window: int, height: int, width: int,
-                 device: torch.device, max_windows: int, vjp: bool = False, per_sample_t: bool = False):
+                 device: torch.device, max_windows: int, vjp: bool = False, per_sample_t: bool = False,
+                 train: bool = False):
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -105,12 +106,23 @@ class Engine:
             _lib.check(self.lib.c2w_finalize_weights(self.handle), "c2w_finalize_weights")
             self.max_windows = 0
             self.workspace = None
-            self.vjp = bool(vjp)
-            self.per_sample_t = bool(per_sample_t)
+            self.vjp = bool(vjp) or bool(train)
+            self.per_sample_t = bool(per_sample_t) or bool(train)
+            self.train = bool(train)
+            self.param_total = int(self.lib.c2w_param_total(self.handle))
+            self.layout: Dict[str, Tuple[int, int]] = {}
+            off, num = ctypes.c_int64(), ctypes.c_int64()
+            for name in net.state_dict():
+                _lib.check(self.lib.c2w_param_layout(self.handle, name.encode(), ctypes.byref(off), ctypes.byref(num)),
+                           f"c2w_param_layout({name})")
+                self.layout[name] = (int(off.value), int(num.value))
+            self._flat_scratch: Optional[Tensor] = None
+            self._train_token = None
             self.bind(max_windows)
 
     def bind(self, max_windows: int) -> None:
-        flags = (_lib.WS_VJP if self.vjp else 0) | (_lib.WS_PER_SAMPLE_T if self.per_sample_t else 0)
+        flags = _lib.WS_TRAIN if self.train else ((_lib.WS_VJP if self.vjp else 0) |
+                                                  (_lib.WS_PER_SAMPLE_T if self.per_sample_t else 0))
         with torch.cuda.device(self.device):
             nbytes = self.lib.c2w_workspace_bytes_ex(self.handle, max_windows, flags)
             if nbytes < 0:
@@ -141,6 +153,48 @@ class Engine:
             _lib.check(self.lib.c2w_unet_forward_t(self.handle, x.data_ptr(), x.shape[0], t.data_ptr(), out.data_ptr(),
                                                    self.stream), "c2w_unet_forward_t")
         return out
+
+    # ------------------------------------------------------------------------------------------ training step
+    def refresh_weights(self, net: "ScoreUNet") -> None:
+        """Re-packs the weights from the module's CURRENT parameters on the device (after an optimiser step): no host
+        round trip, the workspace stays bound.  Zero-copy when the parameters are views of one flat buffer in the
+        library's layout (optim.AdamW); gathered into a scratch buffer otherwise."""
+        params = dict(net.state_dict(keep_vars=True))
+        first = next(iter(self.layout))
+        base = params[first].data_ptr() - 4 * self.layout[first][0]
+        aliased = all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and
+                      p.data_ptr() == base + 4 * self.layout[k][0] for k, p in params.items())
+        with torch.cuda.device(self.device):
+            if aliased:
+                ptr = base
+            else:
+                if self._flat_scratch is None:
+                    self._flat_scratch = torch.zeros(self.param_total, dtype=torch.float32, device=self.device)
+                for k, p in params.items():
+                    o, n = self.layout[k]
+                    self._flat_scratch[o:o + n].copy_(p.detach().reshape(-1))
+                ptr = self._flat_scratch.data_ptr()
+            _lib.check(self.lib.c2w_refresh_weights(self.handle, ptr, self.stream), "c2w_refresh_weights")
+
+    def train_forward(self, x: Tensor, t: Tensor) -> Tensor:
+        """net(x, t) with one diffusion time per sample, stashing for train_backward.  x: fp32 NCHW [n <= max_windows]."""
+        assert self.train, "engine was built without the training workspace"
+        out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.c2w_train_forward(self.handle, x.data_ptr(), x.shape[0], t.data_ptr(), out.data_ptr(),
+                                                  self.stream), "c2w_train_forward")
+        self._t_keepalive = t  # the backward re-reads the diffusion times
+        return out
+
+    def train_backward(self, gout: Tensor, grad_flat: Tensor, want_gin: bool = False, accumulate: bool = False):
+        """All parameter gradients of the last train_forward into grad_flat (fp32, library layout); returns the input
+        gradient if asked."""
+        gin = torch.empty_like(gout) if want_gin else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.c2w_train_backward(self.handle, gout.data_ptr(), gout.shape[0],
+                                                   gin.data_ptr() if gin is not None else None, grad_flat.data_ptr(),
+                                                   int(accumulate), self.stream), "c2w_train_backward")
+        return gin
 
     def unet_vjp(self, x: Tensor, t: float, gout: Tensor):
         """(out, gin): forward and (d out / d x)^T gout for x, gout: fp32 NCHW [n, C*window, H, W], chunked."""
@@ -275,23 +329,32 @@ class ScoreUNet(nn.Module):
         return (getattr(self, "_weights_epoch", 0),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def engine(self, frame_channels: int, window: int, height: int, width: int, device, max_windows: Optional[int] = None,
-               vjp: bool = False, per_sample_t: bool = False) -> Engine:
-        """Packed-weight engine for this geometry; rebuilt if the parameters changed since it was packed."""
+               vjp: bool = False, per_sample_t: bool = False, train: bool = False) -> Engine:
+        """Packed-weight engine for this geometry; if the parameters changed since it was packed (and still live on its
+        device) the weights are re-packed in place on the device, otherwise the engine is rebuilt."""
         device = torch.device(device)
         if device.type == "cuda" and device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
         if frame_channels * window != self.channels:
             raise ValueError(f"frame_channels*window = {frame_channels * window} != channels = {self.channels}")
-        key = (frame_channels, window, height, width, str(device), bool(vjp), bool(per_sample_t))
+        key = (frame_channels, window, height, width, str(device), bool(vjp), bool(per_sample_t), bool(train))
         fp = self._fingerprint()
         hit = self._engines.get(key)
         want = max_windows or self.DEFAULT_MAX_WINDOWS
-        if hit is not None and hit[1] == fp:
+        if hit is not None:
             eng = hit[0]
-            if max_windows is not None and eng.max_windows != max_windows:
-                eng.bind(max_windows)
-            return eng
-        eng = Engine(self, frame_channels, window, height, width, device, want, vjp=vjp, per_sample_t=per_sample_t)
+            if hit[1] != fp:
+                if not all(p.is_cuda and p.device == eng.device for p in self.parameters()):
+                    hit = None  # the module moved: rebuild below
+                else:
+                    eng.refresh_weights(self)
+                    self._engines[key] = (eng, fp)
+            if hit is not None:
+                if max_windows is not None and eng.max_windows != max_windows:
+                    eng.bind(max_windows)
+                return eng
+        eng = Engine(self, frame_channels, window, height, width, device, want, vjp=vjp, per_sample_t=per_sample_t,
+                     train=train)
         self._engines[key] = (eng, fp)
         return eng
 
@@ -310,27 +373,66 @@ class ScoreUNet(nn.Module):
                                 "BatchedScoreFunction moves window batches for you")
         tt = torch.as_tensor(t).reshape(-1).float()
         B, Cc, H, W = x.shape
-        if tt.numel() != 1 and not bool((tt == tt[0]).all()):
+        training = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if tt.numel() not in (1, B):
+            raise ValueError(f"t has {tt.numel()} entries for a batch of {B}")
+        if not training and tt.numel() != 1 and not bool((tt == tt[0]).all()):
             # one diffusion time per sample (model/score.py:61; the DSM objective, src/thor/pipelines.py:27-35)
-            if tt.numel() != B:
-                raise ValueError(f"t has {tt.numel()} entries for a batch of {B}")
             if torch.is_grad_enabled() and x.requires_grad:
-                raise NotImplementedError("input gradients with per-sample diffusion times are not built")
+                raise NotImplementedError("input gradients with per-sample diffusion times need trainable parameters "
+                                          "(the training workspace); freeze nothing or use one diffusion time")
             eng = self.engine(Cc, 1, H, W, x.device, per_sample_t=True)
             out = eng.unet_forward_t(x.detach().float().contiguous(), tt.to(x.device).contiguous())
             return out.to(x.dtype).reshape(x.shape)
         B, Cc, H, W = x.shape
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "ScoreUNet.forward under autograd with trainable parameters: parameter gradients come from "
-                "climate2weather_b200.training.TrainStep (fused forward + backward), not from torch autograd; "
-                "freeze the parameters (requires_grad_(False), as snapshots are: training_loop.py:257) for sampling")
+            # training (training_loop.py:372-378): forward with stashing now, all parameter gradients in backward
+            t_dev = (tt if tt.numel() == B else tt.expand(B)).to(device=x.device, dtype=torch.float32).contiguous()
+            params = [p for p in self.parameters()]
+            return _UNetTrainFn.apply(x, t_dev, self, *params)
         if torch.is_grad_enabled() and x.requires_grad:
             # input gradients only (the weights are frozen in sampling, training_loop.py:257)
             return _UNetInputVJP.apply(x, self, float(tt[0]))
         eng = self.engine(Cc, 1, H, W, x.device)
         out = eng.unet_forward(x.detach().float().contiguous(), float(tt[0]))
         return out.to(x.dtype).reshape(x.shape)
+
+
+class _UNetTrainFn(torch.autograd.Function):
+    """ScoreUNet.forward with trainable parameters under autograd (the reference's training step,
+    training_loop.py:372-378: `loss = pipeline.loss(net, x).mean(); fabric.backward(loss)`): the forward stashes on a
+    training workspace, the backward is c2w_train_backward — input-gradient convs, weight-gradient GEMMs, bias /
+    modulation / time-MLP sums — and hands autograd one gradient per parameter (views of one flat buffer), so gradient
+    accumulation, DDP hooks and any torch optimiser work unchanged."""
+
+    @staticmethod
+    def forward(ctx, x, t_dev, net, *params):
+        B, Cc, H, W = x.shape
+        eng = net.engine(Cc, 1, H, W, x.device, train=True)
+        if eng.max_windows < B:
+            eng.bind(B)
+        out = eng.train_forward(x.detach().float().contiguous(), t_dev)
+        token = object()
+        eng._train_token = token
+        ctx.eng, ctx.net, ctx.token, ctx.want_gin, ctx.dtype = eng, net, token, x.requires_grad, x.dtype
+        ctx.n_params = len(params)
+        ctx.needs = [p.requires_grad for p in params]
+        return out.to(x.dtype).reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, gout):
+        eng = ctx.eng
+        if eng._train_token is not ctx.token:
+            raise RuntimeError("another forward ran on this network's training workspace before this backward(): the "
+                               "stashed activations are gone (one forward -> one backward per accumulation round)")
+        flat = torch.empty(eng.param_total, dtype=torch.float32, device=gout.device)
+        gin = eng.train_backward(gout.detach().float().contiguous(), flat, want_gin=ctx.want_gin)
+        grads = []
+        for (name, p), need in zip(ctx.net.state_dict(keep_vars=True).items(), ctx.needs):
+            o, n = eng.layout[name]
+            grads.append(flat[o:o + n].view_as(p) if need else None)
+        eng._train_token = None
+        return (gin.to(ctx.dtype) if gin is not None else None, None, None, *grads)
 
 
 class _UNetInputVJP(torch.autograd.Function):

@@ -83,6 +83,7 @@ int c2w_bind_workspace(c2w_handle* h, int32_t max_windows, void* dev_ptr, int64_
 /* Workspace variants (flags of the _ex calls; the plain calls use 0, the _vjp calls C2W_WS_VJP). */
 #define C2W_WS_VJP 1          /* forward calls stash what the input-gradient pass needs                          */
 #define C2W_WS_PER_SAMPLE_T 2 /* one diffusion time per sample (c2w_unet_forward_t): per-sample modulation       */
+#define C2W_WS_TRAIN 4        /* training step: both of the above plus the parameter-gradient scratch             */
 int64_t c2w_workspace_bytes_ex(c2w_handle* h, int32_t max_windows, int32_t flags);
 int c2w_bind_workspace_ex(c2w_handle* h, int32_t max_windows, void* dev_ptr, int64_t bytes, int32_t flags);
 
@@ -218,6 +219,32 @@ int c2w_op_wgrad(const void* x, const void* dy, int32_t n_img, int32_t H, int32_
                  int32_t cout, int32_t accumulate, void* stream);
 int c2w_op_colsum(const void* x_bf16, float* out, int64_t rows, int32_t C, int64_t rows_per_group, int32_t out_stride,
                   float scale, void* stream);
+
+/* ---- training step (training_loop.py:372-391, src/thor/pipelines.py:27-35) ----------------------
+ * Parameter gradients of the ScoreUNet for the denoising-score-matching objective, on a C2W_WS_TRAIN workspace of
+ * max_windows >= batch samples.  The flat fp32 gradient buffer holds every parameter in the order the weights were
+ * loaded (the reference state_dict order), each start aligned to 4 floats: c2w_param_total floats in all,
+ * c2w_param_layout(name) -> offset / numel, tensors in torch's own layouts (conv weights OIHW) — the buffer
+ * climate2weather_b200.optim.AdamW steps on (c2w_adamw_ema_step) without a copy.
+ *   c2w_train_forward : net(xt, t) with one diffusion time per sample (device array), stashing for the backward
+ *   c2w_train_backward: gout = d loss / d prediction (fp32 NCHW) -> all parameter gradients (input-gradient convs K1,
+ *                       weight-gradient GEMMs K10, bias / modulation / time-MLP sums); gin_nchw (may be NULL) receives
+ *                       the gradient w.r.t. xt
+ *   c2w_dsm_loss_grad : sum((out - eps)^2) and gout = 2 loss_scale (out - eps) / numel in one pass
+ *   c2w_train_step    : the three calls above for one batch (loss value: *loss_sum_dev / numel * loss_scale)        */
+int64_t c2w_param_total(c2w_handle* h);
+/* After an optimiser step: re-pack every weight from a DEVICE copy of the parameters in the flat layout (no host round
+ * trip, no re-allocation; `optimizer.step()` -> next forward, training_loop.py:384 -> :377). */
+int c2w_refresh_weights(c2w_handle* h, const float* flat_params_dev, void* stream);
+int c2w_param_layout(c2w_handle* h, const char* name, int64_t* offset, int64_t* numel);
+int c2w_train_forward(c2w_handle* h, const float* x_nchw, int32_t n, const float* t_dev, float* out_nchw, void* stream);
+int c2w_train_backward(c2w_handle* h, const float* gout_nchw, int32_t n, float* gin_nchw, float* grad_flat,
+                       int32_t accumulate, void* stream);
+int c2w_dsm_loss_grad(const float* out, const float* eps, float* gout, int64_t numel, float loss_scale, float* partials4096,
+                      double* loss_sum_dev, void* stream);
+int c2w_train_step(c2w_handle* h, const float* xt_nchw, int32_t n, const float* t_dev, const float* eps_nchw,
+                   float* out_nchw, float* gout_nchw, float loss_scale, float* grad_flat, int32_t accumulate,
+                   double* loss_sum_dev, void* stream);
 
 /* ---- measurement hooks (bench.py): kernel launches issued by this library so far; optional CUDA-event timing of
  * every forward-pass launch on its own stream, summed per class: [0] K1 conv/GEMM (tensor cores), [1] the rest --- */

@@ -72,7 +72,7 @@ def test_wgrad_gemm_vs_torch(rows, cin, cout):
     assert ((got - want).norm() / want.norm()).item() < 5e-3
 
 
-@pytest.mark.parametrize("rows,C,rpg", [(1000, 128, 1000), (4096, 512, 1024), (777, 64, 100), (2 * 16384, 128, 16384)])
+@pytest.mark.parametrize("rows,C,rpg", [(1000, 128, 1000), (4096, 512, 1024), (777, 64, 100), (2 * 16384, 128, 16384), (640, 1536, 640), (300, 1000, 64)])
 def test_colsum_vs_torch(rows, C, rpg):
     """Bias gradients (one group) and per-sample modulation gradients (one group per image)."""
     from climate2weather_b200 import _lib
