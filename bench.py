@@ -682,7 +682,8 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     elif args.mode == "train":
-        args.warmup = max(args.warmup, 3)
+        if not args.profile:
+            args.warmup = max(args.warmup, 3)
         run_train(args)
     else:
         if args.profile:

@@ -121,7 +121,7 @@ SIGNATURES = {
     "c2w_op_conv_ex": (_i, [C.POINTER(ConvDesc), _vp]),
     "c2w_conv_tile_width": (_i, [_i, _i, _i, _i, _i, _i, _i]),
     "c2w_op_wgrad": (_i, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _i64,
-                          _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
+                          _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "c2w_op_colsum": (_i, [_vp, _vp, _i64, C.c_int32, _i64, C.c_int32, _f, _vp]),
     "c2w_op_conv": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "c2w_op_layernorm": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),

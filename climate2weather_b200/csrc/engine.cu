@@ -81,6 +81,7 @@ struct Op {
   // training: OP_COPY (in -> out, C*H*W elements per image); OP_WGRAD (dW of one conv: x = spec.in, dy = in; spec.H/W/cin/
   // cout_pad/stride/c3 as in the forward conv) and OP_COLSUM (bias gradient: column sums of `in`, C padded channels)
   long long dst = -1;        // offset in the flat gradient buffer
+  long long dst_bias = -1;   // OP_WGRAD: offset of the conv's bias gradient
   int cin_real = 0, cout_real = 0;
   WgradLaunch wg;            // built for `wg_n` images
   int wg_n = -1;
@@ -595,20 +596,10 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
       op.spec.cout_pad = w.cout_pad;
       op.spec.stride = stride;
       op.dst = w.gw;
+      op.dst_bias = w.gb;  // the bias gradient (column sums of dy) is collected by the same GEMM
       op.cin_real = w.cin;
       op.cout_real = w.cout;
       unit.push_back(op);
-    }
-    if (w.gb >= 0) {
-      Op b;
-      b.kind = OP_COLSUM;
-      b.in = dy;
-      b.C = w.cout_pad;
-      b.H = H / stride;
-      b.W = W / stride;
-      b.dst = w.gb;
-      b.cout_real = w.cout;
-      unit.push_back(b);
     }
   };
   auto add_ln_bwd = [&](std::vector<Op>& unit, const bf16* gy, const bf16* y, const float* inv, const bf16* gres,
@@ -937,7 +928,8 @@ int run_ops(c2w_handle* h, std::vector<Op>& ops, int nn, const FinalSpec& fs, cu
         }
         SpanGuard sg(h, 0, st);
         ++g_launches;  // GEMM + slab reduction
-        C2W_CUDA(wgrad_run(op.wg, P.grad + op.dst, op.cout_real, op.cin_real, 1, 1.0f, st));
+        C2W_CUDA(wgrad_run(op.wg, P.grad + op.dst, op.cout_real, op.cin_real, 1, 1.0f, st,
+                           op.dst_bias >= 0 ? P.grad + op.dst_bias : nullptr));
         break;
       }
       case OP_COLSUM: {
@@ -1680,8 +1672,8 @@ int c2w_op_gather_windows(const float* traj, void* out, int n, int hw, int C, in
 
 // ---- weight-gradient kernels, op level (parity tests of single kernels; the training step launches the same kernels)
 int c2w_op_wgrad(const void* x, const void* dy, int32_t n_img, int32_t H, int32_t W, int32_t cin_pad, int32_t cout_pad,
-                 int32_t stride, int32_t conv3x3, float* scratch, int64_t scratch_floats, float* dw, int32_t cin,
-                 int32_t cout, int32_t accumulate, void* stream) {
+                 int32_t stride, int32_t conv3x3, float* scratch, int64_t scratch_floats, float* dw, float* db,
+                 int32_t cin, int32_t cout, int32_t accumulate, void* stream) {
   C2W_REQUIRE(x && dy && dw && scratch && n_img >= 1 && cin >= 1 && cout >= 1 && cin <= cin_pad && cout <= cout_pad,
               "c2w_op_wgrad: bad argument");
   const int sms = c2w_num_sms();
@@ -1692,7 +1684,7 @@ int c2w_op_wgrad(const void* x, const void* dy, int32_t n_img, int32_t H, int32_
     return fail(C2W_ERR_INVALID, "c2w_op_wgrad: cannot build launch (n=%d H=%d W=%d cin=%d cout=%d stride=%d; channel "
                 "counts must be multiples of 64, output images multiples of 8 x 8, GEMM rows a multiple of 64; scratch "
                 "%lld floats) %s", n_img, H, W, cin_pad, cout_pad, stride, (long long)scratch_floats, tmap_error_slot());
-  C2W_CUDA(wgrad_run(L, dw, cout, cin, accumulate, 1.0f, static_cast<cudaStream_t>(stream)));
+  C2W_CUDA(wgrad_run(L, dw, cout, cin, accumulate, 1.0f, static_cast<cudaStream_t>(stream), db));
   return C2W_OK;
 }
 

@@ -18,7 +18,12 @@
 // (split-K) and every CTA writes its three fp32 accumulators to a scratch slab; wgrad_reduce_kernel sums the slabs in
 // a fixed order (deterministic) into the fp32 OIHW gradient tensor.
 //
-// Roles: warp 0 TMA producer, warp 1 tcgen05.mma issuer (one elected lane), warp 2 TMEM allocator, warps 4-7 epilogue.
+// The conv's BIAS gradient, sum over pixels of dY[p, co], rides along: the dY tiles already pass through shared memory,
+// so in the CTAs of group 0 / N tile 0 the (otherwise idle) epilogue warps add up their channel's 64 pixels of every
+// stage before it is released — no second pass over dY.
+//
+// Roles: warp 0 TMA producer, warp 1 tcgen05.mma issuer (one elected lane), warp 2 TMEM allocator, warps 4-7 epilogue
+// (+ bias column sums during the main loop).
 #pragma once
 #include "conv_tcgen05.cuh"
 
@@ -36,6 +41,7 @@ struct WgradParams {
   int groups;          // work items per (m, n, split): 3 (filter columns, or filter rows when !share) or 1 (GEMM)
   int cout_slab, cin_slab;  // slab dims: m_tiles * 128, n_tiles * BN
   float* partial;      // [splits][taps][cout_slab][cin_slab]
+  float* bias_partial; // [splits][cout_slab]: per-split column sums of dY (the bias gradient), or null
   int num_stages;
 };
 
@@ -103,6 +109,7 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   const int ntap = p.taps == 1 ? 1 : 3;  // accumulators of this CTA
   const int kb0 = static_cast<int>(static_cast<long long>(p.k_blocks) * split / p.splits);
   const int kb1 = static_cast<int>(static_cast<long long>(p.k_blocks) * (split + 1) / p.splits);
+  const bool do_bias = p.bias_partial != nullptr && g == 0 && nt == 0;
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmDY);
@@ -111,7 +118,7 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   if (warp_idx == 1 && lane == 0) {
     for (int i = 0; i < num_stages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], do_bias ? 5 : 1);  // the MMA commit (+ the four column-sum warps)
     }
     mbar_init(acc_full, 1);
     fence_mbar_init();
@@ -190,6 +197,30 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
     const int q = warp_idx & 3;  // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;
     const bool any = kb1 > kb0;
+    if (do_bias) {
+      // column sums of dY for output channel `row`: element (pixel k, channel row) of the swizzled MN-major tile
+      float bsum = 0.f;
+      const uint32_t grp = static_cast<uint32_t>(row >> 6) * (kWgPix * 128), chunk = static_cast<uint32_t>((row & 63) >> 3),
+                     within = static_cast<uint32_t>(row & 7) * 2;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full[stage], phase);
+        const uint8_t* sA = smem + stage * stage_bytes + grp + within;
+#pragma unroll 8
+        for (int k = 0; k < kWgPix; ++k) {
+          const __nv_bfloat16 v = *reinterpret_cast<const __nv_bfloat16*>(sA + k * 128 + ((chunk ^ (k & 7)) << 4));
+          bsum += __bfloat162float(v);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == num_stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      p.bias_partial[static_cast<size_t>(split) * p.cout_slab + mt * 128 + row] = bsum;
+    }
     if (any) {
       mbar_wait(acc_full, 0);
       tc_fence_after();
@@ -226,8 +257,14 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
 
 // dw[co][ci][tap] (fp32 OIHW / OI1, real Cout x Cin) (+)= sum over splits of partial[split][tap][co][ci]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int taps,
-                                    int cout, int cin, int cout_slab, int cin_slab, int accumulate, float scale) {
+                                    int cout, int cin, int cout_slab, int cin_slab, int accumulate, float scale,
+                                    const float* __restrict__ bias_partial, float* __restrict__ db) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (db != nullptr && i < cout) {  // bias gradient: sum of the per-split column sums, fixed order
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += bias_partial[static_cast<size_t>(s) * cout_slab + i];
+    db[i] = accumulate ? db[i] + acc * scale : acc * scale;
+  }
   if (i >= static_cast<long long>(cout) * cin) return;
   const int co = static_cast<int>(i / cin), ci = static_cast<int>(i - static_cast<long long>(co) * cin);
   const size_t slab = static_cast<size_t>(cout_slab) * cin_slab;
@@ -338,11 +375,13 @@ inline bool wgrad_launch_init(WgradLaunch* L, bool conv3x3, const __nv_bfloat16*
   if (splits < 1) splits = 1;
   if (splits > k_blocks) splits = k_blocks;
   const size_t per_split = static_cast<size_t>(p.taps) * p.cout_slab * p.cin_slab;
-  while (splits > 1 && per_split * splits > scratch_floats) --splits;
-  if (per_split * splits > scratch_floats) return false;
+  const size_t bias_floats = static_cast<size_t>(p.cout_slab);
+  while (splits > 1 && (per_split + bias_floats) * splits > scratch_floats) --splits;
+  if ((per_split + bias_floats) * splits > scratch_floats) return false;
   p.splits = static_cast<int>(splits);
   p.partial = scratch;
-  L->scratch_floats = per_split * splits;
+  p.bias_partial = nullptr;  // wgrad_run binds it behind the slabs when a bias gradient is asked for
+  L->scratch_floats = per_split * splits + static_cast<size_t>(splits) * p.cout_slab;
   L->grid = tiles * p.splits;
   p.num_stages = bn == 128 ? WgradCfg<128>::stages(p.share != 0) : WgradCfg<64>::stages(p.share != 0);
   return true;
@@ -375,14 +414,18 @@ inline cudaError_t wgrad_launch_bn(const WgradLaunch& L, cudaStream_t stream) {
   return cudaLaunchKernelEx(&cfg, wgrad_tcgen05_kernel<BN>, L.tmDY, L.tmX, L.p);
 }
 
-// GEMM + slab reduction into dw (fp32 [cout][cin][taps], real channel counts)
-inline cudaError_t wgrad_run(const WgradLaunch& L, float* dw, int cout, int cin, int accumulate, float scale,
-                             cudaStream_t stream) {
+// GEMM + slab reduction into dw (fp32 [cout][cin][taps], real channel counts) and, if db != null, the bias gradient
+// db fp32 [cout] from the column sums the GEMM collected on the way.
+inline cudaError_t wgrad_run(const WgradLaunch& L0, float* dw, int cout, int cin, int accumulate, float scale,
+                             cudaStream_t stream, float* db = nullptr) {
+  WgradLaunch L = L0;
+  const size_t slab_floats = static_cast<size_t>(L.p.splits) * L.p.taps * L.p.cout_slab * L.p.cin_slab;
+  L.p.bias_partial = db ? L.p.partial + slab_floats : nullptr;
   cudaError_t e = L.bn == 128 ? wgrad_launch_bn<128>(L, stream) : wgrad_launch_bn<64>(L, stream);
   if (e != cudaSuccess) return e;
   const long long items = static_cast<long long>(cout) * cin;
   wgrad_reduce_kernel<<<static_cast<int>((items + 255) / 256), 256, 0, stream>>>(
-      L.p.partial, dw, L.p.splits, L.p.taps, cout, cin, L.p.cout_slab, L.p.cin_slab, accumulate, scale);
+      L.p.partial, dw, L.p.splits, L.p.taps, cout, cin, L.p.cout_slab, L.p.cin_slab, accumulate, scale, L.p.bias_partial, db);
   return cudaGetLastError();
 }
 

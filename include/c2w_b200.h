@@ -212,11 +212,13 @@ int c2w_total_mod_channels(c2w_handle* h);
  *   dw fp32 [cout][cin][taps] (= torch's OIHW / OI1 layout, REAL channel counts), overwritten or accumulated.
  *   x  bf16 NHWC [n_img, H, W, cin_pad]  (GEMM: H = 1, W = rows per image; rows in total a multiple of 64)
  *   dy bf16 NHWC [n_img, H/stride, W/stride, cout_pad]
+ *   db (may be NULL) fp32 [cout]: the conv's bias gradient, the column sums of dy, collected by the same GEMM from the
+ *      dy tiles in shared memory (no second pass over dy)
  * c2w_op_colsum: out[group][c] += scale * sum over the group's rows of x[row][c] (bias gradients: one group; the
  * per-sample modulation gradients: one group per image), atomically accumulated — zero `out` first. */
 int c2w_op_wgrad(const void* x, const void* dy, int32_t n_img, int32_t H, int32_t W, int32_t cin_pad, int32_t cout_pad,
-                 int32_t stride, int32_t conv3x3, float* scratch, int64_t scratch_floats, float* dw, int32_t cin,
-                 int32_t cout, int32_t accumulate, void* stream);
+                 int32_t stride, int32_t conv3x3, float* scratch, int64_t scratch_floats, float* dw, float* db,
+                 int32_t cin, int32_t cout, int32_t accumulate, void* stream);
 int c2w_op_colsum(const void* x_bf16, float* out, int64_t rows, int32_t C, int64_t rows_per_group, int32_t out_stride,
                   float scale, void* stream);
 

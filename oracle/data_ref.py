@@ -2,9 +2,10 @@
 quantiles) of the reference's normalisation and layout helpers, data/pipeline.py:183-272, on plain dicts of arrays
 instead of xarray Datasets.  Only tests/ may import this module; the product path is the CUDA library.
 
-PARITY UNPINNED: data/pipeline.py imports xarray at module level and xarray is not installed in this image, so the
-reference functions cannot be executed here to generate fixtures.  The arithmetic restated below is two lines per
-mode; tests pin it with hand-computed known answers instead.
+Pinned: tests/golden/data_norm.npz holds outputs of the REFERENCE's own four functions (tests/golden/make_golden_data.py
+runs data/pipeline.py unmodified on a minimal xarray stand-in — xarray itself is not installed in this image) for all
+five modes, scalar and per-grid-point quantiles and both orderings; tests/test_data_norm.py checks this restatement
+against them to 1e-12, next to hand-computed known answers.
 
   normalize_ds    data/pipeline.py:183-215     unnormalize_ds   data/pipeline.py:218-247
   ds_to_sorted_np data/pipeline.py:250-261     np_to_ds         data/pipeline.py:264-272

@@ -1,8 +1,9 @@
 """N4: normalisation fused with the layout change (data/pipeline.py:183-272).
 
-CPU: the oracle restatement against hand-computed known answers (the reference functions need xarray, which is not in
-this image — parity of this row is pinned by these known answers, see oracle/data_ref.py) and the host-side coefficient
-logic.  GPU (`-m gpu`): `c2w_normalize_pack` / `c2w_unpack_unnormalize` through the package's `data` module against the
+CPU: the oracle restatement against outputs of the REFERENCE's own functions (tests/golden/data_norm.npz, written by
+tests/golden/make_golden_data.py running data/pipeline.py on an xarray stand-in: all five modes, scalar and per-grid-
+point quantiles, both orderings, the unnormalise round trip), against hand-computed known answers, and the host-side
+coefficient logic.  GPU (`-m gpu`): `c2w_normalize_pack` / `c2w_unpack_unnormalize` through the package's `data` module against the
 oracle for all five modes, scalar and per-grid-point quantiles, plus the round trip and the kernel's HBM rate.
 """
 import numpy as np
@@ -30,6 +31,28 @@ def _problem(L=5, H=16, W=24, field=False, seed=0):
 
 
 # ---------------------------------------------------------------------------------------------------- CPU
+@pytest.mark.parametrize("tag", ["scalar", "field"])
+def test_oracle_matches_reference_functions(golden_dir, tag):
+    """oracle/data_ref.py against normalize_ds / ds_to_sorted_np / np_to_ds / unnormalize_ds of the reference itself
+    (data/pipeline.py:183-272): float64 results equal to 1e-12 (same two numpy operations per mode)."""
+    g = np.load(golden_dir / "data_norm.npz")
+    qs = [float(q) for q in g["qs"]]
+    names = [str(v) for v in g["vars"]]
+    ds = {v: g[f"{tag}::data::{v}"] for v in names}
+    quantiles = {q: {v: g[f"{tag}::quant::{v}"][i] for v in names} for i, q in enumerate(qs)}
+    for mode in (str(m) for m in g["modes"]):
+        n = data_ref.normalize_ds(ds, quantiles, mode)
+        lchw = data_ref.ds_to_sorted_np(n, names)
+        assert lchw.dtype == np.float64 and lchw.shape == g[f"{tag}::{mode}::normalized_lchw"].shape
+        assert np.allclose(lchw, g[f"{tag}::{mode}::normalized_lchw"], rtol=1e-12, atol=0)
+        assert np.allclose(data_ref.ds_to_sorted_np(n, names, ordering="CLHW"), g[f"{tag}::{mode}::normalized_clhw"],
+                           rtol=1e-12, atol=0)
+        back = data_ref.unnormalize_ds(data_ref.np_to_ds(lchw, names), quantiles, mode)
+        assert np.allclose(data_ref.ds_to_sorted_np(back, names), g[f"{tag}::{mode}::roundtrip_lchw"], rtol=1e-12, atol=0)
+    # variables come out sorted (data/pipeline.py:255): psl, tas, uas, vas
+    assert np.array_equal(data_ref.ds_to_sorted_np(ds, names)[:, 0], ds["psl"])
+
+
 def test_oracle_known_answers():
     ds = {"a": np.array([[[2.0, 4.0]]]), "b": np.array([[[10.0, 30.0]]])}
     quantiles = {q: {"a": 0.0, "b": 0.0} for q in QS}

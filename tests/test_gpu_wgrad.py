@@ -12,7 +12,7 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def _wgrad(lib, x_nhwc, dy_nhwc, stride, conv3x3, cin, cout, accumulate=False, into=None):
+def _wgrad(lib, x_nhwc, dy_nhwc, stride, conv3x3, cin, cout, accumulate=False, into=None, db=None):
     from climate2weather_b200 import _lib
     dev = x_nhwc.device
     n, H, W, cin_pad = x_nhwc.shape
@@ -21,7 +21,8 @@ def _wgrad(lib, x_nhwc, dy_nhwc, stride, conv3x3, cin, cout, accumulate=False, i
     scratch = torch.empty(48 * 1024 * 1024, device=dev)  # 192 MB of fp32 partial sums
     dw = into if into is not None else torch.full((cout, cin, taps), 7.0, device=dev)
     _lib.check(lib.c2w_op_wgrad(x_nhwc.data_ptr(), dy_nhwc.data_ptr(), n, H, W, cin_pad, cout_pad, stride, int(conv3x3),
-                                scratch.data_ptr(), scratch.numel(), dw.data_ptr(), cin, cout, int(accumulate), _stream()),
+                                scratch.data_ptr(), scratch.numel(), dw.data_ptr(), db.data_ptr() if db is not None else None,
+                                cin, cout, int(accumulate), _stream()),
                "c2w_op_wgrad")
     torch.cuda.synchronize()
     return dw
@@ -42,7 +43,10 @@ def test_wgrad_conv3x3_vs_autograd(n, H, W, cin, cout, stride):
     x[..., :cin] = torch.randn(n, H, W, cin, generator=g).to(dev).to(torch.bfloat16)
     dy = torch.zeros(n, Ho, Wo, cout_pad, dtype=torch.bfloat16, device=dev)
     dy[..., :cout] = torch.randn(n, Ho, Wo, cout, generator=g).to(dev).to(torch.bfloat16)
-    got = _wgrad(lib, x, dy, stride, True, cin, cout).reshape(cout, cin, 3, 3)
+    db = torch.full((cout,), 7.0, device=dev)
+    got = _wgrad(lib, x, dy, stride, True, cin, cout, db=db).reshape(cout, cin, 3, 3)
+    want_db = dy[..., :cout].float().sum(dim=(0, 1, 2))  # the bias gradient rides along with the GEMM
+    assert ((db - want_db).abs().max() / want_db.abs().max()).item() < 1e-5
     w = torch.zeros(cout, cin, 3, 3, device=dev, requires_grad=True)
     y = F.conv2d(x[..., :cin].float().permute(0, 3, 1, 2), w, None, stride=stride, padding=1)
     (want,) = torch.autograd.grad(y, w, dy[..., :cout].float().permute(0, 3, 1, 2))
@@ -66,7 +70,9 @@ def test_wgrad_gemm_vs_torch(rows, cin, cout):
     g = torch.Generator().manual_seed(rows + cin)
     x = torch.randn(rows, cin, generator=g).to(dev).to(torch.bfloat16)
     dy = torch.randn(rows, cout, generator=g).to(dev).to(torch.bfloat16)
-    got = _wgrad(lib, x.reshape(1, 1, rows, cin), dy.reshape(1, 1, rows, cout), 1, False, cin, cout).reshape(cout, cin)
+    db = torch.zeros(cout, device=dev)
+    got = _wgrad(lib, x.reshape(1, 1, rows, cin), dy.reshape(1, 1, rows, cout), 1, False, cin, cout, db=db).reshape(cout, cin)
+    assert torch.allclose(db, dy.float().sum(0), rtol=1e-5, atol=1e-4)
     want = dy.float().t() @ x.float()
     assert ((got - want).abs().max() / want.abs().max()).item() < 2 ** -8
     assert ((got - want).norm() / want.norm()).item() < 5e-3
