@@ -370,6 +370,9 @@ def run_ours(args):
         pipe2.nan_check_every = 1
         noise_pinned = noise.pin_memory()
         ke = max(1, args.e2e_steps)  # one full sample() call of this many denoising steps (independent of --steps)
+        # untimed warm-up of the API path itself (3 steps): pinned-buffer allocation and, time-sharded, the first-use
+        # NCCL connections of the final gather to rank 0
+        pipe2.sample(st.sf, noise_pinned, steps=3, corrections=0, tau=0.5, show_progressbar=False)
         barrier()
         t0 = time.perf_counter()
         out = pipe2.sample(st.sf, noise_pinned, steps=ke, corrections=0, tau=0.5, show_progressbar=False)

@@ -139,6 +139,11 @@ SIGNATURES = {
     "c2w_train_backward": (_i, [_vp, _vp, C.c_int32, _vp, _vp, C.c_int32, _vp]),
     "c2w_dsm_loss_grad": (_i, [_vp, _vp, _vp, _i64, _f, _vp, _vp, _vp]),
     "c2w_train_step": (_i, [_vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _f, _vp, C.c_int32, _vp, _vp]),
+    "c2w_halo_create": (_i, [_i64, C.POINTER(_vp)]),
+    "c2w_halo_destroy": (None, [_vp]),
+    "c2w_halo_handle": (_i, [_vp, _vp]),
+    "c2w_halo_connect": (_i, [_vp, _vp, _vp]),
+    "c2w_halo_exchange": (_i, [_vp, _vp, _i64, _i64, C.c_int32, _vp]),
     "c2w_launch_count": (_i64, []),
     "c2w_set_timing": (_i, [_vp, _i]),
     "c2w_timing_read": (_i, [_vp, _vp, _vp]),

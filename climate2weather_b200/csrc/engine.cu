@@ -374,6 +374,27 @@ int launch_attention(const bf16* qkv, bf16* out, int n, int T, int C, cudaStream
   }
 }
 
+int grid_for(long long items, int threads, int sms);
+
+// K0: window batch [n, hw, cin_pad] bf16 from the resident trajectory (tiled form for 4-variable frames)
+int launch_gather(const float* traj, bf16* out, int n, int hw, int C, int w, int cin_pad, int f0, int sms, cudaStream_t st) {
+  static int tiled = -1;
+  if (tiled < 0) {
+    const char* e = getenv("C2W_GATHER_TILED");
+    tiled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (tiled && C == 4 && hw % kGatherPix == 0 && w <= 64) {
+    const size_t smem = static_cast<size_t>(kGatherWin + w - 1) * kGatherPix * sizeof(uint2);
+    gather_windows_tiled_kernel<<<dim3(hw / kGatherPix, (n + kGatherWin - 1) / kGatherWin), 256, smem, st>>>(traj, out, n, hw, w,
+                                                                                                       cin_pad, f0);
+  } else {
+    const long long items = static_cast<long long>(n) * hw * (cin_pad / 8);
+    gather_windows_kernel<<<grid_for(items, 256, sms), 256, 0, st>>>(traj, out, n, hw, C, w * C, cin_pad, f0);
+  }
+  C2W_CUDA(cudaGetLastError());
+  return C2W_OK;
+}
+
 int grid_for(long long items, int threads, int sms) {
   long long b = (items + threads - 1) / threads;
   const long long cap = static_cast<long long>(sms) * 16;
@@ -1247,11 +1268,8 @@ int c2w_window_score(c2w_handle* h, const float* traj, int32_t n_frames_local, i
   for (int c0 = 0; c0 < n_win; c0 += P.n_max) {
     const int nn = std::min(P.n_max, n_win - c0);
     const int j0 = win_first + c0;
-    const long long items = static_cast<long long>(nn) * hw * (h->cin_pad / 8);
-    gather_windows_kernel<<<grid_for(items, 256, h->sms), 256, 0, st>>>(traj, P.xin, nn, hw, C, w * C, h->cin_pad,
-                                                                        j0 - frame_global0);
+    if ((rc = launch_gather(traj, P.xin, nn, hw, C, w, h->cin_pad, j0 - frame_global0, h->sms, st))) return rc;
     ++g_launches;
-    C2W_CUDA(cudaGetLastError());
     FinalSpec fs;
     fs.mode = EPI_COMPOSE;
     fs.eps = eps;
@@ -1663,11 +1681,8 @@ int c2w_op_attention(const void* qkv, void* out, int n, int T, int C, void* stre
 int c2w_op_gather_windows(const float* traj, void* out, int n, int hw, int C, int window, int cin_pad, int frame0,
                           void* stream) {
   C2W_REQUIRE(traj && out && n >= 1 && cin_pad % 8 == 0 && cin_pad >= C * window, "c2w_op_gather_windows: bad argument");
-  const long long items = static_cast<long long>(n) * hw * (cin_pad / 8);
-  gather_windows_kernel<<<grid_for(items, 256, c2w_num_sms()), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      traj, static_cast<bf16*>(out), n, hw, C, window * C, cin_pad, frame0);
-  C2W_CUDA(cudaGetLastError());
-  return C2W_OK;
+  return launch_gather(traj, static_cast<bf16*>(out), n, hw, C, window, cin_pad, frame0, c2w_num_sms(),
+                       static_cast<cudaStream_t>(stream));
 }
 
 // ---- weight-gradient kernels, op level (parity tests of single kernels; the training step launches the same kernels)

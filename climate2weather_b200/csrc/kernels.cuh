@@ -75,6 +75,36 @@ __global__ void gather_windows_kernel(const float* __restrict__ traj, bf16* __re
   }
 }
 
+// Tiled form for C = 4 (the shipped 4-variable frames): a CTA owns 64 pixels x kGatherWin consecutive windows, reads the
+// kGatherWin + w - 1 frames they span ONCE (coalesced float4 -> packed bf16x4 in shared memory) and writes every
+// window's 128-byte pixel rows from there: each frame pixel leaves L2 1.75 times (w = 13) instead of 13 times.
+constexpr int kGatherWin = 16, kGatherPix = 64;
+__global__ void __launch_bounds__(256) gather_windows_tiled_kernel(const float* __restrict__ traj, bf16* __restrict__ out,
+                                                                   int n, int hw, int w, int cin_pad, int f0) {
+  extern __shared__ uint2 gtile[];  // [frames][kGatherPix] bf16x4
+  const int pix0 = blockIdx.x * kGatherPix, i0 = blockIdx.y * kGatherWin;
+  const int nwin = (n - i0) < kGatherWin ? (n - i0) : kGatherWin;
+  const int nfr = nwin + w - 1;
+  for (int idx = threadIdx.x; idx < nfr * kGatherPix; idx += blockDim.x) {
+    const int fr = idx / kGatherPix, px = idx - fr * kGatherPix;
+    const float4 q = __ldg(reinterpret_cast<const float4*>(traj + (static_cast<long long>(f0 + i0 + fr) * hw + pix0 + px) * 4));
+    gtile[idx] = make_uint2(pack_bf16x2(q.x, q.y), pack_bf16x2(q.z, q.w));
+  }
+  __syncthreads();
+  const int groups = cin_pad >> 3;
+  for (int idx = threadIdx.x; idx < nwin * kGatherPix * groups; idx += blockDim.x) {
+    const int g = idx % groups;
+    const int t = idx / groups;
+    const int px = t % kGatherPix, il = t / kGatherPix;
+    const int tau = 2 * g;
+    uint2 a = make_uint2(0u, 0u), b = make_uint2(0u, 0u);
+    if (tau < w) a = gtile[(il + tau) * kGatherPix + px];
+    if (tau + 1 < w) b = gtile[(il + tau + 1) * kGatherPix + px];
+    *reinterpret_cast<uint4*>(out + (static_cast<long long>(i0 + il) * hw + pix0 + px) * cin_pad + 8 * g) =
+        make_uint4(a.x, a.y, b.x, b.y);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ K2
 // y = (v - mean_C(v)) / sqrt(var_C(v) + eps), v = x + mod, unbiased variance (torch.var_mean default), no affine.
 // One warp per pixel; lane owns NCH chunks of VEC channels: chunk j = channels [j*32*VEC + lane*VEC, +VEC)

@@ -17,7 +17,7 @@ from torch import Tensor
 
 from . import _lib
 from .model import ScoreUNet, build_from_reference
-from .sharding import ShardPlan, exchange_halos, exchange_halos_adjoint, make_plan
+from .sharding import PeerHalo, ShardPlan, exchange_halos, exchange_halos_adjoint, halo_transport, make_plan
 
 
 class CoarseGrain:
@@ -95,6 +95,8 @@ class _Runtime:
         self.partials: Optional[Tensor] = None
         self.cond = None
         self.s_tile = next(s for s in (16, 8, 32, 4, 64, 2, 128, 1) if H % s == 0 and W % s == 0 and W // s <= 32)
+        self._peer_halo: Optional[PeerHalo] = None
+        self._peer_halo_ok = True
 
     # ------------------------------------------------------------------------------------------------ engine
     def refresh_engine(self) -> None:
@@ -242,7 +244,20 @@ class _Runtime:
                 int(step_id), self.nan_flag.data_ptr(), self.stream), "c2w_corrector_update")
 
     def halo(self, group=None) -> None:
-        exchange_halos(self.x, self.plan, group)
+        """Refresh the k halo frames of x from the neighbours (after every state update).  Over NVLink peer memory
+        (c2w_halo_exchange) when the ranks' GPUs can map each other; torch.distributed send/recv pairs otherwise."""
+        if self.plan.world == 1:
+            return
+        if self._peer_halo is None and self._peer_halo_ok and halo_transport() != "nccl":
+            try:
+                self._peer_halo = PeerHalo(self.plan, self.x.shape[1:], self.device, group)
+            except _lib.C2WError as e:  # no peer access between neighbours: say so once, use NCCL
+                print(f"climate2weather_b200: peer-memory halo exchange unavailable ({e}); using NCCL send/recv")
+                self._peer_halo_ok = False
+        if self._peer_halo is not None:
+            self._peer_halo.exchange(self.x)
+        else:
+            exchange_halos(self.x, self.plan, group)
 
     def check_finite(self) -> None:
         if int(self.nan_flag.item()) != 0:

@@ -7,6 +7,8 @@ current state: one send/recv pair per neighbour (NCCL over NVLink on GPUs; gloo 
 """
 from __future__ import annotations
 
+import ctypes
+import os
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -148,3 +150,59 @@ def gather_frames(x_owned: torch.Tensor, plan: ShardPlan, group: Optional[dist.P
     for req in dist.batch_isend_irecv(ops):
         req.wait()
     return full
+
+
+class PeerHalo:
+    """The halo exchange over NVLink peer memory (csrc/halo.cu behind c2w_halo_*): every rank's k boundary frames are
+    stored straight into the neighbours' mailboxes by a kernel on the compute stream and picked up by a second one —
+    no NCCL launch, no host synchronisation.  The 64-byte IPC handles travel once, at construction, through
+    torch.distributed.  Same result as `exchange_halos` (bit-exact: it is a copy)."""
+
+    def __init__(self, plan: ShardPlan, frame_shape, device: torch.device, group: Optional[dist.ProcessGroup] = None):
+        from . import _lib
+
+        self.lib = _lib.load()
+        self.plan, self.device = plan, torch.device(device)
+        self.frame_floats = 1
+        for d in frame_shape:
+            self.frame_floats *= int(d)
+        self.handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.c2w_halo_create(plan.k * self.frame_floats * 4, ctypes.byref(self.handle)), "c2w_halo_create")
+            mine = (ctypes.c_uint8 * 64)()
+            _lib.check(self.lib.c2w_halo_handle(self.handle, mine), "c2w_halo_handle")
+            t = torch.tensor(list(mine), dtype=torch.uint8, device=self.device)
+            every = [torch.empty_like(t) for _ in range(plan.world)]
+            dist.all_gather(every, t, group=group)
+            raw = [bytes(e.cpu().tolist()) for e in every]
+            left = ctypes.create_string_buffer(raw[plan.rank - 1], 64) if plan.rank > 0 else None
+            right = ctypes.create_string_buffer(raw[plan.rank + 1], 64) if plan.rank < plan.world - 1 else None
+            rc = self.lib.c2w_halo_connect(self.handle, left, right)
+            msg = self.lib.c2w_last_error() if rc != 0 else b""
+            ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # also the barrier: every mailbox is mapped before a push
+            if int(ok.item()) == 0:  # all ranks agree to fall back (a one-sided failure would deadlock the exchange)
+                raise _lib.C2WError(f"c2w_halo_connect failed on at least one rank ({msg.decode() if msg else 'a peer'})")
+
+    def exchange(self, x_local: torch.Tensor) -> None:
+        from . import _lib
+
+        assert x_local.is_contiguous() and x_local.dtype == torch.float32 and x_local.shape[0] == self.plan.n_local
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(self.lib.c2w_halo_exchange(self.handle, x_local.data_ptr(), self.plan.n_local, self.frame_floats,
+                                                  self.plan.k, st), "c2w_halo_exchange")
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and self.handle.value:
+                self.lib.c2w_halo_destroy(self.handle)
+                self.handle = ctypes.c_void_p()
+        except Exception:
+            pass
+
+
+def halo_transport() -> str:
+    """C2W_HALO=nccl keeps the torch.distributed send/recv pairs (A/B runs, and the only choice on gloo); default on
+    CUDA: peer memory."""
+    return os.environ.get("C2W_HALO", "p2p").lower()

@@ -248,6 +248,22 @@ int c2w_train_step(c2w_handle* h, const float* xt_nchw, int32_t n, const float* 
                    float* out_nchw, float* gout_nchw, float loss_scale, float* grad_flat, int32_t accumulate,
                    double* loss_sum_dev, void* stream);
 
+/* ---- time-axis halo exchange over NVLink peer memory (replaces nothing in the reference, which
+ * never shards a trajectory: frame i's score needs frames i-k .. i+k, src/thor/score.py:68-93) -----------------------
+ * One handle per process / GPU.  c2w_halo_create allocates this rank's mailbox ([2 parities][2 sides][k frames] + step
+ * counters); c2w_halo_handle exports it as a 64-byte CUDA IPC handle, which the HOST passes to the two neighbours by any
+ * means (torch.distributed in the Python mirror; MPI / files for another host); c2w_halo_connect maps the neighbours'
+ * mailboxes (NULL = no neighbour on that side).  c2w_halo_exchange(x_local) then refreshes the k halo frames on each
+ * side of x_local [n_local_frames][frame_floats] from the neighbours' boundary frames with two small kernels on the
+ * caller's stream: peer stores through NVLink + a system-scope step counter, no NCCL launch, no host synchronisation.
+ * Every rank must call it the same number of times. */
+typedef struct c2w_halo c2w_halo;
+int c2w_halo_create(int64_t halo_bytes, c2w_halo** out);
+void c2w_halo_destroy(c2w_halo* h);
+int c2w_halo_handle(c2w_halo* h, void* out64);
+int c2w_halo_connect(c2w_halo* h, const void* left_handle64, const void* right_handle64);
+int c2w_halo_exchange(c2w_halo* h, float* x_local, int64_t n_local_frames, int64_t frame_floats, int32_t k, void* stream);
+
 /* ---- measurement hooks (bench.py): kernel launches issued by this library so far; optional CUDA-event timing of
  * every forward-pass launch on its own stream, summed per class: [0] K1 conv/GEMM (tensor cores), [1] the rest --- */
 int64_t c2w_launch_count(void);

@@ -60,6 +60,12 @@ def _worker(rank, world, port, L, out_dir):
         out = _sample(net, noise, y, dev, 0, shard=True, exact=True)
         if rank == 0:
             torch.save(out.cpu(), os.path.join(out_dir, "sharded_exact.pt"))
+        # the same run over torch.distributed send/recv instead of the peer-memory mailboxes (c2w_halo_exchange)
+        os.environ["C2W_HALO"] = "nccl"
+        out = _sample(net, noise, y, dev, 0, shard=True)
+        if rank == 0:
+            torch.save(out.cpu(), os.path.join(out_dir, "sharded_c0_nccl.pt"))
+        os.environ["C2W_HALO"] = "p2p"
     finally:
         dist.destroy_process_group()
 
@@ -77,6 +83,7 @@ def test_time_sharded_sampling_matches_single_gpu(tmp_path, world):
     got1 = torch.load(tmp_path / "sharded_c1.pt")
     assert torch.isfinite(got0).all() and torch.isfinite(got1).all()
     assert torch.equal(got0, ref[0]), float((got0 - ref[0]).abs().max())
+    assert torch.equal(torch.load(tmp_path / "sharded_c0_nccl.pt"), ref[0])  # both halo transports: bit-exact
     rel = ((got1 - ref[1]).abs().max() / ref[1].abs().max()).item()
     assert rel < 1e-5, rel
     # exact_grad: the UNet VJP reaches k frames into the neighbours' shards (reverse halo exchange, send-and-add);

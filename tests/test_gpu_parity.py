@@ -302,10 +302,11 @@ def test_attention_core(lib, dev, T, C):
 
 
 @pytest.mark.parametrize("L,k,first,n", [(16, 6, 0, 4), (16, 6, 2, 2), (9, 2, 1, 4)])
-def test_gather_windows_bit_exact(lib, dev, L, k, first, n):
+@pytest.mark.parametrize("H,W", [(4, 8), (16, 16), (8, 24)])  # 256 pixels: the tiled kernel (64-pixel tiles); others: generic
+def test_gather_windows_bit_exact(lib, dev, L, k, first, n, H, W):
     """K0 vs the oracle unfold index map (src/thor/score.py:68-74): pure indexing + one bf16 rounding."""
     from climate2weather_b200 import _lib
-    C, H, W = 4, 4, 8
+    C = 4
     w = 2 * k + 1
     x = torch.randn(L, C, H, W, generator=torch.Generator().manual_seed(L))
     traj = x.permute(0, 2, 3, 1).contiguous().to(dev)
