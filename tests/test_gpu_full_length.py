@@ -71,6 +71,8 @@ def net():
 
 def _run(net, name, golden_dir):
     import climate2weather_b200 as c2w
+    if not (golden_dir / f"full_sample_{name}.npz").exists():
+        pytest.skip(f"tests/golden/full_sample_{name}.npz has not been generated (make_golden_full.py {name})")
     g = np.load(golden_dir / f"full_sample_{name}.npz")
     steps, corrections, exact = int(g["steps"]), int(g["corrections"]), bool(int(g["exact"]))
     noise, y, A = _problem()
