@@ -92,6 +92,8 @@ struct ConvParams {
   __nv_bfloat16* ln_out;
   float* ln_inv;  // optional: 1 / sqrt(var + eps) per row (stash for the LayerNorm backward)
   const float* ln_mod;
+  int ln_mod_stride;  // 0: one modulation vector for the batch; else floats between consecutive IMAGES' vectors (one
+                      // diffusion time per sample, training) — needs tiles that lie inside one image
   int ln_up, ln_H, ln_W;  // ln_H x ln_W: output image of this conv (for the upsampled addressing)
   float ln_eps;
   // EPI_COMPOSE
@@ -214,7 +216,8 @@ __device__ __forceinline__ void epilogue_chunk_direct(const ConvParams& p, const
 // instructions, no measurable change: the epilogue is bound by latency, not by issue slots.)
 template <bool LN>
 __device__ __forceinline__ void epilogue_chunk_staged(const ConvParams& p, const uint32_t (&v)[32], int gcol, int col,
-                                                      uint8_t* stg_row, int row, float& s1, float& s2) {
+                                                      uint8_t* stg_row, int row, float& s1, float& s2,
+                                                      const float* ln_mod) {
   float f[32];
   const float4* b4 = reinterpret_cast<const float4*>(p.bias + gcol);
 #pragma unroll
@@ -279,7 +282,7 @@ __device__ __forceinline__ void epilogue_chunk_staged(const ConvParams& p, const
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float4 mv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.ln_mod) mv = __ldg(reinterpret_cast<const float4*>(p.ln_mod + gcol) + i);
+      if (ln_mod) mv = __ldg(reinterpret_cast<const float4*>(ln_mod + gcol) + i);
       const float mm[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -695,6 +698,10 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             m = ((2 * img + ((row >> 3) & 1)) * p.img_h + (row >> 4)) * p.img_w + tt * Cfg::kARTileW + (row & 7);
         }
         const bool valid = m < p.m_total;
+        // modulation vector of this tile's image (per-sample diffusion times) or of the whole batch
+        const float* ln_mod_t = nullptr;
+        if (LN && p.ln_mod != nullptr)
+          ln_mod_t = p.ln_mod + static_cast<size_t>(p.ln_mod_stride) * (mt / p.tiles_per_img);
         C2W_TIMED_WAIT(w_tfull, &tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col_base;
@@ -729,10 +736,10 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           tmem_ld_wait();
           release_acc();
           wait_staging();
-          if (staged) epilogue_chunk_staged<LN>(p, va, nt * BN + col_base, col_base, stg_row, row, s1, s2);
+          if (staged) epilogue_chunk_staged<LN>(p, va, nt * BN + col_base, col_base, stg_row, row, s1, s2, ln_mod_t);
           else if constexpr (BN == 64) epilogue_chunk_direct(p, va, nt * BN + col_base, m, valid);
           if (kChunks == 2) {
-            if (staged) epilogue_chunk_staged<LN>(p, vb, nt * BN + col_base + 32, col_base + 32, stg_row, row, s1, s2);
+            if (staged) epilogue_chunk_staged<LN>(p, vb, nt * BN + col_base + 32, col_base + 32, stg_row, row, s1, s2, ln_mod_t);
             else if constexpr (BN == 64) epilogue_chunk_direct(p, vb, nt * BN + col_base + 32, m, valid);
           }
         } else {
@@ -745,7 +752,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             if (c + 1 < kChunks) tmem_ld_32x32(taddr + 32 * (c + 1), (c & 1) ? va : vb);
             else release_acc();
             const int col = col_base + 32 * c;
-            if (staged) epilogue_chunk_staged<LN>(p, (c & 1) ? vb : va, nt * BN + col, col, stg_row, row, s1, s2);
+            if (staged) epilogue_chunk_staged<LN>(p, (c & 1) ? vb : va, nt * BN + col, col, stg_row, row, s1, s2, ln_mod_t);
           }
         }
         if (staged) {
@@ -784,6 +791,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       float ln_m[8];
   #pragma unroll
       for (int e = 0; e < 8; ++e) ln_m[e] = (LN && p.ln_mod) ? __ldg(p.ln_mod + (ln_chunk * 8 + e) % BN) : 0.f;
+      const bool ln_per_img = LN && p.ln_mod != nullptr && p.ln_mod_stride != 0;
 
 
       [[maybe_unused]] long long w_lnfull = 0, c_ln = 0;
@@ -793,6 +801,11 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int buf = two_bufs ? (it_local & 1) : 0;
         const int use = two_bufs ? (it_local >> 1) : it_local;
         uint8_t* stg = stg0 + buf * Cfg::kStagingBytes;
+        if (ln_per_img) {  // one diffusion time per sample: this tile's image has its own modulation vector
+          const float* mv = p.ln_mod + static_cast<size_t>(p.ln_mod_stride) * (mt / p.tiles_per_img);
+  #pragma unroll
+          for (int e = 0; e < 8; ++e) ln_m[e] = __ldg(mv + (ln_chunk * 8 + e) % BN);
+        }
         [[maybe_unused]] const long long t_ln0 = C2W_DIAG_CLOCK();
         if (LN) {
           C2W_TIMED_WAIT(w_lnfull, &stg_full[buf], use & 1);  // every warp's columns of the tile and the row statistics are in place
@@ -1151,11 +1164,16 @@ inline bool conv_launch_can_ln(const ConvLaunch* L, int upsample) {
 }
 
 // Fused LayerNorm output: ln_out is [M, C] or, upsampled, [n_img, 2Ho, 2Wo, C]
-inline bool conv_launch_set_ln(ConvLaunch* L, __nv_bfloat16* ln_out, const float* ln_mod, int upsample) {
+// ln_mod_stride != 0: one modulation vector per image (tiles must lie inside one image: 16 x 8 blocks, or 128-pixel row
+// tiles of images with a multiple of 128 pixels)
+inline bool conv_launch_set_ln(ConvLaunch* L, __nv_bfloat16* ln_out, const float* ln_mod, int upsample,
+                               int ln_mod_stride = 0) {
   ConvParams& p = L->p;
   if (!conv_launch_can_ln(L, upsample)) return false;
+  if (ln_mod_stride != 0 && !(L->ar || (p.taps == 9 && p.tile_n == 1))) return false;
   p.ln_out = ln_out;
   p.ln_mod = ln_mod;
+  p.ln_mod_stride = ln_mod_stride;
   p.ln_up = upsample;
   p.ln_H = L->Ho;
   p.ln_W = L->Wo;

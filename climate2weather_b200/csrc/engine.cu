@@ -571,7 +571,10 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
   // tile holds all C channels of a pixel, the normalisation is done in that conv's epilogue (no extra HBM pass).
   auto add_ln = [&](const bf16* in, bf16* out, float* inv, int C, int H, int W, int upf, int mod_off) {
     if (!real) return;
-    if (h->fuse_ln && !per_t && !P.ops.empty()) {
+    // one diffusion time per sample (training): the fused form takes a per-image modulation vector; LayerNorms without
+    // modulation (attention, tails) fuse as usual
+    const int mod_stride = (per_t && mod_off >= 0) ? h->total_mod : 0;
+    if (h->fuse_ln && !P.ops.empty()) {
       Op& prev = P.ops.back();
       if (prev.kind == OP_CONV && !prev.is_final && prev.conv.out_ptr == in && prev.conv.cout_pad == C &&
           prev.conv.p.num_n_tiles != 1 && (C == 128 || C == 256)) {
@@ -584,7 +587,7 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
       }
       if (prev.kind == OP_CONV && !prev.is_final && prev.conv.out_ptr == in && prev.conv.cout_pad == C &&
           conv_launch_can_ln(&prev.conv, upf) &&
-          conv_launch_set_ln(&prev.conv, out, mod_off >= 0 ? mods + mod_off : nullptr, upf)) {
+          conv_launch_set_ln(&prev.conv, out, mod_off >= 0 ? mods + mod_off : nullptr, upf, mod_stride)) {
         prev.conv.p.ln_inv = inv;
         return;
       }
