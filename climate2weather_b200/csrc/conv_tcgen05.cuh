@@ -61,6 +61,8 @@ enum EpiMode : int {
   EPI_COMPOSE = 3,    // centre-pick / edge-fill compose        -> fp32 eps [L, H, W, 4]
   EPI_F32 = 4,        // out = acc + bias                       -> fp32 [M, ldc]
   EPI_MUL_DSILU = 5,  // out = (acc + bias) * silu'(out)        -> bf16   (in place: `out` holds the pre-activation)
+  EPI_BIAS_SILU_DUAL = 6,  // out = acc + bias AND out2 = silu(acc + bias) -> two bf16 tensors (stashing forward: the
+                           // backward needs the pre-activation, the next conv its SiLU; BN <= 128)
 };
 
 struct ConvParams {
@@ -217,7 +219,7 @@ __device__ __forceinline__ void epilogue_chunk_direct(const ConvParams& p, const
 template <bool LN>
 __device__ __forceinline__ void epilogue_chunk_staged(const ConvParams& p, const uint32_t (&v)[32], int gcol, int col,
                                                       uint8_t* stg_row, int row, float& s1, float& s2,
-                                                      const float* ln_mod) {
+                                                      const float* ln_mod, uint32_t dual_off = 0) {
   float f[32];
   const float4* b4 = reinterpret_cast<const float4*>(p.bias + gcol);
 #pragma unroll
@@ -233,6 +235,18 @@ __device__ __forceinline__ void epilogue_chunk_staged(const ConvParams& p, const
   if (p.mode == EPI_BIAS_SILU) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = silu_f(f[i]);
+  } else if (p.mode == EPI_BIAS_SILU_DUAL) {
+    // second staging tile (dual_off bytes further on): silu of the same values; the pre-activation goes out below
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(silu_f(f[8 * i + 2 * j]), silu_f(f[8 * i + 2 * j + 1]));
+        o[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      st_shared_v4(stg_row, dual_off + boff + (static_cast<uint32_t>((j0 + i) ^ (row & 7)) << 4), o[0], o[1], o[2], o[3]);
+    }
   } else if (p.mode == EPI_BIAS_RES) {
     // all residual loads of the chunk first: the in-place stores below alias them as far as the compiler can tell
     uint4 aux[4];
@@ -299,7 +313,8 @@ __device__ __forceinline__ void epilogue_chunk_staged(const ConvParams& p, const
 template <int BN, int CG, bool LN, bool AR>
 __global__ void __launch_bounds__(kConvThreads + (LN ? kLnThreads : 0), 1)
 conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmOut, const ConvParams p) {
+                         const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+                         const ConvParams p) {
   using Cfg = ConvCfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   // 1024 B alignment by POINTER arithmetic (an integer round trip hides the address space from the compiler and
@@ -333,12 +348,16 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   // TMA-prefetched auxiliary tile (the residual / the pre-activation the gradient is multiplied with), overwritten in place
   const bool has_aux = p.mode == EPI_BIAS_RES || p.mode == EPI_MUL_DSILU;
   // two staging tiles used alternately (residual convs: the residual tile is prefetched two tiles ahead)
-  const bool two_bufs = p.num_staging == 2;
+  // EPI_BIAS_SILU_DUAL fills BOTH staging tiles for every output tile (pre-activation and its SiLU) and stores them
+  // through two tensor maps; the auxiliary-tile modes use the two tiles alternately
+  const bool dual = p.mode == EPI_BIAS_SILU_DUAL;
+  const bool two_bufs = p.num_staging == 2 && !dual;
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (staged) tma_prefetch_desc(&tmOut);
+    if (dual) tma_prefetch_desc(&tmOut2);
   }
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < num_stages; ++s) {
@@ -646,8 +665,14 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               box_coords(mt, c1, c2, c3);
               tma_store_4d(&tmOut, stg + b * kATileBytes, nt * BN + b * 64, c1, c2, c3);
               if (p.ar2) tma_store_4d(&tmOut, stg + b * kATileBytes + kATileBytes / 2, nt * BN + b * 64, c1, c2, c3 + 1);
+              if (dual) {
+                const uint8_t* s2 = stg + Cfg::kStagingBytes + b * kATileBytes;
+                tma_store_4d(&tmOut2, s2, nt * BN + b * 64, c1, c2, c3);
+                if (p.ar2) tma_store_4d(&tmOut2, s2 + kATileBytes / 2, nt * BN + b * 64, c1, c2, c3 + 1);
+              }
             } else {
               tma_store_2d(&tmOut, stg + b * kATileBytes, nt * BN + b * 64, mt * kBlockM);
+              if (dual) tma_store_2d(&tmOut2, stg + Cfg::kStagingBytes + b * kATileBytes, nt * BN + b * 64, mt * kBlockM);
             }
           }
           bulk_commit();
@@ -736,10 +761,10 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           tmem_ld_wait();
           release_acc();
           wait_staging();
-          if (staged) epilogue_chunk_staged<LN>(p, va, nt * BN + col_base, col_base, stg_row, row, s1, s2, ln_mod_t);
+          if (staged) epilogue_chunk_staged<LN>(p, va, nt * BN + col_base, col_base, stg_row, row, s1, s2, ln_mod_t, dual ? static_cast<uint32_t>(Cfg::kStagingBytes) : 0u);
           else if constexpr (BN == 64) epilogue_chunk_direct(p, va, nt * BN + col_base, m, valid);
           if (kChunks == 2) {
-            if (staged) epilogue_chunk_staged<LN>(p, vb, nt * BN + col_base + 32, col_base + 32, stg_row, row, s1, s2, ln_mod_t);
+            if (staged) epilogue_chunk_staged<LN>(p, vb, nt * BN + col_base + 32, col_base + 32, stg_row, row, s1, s2, ln_mod_t, dual ? static_cast<uint32_t>(Cfg::kStagingBytes) : 0u);
             else if constexpr (BN == 64) epilogue_chunk_direct(p, vb, nt * BN + col_base + 32, m, valid);
           }
         } else {
@@ -752,7 +777,7 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             if (c + 1 < kChunks) tmem_ld_32x32(taddr + 32 * (c + 1), (c & 1) ? va : vb);
             else release_acc();
             const int col = col_base + 32 * c;
-            if (staged) epilogue_chunk_staged<LN>(p, (c & 1) ? vb : va, nt * BN + col, col, stg_row, row, s1, s2, ln_mod_t);
+            if (staged) epilogue_chunk_staged<LN>(p, (c & 1) ? vb : va, nt * BN + col, col, stg_row, row, s1, s2, ln_mod_t, dual ? static_cast<uint32_t>(Cfg::kStagingBytes) : 0u);
           }
         }
         if (staged) {
@@ -1011,7 +1036,7 @@ inline bool make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uin
 
 // One prepared launch of K1: tensor maps + parameters.  Built once per (layer, batch) and replayed.
 struct ConvLaunch {
-  CUtensorMap tmA, tmB, tmOut;
+  CUtensorMap tmA, tmB, tmOut, tmOut2;
   ConvParams p;
   int bn;
   int cg;     // CTAs per MMA (1 or 2)
@@ -1046,6 +1071,7 @@ inline bool conv_launch_init(ConvLaunch* L, bool is_conv3x3, const __nv_bfloat16
   ConvParams& p = L->p;
   memset(&p, 0, sizeof(p));
   memset(&L->tmOut, 0, sizeof(CUtensorMap));
+  memset(&L->tmOut2, 0, sizeof(CUtensorMap));
   L->bn = bn;
   L->ln = 0;
   L->out_ptr = nullptr;
@@ -1154,6 +1180,12 @@ inline bool conv_launch_set_out(ConvLaunch* L, __nv_bfloat16* out) {
   return conv_make_epi_map(L, &L->tmOut, out);
 }
 
+// Second bf16 output of EPI_BIAS_SILU_DUAL (the SiLU of the first)
+inline bool conv_launch_set_out2(ConvLaunch* L, __nv_bfloat16* out2) {
+  if (L->bn > 128) return false;  // two staging tiles of a wider tile leave no operand ring
+  return conv_make_epi_map(L, &L->tmOut2, out2);
+}
+
 // Whether this launch can also emit the channel LayerNorm of its output (one N tile = all channels of a pixel).
 inline bool conv_launch_can_ln(const ConvLaunch* L, int upsample) {
   const ConvParams& p = L->p;
@@ -1212,6 +1244,10 @@ inline cudaError_t conv_launch_variant(const ConvLaunch& L, cudaStream_t stream)
   // more as ring stages (G2: 1239 -> 1345 TFLOP/s with 4 instead of 3 activation-reuse stages).  Residual convs with
   // ONE staging tile and a 4-deep ring were measured too: residual 1215 -> 1187, residual + LayerNorm 1050 -> 860.
   p.num_staging = ((p.mode == EPI_BIAS_RES || p.mode == EPI_MUL_DSILU) && BN <= 128) ? 2 : 1;
+  if (p.mode == EPI_BIAS_SILU_DUAL) {
+    if (BN > 128) return cudaErrorInvalidValue;
+    p.num_staging = 2;
+  }
   p.num_stages = AR ? Cfg::ar_stages_for(p.num_staging) : Cfg::stages_for(p.num_staging);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -1231,7 +1267,7 @@ inline cudaError_t conv_launch_variant(const ConvLaunch& L, cudaStream_t stream)
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.numAttrs = 2;
   }
-  return cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<BN, CG, LN, AR>, L.tmA, L.tmB, L.tmOut, p);
+  return cudaLaunchKernelEx(&cfg, conv_gemm_tcgen05_kernel<BN, CG, LN, AR>, L.tmA, L.tmB, L.tmOut, L.tmOut2, p);
 }
 
 template <int BN, bool LN>

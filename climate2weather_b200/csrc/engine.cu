@@ -135,6 +135,7 @@ struct c2w_handle {
   bool timing = false;
   bool fuse_ln = true;  // C2W_NO_FUSE_LN=1 keeps every LayerNorm a separate kernel (A/B runs)
   bool fuse_dsilu = true;  // C2W_NO_FUSE_DSILU=1: silu' of the input-gradient pass as a separate elementwise kernel
+  bool fuse_dual = true;   // C2W_NO_FUSE_DUAL=1: stashing forward with a separate SiLU pass after conv1
   std::vector<TimedSpan> spans;
   size_t spans_used = 0;
 };
@@ -659,7 +660,18 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
       float* inv = vjp ? stash_f(npix) : nullptr;
       add_ln(xs[l], y, inv, L.C, L.H, L.W, 0, bw.mod_off);
       int rc;
-      if (vjp) {  // the pre-activation is stashed; SiLU is a separate elementwise pass
+      bool dual_done = false;
+      if (vjp && real && h->fuse_dual) {  // pre-activation AND its SiLU as two TMA-stored outputs of conv1's epilogue
+        Op op;
+        rc = make_conv(&op, true, y, L.H, L.W, L.C, bw.c1.w, bw.c1.b, bw.c1.cout_pad, EPI_BIAS_SILU_DUAL, pre, false, 1);
+        if (rc) return rc;
+        if (conv_launch_set_out2(&op.conv, hs[l])) {
+          P.ops.push_back(op);
+          dual_done = true;
+        }
+      }
+      if (vjp && dual_done) {
+      } else if (vjp) {  // the pre-activation is stashed; SiLU is a separate elementwise pass
         rc = add_conv(true, y, L.H, L.W, L.C, bw.c1, EPI_BIAS, pre, false);
         if (rc) return rc;
         if (real) {
@@ -1029,6 +1041,8 @@ int c2w_create(const c2w_config* cfg, c2w_handle** out) {
     h->fuse_ln = !(e && e[0] == '1');
     const char* e2 = getenv("C2W_NO_FUSE_DSILU");
     h->fuse_dsilu = !(e2 && e2[0] == '1');
+    const char* e3 = getenv("C2W_NO_FUSE_DUAL");
+    h->fuse_dual = !(e3 && e3[0] == '1');
   }
   *out = h;
   return C2W_OK;
