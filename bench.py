@@ -467,10 +467,15 @@ def run_train(args):
     torch.manual_seed(0)
     net = c2w.ScoreUNet(activation=torch.nn.SiLU, **ARCH).to(dev).train()
     model = net
-    if world > 1:
+    use_ddp = world > 1 and args.ddp == "torch"
+    if use_ddp:  # the reference's own route: Fabric strategy="ddp" (train.py:93-100) = torch DDP hooks on our gradients
         model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank])
     pipe = c2w.SDAPipeline()
-    opt = optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-3, betas=(0.9, 0.999))  # train.py:176-181
+    # default for N > 1: one in-place NCCL all-reduce of the flat gradient buffer inside optimizer.step()
+    opt = optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-3, betas=(0.9, 0.999),  # train.py:176-181
+                      data_parallel_group=(None if (world > 1 and not use_ddp) else "none"))
+    if world > 1 and not use_ddp:
+        opt.broadcast_parameters(0)
     ema = optim.StandardEMA(net, rates=[0.9999])
     opt.fuse_ema(ema)
     g = torch.Generator(device=dev).manual_seed(1 + rank)
@@ -527,7 +532,8 @@ def run_train(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"config5: DSM training step, batch {B}/GPU x{world} of 52x128x128 windows, "
                                        "sda_unet.yml ScoreUNet (72.1 M parameters), AdamW lr 1e-4 wd 1e-3 + EMA 0.9999 "
-                                       "(fused), per-sample diffusion times" + (", DDP all-reduce over NCCL" if world > 1 else ""),
+                                       "(fused), per-sample diffusion times" + (("" if world == 1 else ", torch DDP all-reduce over NCCL" if use_ddp
+                                                                  else ", flat-buffer gradient all-reduce over NCCL")),
                            "name": "config5", "batch_per_gpu": B, "global_batch": B * world,
                            "l2": "activations of a 128-sample batch (~14 GB) exceed the 126 MB L2; no explicit flush"},
                 "clocks": clocks.summary(), "gpu_launches": int(launches),
@@ -679,6 +685,8 @@ def main():
     ap.add_argument("--mode", default="sample", choices=["sample", "train"],
                     help="train: BASELINE config 5, the DSM training step (forward + backward + AdamW + EMA)")
     ap.add_argument("--batch", type=int, default=128, help="--mode train: samples per GPU (run_training.sh: 128)")
+    ap.add_argument("--ddp", default="flat", choices=["flat", "torch"],
+                    help="--mode train, N > 1: gradient averaging by one all-reduce of the flat buffer (default) or torch DDP")
     args = ap.parse_args()
     if args.e2e_steps is None:
         args.e2e_steps = 8 if args.config == 4 else SAMPLER_STEPS

@@ -36,7 +36,7 @@ class AdamW:
     """torch.optim.AdamW (decoupled weight decay, bias correction; no amsgrad / maximize / foreach options)."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 1e-2, loss_scaling: float = 1.0):
+                 weight_decay: float = 1e-2, loss_scaling: float = 1.0, data_parallel_group="none"):
         self.lib = _lib.load()
         ps = [p for p in params if p.requires_grad]
         if not ps:
@@ -55,6 +55,11 @@ class AdamW:
             p.data = self.flat[o:o + p.numel()].view_as(p)
             p.grad = self.grad[o:o + p.numel()].view_as(p)
         self.step_count = 0
+        # data-parallel training without a DDP wrapper (training_loop.py:116,375-378): the gradients of all ranks are
+        # averaged with ONE in-place NCCL all-reduce of the flat gradient buffer at the start of step() — no bucket
+        # copies.  "none": gradients are taken as they are (single process, or a DDP wrapper already averaged them);
+        # None: the default process group; or a torch.distributed group.
+        self.dp_group = data_parallel_group
         self._ema: Optional["StandardEMA"] = None
         self._owners: List[torch.nn.Module] = []  # modules whose packed-weight engines go stale when we step
         from .model import owner_of
@@ -112,9 +117,19 @@ class AdamW:
             self.exp_avg_sq[sl].view_as(p).copy_(st["exp_avg_sq"])
             self.step_count = max(self.step_count, int(float(st["step"])))
 
+    def broadcast_parameters(self, src: int = 0) -> None:
+        """Every rank starts from rank `src`'s parameters (what a DDP wrapper does at construction)."""
+        import torch.distributed as dist
+
+        dist.broadcast(self.flat, src=src, group=None if isinstance(self.dp_group, str) else self.dp_group)
+        for m in self._owners:
+            m.invalidate_engines()
+
     def __getstate__(self):
         d = self.__dict__.copy()
         d.pop("lib", None)  # a ctypes.CDLL cannot be pickled; reloaded on demand
+        if not isinstance(d.get("dp_group"), str):
+            d["dp_group"] = None  # process groups do not pickle; the default group is re-resolved
         return d
 
     def __setstate__(self, d):
@@ -143,6 +158,10 @@ class AdamW:
                 raise RuntimeError("a parameter has no gradient; call backward() before step()")
             if p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:  # autograd installed a fresh tensor
                 self.grad[o:o + p.numel()].view_as(p).copy_(p.grad)
+        if not (isinstance(self.dp_group, str) and self.dp_group == "none"):
+            import torch.distributed as dist
+
+            dist.all_reduce(self.grad, op=dist.ReduceOp.AVG, group=self.dp_group)
         g = self.param_groups[0]
         self.step_count += 1
         hp = _lib.AdamW(float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
