@@ -28,6 +28,7 @@ class Config(C.Structure):
         ("hidden_channels", C.c_int32 * MAX_LEVELS),
         ("hidden_blocks", C.c_int32 * MAX_LEVELS),
         ("attention_mask", C.c_int32),
+        ("forcing_dim", C.c_int32),
     ]
 
 
@@ -132,6 +133,7 @@ SIGNATURES = {
     "c2w_op_gather_windows": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "c2w_op_modulation": (_i, [_vp, _f, _vp, _vp, _vp]),
     "c2w_total_mod_channels": (_i, [_vp]),
+    "c2w_set_forcing": (_i, [_vp, _vp]),
     "c2w_param_total": (_i64, [_vp]),
     "c2w_refresh_weights": (_i, [_vp, _vp, _vp]),
     "c2w_param_layout": (_i, [_vp, C.c_char_p, C.POINTER(_i64), C.POINTER(_i64)]),

@@ -99,6 +99,7 @@ struct Plan {
   size_t wg_scratch_floats = 0;
   float *feat = nullptr, *pre0 = nullptr, *pre1 = nullptr, *demb = nullptr, *dh0 = nullptr;  // time-MLP backward
   float* loss_partials = nullptr;
+  float *forc_pad = nullptr, *fvec = nullptr;  // forcing rows padded to float4 lanes [n, forcing_pad]; Wf forcing + bf [n, E]
   float* grad = nullptr;   // flat gradient buffer of the running c2w_train_backward call
   std::vector<Op> ops;
   std::vector<Op> bwd;     // input-gradient pass (vjp plans only), in execution order
@@ -127,6 +128,9 @@ struct c2w_handle {
   std::vector<void*> allocs;
   float *map0_w = nullptr, *map0_b = nullptr, *map1_w = nullptr, *map1_b = nullptr;
   float *proj_w = nullptr, *proj_b = nullptr;
+  float *mapf_w = nullptr, *mapf_b = nullptr;  // forcing branch: [E, forcing_pad] (columns zero-padded to 4), [E]
+  int forcing_pad = 0;
+  const float* forcing = nullptr;  // c2w_set_forcing: device [n, forcing_dim] for the next per-sample forwards
   float* zero_bias = nullptr;  // 512 zeros: the input-gradient convs have no bias
   int total_mod = 0;
   std::vector<LevelW> levels;
@@ -409,8 +413,18 @@ int run_modulation(c2w_handle* h, float t, const float* t_dev, int ns, float* h0
                    cudaStream_t st) {
   const int E = h->cfg.embedding_dim, nf = h->cfg.noise_features;
   time_embed_kernel<<<ns, 256, nf * sizeof(float), st>>>(t, t_dev, h->map0_w, h->map0_b, h0, E, nf);
+  const float* fvec = nullptr;
+  if (h->forcing != nullptr && h->plan.per_t && h->forcing_pad > 0) {  // + map_forcing(forcing), model/score.py:65-66
+    const int fp = h->forcing_pad;
+    pad_rows_kernel<<<ceil_div(static_cast<long long>(ns) * fp, 256), 256, 0, st>>>(h->forcing, h->plan.forc_pad, ns,
+                                                                                  h->cfg.forcing_dim, fp);
+    matvec_kernel<<<dim3(ceil_div(static_cast<long long>(E) * 32, 256), ns), 256, 0, st>>>(h->mapf_w, h->mapf_b, h->plan.forc_pad,
+                                                                                        h->plan.fvec, E, fp, 0);
+    fvec = h->plan.fvec;
+    g_launches += 2;
+  }
   matvec_kernel<<<dim3(ceil_div(static_cast<long long>(E) * 32, 256), ns), 256, 0, st>>>(h->map1_w, h->map1_b, h0, emb, E,
-                                                                                      E, 1);
+                                                                                      E, 1, fvec);
   if (h->total_mod > 0)  // a network without residual blocks has no modulation projections
     matvec_kernel<<<dim3(ceil_div(static_cast<long long>(h->total_mod) * 32, 256), ns), 256, 0, st>>>(
         h->proj_w, h->proj_b, emb, mods, h->total_mod, E, 0);
@@ -443,6 +457,8 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
   float* emb = B.take<float>(ns * h->cfg.embedding_dim);
   float* mods = B.take<float>(ns * h->total_mod);
   float* out32 = B.take<float>(n * HW0 * h->levels[0].tail.cout_pad);
+  float* forc_pad = h->forcing_pad > 0 ? B.take<float>(ns * h->forcing_pad) : nullptr;
+  float* fvec = h->forcing_pad > 0 ? B.take<float>(ns * h->cfg.embedding_dim) : nullptr;
   std::vector<bf16*> xs(nl), as(nl), hs(nl), gs(nl), ga(nl), gh(nl);
   size_t up_elems = 0, qkv_elems = 0, att_elems = 0;
   for (int l = 0; l < nl; ++l) {
@@ -517,6 +533,8 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
     P.emb = emb;
     P.mods = mods;
     P.out32 = out32;
+    P.forc_pad = forc_pad;
+    P.fvec = fvec;
     P.cot = cot;
     P.g0 = vjp ? gs[0] : nullptr;
   }
@@ -658,6 +676,8 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
       bf16* y = vjp ? stash(e) : as[l];
       bf16* pre = vjp ? stash(e) : nullptr;
       float* inv = vjp ? stash_f(npix) : nullptr;
+      // training keeps every block's SiLU output (conv2's wgrad operand) instead of recomputing it from `pre`
+      bf16* hsb = train ? stash(e) : hs[l];
       add_ln(xs[l], y, inv, L.C, L.H, L.W, 0, bw.mod_off);
       int rc;
       bool dual_done = false;
@@ -665,7 +685,7 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
         Op op;
         rc = make_conv(&op, true, y, L.H, L.W, L.C, bw.c1.w, bw.c1.b, bw.c1.cout_pad, EPI_BIAS_SILU_DUAL, pre, false, 1);
         if (rc) return rc;
-        if (conv_launch_set_out2(&op.conv, hs[l])) {
+        if (conv_launch_set_out2(&op.conv, hsb)) {
           P.ops.push_back(op);
           dual_done = true;
         }
@@ -679,7 +699,7 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
           op.kind = OP_SILU;
           op.aux = pre;
           op.in = nullptr;
-          op.out = hs[l];
+          op.out = hsb;
           op.C = L.C;
           op.H = L.H;
           op.W = L.W;
@@ -687,27 +707,15 @@ int build_plan(c2w_handle* h, int n, bool vjp, bool per_t, void* base, size_t* b
           P.ops.push_back(op);
         }
       } else {
-        rc = add_conv(true, y, L.H, L.W, L.C, bw.c1, EPI_BIAS_SILU, hs[l], false);
+        rc = add_conv(true, y, L.H, L.W, L.C, bw.c1, EPI_BIAS_SILU, hsb, false);
         if (rc) return rc;
       }
-      rc = add_conv(true, hs[l], L.H, L.W, L.C, bw.c2, EPI_BIAS_RES, xs[l], false);
+      rc = add_conv(true, hsb, L.H, L.W, L.C, bw.c2, EPI_BIAS_RES, xs[l], false);
       if (rc) return rc;
       if (vjp) {
         units.emplace_back();
         std::vector<Op>& u = units.back();
-        if (train && real) {  // conv2's input, silu(pre), lives in the level's shared buffer: recompute it for the wgrad
-          Op op;
-          op.kind = OP_SILU;
-          op.aux = pre;
-          op.in = nullptr;
-          op.out = hs[l];
-          op.C = L.C;
-          op.H = L.H;
-          op.W = L.W;
-          op.up = 0;
-          u.push_back(op);
-        }
-        add_wgrad(u, true, hs[l], gs[l], L.H, L.W, bw.c2, 1);
+        add_wgrad(u, true, hsb, gs[l], L.H, L.W, bw.c2, 1);  // conv2's input: this block's stashed SiLU output
         if (h->fuse_dsilu) {
           // conv2's input gradient times silu'(pre), written in place over the stashed pre-activation (the epilogue
           // prefetches `pre` like a residual tile), then conv1's input gradient from it
@@ -1028,6 +1036,7 @@ int c2w_create(const c2w_config* cfg, c2w_handle** out) {
       W /= 2;
     }
   }
+  C2W_REQUIRE(cfg->forcing_dim >= 0 && cfg->forcing_dim <= 4096, "forcing_dim=%d out of range", cfg->forcing_dim);
   int sms = c2w_num_sms();
   C2W_REQUIRE(sms > 0, "c2w_create: no CUDA device available (this library has no CPU path)");
   c2w_handle* h = new c2w_handle();
@@ -1080,6 +1089,17 @@ int c2w_finalize_weights(c2w_handle* h) {
   if ((rc = upload_named(h, "map_layer0.bias", E, &h->map0_b))) return rc;
   if ((rc = upload_named(h, "map_layer1.weight", static_cast<size_t>(E) * E, &h->map1_w))) return rc;
   if ((rc = upload_named(h, "map_layer1.bias", E, &h->map1_b))) return rc;
+  if (c.forcing_dim > 0) {
+    const std::vector<float>*fw, *fb;
+    if ((rc = need(h, "map_forcing.weight", static_cast<size_t>(E) * c.forcing_dim, &fw))) return rc;
+    if ((rc = need(h, "map_forcing.bias", E, &fb))) return rc;
+    h->forcing_pad = (c.forcing_dim + 3) / 4 * 4;
+    std::vector<float> padded(static_cast<size_t>(E) * h->forcing_pad, 0.f);
+    for (int r = 0; r < E; ++r)
+      for (int j = 0; j < c.forcing_dim; ++j) padded[static_cast<size_t>(r) * h->forcing_pad + j] = (*fw)[static_cast<size_t>(r) * c.forcing_dim + j];
+    if ((rc = dev_upload(h, padded.data(), padded.size() * sizeof(float), reinterpret_cast<void**>(&h->mapf_w)))) return rc;
+    if ((rc = dev_upload(h, fb->data(), E * sizeof(float), reinterpret_cast<void**>(&h->mapf_b)))) return rc;
+  }
   h->levels.assign(nl, LevelW());
   std::vector<float> proj_w, proj_b;
   int H = c.height, W = c.width;
@@ -1367,6 +1387,13 @@ int c2w_window_score_backward(c2w_handle* h, const float* cot, int32_t n_frames_
   return C2W_OK;
 }
 
+int c2w_set_forcing(c2w_handle* h, const float* forcing_dev) {
+  C2W_REQUIRE(h, "c2w_set_forcing: null handle");
+  C2W_REQUIRE(forcing_dev == nullptr || h->cfg.forcing_dim > 0, "c2w_set_forcing: the network has no forcing branch (forcing_dim = 0)");
+  h->forcing = forcing_dev;
+  return C2W_OK;
+}
+
 // Re-packs every weight from a DEVICE copy of the parameters in the flat layout of c2w_param_layout (after an optimiser
 // step: the buffer optim.AdamW steps on, no host round trip, no re-allocation): bf16 tensor-core operands of all convs,
 // biases, modulation projections, time MLP.
@@ -1398,6 +1425,13 @@ int c2w_refresh_weights(c2w_handle* h, const float* flat_dev, void* stream) {
       for (AttnW& aw : attns)
         if ((rc = conv(aw.qkv)) || (rc = conv(aw.proj))) return rc;
     }
+  }
+  if (h->cfg.forcing_dim > 0) {  // forcing branch: weight rows re-padded, bias copied
+    auto iw = h->param_off.find("map_forcing.weight"), ib = h->param_off.find("map_forcing.bias");
+    C2W_REQUIRE(iw != h->param_off.end() && ib != h->param_off.end(), "map_forcing has no slot in the flat layout");
+    pad_rows_kernel<<<ceil_div(static_cast<long long>(E) * h->forcing_pad, 256), 256, 0, st>>>(flat_dev + iw->second, h->mapf_w, E,
+                                                                                             h->cfg.forcing_dim, h->forcing_pad);
+    C2W_CUDA(cudaMemcpyAsync(h->mapf_b, flat_dev + ib->second, E * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
   struct { const char* name; float* dst; size_t n; } mlp[4] = {
       {"map_layer0.weight", h->map0_w, static_cast<size_t>(E) * h->cfg.noise_features}, {"map_layer0.bias", h->map0_b, (size_t)E},
@@ -1487,8 +1521,8 @@ int c2w_train_backward(c2w_handle* h, const float* gout_nchw, int32_t n, float* 
         }
     // d emb = dmods . W_proj  ([n, TM] x [TM, E]);  emb = silu(pre1), pre1 = W1 h0 + b1;  h0 = silu(pre0), pre0 = W0 feat + b0
     gemm_nn_f32_kernel<<<blocks1d(static_cast<long long>(n) * E), 256, 0, st>>>(P.dmods, TM, h->proj_w, E, P.demb, E, n, TM, E);
-    matvec_kernel<<<dim3(ceil_div(static_cast<long long>(E) * 32, 256), n), 256, 0, st>>>(h->map1_w, h->map1_b, P.h0, P.pre1,
-                                                                                          E, E, 0);
+    matvec_kernel<<<dim3(ceil_div(static_cast<long long>(E) * 32, 256), n), 256, 0, st>>>(
+        h->map1_w, h->map1_b, P.h0, P.pre1, E, E, 0, (h->forcing != nullptr && h->forcing_pad > 0) ? P.fvec : nullptr);
     dsilu_f32_kernel<<<blocks1d(static_cast<long long>(n) * E), 256, 0, st>>>(P.demb, P.pre1, static_cast<long long>(n) * E);
     const long long o1w = off("map_layer1.weight"), o1b = off("map_layer1.bias");
     const long long o0w = off("map_layer0.weight"), o0b = off("map_layer0.bias");
@@ -1496,6 +1530,14 @@ int c2w_train_backward(c2w_handle* h, const float* gout_nchw, int32_t n, float* 
       gemm_tn_f32_kernel<<<blocks1d(static_cast<long long>(E) * E), 256, 0, st>>>(P.demb, E, P.h0, E, grad_flat + o1w, E, n, E,
                                                                                   E, 1);
     if (o1b >= 0) colsum_f32_kernel<<<blocks1d(E), 256, 0, st>>>(P.demb, E, grad_flat + o1b, n, E, 1);
+    if (h->forcing != nullptr && h->forcing_pad > 0) {  // emb = silu(pre1 + Wf f + bf): same d pre1
+      const long long ofw = off("map_forcing.weight"), ofb = off("map_forcing.bias");
+      const int F = h->cfg.forcing_dim;
+      if (ofw >= 0)
+        gemm_tn_f32_kernel<<<blocks1d(static_cast<long long>(E) * F), 256, 0, st>>>(P.demb, E, P.forc_pad, h->forcing_pad,
+                                                                                  grad_flat + ofw, F, n, E, F, 1);
+      if (ofb >= 0) colsum_f32_kernel<<<blocks1d(E), 256, 0, st>>>(P.demb, E, grad_flat + ofb, n, E, 1);
+    }
     gemm_nn_f32_kernel<<<blocks1d(static_cast<long long>(n) * E), 256, 0, st>>>(P.demb, E, h->map1_w, E, P.dh0, E, n, E, E);
     time_features_kernel<<<n, 128, 0, st>>>(P.t_last, P.feat, nf);
     matvec_kernel<<<dim3(ceil_div(static_cast<long long>(E) * 32, 256), n), 256, 0, st>>>(h->map0_w, h->map0_b, P.feat, P.pre0,

@@ -225,8 +225,10 @@ __global__ void time_embed_kernel(float t_scalar, const float* __restrict__ t_de
 }
 // y[r] = act(b[r] + W[r, :] . x)   warp per row, float4 lanes.  act: 0 none, 1 SiLU
 // blockIdx.y = sample: x and y advance by cols / rows per sample
+// add_all (optional): a per-sample vector added before the activation (the forcing term, model/score.py:65-66)
 __global__ void matvec_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ x_all,
-                              float* __restrict__ y_all, int rows, int cols, int act) {
+                              float* __restrict__ y_all, int rows, int cols, int act,
+                              const float* __restrict__ add_all = nullptr) {
   const int lane = threadIdx.x & 31;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
@@ -242,8 +244,16 @@ __global__ void matvec_kernel(const float* __restrict__ W, const float* __restri
   acc = warp_sum(acc);
   if (lane == 0) {
     acc += b[row];
+    if (add_all) acc += add_all[static_cast<size_t>(blockIdx.y) * rows + row];
     y[row] = act ? acc / (1.0f + expf(-acc)) : acc;
   }
+}
+// rows of `cols` floats -> rows of `cols_pad` floats, zero-padded (matvec_kernel reads float4 lanes)
+__global__ void pad_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int cols, int cols_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * cols_pad) return;
+  const int r = i / cols_pad, c = i - r * cols_pad;
+  out[i] = c < cols ? in[r * cols + c] : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------ K4

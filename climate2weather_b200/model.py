@@ -20,12 +20,14 @@ NOISE_FEATURES = 32  # model/score.py:53
 
 
 def _layer_specs(channels: int, embedding_dim: int, hidden_channels: Sequence[int], hidden_blocks: Sequence[int],
-                 attention_levels: Sequence[int], ks: int) -> List[Tuple[str, Tuple[int, ...]]]:
+                 attention_levels: Sequence[int], ks: int, forcing_dim: int = 0) -> List[Tuple[str, Tuple[int, ...]]]:
     """state_dict prefixes and weight shapes in the reference's construction order (model/nn.py:165-218;
     `tails` / `ascent` are stored reversed, :216,218), followed by the time MLP (model/score.py:56-57)."""
     nl = len(hidden_blocks)
     ch = list(hidden_channels)
     specs: List[Tuple[str, Tuple[int, ...]]] = []
+    if forcing_dim > 0:  # model/score.py:49-51: the forcing Linear is constructed before the UNet
+        specs.append(("map_forcing", (embedding_dim, forcing_dim)))
     for lvl in range(nl):
         rev = nl - 1 - lvl
         if lvl == 0:
@@ -95,6 +97,7 @@ class Engine:
         for i, (c, b) in enumerate(zip(net.hidden_channels, net.hidden_blocks)):
             cfg.hidden_channels[i], cfg.hidden_blocks[i] = c, b
         cfg.attention_mask = sum(1 << l for l in net.attention_levels)
+        cfg.forcing_dim = int(getattr(net, "forcing_dim", 0))
         self.frame_channels, self.window, self.height, self.width = frame_channels, window, height, width
         self.handle = ctypes.c_void_p()
         with torch.cuda.device(self.device):
@@ -144,6 +147,13 @@ class Engine:
             _lib.check(self.lib.c2w_unet_forward(self.handle, x.data_ptr(), x.shape[0], float(t), out.data_ptr(),
                                                  self.stream), "c2w_unet_forward")
         return out
+
+    def set_forcing(self, forcing: Optional[Tensor]) -> None:
+        """Forcing rows [n, forcing_dim] (device fp32) of the next per-sample forward / training calls, or None."""
+        self._forcing_keepalive = forcing
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.c2w_set_forcing(self.handle, forcing.data_ptr() if forcing is not None else None),
+                       "c2w_set_forcing")
 
     def unet_forward_t(self, x: Tensor, t: Tensor) -> Tensor:
         """x: fp32 NCHW [n, C*window, H, W]; t: fp32 [n] on self.device (one diffusion time per sample)."""
@@ -255,8 +265,6 @@ class ScoreUNet(nn.Module):
         ks = kernel_size if isinstance(kernel_size, int) else kernel_size[0]
         st = stride if isinstance(stride, int) else stride[0]
         unsupported = []
-        if forcing_dim != 0:
-            unsupported.append("forcing_dim != 0")
         if ks != 3 or st != 2 or spatial != 2:
             unsupported.append("kernel_size/stride/spatial other than 3/2/2")
         if padding_mode != "zeros":
@@ -273,11 +281,11 @@ class ScoreUNet(nn.Module):
         self.hidden_channels = [int(c) for c in hidden_channels]
         self.hidden_blocks = [int(b) for b in hidden_blocks]
         self.attention_levels = sorted(int(a) for a in attention_levels)
-        self.map_forcing = None
+        self.forcing_dim = int(forcing_dim)
         # Parameters are created by torch's own Conv/Linear initialisers in the reference's construction order, so
         # `torch.manual_seed(s); ScoreUNet(...)` yields the same weights as the reference module.
         for prefix, shape in _layer_specs(self.channels, self.embedding_dim, self.hidden_channels, self.hidden_blocks,
-                                          self.attention_levels, ks):
+                                          self.attention_levels, ks, self.forcing_dim):
             w = torch.empty(shape)
             nn.init.kaiming_uniform_(w, a=math.sqrt(5))
             bound = 1.0 / math.sqrt(w[0].numel())
@@ -320,9 +328,8 @@ class ScoreUNet(nn.Module):
             self.noise_features = NOISE_FEATURES
             self.hidden_channels, self.hidden_blocks = arch["hidden_channels"], arch["hidden_blocks"]
             self.attention_levels = arch["attention_levels"]
-            if getattr(self, "map_forcing", None) is not None:
-                raise NotImplementedError("snapshot has a forcing branch (forcing_dim != 0); not supported")
-            self.map_forcing = None
+            mf = self.state_dict().get("map_forcing.weight")
+            self.forcing_dim = int(mf.shape[1]) if mf is not None else 0
 
     # ---------------------------------------------------------------------------------------------- engines
     def _fingerprint(self) -> tuple:
@@ -366,8 +373,10 @@ class ScoreUNet(nn.Module):
     # ---------------------------------------------------------------------------------------------- forward
     def forward(self, x: Tensor, t: Tensor, forcing: Optional[Tensor] = None) -> Tensor:
         """model/score.py:59-70.  x: [B, channels, H, W] on a CUDA device; t: one diffusion time for the batch."""
-        if forcing is not None:
-            raise NotImplementedError("forcing is not supported (forcing_dim=0 in every reference config)")
+        fdim = int(getattr(self, "forcing_dim", 0))
+        assert (forcing is None) or fdim > 0  # model/score.py:60
+        if fdim > 0 and forcing is None:
+            raise ValueError("this ScoreUNet has a forcing branch (forcing_dim > 0): pass forcing=")
         if not x.is_cuda:
             raise _lib.C2WError("ScoreUNet.forward: input must live on a CUDA device (no CPU path); "
                                 "BatchedScoreFunction moves window batches for you")
@@ -376,20 +385,27 @@ class ScoreUNet(nn.Module):
         training = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if tt.numel() not in (1, B):
             raise ValueError(f"t has {tt.numel()} entries for a batch of {B}")
-        if not training and tt.numel() != 1 and not bool((tt == tt[0]).all()):
+        f_dev = None
+        if forcing is not None:  # [B, forcing_dim] (a single row is broadcast like the reference's emb + Linear(forcing))
+            f_dev = torch.as_tensor(forcing, dtype=torch.float32).reshape(-1, fdim).to(x.device)
+            f_dev = (f_dev if f_dev.shape[0] == B else f_dev.expand(B, fdim)).contiguous()
+        if not training and (f_dev is not None or (tt.numel() != 1 and not bool((tt == tt[0]).all()))):
             # one diffusion time per sample (model/score.py:61; the DSM objective, src/thor/pipelines.py:27-35)
             if torch.is_grad_enabled() and x.requires_grad:
                 raise NotImplementedError("input gradients with per-sample diffusion times need trainable parameters "
                                           "(the training workspace); freeze nothing or use one diffusion time")
             eng = self.engine(Cc, 1, H, W, x.device, per_sample_t=True)
-            out = eng.unet_forward_t(x.detach().float().contiguous(), tt.to(x.device).contiguous())
+            eng.set_forcing(f_dev)
+            t_all = (tt if tt.numel() == B else tt.expand(B)).to(x.device).contiguous()
+            out = eng.unet_forward_t(x.detach().float().contiguous(), t_all)
+            eng.set_forcing(None)
             return out.to(x.dtype).reshape(x.shape)
         B, Cc, H, W = x.shape
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             # training (training_loop.py:372-378): forward with stashing now, all parameter gradients in backward
             t_dev = (tt if tt.numel() == B else tt.expand(B)).to(device=x.device, dtype=torch.float32).contiguous()
             params = [p for p in self.parameters()]
-            return _UNetTrainFn.apply(x, t_dev, self, *params)
+            return _UNetTrainFn.apply(x, t_dev, self, f_dev, *params)
         if torch.is_grad_enabled() and x.requires_grad:
             # input gradients only (the weights are frozen in sampling, training_loop.py:257)
             return _UNetInputVJP.apply(x, self, float(tt[0]))
@@ -406,11 +422,12 @@ class _UNetTrainFn(torch.autograd.Function):
     accumulation, DDP hooks and any torch optimiser work unchanged."""
 
     @staticmethod
-    def forward(ctx, x, t_dev, net, *params):
+    def forward(ctx, x, t_dev, net, forcing, *params):
         B, Cc, H, W = x.shape
         eng = net.engine(Cc, 1, H, W, x.device, train=True)
         if eng.max_windows < B:
             eng.bind(B)
+        eng.set_forcing(forcing)  # stays set until this step's backward (map_forcing's gradients need the rows)
         out = eng.train_forward(x.detach().float().contiguous(), t_dev)
         token = object()
         eng._train_token = token
@@ -432,7 +449,8 @@ class _UNetTrainFn(torch.autograd.Function):
             o, n = eng.layout[name]
             grads.append(flat[o:o + n].view_as(p) if need else None)
         eng._train_token = None
-        return (gin.to(ctx.dtype) if gin is not None else None, None, None, *grads)
+        eng.set_forcing(None)
+        return (gin.to(ctx.dtype) if gin is not None else None, None, None, None, *grads)
 
 
 class _UNetInputVJP(torch.autograd.Function):
@@ -473,8 +491,11 @@ def _arch_from_state_dict(sd) -> dict:
             blocks.append(len(idxs) // 2)
         else:
             blocks.append(len(idxs))
-    return dict(channels=int(sd["unet.heads.0.weight"].shape[1]), embedding_dim=int(sd["map_layer1.weight"].shape[0]),
-                hidden_channels=ch, hidden_blocks=blocks, attention_levels=attn)
+    out = dict(channels=int(sd["unet.heads.0.weight"].shape[1]), embedding_dim=int(sd["map_layer1.weight"].shape[0]),
+               hidden_channels=ch, hidden_blocks=blocks, attention_levels=attn)
+    if "map_forcing.weight" in sd:
+        out["forcing_dim"] = int(sd["map_forcing.weight"].shape[1])
+    return out
 
 
 def _validate_reference_tree(module: nn.Module) -> None:
@@ -488,8 +509,6 @@ def _validate_reference_tree(module: nn.Module) -> None:
         pm = getattr(m, "padding_mode", None)
         if pm is not None and pm != "zeros":
             raise NotImplementedError(f"{name} has padding_mode={pm!r}: only zero padding is built")
-    if getattr(module, "map_forcing", None) is not None:
-        raise NotImplementedError("the network has a forcing branch (forcing_dim != 0); not supported")
 
 
 def build_from_reference(module: nn.Module) -> ScoreUNet:

@@ -37,6 +37,7 @@ typedef struct c2w_config {
   int32_t hidden_channels[C2W_MAX_LEVELS]; /* configs/sda_unet.yml:8-13                                     */
   int32_t hidden_blocks[C2W_MAX_LEVELS];   /* configs/sda_unet.yml:2-7                                      */
   int32_t attention_mask;                  /* bit l set: AttentionBlock after every block of level l        */
+  int32_t forcing_dim;                     /* model/score.py:46-51: Linear(forcing_dim, embedding_dim); 0 = none */
 } c2w_config;
 
 typedef struct c2w_handle c2w_handle;
@@ -98,6 +99,11 @@ int c2w_unet_forward(c2w_handle* h, const float* x_nchw, int32_t n, float t, flo
 /* One diffusion time per sample, t_dev: DEVICE array of n floats (the DSM objective draws t ~ U[0,1) per sample,
  * src/thor/pipelines.py:27-35; model/score.py:61 reshapes t to [B]).  Needs a C2W_WS_PER_SAMPLE_T workspace. */
 int c2w_unet_forward_t(c2w_handle* h, const float* x_nchw, int32_t n, const float* t_dev, float* out_nchw, void* stream);
+
+/* Forcing vectors of the NEXT per-sample forward / training calls (model/score.py:63-66: emb += map_forcing(forcing)):
+ * DEVICE fp32 [n, forcing_dim], one row per sample; NULL clears it.  Needs forcing_dim > 0 and a per-sample workspace
+ * (C2W_WS_PER_SAMPLE_T or C2W_WS_TRAIN); the training backward also delivers map_forcing's gradients. */
+int c2w_set_forcing(c2w_handle* h, const float* forcing_dev);
 
 /* Vector-Jacobian product of ScoreUNet.forward w.r.t. x (what torch.func.jacrev / autograd computes through the UNet
  * when condition_on(exact_grad=True), src/thor/score.py:28-33,51-52): gin = (d out / d x)^T gout.  n <= max_windows

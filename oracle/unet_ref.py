@@ -42,6 +42,8 @@ def param_specs(cfg: dict) -> List[Tuple[str, str, Tuple[int, ...]]]:
     ks = cfg.get("kernel_size", 3)
     nl = len(blocks)
     out: List[Tuple[str, str, Tuple[int, ...]]] = []
+    if cfg.get("forcing_dim", 0) > 0:  # model/score.py:49-51: constructed before the UNet
+        out.append(("map_forcing", "linear", (emb, cfg["forcing_dim"])))
     for lvl in range(nl):
         rev = nl - 1 - lvl
         if lvl > 0:
@@ -99,11 +101,15 @@ def channel_layernorm(x: Tensor, dim: int = 1, eps: float = 1e-5) -> Tensor:
     return (x - mean) / torch.sqrt(var + eps)
 
 
-def time_modulation(sd: Dict[str, Tensor], t: Tensor) -> Tensor:
-    """model/score.py:61-67 with forcing_dim = 0."""
+def time_modulation(sd: Dict[str, Tensor], t: Tensor, forcing=None) -> Tensor:
+    """model/score.py:61-67: emb = silu(W1 silu(W0 e + b0) + b1 [+ Wf forcing + bf])."""
     e = timestep_embedding(t.reshape(-1))
     e = F.silu(F.linear(e, sd["map_layer0.weight"], sd["map_layer0.bias"]))
     e = F.linear(e, sd["map_layer1.weight"], sd["map_layer1.bias"])
+    if "map_forcing.weight" in sd:  # model/score.py:65-66 (asserted: forcing is None only without the branch, :60)
+        e = e + F.linear(forcing, sd["map_forcing.weight"], sd["map_forcing.bias"])
+    else:
+        assert forcing is None
     return F.silu(e)
 
 
@@ -142,9 +148,9 @@ def _level(sd, cfg, side: str, lvl: int, x: Tensor, emb: Tensor) -> Tensor:
     return x
 
 
-def score_unet_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor, t: Tensor) -> Tensor:
+def score_unet_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor, t: Tensor, forcing=None) -> Tensor:
     """ScoreUNet.forward (model/score.py:59-70) -> UNet.forward (model/nn.py:220-242)."""
-    emb = time_modulation(sd, t)
+    emb = time_modulation(sd, t, forcing)
     nl = len(cfg["hidden_blocks"])
     skips = []
     h = x
@@ -176,5 +182,5 @@ class RefNet:
     def eval(self):
         return self
 
-    def __call__(self, x: Tensor, t: Tensor) -> Tensor:
-        return score_unet_forward(self.sd, self.cfg, x, t)
+    def __call__(self, x: Tensor, t: Tensor, forcing=None) -> Tensor:
+        return score_unet_forward(self.sd, self.cfg, x, t, forcing)

@@ -161,3 +161,37 @@ def test_training_step_full_architecture_vs_oracle():
     print(f"\nfull architecture: loss {loss.item():.5f} (oracle {want_loss.item():.5f}); parameter gradients rel-L2 overall "
           f"{tot:.3e}, worst tensor {errs[worst]:.3e} ({worst})")
     assert tot < 3e-2 and errs[worst] < 8e-2
+
+
+def test_forcing_branch_forward_and_gradients(golden_dir):
+    """ScoreUNet(forcing_dim=3) (model/score.py:46-67: emb += map_forcing(forcing)): the per-sample forward and the
+    training step's gradients — map_forcing's included — against the REFERENCE's own outputs (tests/golden/forcing.npz)
+    and the fp32 oracle's autograd."""
+    import climate2weather_b200 as c2w
+    dev = torch.device("cuda:0")
+    g = np.load(golden_dir / "forcing.npz")
+    cfg = dict(SMALL, forcing_dim=3)
+    torch.manual_seed(3)
+    net = c2w.ScoreUNet(activation=torch.nn.SiLU, **cfg)
+    sd0 = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.to(dev)
+    x, t, f, eps = (torch.from_numpy(g[k]) for k in ("x", "t", "forcing", "eps"))
+    with torch.no_grad():
+        y = net(x.to(dev), t.to(dev), forcing=f.to(dev))
+    e = rel_l2(y, torch.from_numpy(g["out"]))
+    print(f"\nforcing forward rel-L2 vs reference: {e:.3e}")
+    assert e < 2e-2
+    with pytest.raises(ValueError):
+        net(x.to(dev), t.to(dev))  # a network with the branch needs forcing, like the reference's assert (model/score.py:60)
+    out = net(x.to(dev), t.to(dev), forcing=f.to(dev))
+    loss = ((out - eps.to(dev)) ** 2).mean()
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= 2e-3 * float(g["loss"])
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
+    o = unet_ref.score_unet_forward(sd, cfg, x, t, f)
+    want = dict(zip(sd, torch.autograd.grad(((o - eps) ** 2).mean(), list(sd.values()))))
+    worst = max((rel_l2(p.grad, want[n]), n) for n, p in net.named_parameters())
+    print(f"worst parameter-gradient rel-L2 (forcing net): {worst[0]:.3e} ({worst[1]})")
+    assert worst[0] < 5e-2
+    for k in ("map_forcing.weight", "map_forcing.bias"):
+        assert rel_l2(dict(net.named_parameters())[k].grad, torch.from_numpy(g["g::" + k])) < 3e-2, k

@@ -188,3 +188,25 @@ def test_full_fixture_consistency_and_bf16_yardstick(golden_dir):
             continue  # a run make_golden_full.py has not finished yet
         g = np.load(golden_dir / f"full_sample_{name}.npz")
         assert np.isfinite(g["final"]).all() and g["final"].shape == (FULL_L, 4, 32, 32)
+
+
+def test_forcing_branch_matches_reference(golden_dir):
+    """ScoreUNet with forcing_dim = 3 (model/score.py:46-67): the oracle's forward and autograd gradients against the
+    reference's own (tests/golden/make_golden_forcing.py)."""
+    g = np.load(golden_dir / "forcing.npz")
+    cfg = dict(SMALL, forcing_dim=3)
+    sd = unet_ref.init_state_dict(cfg, seed=3)
+    names = [str(n) for n in g["names"]]
+    assert sorted(sd) == sorted(names)
+    for n, s in zip(names, g["w_sum"]):
+        assert abs(sd[n].double().sum().item() - s) <= 1e-9 * max(1.0, sd[n].double().abs().sum().item()), n
+    for v in sd.values():
+        v.requires_grad_(True)
+    x, t, f, eps = (torch.from_numpy(g[k]) for k in ("x", "t", "forcing", "eps"))
+    out = unet_ref.score_unet_forward(sd, cfg, x, t, f)
+    assert close(out.detach().numpy(), g["out"], rel=5e-5)
+    loss = ((out - eps) ** 2).mean()
+    assert abs(loss.item() - float(g["loss"])) <= 2e-5 * float(g["loss"])
+    grads = dict(zip(sd, torch.autograd.grad(loss, list(sd.values()))))
+    for k in [k for k in g.files if k.startswith("g::")]:
+        assert close(grads[k[3:]].numpy(), g[k], rel=5e-4), k
