@@ -62,6 +62,8 @@ class Guide(C.Structure):
         ("nan_flag", C.c_void_p),
         ("vjp", C.c_void_p),
         ("cot_out", C.c_void_p),
+        ("halo", C.c_void_p),
+        ("halo_k", C.c_int32),
     ]
 
 
@@ -146,6 +148,9 @@ SIGNATURES = {
     "c2w_halo_handle": (_i, [_vp, _vp]),
     "c2w_halo_connect": (_i, [_vp, _vp, _vp]),
     "c2w_halo_exchange": (_i, [_vp, _vp, _i64, _i64, C.c_int32, _vp]),
+    "c2w_halo_pull": (_i, [_vp, _vp, _i64, _i64, C.c_int32, _vp]),
+    "c2w_halo_push_targets": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
+                                   C.POINTER(C.c_uint32)]),
     "c2w_launch_count": (_i64, []),
     "c2w_set_timing": (_i, [_vp, _i]),
     "c2w_timing_read": (_i, [_vp, _vp, _vp]),

@@ -1682,6 +1682,24 @@ int c2w_guided_step(const c2w_guide* g, void* stream) {
   p.nan_flag = g->nan_flag;
   p.vjp = g->vjp;
   p.cot_out = g->cot_out;
+  p.push_l = p.push_r = nullptr;
+  p.flag_l = p.flag_r = p.push_done = nullptr;
+  p.publish = 0;
+  p.halo_k = g->halo_k;
+  p.own_n = g->own_n;
+  if (g->halo != nullptr && g->mode == 0) {  // fused halo push (csrc/halo.cu)
+    C2W_REQUIRE(g->halo_k >= 1 && g->own_n >= g->halo_k, "c2w_guided_step: fused halo push needs 1 <= halo_k <= own_n");
+    void *sl, *sr, *fl, *fr, *dn;
+    uint32_t pub;
+    int rc = c2w_halo_push_targets(static_cast<c2w_halo*>(g->halo), &sl, &sr, &fl, &fr, &dn, &pub);
+    if (rc) return rc;
+    p.push_l = static_cast<float4*>(sl);
+    p.push_r = static_cast<float4*>(sr);
+    p.flag_l = static_cast<unsigned int*>(fl);
+    p.flag_r = static_cast<unsigned int*>(fr);
+    p.push_done = (sl || sr) ? static_cast<unsigned int*>(dn) : nullptr;
+    p.publish = pub;
+  }
   dim3 grid(g->H / g->s_step, g->own_n);
   guided_step_kernel<<<grid, 32 * (g->W / g->s_step), 0, static_cast<cudaStream_t>(stream)>>>(p);
   ++g_launches;

@@ -144,6 +144,43 @@ int c2w_halo_connect(c2w_halo* h, const void* left_handle64, const void* right_h
   return C2W_OK;
 }
 
+// Targets of a push FUSED into another kernel (c2w_guided_step with g->halo set): the neighbours' mailbox slots of the
+// current parity, their step counters, the CTA counter and the value to publish.  The caller then completes the exchange
+// with c2w_halo_pull, which also advances the step.
+int c2w_halo_push_targets(c2w_halo* h, void** slot_left, void** slot_right, void** flag_left, void** flag_right, void** done,
+                          uint32_t* publish) {
+  C2W_REQUIRE(h && slot_left && slot_right && flag_left && flag_right && done && publish, "c2w_halo_push_targets: bad argument");
+  const uint32_t par = h->step & 1u;
+  const bool has_l = h->peer_box[0] != nullptr, has_r = h->peer_box[1] != nullptr;
+  *slot_left = has_l ? h->peer_box[0] + (par * 2 + 1) * h->halo_bytes : nullptr;   // the left rank's "from the right" slot
+  *slot_right = has_r ? h->peer_box[1] + (par * 2 + 0) * h->halo_bytes : nullptr;  // the right rank's "from the left" slot
+  *flag_left = has_l ? h->peer_flags[0] + 1 : nullptr;
+  *flag_right = has_r ? h->peer_flags[1] + 0 : nullptr;
+  *done = h->done;
+  *publish = h->step + 1;
+  return C2W_OK;
+}
+
+// Second half of an exchange whose push was fused into the producing kernel: wait for the neighbours' counters, copy
+// the mailbox into the halo frames of x_local, advance the step.
+int c2w_halo_pull(c2w_halo* h, float* x_local, int64_t n_local_frames, int64_t frame_floats, int32_t k, void* stream) {
+  C2W_REQUIRE(h && x_local && k >= 1 && n_local_frames >= 3 * k, "c2w_halo_pull: bad argument");
+  const int64_t hb = static_cast<int64_t>(k) * frame_floats * 4;
+  C2W_REQUIRE(hb == h->halo_bytes, "c2w_halo_pull: %lld halo bytes, the mailbox was created for %lld", (long long)hb,
+              (long long)h->halo_bytes);
+  const bool has_l = h->peer_box[0] != nullptr, has_r = h->peer_box[1] != nullptr;
+  if (!has_l && !has_r) return C2W_OK;
+  const uint32_t par = h->step & 1u;
+  auto slot = [&](int side) { return reinterpret_cast<const float4*>(h->mailbox + (par * 2 + side) * hb); };
+  halo_pull_kernel<<<64, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      slot(0), has_l ? reinterpret_cast<float4*>(x_local) : nullptr, has_l ? h->flags + 0 : nullptr, slot(1),
+      has_r ? reinterpret_cast<float4*>(x_local + (n_local_frames - k) * frame_floats) : nullptr, has_r ? h->flags + 1 : nullptr,
+      hb / 16, h->step + 1);
+  C2W_CUDA(cudaGetLastError());
+  h->step += 1;
+  return C2W_OK;
+}
+
 // x_local: [n_local_frames][frame_floats] fp32 with k halo frames on every side that has a neighbour.
 int c2w_halo_exchange(c2w_halo* h, float* x_local, int64_t n_local_frames, int64_t frame_floats, int32_t k, void* stream) {
   C2W_REQUIRE(h && x_local && k >= 1 && n_local_frames >= 3 * k, "c2w_halo_exchange: bad argument");

@@ -1215,6 +1215,16 @@ struct GuideParams {
   int* nan_flag;
   const float* vjp;   // exact_grad: J_eps^T g per pixel (UNet vector-Jacobian product), null = closed-form guidance
   float* cot_out;     // mode 2: g = A^T((y - A x0) / var), the cotangent fed to the UNet VJP
+  // mode 0, time-sharded: the halo PUSH fused into the predictor update (K8, csrc/halo.cu) — the updated pixels of the
+  // first / last k owned frames are also stored into the left / right neighbour's mailbox over NVLink, and the last CTA
+  // publishes the step counter.  Null pointers: no neighbour on that side / not sharded.
+  float4* push_l;          // left neighbour's mailbox slot (receives local frames [own_lo, own_lo + halo_k))
+  float4* push_r;          // right neighbour's slot (receives local frames [own_lo + own_n - halo_k, own_lo + own_n))
+  unsigned int* flag_l;    // neighbours' step counters
+  unsigned int* flag_r;
+  unsigned int* push_done; // CTA counter (local)
+  unsigned int publish;    // value to publish: step + 1
+  int halo_k, own_n;
 };
 
 // CTA = one s-row strip of one frame; one warp per s x s observation tile (warp-shuffle tile mean, deterministic).
@@ -1292,6 +1302,13 @@ __global__ void guided_step_kernel(const GuideParams p) {
       xv.w = p.mu_next * ((xv.w - p.sigma * ev.w) * inv_mu) + p.sigma_next * ev.w;
       bad |= !(isfinite(xv.x) && isfinite(xv.y) && isfinite(xv.z) && isfinite(xv.w));
       *reinterpret_cast<float4*>(p.x + o) = xv;
+      // boundary frames also go straight into the neighbours' halo mailboxes (peer stores through NVLink)
+      const long long pix_in_frame = static_cast<long long>(h0 + i / s) * p.W + (w0 + i % s);
+      const long long hw = static_cast<long long>(p.H) * p.W;
+      const int own_idx = static_cast<int>(blockIdx.y);
+      if (p.push_l != nullptr && own_idx < p.halo_k) p.push_l[own_idx * hw + pix_in_frame] = xv;
+      if (p.push_r != nullptr && own_idx >= p.own_n - p.halo_k)
+        p.push_r[(own_idx - (p.own_n - p.halo_k)) * hw + pix_in_frame] = xv;
     } else {
       sq += ev.x * ev.x + ev.y * ev.y + ev.z * ev.z + ev.w * ev.w;
       *reinterpret_cast<float4*>(p.eps_out + o) = ev;
@@ -1299,6 +1316,19 @@ __global__ void guided_step_kernel(const GuideParams p) {
   }
   if (p.mode == 0) {
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(p.nan_flag, 1);
+    if (p.push_done != nullptr) {  // fused halo push: fence this CTA's peer stores, the last CTA publishes the step
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned int total = gridDim.x * gridDim.y;
+        if (atomicAdd(p.push_done, 1u) == total - 1) {
+          *p.push_done = 0;
+          __threadfence_system();
+          if (p.flag_l) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flag_l), "r"(p.publish) : "memory");
+          if (p.flag_r) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flag_r), "r"(p.publish) : "memory");
+        }
+      }
+    }
   } else {
     __shared__ float wsum[32];
     sq = warp_sum(sq);

@@ -97,6 +97,7 @@ class _Runtime:
         self.s_tile = next(s for s in (16, 8, 32, 4, 64, 2, 128, 1) if H % s == 0 and W % s == 0 and W // s <= 32)
         self._peer_halo: Optional[PeerHalo] = None
         self._peer_halo_ok = True
+        self._halo_pushed = False  # the last update kernel already stored the boundary frames into the neighbours' mailboxes
 
     # ------------------------------------------------------------------------------------------------ engine
     def refresh_engine(self) -> None:
@@ -188,6 +189,12 @@ class _Runtime:
         g.nan_flag = self.nan_flag.data_ptr()
         g.vjp = self.vjp.data_ptr() if (self.exact and self.cond is not None and mode != 2) else None
         g.cot_out = self.cot.data_ptr() if mode == 2 else None
+        g.halo, g.halo_k = None, self.sf.markov_order
+        if mode == 0 and frames is None and p.world > 1:  # predictor update of the owned frames: fuse the halo push
+            ph = self._ensure_peer_halo()
+            if ph is not None:
+                g.halo = ph.handle
+                self._halo_pushed = True
         if mode == 1:
             n_part = p.own_n * (self.H // s)
             if self.partials is None or self.partials.numel() < n_part:
@@ -243,21 +250,34 @@ class _Runtime:
                 float(self.L * self.C * hw), float(tau), float(sigma_next), p.own_lo * hw, p.own_n * hw, int(seed),
                 int(step_id), self.nan_flag.data_ptr(), self.stream), "c2w_corrector_update")
 
-    def halo(self, group=None) -> None:
-        """Refresh the k halo frames of x from the neighbours (after every state update).  Over NVLink peer memory
-        (c2w_halo_exchange) when the ranks' GPUs can map each other; torch.distributed send/recv pairs otherwise."""
+    def _ensure_peer_halo(self) -> Optional[PeerHalo]:
+        """The peer-memory mailboxes (set up collectively on first use by every rank at the same point)."""
         if self.plan.world == 1:
-            return
+            return None
         if self._peer_halo is None and self._peer_halo_ok and halo_transport() != "nccl":
+            group = self.sf.shard[2] if self.sf.shard else None
             try:
                 self._peer_halo = PeerHalo(self.plan, self.x.shape[1:], self.device, group)
             except _lib.C2WError as e:  # no peer access between neighbours: say so once, use NCCL
                 print(f"climate2weather_b200: peer-memory halo exchange unavailable ({e}); using NCCL send/recv")
                 self._peer_halo_ok = False
-        if self._peer_halo is not None:
-            self._peer_halo.exchange(self.x)
-        else:
+        return self._peer_halo
+
+    def halo(self, group=None) -> None:
+        """Refresh the k halo frames of x from the neighbours (after every state update).  Over NVLink peer memory when
+        the ranks' GPUs can map each other — the push half already happened inside the predictor kernel when that was
+        the update (c2w_guided_step with g.halo), so only the pull remains; after a corrector update both halves run
+        (c2w_halo_exchange).  torch.distributed send/recv pairs otherwise."""
+        if self.plan.world == 1:
+            return
+        ph = self._ensure_peer_halo()
+        if ph is None:
             exchange_halos(self.x, self.plan, group)
+        elif self._halo_pushed:
+            ph.pull(self.x)
+        else:
+            ph.exchange(self.x)
+        self._halo_pushed = False
 
     def check_finite(self) -> None:
         if int(self.nan_flag.item()) != 0:

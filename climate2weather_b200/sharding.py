@@ -193,6 +193,16 @@ class PeerHalo:
             _lib.check(self.lib.c2w_halo_exchange(self.handle, x_local.data_ptr(), self.plan.n_local, self.frame_floats,
                                                   self.plan.k, st), "c2w_halo_exchange")
 
+    def pull(self, x_local: torch.Tensor) -> None:
+        """Second half of an exchange whose push was fused into the kernel that updated x (c2w_guided_step)."""
+        from . import _lib
+
+        assert x_local.is_contiguous() and x_local.dtype == torch.float32 and x_local.shape[0] == self.plan.n_local
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(self.lib.c2w_halo_pull(self.handle, x_local.data_ptr(), self.plan.n_local, self.frame_floats,
+                                              self.plan.k, st), "c2w_halo_pull")
+
     def __del__(self):
         try:
             if getattr(self, "handle", None) and self.handle.value:

@@ -65,6 +65,10 @@ typedef struct c2w_guide {
   const float* vjp;      /* exact_grad=True: J_eps^T g from c2w_window_score_backward (src/thor/score.py:28-35,
                             48-60 with grad enabled); NULL = closed-form guidance (exact_grad=False)        */
   float* cot_out;        /* mode 2 output, [frames_local, H, W, 4]                                         */
+  void* halo;            /* c2w_halo* or NULL.  mode 0, time-sharded: the halo PUSH is fused into this kernel — the
+                            updated pixels of the first / last k owned frames are also stored into the neighbours'
+                            mailboxes over NVLink and the last CTA publishes the step; complete with c2w_halo_pull  */
+  int32_t halo_k;        /* Markov order k (frames per side)                                                       */
 } c2w_guide;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------ */
@@ -269,6 +273,12 @@ void c2w_halo_destroy(c2w_halo* h);
 int c2w_halo_handle(c2w_halo* h, void* out64);
 int c2w_halo_connect(c2w_halo* h, const void* left_handle64, const void* right_handle64);
 int c2w_halo_exchange(c2w_halo* h, float* x_local, int64_t n_local_frames, int64_t frame_floats, int32_t k, void* stream);
+/* Fused form: c2w_guided_step(mode 0) with g->halo set does the push inside the predictor kernel; c2w_halo_pull is the
+ * second half (wait for the neighbours' counters, copy the mailbox into the halo frames, advance the step).
+ * c2w_halo_push_targets exposes the current slots / counters for a caller fusing the push into a kernel of its own. */
+int c2w_halo_pull(c2w_halo* h, float* x_local, int64_t n_local_frames, int64_t frame_floats, int32_t k, void* stream);
+int c2w_halo_push_targets(c2w_halo* h, void** slot_left, void** slot_right, void** flag_left, void** flag_right, void** done,
+                          uint32_t* publish);
 
 /* ---- measurement hooks (bench.py): kernel launches issued by this library so far; optional CUDA-event timing of
  * every forward-pass launch on its own stream, summed per class: [0] K1 conv/GEMM (tensor cores), [1] the rest --- */
