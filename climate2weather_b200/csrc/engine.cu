@@ -128,6 +128,7 @@ struct c2w_handle {
   std::vector<void*> allocs;
   float *map0_w = nullptr, *map0_b = nullptr, *map1_w = nullptr, *map1_b = nullptr;
   float *proj_w = nullptr, *proj_b = nullptr;
+  long long *row_w = nullptr, *row_b = nullptr;  // per modulation channel: where its project.weight row / bias lives in the flat gradient
   float *mapf_w = nullptr, *mapf_b = nullptr;  // forcing branch: [E, forcing_pad] (columns zero-padded to 4), [E]
   int forcing_pad = 0;
   const float* forcing = nullptr;  // c2w_set_forcing: device [n, forcing_dim] for the next per-sample forwards
@@ -1159,6 +1160,18 @@ int c2w_finalize_weights(c2w_handle* h) {
     if ((rc = dev_upload(h, z.data(), z.size() * sizeof(float), reinterpret_cast<void**>(&h->zero_bias)))) return rc;
   }
   h->total_mod = static_cast<int>(proj_b.size());
+  if (h->total_mod > 0) {
+    std::vector<long long> row_w(h->total_mod, -1), row_b(h->total_mod, -1);
+    for (LevelW& L : h->levels)
+      for (std::vector<BlockW>* side : {&L.desc, &L.asc})
+        for (BlockW& bw : *side)
+          for (int cidx = 0; cidx < L.C; ++cidx) {
+            if (bw.g_pw >= 0) row_w[bw.mod_off + cidx] = bw.g_pw + static_cast<long long>(cidx) * E;
+            if (bw.g_pb >= 0) row_b[bw.mod_off + cidx] = bw.g_pb + cidx;
+          }
+    if ((rc = dev_upload(h, row_w.data(), row_w.size() * sizeof(long long), reinterpret_cast<void**>(&h->row_w)))) return rc;
+    if ((rc = dev_upload(h, row_b.data(), row_b.size() * sizeof(long long), reinterpret_cast<void**>(&h->row_b)))) return rc;
+  }
   if ((rc = dev_upload(h, proj_w.data(), proj_w.size() * sizeof(float), reinterpret_cast<void**>(&h->proj_w)))) return rc;
   if ((rc = dev_upload(h, proj_b.data(), proj_b.size() * sizeof(float), reinterpret_cast<void**>(&h->proj_b)))) return rc;
   h->raw.clear();
@@ -1510,17 +1523,13 @@ int c2w_train_backward(c2w_handle* h, const float* gout_nchw, int32_t n, float* 
   };
   auto blocks1d = [](long long items) { return static_cast<int>((items + 255) / 256); };
   if (TM > 0) {
-    for (LevelW& L : h->levels)
-      for (std::vector<BlockW>* side : {&L.desc, &L.asc})
-        for (BlockW& bw : *side) {
-          if (bw.g_pw >= 0)  // dW_p[c][e] += sum_s dmod[s][c] emb[s][e]
-            gemm_tn_f32_kernel<<<blocks1d(static_cast<long long>(L.C) * E), 256, 0, st>>>(
-                P.dmods + bw.mod_off, TM, P.emb, E, grad_flat + bw.g_pw, E, n, L.C, E, 1);
-          if (bw.g_pb >= 0)
-            colsum_f32_kernel<<<blocks1d(L.C), 256, 0, st>>>(P.dmods + bw.mod_off, TM, grad_flat + bw.g_pb, n, L.C, 1);
-        }
+    // all 30 project Linears in one launch: dW_p[c][e] += sum_s dmod[s][c] emb[s][e], db_p[c] += sum_s dmod[s][c]
+    proj_grad_kernel<<<blocks1d(static_cast<long long>(TM) * E), 256, 0, st>>>(P.dmods, TM, P.emb, E, n, grad_flat, h->row_w,
+                                                                              h->row_b);
     // d emb = dmods . W_proj  ([n, TM] x [TM, E]);  emb = silu(pre1), pre1 = W1 h0 + b1;  h0 = silu(pre0), pre0 = W0 feat + b0
-    gemm_nn_f32_kernel<<<blocks1d(static_cast<long long>(n) * E), 256, 0, st>>>(P.dmods, TM, h->proj_w, E, P.demb, E, n, TM, E);
+    C2W_CUDA(cudaMemsetAsync(P.demb, 0, static_cast<size_t>(n) * E * sizeof(float), st));
+    gemm_nn_f32_kernel<<<dim3(blocks1d(static_cast<long long>(n) * E), 32), 256, 0, st>>>(P.dmods, TM, h->proj_w, E, P.demb, E,
+                                                                                         n, TM, E);
     matvec_kernel<<<dim3(ceil_div(static_cast<long long>(E) * 32, 256), n), 256, 0, st>>>(
         h->map1_w, h->map1_b, P.h0, P.pre1, E, E, 0, (h->forcing != nullptr && h->forcing_pad > 0) ? P.fvec : nullptr);
     dsilu_f32_kernel<<<blocks1d(static_cast<long long>(n) * E), 256, 0, st>>>(P.demb, P.pre1, static_cast<long long>(n) * E);

@@ -853,15 +853,38 @@ __global__ void gemm_tn_f32_kernel(const float* __restrict__ A, int lda, const f
   float* d = Cm + static_cast<size_t>(m) * ldc + n;
   *d = accumulate ? *d + acc : acc;
 }
-//   C[m][n] = sum_k A[m][k] * B[k][n]           (d input = dpre . W)
+//   C[m][n] (+)= sum_k A[m][k] * B[k][n]          (d input = dpre . W); gridDim.y > 1 splits K and adds atomically
+//   into a ZEROED C (the long reduction over all modulation channels would otherwise run on 64 K threads only)
 __global__ void gemm_nn_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                                    float* __restrict__ Cm, int ldc, int M, int K, int N) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long long>(M) * N) return;
   const int m = static_cast<int>(i / N), n = static_cast<int>(i - static_cast<long long>(m) * N);
+  const int kper = (K + gridDim.y - 1) / gridDim.y;
+  const int k0 = blockIdx.y * kper, k1 = (k0 + kper < K) ? k0 + kper : K;
   float acc = 0.f;
-  for (int k = 0; k < K; ++k) acc = fmaf(A[static_cast<size_t>(m) * lda + k], B[static_cast<size_t>(k) * ldb + n], acc);
-  Cm[static_cast<size_t>(m) * ldc + n] = acc;
+  for (int k = k0; k < k1; ++k) acc = fmaf(A[static_cast<size_t>(m) * lda + k], B[static_cast<size_t>(k) * ldb + n], acc);
+  float* d = Cm + static_cast<size_t>(m) * ldc + n;
+  if (gridDim.y > 1) atomicAdd(d, acc);
+  else *d = acc;
+}
+// All modulation projections at once (model/nn.py:149, 30 Linear layers): row m of dmods^T . emb is one output channel
+// of one block's `project` weight and goes to its own place in the flat gradient buffer:
+//   grad[row_w[m] + e] += sum_s dmods[s][m] * emb[s][e]      grad[row_b[m]] += sum_s dmods[s][m]
+__global__ void proj_grad_kernel(const float* __restrict__ dmods, int TM, const float* __restrict__ emb, int E, int ns,
+                                 float* __restrict__ grad, const long long* __restrict__ row_w,
+                                 const long long* __restrict__ row_b) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(TM) * E) return;
+  const int m = static_cast<int>(i / E), e = static_cast<int>(i - static_cast<long long>(m) * E);
+  float acc = 0.f, bsum = 0.f;
+  for (int sidx = 0; sidx < ns; ++sidx) {
+    const float d = dmods[static_cast<size_t>(sidx) * TM + m];
+    acc = fmaf(d, emb[static_cast<size_t>(sidx) * E + e], acc);
+    bsum += d;
+  }
+  if (row_w[m] >= 0) grad[row_w[m] + e] += acc;
+  if (e == 0 && row_b[m] >= 0) grad[row_b[m]] += bsum;
 }
 //   out[m] (+)= sum_k A[k][m]                    (bias gradients)
 __global__ void colsum_f32_kernel(const float* __restrict__ A, int lda, float* __restrict__ out, int K, int M, int accumulate) {
