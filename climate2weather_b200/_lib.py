@@ -152,6 +152,7 @@ SIGNATURES = {
     "c2w_halo_push_targets": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
                                    C.POINTER(C.c_uint32)]),
     "c2w_launch_count": (_i64, []),
+    "c2w_set_timeline": (_i, [_vp, _vp, _i]),
     "c2w_set_timing": (_i, [_vp, _i]),
     "c2w_timing_read": (_i, [_vp, _vp, _vp]),
 }

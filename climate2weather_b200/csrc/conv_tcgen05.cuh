@@ -105,6 +105,8 @@ struct ConvParams {
   int win_first;    // global index of the first window of this launch
   int win_last_global;  // global index of the last window of the trajectory (Nw - 1)
   int frame_base;   // global frame index of eps[0]
+  long long* dbg_timeline;  // diagnostics only (-DC2W_DIAG): [2] = {min over CTAs of the start, max of the end} in
+                            // %globaltimer ns for THIS launch (tools/timeline.py: kernel-inside time vs gaps)
   long long* dbg_stats;  // diagnostics only: per-CTA wait cycles [grid][12] (see tools/bringup_conv.py --stats)
   int dbg_skip_loads;  // diagnostics only: after the ring is primed, signal `full` without issuing TMA loads
 };
@@ -393,6 +395,13 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   // (No-ops when the kernel was launched without the programmatic-serialization attribute.)
   griddep_launch_dependents();
   griddep_wait();
+#ifdef C2W_DIAG
+  if (p.dbg_timeline != nullptr && threadIdx.x == 0) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    atomicMin(reinterpret_cast<unsigned long long*>(p.dbg_timeline), now);
+  }
+#endif
 
   // Producer and MMA warps run CONVERGED (all 32 lanes wait on the barriers) and issue under elect_one():
   // operands stay warp-uniform, so ptxas keeps descriptors/coordinates in uniform registers instead of wrapping
@@ -965,6 +974,13 @@ conv_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   tc_fence_before();
   if (CG == 2) cluster_sync_all();  // the leader's MMAs read the peer's shared memory until the last commit
   else __syncthreads();
+#ifdef C2W_DIAG
+  if (p.dbg_timeline != nullptr && threadIdx.x == 0) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    atomicMax(reinterpret_cast<unsigned long long*>(p.dbg_timeline) + 1, now);
+  }
+#endif
   if (warp_idx == 2) {
     tc_fence_after();
     if (CG == 2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);

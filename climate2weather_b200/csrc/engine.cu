@@ -143,6 +143,8 @@ struct c2w_handle {
   bool fuse_dual = true;   // C2W_NO_FUSE_DUAL=1: stashing forward with a separate SiLU pass after conv1
   std::vector<TimedSpan> spans;
   size_t spans_used = 0;
+  long long* timeline = nullptr;  // diagnostics build: device [capacity][2] start / end of every K1 launch (c2w_set_timeline)
+  int timeline_cap = 0, timeline_used = 0;
 };
 
 namespace {
@@ -928,6 +930,9 @@ int run_ops(c2w_handle* h, std::vector<Op>& ops, int nn, const FinalSpec& fs, cu
           L.p.win_last_global = fs.win_last_global;
           L.p.frame_base = fs.frame_base;
         }
+#ifdef C2W_DIAG
+        if (h->timeline != nullptr && h->timeline_used < h->timeline_cap) L.p.dbg_timeline = h->timeline + 2 * h->timeline_used++;
+#endif
         {
           SpanGuard sg(h, 0, st);
           C2W_CUDA(conv_launch(L, st));
@@ -1206,6 +1211,24 @@ int c2w_timing_read(c2w_handle* h, double* ms, int64_t* n) {
   }
   h->spans_used = 0;
   return C2W_OK;
+}
+
+// Diagnostics (-DC2W_DIAG build only): every following K1 launch of this handle writes {first CTA start, last CTA end}
+// (%globaltimer, ns) into buf_dev[launch][2]; initialise starts to LLONG_MAX and ends to 0.  Returns the number of slots
+// used so far when buf_dev is NULL.
+int c2w_set_timeline(c2w_handle* h, long long* buf_dev, int capacity) {
+  C2W_REQUIRE(h, "c2w_set_timeline: null handle");
+#ifdef C2W_DIAG
+  if (buf_dev == nullptr) return h->timeline_used;
+  h->timeline = buf_dev;
+  h->timeline_cap = capacity;
+  h->timeline_used = 0;
+  return C2W_OK;
+#else
+  (void)buf_dev;
+  (void)capacity;
+  return fail(C2W_ERR_STATE, "c2w_set_timeline needs the diagnostics build (python -m climate2weather_b200.build --diag)");
+#endif
 }
 
 int64_t c2w_workspace_bytes_ex(c2w_handle* h, int32_t max_windows, int32_t flags) {

@@ -283,6 +283,9 @@ int c2w_halo_push_targets(c2w_halo* h, void** slot_left, void** slot_right, void
 /* ---- measurement hooks (bench.py): kernel launches issued by this library so far; optional CUDA-event timing of
  * every forward-pass launch on its own stream, summed per class: [0] K1 conv/GEMM (tensor cores), [1] the rest --- */
 int64_t c2w_launch_count(void);
+/* Diagnostics build (-DC2W_DIAG, libc2w_b200_diag.so) only: per-launch {start, end} %globaltimer stamps of K1
+ * (tools/timeline.py: time inside the kernels vs the gaps between them); an error in the shipped library. */
+int c2w_set_timeline(c2w_handle* h, long long* buf_dev, int capacity);
 int c2w_set_timing(c2w_handle* h, int enable);
 int c2w_timing_read(c2w_handle* h, double* ms, int64_t* n);
 
