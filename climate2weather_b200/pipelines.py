@@ -22,7 +22,8 @@ from .sharding import all_gather_frames, gather_frames
 
 class SDAPipeline:
     #: corrector noise: "device" = on-chip Philox keyed by the global pixel index (default, sharding-invariant);
-    #: "reference" = z.normal_() from the global CPU generator exactly like src/thor/pipelines.py:82 (parity runs).
+    #: "reference" = z.normal_() on a HOST tensor from the global CPU generator — what src/thor/pipelines.py:82 does when
+    #: sample() runs on its default device (CPU, :59-60; the shipped driver calls it that way) — then uploaded (parity runs).
     rng: str = "device"
     #: read the device NaN flag every this many steps (0 = only at the end); the reference syncs every step (:90).
     #: The per-step read is asynchronous and inspected one check later, so a NaN raises one step after it appeared.
