@@ -473,7 +473,7 @@ def run_train(args):
     pipe = c2w.SDAPipeline()
     # default for N > 1: one in-place NCCL all-reduce of the flat gradient buffer inside optimizer.step()
     opt = optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-3, betas=(0.9, 0.999),  # train.py:176-181
-                      data_parallel_group=(None if (world > 1 and not use_ddp) else "none"))
+                      data_parallel_group=(None if (world > 1 and not use_ddp) else "none"), direct_grads=not use_ddp)
     if world > 1 and not use_ddp:
         opt.broadcast_parameters(0)
     ema = optim.StandardEMA(net, rates=[0.9999])

@@ -256,24 +256,27 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
 }
 
 // dw[co][ci][tap] (fp32 OIHW / OI1, real Cout x Cin) (+)= sum over splits of partial[split][tap][co][ci]
+// One thread per (tap, co, ci): consecutive threads read consecutive ci of one slab row (coalesced), the 36-byte-strided
+// writes into the OIHW tensor are the small side.  Threads of tap 0 with ci == 0 also finish the bias gradient.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int taps,
                                     int cout, int cin, int cout_slab, int cin_slab, int accumulate, float scale,
                                     const float* __restrict__ bias_partial, float* __restrict__ db) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (db != nullptr && i < cout) {  // bias gradient: sum of the per-split column sums, fixed order
-    float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += bias_partial[static_cast<size_t>(s) * cout_slab + i];
-    db[i] = accumulate ? db[i] + acc * scale : acc * scale;
-  }
-  if (i >= static_cast<long long>(cout) * cin) return;
-  const int co = static_cast<int>(i / cin), ci = static_cast<int>(i - static_cast<long long>(co) * cin);
+  const long long per_tap = static_cast<long long>(cout) * cin;
+  if (i >= per_tap * taps) return;
+  const int t = static_cast<int>(i / per_tap);
+  const long long r = i - t * per_tap;
+  const int co = static_cast<int>(r / cin), ci = static_cast<int>(r - static_cast<long long>(co) * cin);
   const size_t slab = static_cast<size_t>(cout_slab) * cin_slab;
-  for (int t = 0; t < taps; ++t) {
-    float acc = 0.f;
-    const float* src = partial + static_cast<size_t>(t) * slab + static_cast<size_t>(co) * cin_slab + ci;
-    for (int s = 0; s < splits; ++s) acc += src[static_cast<size_t>(s) * taps * slab];
-    float* d = dw + (static_cast<size_t>(co) * cin + ci) * taps + t;
-    *d = accumulate ? *d + acc * scale : acc * scale;
+  const float* src = partial + static_cast<size_t>(t) * slab + static_cast<size_t>(co) * cin_slab + ci;
+  float acc = 0.f;
+  for (int s = 0; s < splits; ++s) acc += src[static_cast<size_t>(s) * taps * slab];
+  float* d = dw + (static_cast<size_t>(co) * cin + ci) * taps + t;
+  *d = accumulate ? *d + acc * scale : acc * scale;
+  if (db != nullptr && t == 0 && ci == 0) {  // bias gradient: sum of the per-split column sums, fixed order
+    float b = 0.f;
+    for (int s = 0; s < splits; ++s) b += bias_partial[static_cast<size_t>(s) * cout_slab + co];
+    db[co] = accumulate ? db[co] + b * scale : b * scale;
   }
 }
 
@@ -423,7 +426,7 @@ inline cudaError_t wgrad_run(const WgradLaunch& L0, float* dw, int cout, int cin
   L.p.bias_partial = db ? L.p.partial + slab_floats : nullptr;
   cudaError_t e = L.bn == 128 ? wgrad_launch_bn<128>(L, stream) : wgrad_launch_bn<64>(L, stream);
   if (e != cudaSuccess) return e;
-  const long long items = static_cast<long long>(cout) * cin;
+  const long long items = static_cast<long long>(cout) * cin * L.p.taps;
   wgrad_reduce_kernel<<<static_cast<int>((items + 255) / 256), 256, 0, stream>>>(
       L.p.partial, dw, L.p.splits, L.p.taps, cout, cin, L.p.cout_slab, L.p.cin_slab, accumulate, scale, L.p.bias_partial, db);
   return cudaGetLastError();

@@ -311,6 +311,7 @@ class ScoreUNet(nn.Module):
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_engines"] = {}  # device handles are rebuilt lazily after unpickling / deepcopy
+        state["_direct_grad"] = None  # an optimiser's buffer: never shared with copies (EMA) or pickled
         return state
 
     def __setstate__(self, state):
@@ -442,6 +443,14 @@ class _UNetTrainFn(torch.autograd.Function):
         if eng._train_token is not ctx.token:
             raise RuntimeError("another forward ran on this network's training workspace before this backward(): the "
                                "stashed activations are gone (one forward -> one backward per accumulation round)")
+        direct = getattr(ctx.net, "_direct_grad", None)
+        if direct is not None and direct.numel() == eng.param_total and direct.device == gout.device:
+            # the optimiser's flat gradient buffer has the library's layout (optim.AdamW(direct_grads=True)): the kernels
+            # ACCUMULATE into it in place and autograd gets nothing to add (no per-parameter hooks fire on this route)
+            gin = eng.train_backward(gout.detach().float().contiguous(), direct, want_gin=ctx.want_gin, accumulate=True)
+            eng._train_token = None
+            eng.set_forcing(None)
+            return (gin.to(ctx.dtype) if gin is not None else None, None, None, None, *([None] * ctx.n_params))
         flat = torch.empty(eng.param_total, dtype=torch.float32, device=gout.device)
         gin = eng.train_backward(gout.detach().float().contiguous(), flat, want_gin=ctx.want_gin)
         grads = []

@@ -36,7 +36,8 @@ class AdamW:
     """torch.optim.AdamW (decoupled weight decay, bias correction; no amsgrad / maximize / foreach options)."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 1e-2, loss_scaling: float = 1.0, data_parallel_group="none"):
+                 weight_decay: float = 1e-2, loss_scaling: float = 1.0, data_parallel_group="none",
+                 direct_grads: bool = False):
         self.lib = _lib.load()
         ps = [p for p in params if p.requires_grad]
         if not ps:
@@ -67,6 +68,15 @@ class AdamW:
             owner = owner_of(p)
             if owner is not None:
                 self.track(owner)
+        # direct_grads: a ScoreUNet whose parameters are exactly this optimizer's (same order) lets its backward kernels
+        # accumulate straight into self.grad instead of handing autograd 228 tensors to add.  Autograd's per-parameter
+        # hooks do not fire on that route — do not combine with a DDP wrapper (use data_parallel_group instead).
+        if direct_grads:
+            owners = [m for m in self._owners if [id(q) for q in m.parameters()] == [id(q) for q in ps]]
+            if not owners:
+                raise ValueError("direct_grads needs the parameters of exactly one climate2weather_b200.ScoreUNet")
+            for m in owners:
+                m._direct_grad = self.grad
 
     def track(self, *modules: torch.nn.Module) -> "AdamW":
         """Modules holding these parameters (ScoreUNet instances): `step()` updates the flat buffer through raw

@@ -108,6 +108,29 @@ def test_training_step_vs_reference_golden(golden_dir):
     assert torch.equal(y1, y2)
 
 
+def test_direct_gradient_route_matches_autograd_route():
+    """optim.AdamW(direct_grads=True): the backward kernels accumulate straight into the optimiser's flat gradient
+    buffer (same layout as c2w_param_layout) — identical gradients to the autograd route, accumulation included."""
+    import climate2weather_b200 as c2w
+    from climate2weather_b200 import optim
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 20, 32, 32, generator=g)
+    t = torch.rand(2, 1, 1, 1, generator=g)
+    eps = torch.randn(2, 20, 32, 32, generator=g)
+    flats = []
+    for direct in (False, True):
+        torch.manual_seed(1)
+        net = c2w.ScoreUNet(activation=torch.nn.SiLU, **SMALL).to(dev)
+        opt = optim.AdamW(net.parameters(), lr=1e-3, direct_grads=direct)
+        opt.zero_grad()
+        _our_step(net, x, t, eps, dev)
+        _our_step(net, x, t, eps, dev)  # a second accumulation round
+        flats.append(opt.grad.clone())
+    assert torch.allclose(flats[0], flats[1], rtol=1e-5, atol=1e-10)
+    assert float(flats[1].abs().max()) > 0
+
+
 def test_gradient_accumulation_and_input_gradient():
     """Two backward passes accumulate into .grad like autograd does everywhere (training_loop.py:373-378 accumulation
     rounds); the input gradient of the training path agrees with the frozen-weights VJP path."""
