@@ -330,20 +330,28 @@ def run_ours(args):
     rt.check_finite()
 
     # ---- roofline pass: event-time every forward-pass launch of a few steps (same process, right after)
-    eng = rt.engine
-    _lib.check(lib.c2w_set_timing(eng.handle, 1), "c2w_set_timing")
-    ms2 = (ctypes.c_double * 2)()
-    n2 = (ctypes.c_int64 * 2)()
+    engs = rt.engines()
+    for eng in engs:
+        _lib.check(lib.c2w_set_timing(eng.handle, 1), "c2w_set_timing")
+    ms2 = [0.0, 0.0]
+    n2 = [0, 0]
     nprof = 0 if args.profile else min(args.steps, 4 if not ensemble else 1)
     for i in range(nprof):
         st.step(i)
-    _lib.check(lib.c2w_timing_read(eng.handle, ms2, n2), "c2w_timing_read")
-    _lib.check(lib.c2w_set_timing(eng.handle, 0), "c2w_set_timing")
+    for eng in engs:
+        m_, c_ = (ctypes.c_double * 2)(), (ctypes.c_int64 * 2)()
+        _lib.check(lib.c2w_timing_read(eng.handle, m_, c_), "c2w_timing_read")
+        _lib.check(lib.c2w_set_timing(eng.handle, 0), "c2w_set_timing")
+        for q in range(2):
+            ms2[q] += m_[q]
+            n2[q] += c_[q]
     conv_ms_step = ms2[0] / max(nprof, 1)
     other_ms_step = ms2[1] / max(nprof, 1)
-    # K1 work per step: every conv / 1x1 GEMM of the forward pass; exact-grad adds the input-gradient conv of each
-    # (same FLOPs with Cin and Cout swapped), src/thor/score.py:28-33,51-52
-    k1_flops_step = F_WIN_CONV * n_win_local * (2 if args.exact_grad else 1)
+    # K1 work per step: every conv / 1x1 GEMM of the forward pass.  exact-grad (src/thor/score.py:28-33,51-52) adds, for
+    # the windows whose output meets an observed frame (the others have a zero cotangent), a stashing forward and the
+    # input-gradient conv of each layer (same FLOPs with Cin and Cout swapped)
+    n_sel = rt.n_selected if args.exact_grad else 0
+    k1_flops_step = F_WIN_CONV * (n_win_local + 2 * n_sel)
     conv_tf = k1_flops_step / (conv_ms_step * 1e-3) / 1e12 if conv_ms_step > 0 else 0.0
     traffic, traffic_src = k1_traffic()
     k1_per_step = n2[0] // max(nprof, 1)
@@ -400,7 +408,7 @@ def run_ours(args):
                 "config3": f"config3: time-sharded guided PC sampling of a 1-month trajectory, L={L} frames over {world} GPU(s)",
                 "config4": f"config4: {MEMBERS}-member ensemble of a synthetic year, L={L} frames per member, "
                            f"{members_per_gpu} member(s) per GPU as independent replicas"}[name]
-        x2 = 2 if args.exact_grad else 1
+        x2 = (n_win_local + 2 * n_sel) / n_win_local
         line = {
             "metric": "guided-sampling frames/sec", "value": round(value, 3), "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
@@ -410,7 +418,7 @@ def run_ours(args):
                                    f"{'exact-grad (UNet VJP)' if args.exact_grad else 'approx-grad'} guidance "
                                    "t_step=6 s_step=16",
                        "name": name, "frames": L, "members": MEMBERS if ensemble else 1, "sampler_steps": SAMPLER_STEPS,
-                       "windows_per_gpu": n_win_local, "chunk_windows": rt.engine.max_windows,
+                       "windows_per_gpu": n_win_local, "vjp_windows_per_gpu": n_sel, "chunk_windows": rt.engine.max_windows,
                        "workspace_bytes": int(rt.engine.workspace.numel()),
                        "parallelism": (f"{members_per_gpu} replica member(s) per GPU x{world}" if ensemble
                                        else f"time-shard x{world}"),

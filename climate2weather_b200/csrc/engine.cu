@@ -1356,6 +1356,65 @@ int c2w_window_score(c2w_handle* h, const float* traj, int32_t n_frames_local, i
   return C2W_OK;
 }
 
+// Stashing forward of a SELECTION of windows (global indices win_list_dev[0..n_sel), n_sel <= max_windows of a VJP
+// workspace) — no score output.  With the coarse-graining likelihood the cotangent of the composed score is non-zero on
+// the OBSERVED frames only (every t_step-th, exp/downscaling.py:129-132), so only the windows whose centre (or, for
+// the first / last window, edge) frame is observed contribute to the vector-Jacobian product: the caller runs the
+// plain forward for all windows and this + c2w_window_score_backward_sel for ~1/t_step of them.
+int c2w_window_score_sel(c2w_handle* h, const float* traj, int32_t n_frames_local, int32_t frame_global0,
+                         const int32_t* win_list_dev, int32_t n_sel, float t, void* stream) {
+  C2W_REQUIRE(h && traj && win_list_dev && n_sel >= 1, "c2w_window_score_sel: bad argument");
+  Plan& P = h->plan;
+  if (P.n_max < 1 || !P.vjp || P.per_t) return fail(C2W_ERR_STATE, "bind a VJP workspace first (c2w_bind_workspace_vjp)");
+  C2W_REQUIRE(n_sel <= P.n_max, "c2w_window_score_sel: %d windows exceed the bound workspace (%d)", n_sel, P.n_max);
+  const int w = h->cfg.window, C = h->cfg.frame_channels;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int hw = h->cfg.height * h->cfg.width;
+  (void)n_frames_local;
+  int rc = run_modulation(h, t, nullptr, 1, P.h0, P.emb, P.mods, st);
+  if (rc) return rc;
+  const long long items = static_cast<long long>(n_sel) * hw * (h->cin_pad / 8);
+  gather_windows_kernel<<<grid_for(items, 256, h->sms), 256, 0, st>>>(traj, P.xin, n_sel, hw, C, w * C, h->cin_pad,
+                                                                      frame_global0, win_list_dev);
+  ++g_launches;
+  C2W_CUDA(cudaGetLastError());
+  FinalSpec fs;
+  fs.mode = EPI_F32;
+  return run_plan(h, n_sel, fs, st);
+}
+
+// Adjoint of the selected windows whose stashing forward has JUST run (c2w_window_score_sel, same list): compose adjoint
+// -> input-gradient pass -> unfold adjoint; pos_dev[j] = position of global window j in the list or -1 (n_win_global
+// entries); vjp (fp32 [n_frames_local, H, W, C]) is ACCUMULATED.
+int c2w_window_score_backward_sel(c2w_handle* h, const float* cot, int32_t n_frames_local, int32_t frame_global0,
+                                  const int32_t* win_list_dev, const int32_t* pos_dev, int32_t n_sel, int32_t n_win_global,
+                                  float* vjp, void* stream) {
+  C2W_REQUIRE(h && cot && vjp && win_list_dev && pos_dev && n_sel >= 1, "c2w_window_score_backward_sel: bad argument");
+  Plan& P = h->plan;
+  if (P.n_max < 1 || !P.vjp) return fail(C2W_ERR_STATE, "bind a VJP workspace first (c2w_bind_workspace_vjp)");
+  C2W_REQUIRE(n_sel <= P.n_max, "backward handles one chunk: %d windows, workspace %d", n_sel, P.n_max);
+  const int w = h->cfg.window, k = w / 2, C = h->cfg.frame_channels;
+  C2W_REQUIRE(C == 4, "fused compose supports 4 variables per frame (got %d)", C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int hw = h->cfg.height * h->cfg.width;
+  const int cpad = h->levels[0].tail.cout_pad;
+  const long long items = static_cast<long long>(n_sel) * hw * (cpad / 8);
+  compose_adjoint_kernel<<<grid_for(items, 256, h->sms), 256, 0, st>>>(cot, P.cot, n_sel, hw, cpad, k, 0, n_win_global - 1,
+                                                                         frame_global0, win_list_dev);
+  ++g_launches;
+  C2W_CUDA(cudaGetLastError());
+  FinalSpec fs;
+  fs.mode = EPI_F32;
+  int rc = run_ops(h, P.bwd, n_sel, fs, st);
+  if (rc) return rc;
+  const long long items2 = static_cast<long long>(n_frames_local) * hw;
+  unfold_adjoint_sel_kernel<<<grid_for(items2, 256, h->sms), 256, 0, st>>>(P.out32, vjp, n_frames_local, hw, h->cin_pad, w,
+                                                                             frame_global0, n_win_global, pos_dev);
+  ++g_launches;
+  C2W_CUDA(cudaGetLastError());
+  return C2W_OK;
+}
+
 // J^T g of ScoreUNet.forward w.r.t. its input: forward (stashing) + input-gradient pass, n <= max_windows.
 int c2w_unet_vjp(c2w_handle* h, const float* x_nchw, int32_t n, float t, const float* gout_nchw, float* out_nchw,
                  float* gin_nchw, void* stream) {

@@ -38,8 +38,10 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t w) {
 // traj: fp32 [frames, HW, C]; window i of this launch starts at local frame f0 + i.
 // out : bf16 [n, HW, cin_pad], channel tau*C + c  <-  traj[f0 + i + tau, pix, c]; channels >= wC are zero.
 // One thread writes 8 channels (16 B): writes are fully coalesced, reads are 16 B (C = 4) sectors.
+// win_list (optional): GLOBAL window indices of the n windows (a selection, e.g. the windows whose output carries a
+// non-zero cotangent); window i then starts at local frame win_list[i] - f0 (f0 = global index of local frame 0).
 __global__ void gather_windows_kernel(const float* __restrict__ traj, bf16* __restrict__ out, int n, int hw, int C,
-                                      int wC, int cin_pad, int f0) {
+                                      int wC, int cin_pad, int f0, const int* __restrict__ win_list = nullptr) {
   const int groups = cin_pad >> 3;
   const long long total = static_cast<long long>(n) * hw * groups;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -48,6 +50,7 @@ __global__ void gather_windows_kernel(const float* __restrict__ traj, bf16* __re
     const long long pw = idx / groups;
     const int pix = static_cast<int>(pw % hw);
     const int i = static_cast<int>(pw / hw);
+    const int fw = win_list ? (win_list[i] - f0) : (f0 + i);  // first local frame of window i
     float v[8];
     if (C == 4) {
 #pragma unroll
@@ -55,7 +58,7 @@ __global__ void gather_windows_kernel(const float* __restrict__ traj, bf16* __re
         const int tau = 2 * g + h;
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
         if (tau * 4 < wC)
-          q = __ldg(reinterpret_cast<const float4*>(traj + (static_cast<long long>(f0 + i + tau) * hw + pix) * 4));
+          q = __ldg(reinterpret_cast<const float4*>(traj + (static_cast<long long>(fw + tau) * hw + pix) * 4));
         v[4 * h + 0] = q.x;
         v[4 * h + 1] = q.y;
         v[4 * h + 2] = q.z;
@@ -66,7 +69,7 @@ __global__ void gather_windows_kernel(const float* __restrict__ traj, bf16* __re
       for (int e = 0; e < 8; ++e) {
         const int ch = 8 * g + e;
         const int tau = ch / C, c = ch - tau * C;
-        v[e] = (ch < wC) ? __ldg(traj + (static_cast<long long>(f0 + i + tau) * hw + pix) * C + c) : 0.f;
+        v[e] = (ch < wC) ? __ldg(traj + (static_cast<long long>(fw + tau) * hw + pix) * C + c) : 0.f;
       }
     }
     uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
@@ -1161,7 +1164,8 @@ __global__ void zero_upsample_kernel(const bf16* __restrict__ in, bf16* __restri
 // the frame cotangent g[win + tau] where that slot is the frame's source, zero elsewhere.
 // g: fp32 [frames, HW, 4] ; cot: bf16 [n, HW, cpad]
 __global__ void compose_adjoint_kernel(const float* __restrict__ g, bf16* __restrict__ cot, int n, int hw, int cpad,
-                                       int order_k, int win_first, int win_last_global, int frame_base) {
+                                       int order_k, int win_first, int win_last_global, int frame_base,
+                                       const int* __restrict__ win_list = nullptr) {
   const int groups = cpad >> 3;
   const long long total = static_cast<long long>(n) * hw * groups;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -1170,7 +1174,7 @@ __global__ void compose_adjoint_kernel(const float* __restrict__ g, bf16* __rest
     const long long pw = idx / groups;
     const int pix = static_cast<int>(pw % hw);
     const int i = static_cast<int>(pw / hw);
-    const int win = win_first + i;
+    const int win = win_list ? win_list[i] : win_first + i;
     float v[8];
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
@@ -1209,6 +1213,42 @@ __global__ void unfold_adjoint_kernel(const float* __restrict__ gin, float* __re
       acc.w += q.w;
     }
     float4* dst = reinterpret_cast<float4*>(vjp + (static_cast<long long>(win_first + fo - frame_base) * hw + pix) * 4);
+    float4 o = *dst;
+    o.x += acc.x;
+    o.y += acc.y;
+    o.z += acc.z;
+    o.w += acc.w;
+    *dst = o;
+  }
+}
+
+// The same for a SELECTION of windows: pos[j] = index of global window j in this launch's batch or -1.  One thread per
+// (local frame, pixel); vjp is accumulated.
+__global__ void unfold_adjoint_sel_kernel(const float* __restrict__ gin, float* __restrict__ vjp, int n_frames, int hw,
+                                          int cpad, int window, int frame_base, int n_win_global,
+                                          const int* __restrict__ pos) {
+  const long long total = static_cast<long long>(n_frames) * hw;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int pix = static_cast<int>(idx % hw);
+    const int fl = static_cast<int>(idx / hw);
+    const int fg = frame_base + fl;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool any = false;
+    for (int tau = 0; tau < window; ++tau) {
+      const int j = fg - tau;
+      if (j < 0 || j >= n_win_global) continue;
+      const int i = pos[j];
+      if (i < 0) continue;
+      const float4 q = *reinterpret_cast<const float4*>(gin + (static_cast<long long>(i) * hw + pix) * cpad + 4 * tau);
+      acc.x += q.x;
+      acc.y += q.y;
+      acc.z += q.z;
+      acc.w += q.w;
+      any = true;
+    }
+    if (!any) continue;
+    float4* dst = reinterpret_cast<float4*>(vjp + (static_cast<long long>(fl) * hw + pix) * 4);
     float4 o = *dst;
     o.x += acc.x;
     o.y += acc.y;

@@ -225,6 +225,22 @@ class Engine:
                                                           win_first, n_win, n_win_global, vjp.data_ptr(), self.stream),
                        "c2w_window_score_backward")
 
+    def window_score_sel(self, traj: Tensor, frame_global0: int, win_list: Tensor, t: float) -> None:
+        """Stashing forward of the selected windows (global indices, int32 device tensor) on a VJP workspace."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.c2w_window_score_sel(self.handle, traj.data_ptr(), traj.shape[0], frame_global0,
+                                                     win_list.data_ptr(), win_list.numel(), float(t), self.stream),
+                       "c2w_window_score_sel")
+
+    def window_score_backward_sel(self, cot: Tensor, frame_global0: int, win_list: Tensor, pos: Tensor, n_win_global: int,
+                                  vjp: Tensor) -> None:
+        """Adjoint of the last window_score_sel call (same list); accumulates into vjp."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.c2w_window_score_backward_sel(self.handle, cot.data_ptr(), cot.shape[0], frame_global0,
+                                                              win_list.data_ptr(), pos.data_ptr(), win_list.numel(),
+                                                              n_win_global, vjp.data_ptr(), self.stream),
+                       "c2w_window_score_backward_sel")
+
     def window_score(self, traj: Tensor, frame_global0: int, win_first: int, n_win: int, n_win_global: int, t: float,
                      eps: Tensor) -> None:
         """traj / eps: fp32 [frames_local, H, W, C] device layout."""

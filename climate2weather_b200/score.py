@@ -79,10 +79,13 @@ class _Runtime:
         self.lib = _lib.load()
         k = sf.markov_order
         self.exact = bool(exact)  # exact_grad=True: guidance through the UNet VJP (src/thor/score.py:28-33,51-52)
+        self.cond = None
         self._engine_args = (C, 2 * k + 1, H, W, device)
         self._engine_windows = min(max_windows, plan.win_hi - plan.win_lo)
         self._engine = None
+        self._engine_vjp = None   # exact_grad: the stashing engine for the windows that need a backward pass
         self._engine_epoch = None
+        self._sel = None          # exact_grad: cached selection of those windows (per conditioning)
         self.refresh_engine()
         f32 = dict(dtype=torch.float32, device=device)
         self.x = torch.zeros(plan.n_local, H, W, C, **f32)
@@ -103,7 +106,10 @@ class _Runtime:
     def refresh_engine(self) -> None:
         """(Re)binds the packed-weight engine; `ScoreUNet.engine` re-packs if the parameters changed since (full
         fingerprint: data pointers, autograd versions, and the explicit epoch raw-pointer optimisers bump)."""
-        self._engine = self.sf.unet.engine(*self._engine_args, max_windows=self._engine_windows, vjp=self.exact)
+        self._engine = self.sf.unet.engine(*self._engine_args, max_windows=self._engine_windows, vjp=False)
+        if self.exact and self.cond is not None:  # sized by the selection, so only once the operator is known
+            nsel = max(1, len(self._selected_list()))
+            self._engine_vjp = self.sf.unet.engine(*self._engine_args, max_windows=min(nsel, self._engine_windows), vjp=True)
         self._engine_epoch = getattr(self.sf.unet, "_weights_epoch", 0)
 
     @property
@@ -111,6 +117,52 @@ class _Runtime:
         if getattr(self.sf.unet, "_weights_epoch", 0) != self._engine_epoch:  # optimiser / EMA step since the last call
             self.refresh_engine()
         return self._engine
+
+    @property
+    def engine_vjp(self):
+        _ = self.engine
+        return self._engine_vjp
+
+    def engines(self):
+        """Every engine a score evaluation launches kernels on (bench.py's per-launch timing)."""
+        return [e for e in (self.engine, self._engine_vjp) if e is not None]
+
+    # ------------------------------------------------------------------------------------------------ exact_grad
+    def _selected_list(self):
+        """Global indices of this rank's windows whose OUTPUT carries a non-zero cotangent.  The likelihood's cotangent
+        g = A^T((y - A x0)/var) (src/thor/score.py:53-56) is non-zero on observed frames only — frame f with
+        f % t_step == 0 (exp/downscaling.py:131) — and window j contributes frame j + k to the composed score (plus
+        frames 0..k-1 if it is the first window, L-k..L-1 if it is the last, src/thor/score.py:76-88)."""
+        p, k = self.plan, self.sf.markov_order
+        t_step = self.cond["op"].t_step
+        out = []
+        for j in range(p.win_lo, p.win_hi):
+            need = (j + k) % t_step == 0
+            if j == 0:
+                need = need or any(f % t_step == 0 for f in range(0, k))
+            if j == p.n_win_global - 1:
+                need = need or any(f % t_step == 0 for f in range(self.L - k, self.L))
+            if need:
+                out.append(j)
+        return out
+
+    def _selection(self):
+        """(chunks of (win_list_dev, pos_dev), n_selected) for the current conditioning, cached."""
+        if self._sel is None:
+            sel = self._selected_list()
+            step = max(1, self.engine_vjp.max_windows)
+            chunks = []
+            for i in range(0, len(sel), step):
+                part = sel[i:i + step]
+                pos = torch.full((self.plan.n_win_global,), -1, dtype=torch.int32)
+                pos[torch.tensor(part, dtype=torch.long)] = torch.arange(len(part), dtype=torch.int32)
+                chunks.append((torch.tensor(part, dtype=torch.int32, device=self.device), pos.to(self.device)))
+            self._sel = (chunks, len(sel))
+        return self._sel
+
+    @property
+    def n_selected(self) -> int:
+        return self._selection()[1] if (self.exact and self.cond is not None) else 0
 
     # ------------------------------------------------------------------------------------------------ state io
     @property
@@ -146,21 +198,25 @@ class _Runtime:
             self.engine.window_score(self.x, p.frame_lo, p.win_lo, p.win_hi - p.win_lo, p.n_win_global, t, self.eps)
             return
         mu, sigma = _mu_sigma(self.sf.noise_process, t)
-        k = self.sf.markov_order
+        # 1. the score itself: plain forward of every local window
+        self.engine.window_score(self.x, p.frame_lo, p.win_lo, p.win_hi - p.win_lo, p.n_win_global, t, self.eps)
+        # 2. likelihood cotangent g = A^T((y - A x0)/var) on the owned frames (zero on unobserved frames)
+        self._guide(2, mu, sigma, 0.0, 0.0)
+        # 3. J_eps^T g: only windows whose output meets an observed frame have a non-zero cotangent -> stashing forward
+        #    + input-gradient pass for that selection (~1/t_step of the windows), chunk by chunk
         self.vjp.zero_()
-        step = self.engine.max_windows
-        for j0 in range(p.win_lo, p.win_hi, step):
-            n = min(step, p.win_hi - j0)
-            self.engine.window_score(self.x, p.frame_lo, j0, n, p.n_win_global, t, self.eps)
-            # frames whose score these windows produce: their centres, plus the trajectory's edge frames
-            f_lo = 0 if j0 == 0 else j0 + k
-            f_hi = self.L if j0 + n == p.n_win_global else j0 + n + k
-            self._guide(2, mu, sigma, 0.0, 0.0, frames=(f_lo - p.frame_lo, f_hi - f_lo))
-            self.engine.window_score_backward(self.cot, p.frame_lo, j0, n, p.n_win_global, self.vjp)
+        chunks, _ = self._selection()
+        ev = self.engine_vjp
+        for win_list, pos in chunks:
+            ev.window_score_sel(self.x, p.frame_lo, win_list, t)
+            ev.window_score_backward_sel(self.cot, p.frame_lo, win_list, pos, p.n_win_global, self.vjp)
         exchange_halos_adjoint(self.vjp, p, group)
 
     def set_condition(self, cond) -> None:
         self.cond = cond
+        self._sel = None
+        if cond is not None and self.exact:
+            self.refresh_engine()  # the stashing workspace is sized by the selection
         if cond is not None:
             self.y_dev = cond["y"].to(device=self.device, dtype=torch.float32).contiguous()
 
