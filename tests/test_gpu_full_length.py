@@ -141,3 +141,76 @@ def test_full_length_exact_grad_vs_reference(net, golden_dir):
     assert rows[0][1] < 3e-2 and rows[0][2] < 5e-2
     assert rows[1][1] < 3e-2
     assert rows[-1][1] < 5e-2 and rows[-1][2] < 5e-2, rows[-1]
+
+
+# ------------------------------------------------------------------------------------------------ full size, by properties
+# BASELINE config 2 itself (L = 168 frames, 156 windows, sda_unet.yml) has no reference trajectory — 256 CPU steps of it
+# would take hours — so at that size the path is checked through size-independent properties of the reference algorithm.
+def _config2(net):
+    import climate2weather_b200 as c2w
+    g = torch.Generator().manual_seed(33)
+    Lf = 168
+    x = torch.randn(Lf, 4, 128, 128, generator=g)
+    y = c2w.CoarseGrain(6, 16)(torch.randn(Lf, 4, 128, 128, generator=g))
+    pipe = c2w.SDAPipeline()
+    sf = c2w.BatchedScoreFunction(net, markov_order=K, noise_process=pipe, batch_size=32, device=torch.device("cuda:0"))
+    return c2w, pipe, sf, x, y
+
+
+def test_config2_markov_blanket_is_exact(net):
+    """src/thor/score.py:68-93: frame i's score is a function of frames i-k .. i+k only.  Perturbing one frame of a
+    168-frame trajectory must leave the composed score of every frame further than k away BIT-IDENTICAL, and change the
+    frames within k; the same must hold for the guided score (the likelihood term is frame-local)."""
+    c2w, pipe, sf, x, y = _config2(net)
+    t = torch.tensor(0.6)
+    dev = torch.device("cuda:0")
+    j = 77
+    x2 = x.clone()
+    x2[j] += 0.25 * torch.randn(4, 128, 128, generator=torch.Generator().manual_seed(1))
+    for guided in (False, True):
+        if guided:
+            sf.condition_on(A=c2w.CoarseGrain(6, 16), y=y, std=torch.tensor(STD).reshape(1, 4, 1, 1), gamma=GAMMA, exact_grad=False)
+        a, b = sf(x.to(dev), t).cpu(), sf(x2.to(dev), t).cpu()
+        far = [i for i in range(168) if abs(i - j) > K]
+        near = [i for i in range(168) if abs(i - j) <= K]
+        assert torch.equal(a[far], b[far])
+        assert all(not torch.equal(a[i], b[i]) for i in near)
+
+
+def test_config2_guidance_is_affine_in_the_observation(net):
+    """src/thor/score.py:44-60 with exact_grad=False: eps_guided = eps - sigma J, J = A^T((y - A x0)/var)/mu — affine in
+    y.  At config-2 size: eps_g(y1) - eps_g(y2) must equal -sigma A^T((y1 - y2)/var)/mu (zero on unobserved frames,
+    constant per 16 x 16 tile), to fp32 rounding — independent of the network."""
+    from oracle import score_ref
+    c2w, pipe, sf, x, y = _config2(net)
+    dev = torch.device("cuda:0")
+    t = torch.tensor(0.4)
+    std = torch.tensor(STD).reshape(1, 4, 1, 1)
+    y2 = y + 0.1 * torch.randn(y.shape, generator=torch.Generator().manual_seed(2))
+    outs = []
+    for yy in (y, y2):
+        sf.condition_on(A=c2w.CoarseGrain(6, 16), y=yy, std=std, gamma=GAMMA, exact_grad=False)
+        outs.append(sf(x.to(dev), t).cpu())
+    mu, sigma = score_ref.mu_sigma(t)
+    var = std ** 2 + GAMMA * (sigma / mu) ** 2
+    want = -sigma * score_ref.coarse_grain_adjoint((y - y2) / var, 168, 6, 16) / mu
+    got = outs[0] - outs[1]
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) < 2e-4 * scale
+    unobserved = [i for i in range(168) if i % 6]
+    assert float(got[unobserved].abs().max()) == 0.0
+
+
+def test_config2_sampler_chunking_invariance(net):
+    """The result of sample() must not depend on how the 156 windows are batched through the UNet (the reference's
+    batch_size only bounds memory, src/thor/score.py:143-185): 8 guided steps at config-2 size with 156, 64 and 50
+    windows per launch agree bit for bit."""
+    c2w, pipe, sf, x, y = _config2(net)
+    outs = []
+    for mw in (None, 64, 50):
+        sf2 = c2w.BatchedScoreFunction(net, markov_order=K, noise_process=pipe, batch_size=32, device=torch.device("cuda:0"))
+        sf2.max_windows = mw
+        sf2.condition_on(A=c2w.CoarseGrain(6, 16), y=y, std=torch.tensor(STD).reshape(1, 4, 1, 1), gamma=GAMMA, exact_grad=False)
+        outs.append(pipe.sample(sf2, x, steps=8, corrections=0, tau=0.5, show_progressbar=False))
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
