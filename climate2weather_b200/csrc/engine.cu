@@ -18,6 +18,7 @@ using namespace c2w;
 int c2w_num_sms();
 
 static long long g_launches = 0;  // kernels launched by this library (bench.py's gpu_launches)
+void c2w_count_launches(int n) { g_launches += n; }  // for the other translation units (halo.cu)
 
 namespace {
 
@@ -1586,6 +1587,7 @@ int c2w_train_backward(c2w_handle* h, const float* gout_nchw, int32_t n, float* 
   dim3 blk(32, 8);
   dim3 g2(ceil_div(hw, 32), ceil_div(cout_pad, 32), n);
   nchw_to_nhwc_bf16_kernel<<<g2, blk, 0, st>>>(gout_nchw, P.cot, h->cin, hw, cout_pad);
+  ++g_launches;
   C2W_CUDA(cudaGetLastError());
   P.grad = grad_flat;
   FinalSpec fs;
@@ -1608,6 +1610,7 @@ int c2w_train_backward(c2w_handle* h, const float* gout_nchw, int32_t n, float* 
     // all 30 project Linears in one launch: dW_p[c][e] += sum_s dmod[s][c] emb[s][e], db_p[c] += sum_s dmod[s][c]
     proj_grad_kernel<<<blocks1d(static_cast<long long>(TM) * E), 256, 0, st>>>(P.dmods, TM, P.emb, E, n, grad_flat, h->row_w,
                                                                               h->row_b);
+    g_launches += 12;  // this block: projections, embedding gradient, two Linear layers of the time MLP
     // d emb = dmods . W_proj  ([n, TM] x [TM, E]);  emb = silu(pre1), pre1 = W1 h0 + b1;  h0 = silu(pre0), pre0 = W0 feat + b0
     C2W_CUDA(cudaMemsetAsync(P.demb, 0, static_cast<size_t>(n) * E * sizeof(float), st));
     gemm_nn_f32_kernel<<<dim3(blocks1d(static_cast<long long>(n) * E), 32), 256, 0, st>>>(P.dmods, TM, h->proj_w, E, P.demb, E,

@@ -20,6 +20,8 @@
 
 using namespace c2w;
 
+void c2w_count_launches(int n);  // engine.cu: bench.py's gpu_launches
+
 struct c2w_halo {
   int64_t halo_bytes = 0;     // k frames
   uint8_t* mailbox = nullptr; // [2][2][halo_bytes] then 2 x uint32 counters (256-byte aligned block)
@@ -177,6 +179,7 @@ int c2w_halo_pull(c2w_halo* h, float* x_local, int64_t n_local_frames, int64_t f
       has_r ? reinterpret_cast<float4*>(x_local + (n_local_frames - k) * frame_floats) : nullptr, has_r ? h->flags + 1 : nullptr,
       hb / 16, h->step + 1);
   C2W_CUDA(cudaGetLastError());
+  c2w_count_launches(1);
   h->step += 1;
   return C2W_OK;
 }
@@ -209,6 +212,7 @@ int c2w_halo_exchange(c2w_halo* h, float* x_local, int64_t n_local_frames, int64
                                          has_r ? reinterpret_cast<float4*>(x_local + (n_local_frames - k) * frame_floats) : nullptr,
                                          has_r ? h->flags + 1 : nullptr, n16, h->step + 1);
   C2W_CUDA(cudaGetLastError());
+  c2w_count_launches(2);
   h->step += 1;
   return C2W_OK;
 }
