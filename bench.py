@@ -666,6 +666,55 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_reference_train(args):
+    """Reference arm of config 5: the oracle port of the training step body (pipeline.loss(net, x).mean() -> backward
+    through the fp32 UNet with torch autograd -> AdamW update, training_loop.py:372-390) on the host cores, on a bounded
+    batch (--cpu-train-samples per step; cost is linear in the batch)."""
+    import torch
+
+    from oracle import pipeline_ref, unet_ref
+
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    t_start = time.perf_counter()
+    sd = unet_ref.init_state_dict(unet_ref.SDA_UNET, seed=0)
+    for v in sd.values():
+        v.requires_grad_(True)
+    net = unet_ref.RefNet(sd, unet_ref.SDA_UNET)
+    opt = torch.optim.AdamW(list(sd.values()), lr=1e-4, weight_decay=1e-3)
+    pipe = pipeline_ref.RefPipeline()
+    b = max(1, args.cpu_train_samples)
+    x = torch.rand(b, ARCH["channels"], H, W, generator=torch.Generator().manual_seed(1))
+
+    def step():
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        pipe.loss(net, x).mean().backward()
+        opt.step()
+        return time.perf_counter() - t0
+
+    for _ in range(args.warmup_train_ref):
+        step()
+    steps = max(1, min(args.steps, args.ref_train_steps))
+    per = [step() for _ in range(steps)]
+    sec = sum(per) / steps
+    value = b / sec
+    line = {"impl": "reference", "metric": "DSM training samples/sec", "value": round(value, 4), "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup_train_ref, "ms_per_step": round(1e3 * sec, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"config5: DSM training step of the sda_unet.yml ScoreUNet on the host cores (oracle port, "
+                                   f"torch autograd + torch.optim.AdamW), {b} samples of 52x128x128 per step",
+                       "name": "config5", "batch_per_step": b},
+            "cpu_baseline": {"value": round(value, 4), "unit": "samples/s", "cores": cores, "kind": "port",
+                             "sample": f"{steps} timed steps of {b} samples each (the configured batch is 128 per GPU; cost is "
+                                       "linear in the batch)"},
+            "e2e": {"value": round(value, 4), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": round(time.perf_counter() - t_start, 1)}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -693,12 +742,17 @@ def main():
     ap.add_argument("--mode", default="sample", choices=["sample", "train"],
                     help="train: BASELINE config 5, the DSM training step (forward + backward + AdamW + EMA)")
     ap.add_argument("--batch", type=int, default=128, help="--mode train: samples per GPU (run_training.sh: 128)")
+    ap.add_argument("--cpu-train-samples", type=int, default=2, help="--impl reference --mode train: samples per CPU step")
+    ap.add_argument("--ref-train-steps", type=int, default=3)
+    ap.add_argument("--warmup-train-ref", type=int, default=1)
     ap.add_argument("--ddp", default="flat", choices=["flat", "torch"],
                     help="--mode train, N > 1: gradient averaging by one all-reduce of the flat buffer (default) or torch DDP")
     args = ap.parse_args()
     if args.e2e_steps is None:
         args.e2e_steps = 8 if args.config == 4 else SAMPLER_STEPS
-    if args.impl == "reference":
+    if args.impl == "reference" and args.mode == "train":
+        run_reference_train(args)
+    elif args.impl == "reference":
         run_reference(args)
     elif args.mode == "train":
         if not args.profile:
