@@ -167,6 +167,19 @@ def pick_workload(args, world: int):
     return "config3", args.frames or L_MONTH, "strong", 0
 
 
+def workload_config(name: str, L: int, world: int, members_per_gpu: int, exact: bool) -> dict:
+    """The part of `config` both arms (ours and --impl reference) print identically: which BASELINE.json workload it is."""
+    desc = {"config2": f"config2: guided PC sampling of a 1-week trajectory, L={L} frames",
+            "config2-weak": f"config2 weak scaling: L={L} frames ({WINDOWS_PER_GPU} windows per GPU)",
+            "config3": f"config3: time-sharded guided PC sampling of a 1-month trajectory, L={L} frames over {world} GPU(s)",
+            "config4": f"config4: {MEMBERS}-member ensemble of a synthetic year, L={L} frames per member, "
+                       f"{members_per_gpu} member(s) per GPU as independent replicas"}[name]
+    return {"workload": f"{desc} of {C}x{H}x{W}, sda_unet.yml ScoreUNet k={K_ORDER}, {SAMPLER_STEPS} steps, 0 corrections, "
+                        f"{'exact-grad (UNet VJP)' if exact else 'approx-grad'} guidance t_step={T_STEP} s_step={S_STEP}",
+            "name": name, "frames": L, "members": MEMBERS if name == "config4" else 1, "sampler_steps": SAMPLER_STEPS,
+            "windows": L - 2 * K_ORDER}
+
+
 # ====================================================================================================== ours
 class Stepper:
     """One resident trajectory (or this rank's shard of it) and its denoising step."""
@@ -403,21 +416,12 @@ def run_ours(args):
         cpu = cpu_reference(L, sample_windows=args.cpu_windows, steps=1)
 
     if rank == 0:
-        desc = {"config2": f"config2: guided PC sampling of a 1-week trajectory, L={L} frames",
-                "config2-weak": f"config2 weak scaling: L={L} frames ({WINDOWS_PER_GPU} windows per GPU)",
-                "config3": f"config3: time-sharded guided PC sampling of a 1-month trajectory, L={L} frames over {world} GPU(s)",
-                "config4": f"config4: {MEMBERS}-member ensemble of a synthetic year, L={L} frames per member, "
-                           f"{members_per_gpu} member(s) per GPU as independent replicas"}[name]
         x2 = (n_win_local + 2 * n_sel) / n_win_local
         line = {
             "metric": "guided-sampling frames/sec", "value": round(value, 3), "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{desc} ({n_win_local} windows on rank 0) of {C}x{H}x{W}, sda_unet.yml ScoreUNet "
-                                   f"k={K_ORDER}, {SAMPLER_STEPS} steps, 0 corrections, "
-                                   f"{'exact-grad (UNet VJP)' if args.exact_grad else 'approx-grad'} guidance "
-                                   "t_step=6 s_step=16",
-                       "name": name, "frames": L, "members": MEMBERS if ensemble else 1, "sampler_steps": SAMPLER_STEPS,
+            "config": {**workload_config(name, L, world, members_per_gpu, args.exact_grad),
                        "windows_per_gpu": n_win_local, "vjp_windows_per_gpu": n_sel, "chunk_windows": rt.engine.max_windows,
                        "workspace_bytes": int(rt.engine.workspace.numel()),
                        "parallelism": (f"{members_per_gpu} replica member(s) per GPU x{world}" if ensemble
@@ -624,7 +628,7 @@ def run_reference(args):
     if rank != 0:
         return
     world = args.gpus
-    name, L, scaling, _ = pick_workload(args, world)
+    name, L, scaling, members_per_gpu = pick_workload(args, world)
     n_win = L - 2 * K_ORDER
     t_start = time.perf_counter()
     probe = CpuReference(13)
@@ -655,11 +659,8 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step_sample, 3),
             "ms_per_full_step_scaled": round(1e3 * sec_full_step, 3),
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{name}: guided PC sampling, L={L} frames ({n_win} windows) of {C}x{H}x{W}, sda_unet.yml "
-                                   f"ScoreUNet k={K_ORDER}, {SAMPLER_STEPS} steps, 0 corrections, approx-grad guidance "
-                                   f"t_step=6 s_step=16 — CPU oracle port of the reference path; every step = {ws} windows",
-                       "name": name, "frames": L, "members": MEMBERS if name == "config4" else 1, "windows_per_step": ws,
-                       "windows_full": n_win},
+            "config": {**workload_config(name, L, world, members_per_gpu, False),
+                       "arm": "CPU oracle port of the reference path on the host cores", "windows_per_step": ws},
             "cpu_baseline": cpu,
             "e2e": {"value": round(value, 6), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": round(time.perf_counter() - t_start, 1)}
