@@ -18,12 +18,14 @@
 // (split-K) and every CTA writes its three fp32 accumulators to a scratch slab; wgrad_reduce_kernel sums the slabs in
 // a fixed order (deterministic) into the fp32 OIHW gradient tensor.
 //
-// The conv's BIAS gradient, sum over pixels of dY[p, co], rides along: the dY tiles already pass through shared memory,
-// so in the CTAs of group 0 / N tile 0 the (otherwise idle) epilogue warps add up their channel's 64 pixels of every
-// stage before it is released — no second pass over dY.
+// The conv's BIAS gradient, sum over pixels of dY[p, co], rides along on the tensor core: it is the same product with a
+// column of ones for X.  The CTAs of N tile 0 issue, for every `groups`-th K block (so the groups of a split share the
+// work), four extra 128 x 16 x 16 MMAs of the dY tile against a constant all-ones operand in shared memory (any layout
+// of ones is ones, so the tile needs no swizzle care) into 16 spare TMEM columns; the epilogue writes column 0.  No
+// second pass over dY and no LSU traffic (a first version summed the staged tiles with the idle epilogue warps: their
+// shared-memory reads held every stage and made the bias CTAs 1.4x slower than the rest of the grid).
 //
-// Roles: warp 0 TMA producer, warp 1 tcgen05.mma issuer (one elected lane), warp 2 TMEM allocator, warps 4-7 epilogue
-// (+ bias column sums during the main loop).
+// Roles: warp 0 TMA producer, warp 1 tcgen05.mma issuer (one elected lane), warp 2 TMEM allocator, warps 4-7 epilogue.
 #pragma once
 #include "conv_tcgen05.cuh"
 
@@ -41,7 +43,7 @@ struct WgradParams {
   int groups;          // work items per (m, n, split): 3 (filter columns, or filter rows when !share) or 1 (GEMM)
   int cout_slab, cin_slab;  // slab dims: m_tiles * 128, n_tiles * BN
   float* partial;      // [splits][taps][cout_slab][cin_slab]
-  float* bias_partial; // [splits][cout_slab]: per-split column sums of dY (the bias gradient), or null
+  float* bias_partial; // [splits * groups][cout_slab]: per-CTA column sums of dY (the bias gradient), or null
   int num_stages;
 };
 
@@ -69,17 +71,18 @@ struct WgradCfg {
   static constexpr int kBGroupTap = kWgPix * 128;                  // X box of one tap per 64-channel group
   static constexpr int kBBytesShare = (BN / 64) * kBGroupShare;
   static constexpr int kBBytesTaps = 3 * (BN / 64) * kBGroupTap;
-  static constexpr int kTmemCols = (3 * BN <= 256) ? 256 : 512;
+  static constexpr int kTmemCols = (3 * BN + 16 <= 256) ? 256 : 512;  // three accumulators + 16 bias columns
+  static constexpr int kOnesBytes = 2048;                          // all-ones B operand of the bias MMAs (16 pixels x 128 B)
   static constexpr int stage_bytes(bool share) {
     // stages stay 1024-B aligned (the swizzle pattern is a function of the absolute address)
     return ((kABytes + (share ? kBBytesShare : kBBytesTaps)) + 1023) / 1024 * 1024;
   }
   static constexpr int kBarBytes = 512;
   static constexpr int stages(bool share) {
-    const int n = (kSmemLimit - 1024 - kBarBytes) / stage_bytes(share);
+    const int n = (kSmemLimit - 1024 - kBarBytes - kOnesBytes) / stage_bytes(share);
     return n > 8 ? 8 : n;
   }
-  static constexpr int smem_bytes(bool share) { return stages(share) * stage_bytes(share) + kBarBytes + 1024; }
+  static constexpr int smem_bytes(bool share) { return stages(share) * stage_bytes(share) + kOnesBytes + kBarBytes + 1024; }
 };
 
 template <int BN>
@@ -91,7 +94,8 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   const bool share = p.share != 0;
   const int stage_bytes = Cfg::stage_bytes(share);
   const int num_stages = p.num_stages;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + num_stages * stage_bytes);
+  uint8_t* ones = smem + num_stages * stage_bytes;  // 1024-B aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones + Cfg::kOnesBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + 8;
   uint64_t* acc_full = bars + 16;
@@ -109,7 +113,9 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   const int ntap = p.taps == 1 ? 1 : 3;  // accumulators of this CTA
   const int kb0 = static_cast<int>(static_cast<long long>(p.k_blocks) * split / p.splits);
   const int kb1 = static_cast<int>(static_cast<long long>(p.k_blocks) * (split + 1) / p.splits);
-  const bool do_bias = p.bias_partial != nullptr && g == 0 && nt == 0;
+  // bias gradient: this CTA takes the K blocks kb with kb % groups == g of its split
+  const bool do_bias = p.bias_partial != nullptr && nt == 0;
+  const int kb_bias0 = kb0 + ((g - kb0 % p.groups) + p.groups) % p.groups;  // first of them
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmDY);
@@ -118,12 +124,18 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   if (warp_idx == 1 && lane == 0) {
     for (int i = 0; i < num_stages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], do_bias ? 5 : 1);  // the MMA commit (+ the four column-sum warps)
+      mbar_init(&empty[i], 1);
     }
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
   if (warp_idx == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (do_bias && warp_idx >= 4) {  // 128 threads fill the ones tile; the async proxy (tcgen05) reads it
+    uint4* o = reinterpret_cast<uint4*>(ones);
+    const uint4 one8 = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    o[threadIdx.x - 128] = one8;
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -166,6 +178,8 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
   } else if (warp_idx == 1) {
     // ---------------------------------------------------------------- MMA issuer
     constexpr uint32_t idesc = umma_idesc_bf16_mn(128, BN);
+    constexpr uint32_t idesc_bias = umma_idesc_bf16_mn(128, 16);
+    const uint64_t odesc = umma_desc_mnmajor_sw128(smem_u32(ones), 1024);
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = kb0; kb < kb1; ++kb) {
@@ -183,6 +197,11 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
           for (int k = 0; k < kWgPix / 16; ++k)  // 16 pixels = two 8-pixel groups = 2048 B further on
             umma_bf16(tmem_d + a * BN, adesc + k * (2048 >> 4), bdesc + k * (2048 >> 4), idesc, (kb > kb0) || k != 0);
         }
+        if (do_bias && (kb - kb_bias0) % p.groups == 0 && kb >= kb_bias0) {
+#pragma unroll
+          for (int k = 0; k < kWgPix / 16; ++k)
+            umma_bf16(tmem_d + ntap * BN, adesc + k * (2048 >> 4), odesc, idesc_bias, (kb > kb_bias0) || k != 0);
+        }
         umma_commit(&empty[stage]);
         if (kb + 1 == kb1) umma_commit(acc_full);
       }
@@ -197,33 +216,22 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
     const int q = warp_idx & 3;  // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;
     const bool any = kb1 > kb0;
-    if (do_bias) {
-      // column sums of dY for output channel `row`: element (pixel k, channel row) of the swizzled MN-major tile
-      float bsum = 0.f;
-      const uint32_t grp = static_cast<uint32_t>(row >> 6) * (kWgPix * 128), chunk = static_cast<uint32_t>((row & 63) >> 3),
-                     within = static_cast<uint32_t>(row & 7) * 2;
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full[stage], phase);
-        const uint8_t* sA = smem + stage * stage_bytes + grp + within;
-#pragma unroll 8
-        for (int k = 0; k < kWgPix; ++k) {
-          const __nv_bfloat16 v = *reinterpret_cast<const __nv_bfloat16*>(sA + k * 128 + ((chunk ^ (k & 7)) << 4));
-          bsum += __bfloat162float(v);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);
-        if (++stage == num_stages) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-      p.bias_partial[static_cast<size_t>(split) * p.cout_slab + mt * 128 + row] = bsum;
-    }
     if (any) {
       mbar_wait(acc_full, 0);
       tc_fence_after();
+    }
+    if (do_bias) {
+      float bsum = 0.f;
+      if (kb_bias0 < kb1) {  // else: no K block of this split was ours
+        uint32_t v;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];"
+                     : "=r"(v)
+                     : "r"(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + ntap * BN)
+                     : "memory");
+        tmem_ld_wait();
+        bsum = __uint_as_float(v);
+      }
+      p.bias_partial[(static_cast<size_t>(split) * p.groups + g) * p.cout_slab + mt * 128 + row] = bsum;
     }
     for (int a = 0; a < ntap; ++a) {
       const int tap = p.taps == 1 ? 0 : (share ? a * 3 + g : g * 3 + a);  // tap = r * 3 + s
@@ -260,7 +268,7 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
 // writes into the OIHW tensor are the small side.  Threads of tap 0 with ci == 0 also finish the bias gradient.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int taps,
                                     int cout, int cin, int cout_slab, int cin_slab, int accumulate, float scale,
-                                    const float* __restrict__ bias_partial, float* __restrict__ db) {
+                                    const float* __restrict__ bias_partial, float* __restrict__ db, int bias_parts) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long per_tap = static_cast<long long>(cout) * cin;
   if (i >= per_tap * taps) return;
@@ -269,13 +277,21 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   const int co = static_cast<int>(r / cin), ci = static_cast<int>(r - static_cast<long long>(co) * cin);
   const size_t slab = static_cast<size_t>(cout_slab) * cin_slab;
   const float* src = partial + static_cast<size_t>(t) * slab + static_cast<size_t>(co) * cin_slab + ci;
-  float acc = 0.f;
-  for (int s = 0; s < splits; ++s) acc += src[static_cast<size_t>(s) * taps * slab];
+  // four independent partial sums (fixed order: deterministic) keep four loads in flight per thread
+  float a4[4] = {0.f, 0.f, 0.f, 0.f};
+  const size_t sstep = static_cast<size_t>(taps) * slab;
+  int s = 0;
+  for (; s + 4 <= splits; s += 4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a4[j] += src[static_cast<size_t>(s + j) * sstep];
+  }
+  for (; s < splits; ++s) a4[0] += src[static_cast<size_t>(s) * sstep];
+  const float acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
   float* d = dw + (static_cast<size_t>(co) * cin + ci) * taps + t;
   *d = accumulate ? *d + acc * scale : acc * scale;
   if (db != nullptr && t == 0 && ci == 0) {  // bias gradient: sum of the per-split column sums, fixed order
     float b = 0.f;
-    for (int s = 0; s < splits; ++s) b += bias_partial[static_cast<size_t>(s) * cout_slab + co];
+    for (int s = 0; s < bias_parts; ++s) b += bias_partial[static_cast<size_t>(s) * cout_slab + co];
     db[co] = accumulate ? db[co] + b * scale : b * scale;
   }
 }
@@ -378,13 +394,13 @@ inline bool wgrad_launch_init(WgradLaunch* L, bool conv3x3, const __nv_bfloat16*
   if (splits < 1) splits = 1;
   if (splits > k_blocks) splits = k_blocks;
   const size_t per_split = static_cast<size_t>(p.taps) * p.cout_slab * p.cin_slab;
-  const size_t bias_floats = static_cast<size_t>(p.cout_slab);
+  const size_t bias_floats = static_cast<size_t>(p.cout_slab) * p.groups;
   while (splits > 1 && (per_split + bias_floats) * splits > scratch_floats) --splits;
   if ((per_split + bias_floats) * splits > scratch_floats) return false;
   p.splits = static_cast<int>(splits);
   p.partial = scratch;
   p.bias_partial = nullptr;  // wgrad_run binds it behind the slabs when a bias gradient is asked for
-  L->scratch_floats = per_split * splits + static_cast<size_t>(splits) * p.cout_slab;
+  L->scratch_floats = (per_split + bias_floats) * splits;
   L->grid = tiles * p.splits;
   p.num_stages = bn == 128 ? WgradCfg<128>::stages(p.share != 0) : WgradCfg<64>::stages(p.share != 0);
   return true;
@@ -428,7 +444,8 @@ inline cudaError_t wgrad_run(const WgradLaunch& L0, float* dw, int cout, int cin
   if (e != cudaSuccess) return e;
   const long long items = static_cast<long long>(cout) * cin * L.p.taps;
   wgrad_reduce_kernel<<<static_cast<int>((items + 255) / 256), 256, 0, stream>>>(
-      L.p.partial, dw, L.p.splits, L.p.taps, cout, cin, L.p.cout_slab, L.p.cin_slab, accumulate, scale, L.p.bias_partial, db);
+      L.p.partial, dw, L.p.splits, L.p.taps, cout, cin, L.p.cout_slab, L.p.cin_slab, accumulate, scale, L.p.bias_partial, db,
+      L.p.splits * L.p.groups);
   return cudaGetLastError();
 }
 

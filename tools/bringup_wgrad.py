@@ -16,6 +16,7 @@ from climate2weather_b200 import _lib  # noqa: E402
 
 lib = _lib.load()
 dev = torch.device("cuda:0")
+NO_BIAS = "--no-bias" in sys.argv  # weight gradient only (no bias column sums)
 
 
 def run(name, n, H, W, cin, cout, stride=1, iters=10, warm=2):
@@ -29,7 +30,7 @@ def run(name, n, H, W, cin, cout, stride=1, iters=10, warm=2):
 
     def call():
         _lib.check(lib.c2w_op_wgrad(x.data_ptr(), dy.data_ptr(), n, H, W, cin_pad, cout_pad, stride, 1, scratch.data_ptr(),
-                                    scratch.numel(), dw.data_ptr(), db.data_ptr(), cin, cout, 0, st), "wgrad")
+                                    scratch.numel(), dw.data_ptr(), 0 if NO_BIAS else db.data_ptr(), cin, cout, 0, st), "wgrad")
 
     for _ in range(warm):
         call()
