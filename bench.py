@@ -364,7 +364,8 @@ def run_ours(args):
     # the windows whose output meets an observed frame (the others have a zero cotangent), a stashing forward and the
     # input-gradient conv of each layer (same FLOPs with Cin and Cout swapped)
     n_sel = rt.n_selected if args.exact_grad else 0
-    k1_flops_step = F_WIN_CONV * (n_win_local + 2 * n_sel)
+    n_rep = rt.n_repeated if args.exact_grad else 0  # windows whose forward runs twice (several stashing chunks)
+    k1_flops_step = F_WIN_CONV * (n_win_local + n_sel + n_rep)
     conv_tf = k1_flops_step / (conv_ms_step * 1e-3) / 1e12 if conv_ms_step > 0 else 0.0
     traffic, traffic_src = k1_traffic()
     k1_per_step = n2[0] // max(nprof, 1)
@@ -416,7 +417,7 @@ def run_ours(args):
         cpu = cpu_reference(L, sample_windows=args.cpu_windows, steps=1)
 
     if rank == 0:
-        x2 = (n_win_local + 2 * n_sel) / n_win_local
+        x2 = (n_win_local + n_sel + n_rep) / n_win_local
         line = {
             "metric": "guided-sampling frames/sec", "value": round(value, 3), "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,

@@ -111,7 +111,7 @@ SIGNATURES = {
     "c2w_bind_workspace_vjp": (_i, [_vp, C.c_int32, _vp, _i64]),
     "c2w_unet_vjp": (_i, [_vp, _vp, C.c_int32, _f, _vp, _vp, _vp, _vp]),
     "c2w_window_score_backward": (_i, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp]),
-    "c2w_window_score_sel": (_i, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int32, _f, _vp]),
+    "c2w_window_score_sel": (_i, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32, _f, _vp, _vp]),
     "c2w_window_score_backward_sel": (_i, [_vp, _vp, C.c_int32, C.c_int32, _vp, _vp, C.c_int32, C.c_int32, _vp, _vp]),
     "c2w_unet_forward": (_i, [_vp, _vp, C.c_int32, _f, _vp, _vp]),
     "c2w_window_score": (_i, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f, _vp, _vp]),

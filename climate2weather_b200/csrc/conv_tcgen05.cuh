@@ -105,6 +105,7 @@ struct ConvParams {
   int win_first;    // global index of the first window of this launch
   int win_last_global;  // global index of the last window of the trajectory (Nw - 1)
   int frame_base;   // global frame index of eps[0]
+  const int* win_list;  // global window index per image of this launch (a selection), or null: win_first + image
   long long* dbg_timeline;  // diagnostics only (-DC2W_DIAG): [2] = {min over CTAs of the start, max of the end} in
                             // %globaltimer ns for THIS launch (tools/timeline.py: kernel-inside time vs gaps)
   long long* dbg_stats;  // diagnostics only: per-CTA wait cycles [grid][12] (see tools/bringup_conv.py --stats)
@@ -194,7 +195,7 @@ __device__ __forceinline__ void epilogue_chunk_direct(const ConvParams& p, const
   if (p.mode == EPI_COMPOSE) {
     const int n_img = m / p.hw;
     const int pix = m - n_img * p.hw;
-    const int win = p.win_first + n_img;
+    const int win = p.win_list ? __ldg(p.win_list + n_img) : p.win_first + n_img;
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       const int tau = (col0 >> 2) + g;  // window slot of channels [4*tau, 4*tau+4)

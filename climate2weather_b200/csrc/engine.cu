@@ -908,6 +908,7 @@ struct FinalSpec {
   int mode;  // EPI_F32 or EPI_COMPOSE
   float* eps = nullptr;
   int order_k = 0, win_first = 0, win_last_global = 0, frame_base = 0;
+  const int* win_list = nullptr;  // EPI_COMPOSE over a selection of windows
 };
 
 // Runs an op list (the forward pass, or the input-gradient pass) on the first nn windows of the plan.
@@ -930,6 +931,7 @@ int run_ops(c2w_handle* h, std::vector<Op>& ops, int nn, const FinalSpec& fs, cu
           L.p.win_first = fs.win_first;
           L.p.win_last_global = fs.win_last_global;
           L.p.frame_base = fs.frame_base;
+          L.p.win_list = fs.win_list;
         }
 #ifdef C2W_DIAG
         if (h->timeline != nullptr && h->timeline_used < h->timeline_cap) L.p.dbg_timeline = h->timeline + 2 * h->timeline_used++;
@@ -1357,31 +1359,49 @@ int c2w_window_score(c2w_handle* h, const float* traj, int32_t n_frames_local, i
   return C2W_OK;
 }
 
-// Stashing forward of a SELECTION of windows (global indices win_list_dev[0..n_sel), n_sel <= max_windows of a VJP
-// workspace) — no score output.  With the coarse-graining likelihood the cotangent of the composed score is non-zero on
-// the OBSERVED frames only (every t_step-th, exp/downscaling.py:129-132), so only the windows whose centre (or, for
-// the first / last window, edge) frame is observed contribute to the vector-Jacobian product: the caller runs the
-// plain forward for all windows and this + c2w_window_score_backward_sel for ~1/t_step of them.
+// Forward of a SELECTION of windows (global indices win_list_dev[0..n_sel)).  With the coarse-graining likelihood the
+// cotangent of the composed score is non-zero on the OBSERVED frames only (every t_step-th, exp/downscaling.py:129-132),
+// so only the windows whose centre (or, for the first / last window, edge) frame is observed contribute to the
+// vector-Jacobian product: the caller runs this on a VJP workspace (stashing forward, n_sel <= max_windows) for ~1/t_step
+// of the windows, followed by c2w_window_score_backward_sel, and on a plain workspace for the others.
+// eps != null: the windows' part of the composed score goes into eps (the same fold as c2w_window_score, by list), so
+// the two selections together fill it and no window is evaluated twice; eps == null: stash only.
 int c2w_window_score_sel(c2w_handle* h, const float* traj, int32_t n_frames_local, int32_t frame_global0,
-                         const int32_t* win_list_dev, int32_t n_sel, float t, void* stream) {
+                         const int32_t* win_list_dev, int32_t n_sel, int32_t n_win_global, float t, float* eps,
+                         void* stream) {
   C2W_REQUIRE(h && traj && win_list_dev && n_sel >= 1, "c2w_window_score_sel: bad argument");
   Plan& P = h->plan;
-  if (P.n_max < 1 || !P.vjp || P.per_t) return fail(C2W_ERR_STATE, "bind a VJP workspace first (c2w_bind_workspace_vjp)");
-  C2W_REQUIRE(n_sel <= P.n_max, "c2w_window_score_sel: %d windows exceed the bound workspace (%d)", n_sel, P.n_max);
-  const int w = h->cfg.window, C = h->cfg.frame_channels;
+  if (P.n_max < 1 || P.per_t) return fail(C2W_ERR_STATE, "bind a workspace with one diffusion time first");
+  C2W_REQUIRE(!P.vjp || n_sel <= P.n_max, "c2w_window_score_sel: %d windows exceed the bound VJP workspace (%d)", n_sel,
+              P.n_max);
+  C2W_REQUIRE(eps || P.vjp, "c2w_window_score_sel: no output asked for on a plain workspace");
+  const int w = h->cfg.window, k = w / 2, C = h->cfg.frame_channels;
+  C2W_REQUIRE(!eps || C == 4, "fused compose supports 4 variables per frame (got %d)", C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int hw = h->cfg.height * h->cfg.width;
   (void)n_frames_local;
   int rc = run_modulation(h, t, nullptr, 1, P.h0, P.emb, P.mods, st);
   if (rc) return rc;
-  const long long items = static_cast<long long>(n_sel) * hw * (h->cin_pad / 8);
-  gather_windows_kernel<<<grid_for(items, 256, h->sms), 256, 0, st>>>(traj, P.xin, n_sel, hw, C, w * C, h->cin_pad,
-                                                                      frame_global0, win_list_dev);
-  ++g_launches;
-  C2W_CUDA(cudaGetLastError());
-  FinalSpec fs;
-  fs.mode = EPI_F32;
-  return run_plan(h, n_sel, fs, st);
+  for (int c0 = 0; c0 < n_sel; c0 += P.n_max) {
+    const int nn = std::min(P.n_max, n_sel - c0);
+    const long long items = static_cast<long long>(nn) * hw * (h->cin_pad / 8);
+    gather_windows_kernel<<<grid_for(items, 256, h->sms), 256, 0, st>>>(traj, P.xin, nn, hw, C, w * C, h->cin_pad,
+                                                                        frame_global0, win_list_dev + c0);
+    ++g_launches;
+    C2W_CUDA(cudaGetLastError());
+    FinalSpec fs;
+    fs.mode = EPI_F32;
+    if (eps) {
+      fs.mode = EPI_COMPOSE;
+      fs.eps = eps;
+      fs.order_k = k;
+      fs.win_last_global = n_win_global - 1;
+      fs.frame_base = frame_global0;
+      fs.win_list = win_list_dev + c0;
+    }
+    if ((rc = run_plan(h, nn, fs, st))) return rc;
+  }
+  return C2W_OK;
 }
 
 // Adjoint of the selected windows whose stashing forward has JUST run (c2w_window_score_sel, same list): compose adjoint

@@ -225,11 +225,14 @@ class Engine:
                                                           win_first, n_win, n_win_global, vjp.data_ptr(), self.stream),
                        "c2w_window_score_backward")
 
-    def window_score_sel(self, traj: Tensor, frame_global0: int, win_list: Tensor, t: float) -> None:
-        """Stashing forward of the selected windows (global indices, int32 device tensor) on a VJP workspace."""
+    def window_score_sel(self, traj: Tensor, frame_global0: int, win_list: Tensor, t: float, n_win_global: int = 0,
+                         eps: Optional[Tensor] = None) -> None:
+        """Forward of the selected windows (global indices, int32 device tensor): stashing on a VJP workspace, chunked
+        on a plain one; with `eps` their part of the composed score is written into it."""
         with torch.cuda.device(self.device):
             _lib.check(self.lib.c2w_window_score_sel(self.handle, traj.data_ptr(), traj.shape[0], frame_global0,
-                                                     win_list.data_ptr(), win_list.numel(), float(t), self.stream),
+                                                     win_list.data_ptr(), win_list.numel(), n_win_global, float(t),
+                                                     eps.data_ptr() if eps is not None else None, self.stream),
                        "c2w_window_score_sel")
 
     def window_score_backward_sel(self, cot: Tensor, frame_global0: int, win_list: Tensor, pos: Tensor, n_win_global: int,

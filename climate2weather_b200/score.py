@@ -86,6 +86,7 @@ class _Runtime:
         self._engine_vjp = None   # exact_grad: the stashing engine for the windows that need a backward pass
         self._engine_epoch = None
         self._sel = None          # exact_grad: cached selection of those windows (per conditioning)
+        self._rest = None         # exact_grad: the other local windows (int32 device list)
         self.refresh_engine()
         f32 = dict(dtype=torch.float32, device=device)
         self.x = torch.zeros(plan.n_local, H, W, C, **f32)
@@ -157,12 +158,23 @@ class _Runtime:
                 pos = torch.full((self.plan.n_win_global,), -1, dtype=torch.int32)
                 pos[torch.tensor(part, dtype=torch.long)] = torch.arange(len(part), dtype=torch.int32)
                 chunks.append((torch.tensor(part, dtype=torch.int32, device=self.device), pos.to(self.device)))
+            chosen = set(sel)
+            rest = [j for j in range(self.plan.win_lo, self.plan.win_hi) if j not in chosen]
+            self._rest = torch.tensor(rest, dtype=torch.int32, device=self.device)
             self._sel = (chunks, len(sel))
         return self._sel
 
     @property
     def n_selected(self) -> int:
         return self._selection()[1] if (self.exact and self.cond is not None) else 0
+
+    @property
+    def n_repeated(self) -> int:
+        """Windows whose forward runs twice per score evaluation (selection larger than one stashing chunk)."""
+        if not (self.exact and self.cond is not None):
+            return 0
+        chunks, n = self._selection()
+        return 0 if len(chunks) == 1 else n
 
     # ------------------------------------------------------------------------------------------------ state io
     @property
@@ -198,18 +210,30 @@ class _Runtime:
             self.engine.window_score(self.x, p.frame_lo, p.win_lo, p.win_hi - p.win_lo, p.n_win_global, t, self.eps)
             return
         mu, sigma = _mu_sigma(self.sf.noise_process, t)
-        # 1. the score itself: plain forward of every local window
-        self.engine.window_score(self.x, p.frame_lo, p.win_lo, p.win_hi - p.win_lo, p.n_win_global, t, self.eps)
-        # 2. likelihood cotangent g = A^T((y - A x0)/var) on the owned frames (zero on unobserved frames)
-        self._guide(2, mu, sigma, 0.0, 0.0)
-        # 3. J_eps^T g: only windows whose output meets an observed frame have a non-zero cotangent -> stashing forward
-        #    + input-gradient pass for that selection (~1/t_step of the windows), chunk by chunk
-        self.vjp.zero_()
+        # J_eps^T g: only windows whose output meets an observed frame have a non-zero cotangent -> stashing forward +
+        # input-gradient pass for that selection (~1/t_step of the windows)
         chunks, _ = self._selection()
         ev = self.engine_vjp
-        for win_list, pos in chunks:
-            ev.window_score_sel(self.x, p.frame_lo, win_list, t)
+        if len(chunks) == 1:
+            # the selection fits one stashing chunk: its forward also IS its part of the score, the other windows run
+            # on the plain engine, both fold into eps by window list — no window is evaluated twice
+            win_list, pos = chunks[0]
+            if self._rest.numel():
+                self.engine.window_score_sel(self.x, p.frame_lo, self._rest, t, p.n_win_global, self.eps)
+            ev.window_score_sel(self.x, p.frame_lo, win_list, t, p.n_win_global, self.eps)
+            # likelihood cotangent g = A^T((y - A x0)/var) on the owned frames (zero on unobserved frames)
+            self._guide(2, mu, sigma, 0.0, 0.0)
+            self.vjp.zero_()
             ev.window_score_backward_sel(self.cot, p.frame_lo, win_list, pos, p.n_win_global, self.vjp)
+        else:
+            # several stashing chunks (or none): the cotangent needs the whole score first, so every window runs on the
+            # plain engine and each chunk of the selection repeats its forward, stashing, right before its backward
+            self.engine.window_score(self.x, p.frame_lo, p.win_lo, p.win_hi - p.win_lo, p.n_win_global, t, self.eps)
+            self._guide(2, mu, sigma, 0.0, 0.0)
+            self.vjp.zero_()
+            for win_list, pos in chunks:
+                ev.window_score_sel(self.x, p.frame_lo, win_list, t)
+                ev.window_score_backward_sel(self.cot, p.frame_lo, win_list, pos, p.n_win_global, self.vjp)
         exchange_halos_adjoint(self.vjp, p, group)
 
     def set_condition(self, cond) -> None:

@@ -130,12 +130,15 @@ int c2w_window_score_backward(c2w_handle* h, const float* cot, int32_t n_frames_
 
 /* The same for a SELECTION of windows (global indices, device array).  The cotangent of the composed score under the
  * coarse-graining likelihood is non-zero on the observed frames only (every t_step-th frame, exp/downscaling.py:129-132),
- * so the vector-Jacobian product of src/thor/score.py:28-33 needs the backward of ~1/t_step of the windows: the plain
- * c2w_window_score for all of them, then c2w_window_score_sel (stashing forward, no score output) +
- * c2w_window_score_backward_sel for the windows whose centre / edge frames are observed.  pos_dev[j] = position of
- * global window j in win_list_dev, or -1. */
+ * so the vector-Jacobian product of src/thor/score.py:28-33 needs the backward of ~1/t_step of the windows only.
+ * c2w_window_score_sel is the forward of a selection: on a VJP workspace it stashes (n_sel <= max_windows) and is
+ * followed by c2w_window_score_backward_sel; on a plain workspace it chunks like c2w_window_score.  With eps != NULL the
+ * selection's part of the composed score is written into eps (same fold, by list), so the observed selection on the VJP
+ * workspace and the rest on the plain one fill eps together and no window runs twice; eps == NULL stashes only.
+ * pos_dev[j] = position of global window j in win_list_dev, or -1. */
 int c2w_window_score_sel(c2w_handle* h, const float* traj, int32_t n_frames_local, int32_t frame_global0,
-                         const int32_t* win_list_dev, int32_t n_sel, float t, void* stream);
+                         const int32_t* win_list_dev, int32_t n_sel, int32_t n_win_global, float t, float* eps,
+                         void* stream);
 int c2w_window_score_backward_sel(c2w_handle* h, const float* cot, int32_t n_frames_local, int32_t frame_global0,
                                   const int32_t* win_list_dev, const int32_t* pos_dev, int32_t n_sel, int32_t n_win_global,
                                   float* vjp, void* stream);
