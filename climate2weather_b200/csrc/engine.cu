@@ -301,9 +301,32 @@ int ensure_smem(K kernel, size_t smem, unsigned long long* done) {
   return C2W_OK;
 }
 
+template <int C>
+int launch_attention_bwd_mma(const bf16* qkv, const bf16* go, bf16* gqkv, int n, cudaStream_t st) {
+  const size_t smem = attention_bwd_mma_smem_bytes(C);
+  static unsigned long long done = 0;
+  int rc = ensure_smem(attention_bwd_mma_kernel<C>, smem, &done);
+  if (rc) return rc;
+  attention_bwd_mma_kernel<C><<<n, 256, smem, st>>>(qkv, go, gqkv, 1.0f / sqrtf(static_cast<float>(C)));
+  C2W_CUDA(cudaGetLastError());
+  return C2W_OK;
+}
+
 int launch_attention_bwd(const bf16* qkv, const bf16* go, bf16* gqkv, float* scratch, int n, int T, int C,
                          cudaStream_t st) {
   C2W_REQUIRE(T % 8 == 0 && C % 8 == 0 && scratch, "attention backward: T %% 8 and C %% 8 must be 0 (T=%d C=%d)", T, C);
+  {  // 64 tokens (8 x 8 attention level): tensor-core kernel; C2W_ATTN_MMA=0 keeps the CUDA-core kernels (A/B runs)
+    static int use_mma = -1;
+    if (use_mma < 0) {
+      const char* e = getenv("C2W_ATTN_MMA");
+      use_mma = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (use_mma && T == 64) {
+      if (C == 512) return launch_attention_bwd_mma<512>(qkv, go, gqkv, n, st);
+      if (C == 256) return launch_attention_bwd_mma<256>(qkv, go, gqkv, n, st);
+      if (C == 128) return launch_attention_bwd_mma<128>(qkv, go, gqkv, n, st);
+    }
+  }
   const int QB = std::min(T, kAttnBwdRows);
   const size_t smem1 = attention_bwd_scores_smem(T, C, QB), smem2 = attention_bwd_grads_smem(T, C, QB);
   C2W_REQUIRE(std::max(smem1, smem2) <= static_cast<size_t>(kSmemLimit),

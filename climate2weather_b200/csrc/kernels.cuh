@@ -703,6 +703,193 @@ __global__ void __launch_bounds__(256) attention_mma_kernel(const bf16* __restri
   }
 }
 
+// ---- backward of the T = 64 attention core on the same warp MMAs (exact_grad / training: K8)
+//   P = softmax(scale2 q k^T),  gP = go v^T,  gS = P o (gP - rowsum(gP o P)),
+//   gq = scale2 gS k,  gk = scale2 gS^T q,  gv = P^T go            (model/nn.py:79-84 differentiated)
+// One CTA (8 warps) per window, three [64, C] operand slots in shared memory (same XOR-swizzled 16 B chunks as the
+// forward kernel) that q, k, v, go rotate through, P and scale2 gS as bf16 [64, 64] tiles for the three output GEMMs:
+//   slots {q, k, v}:  warps 0-3: S, softmax -> P in registers
+//   slots {go, k, v}: warps 0-3: gP -> gS; P, gS -> shared
+//   slots {go, k, q}: all warps: gv = P^T go, gq = gS k, then gk = gS^T q (q reloaded under the first two)
+template <int C>
+__device__ __forceinline__ void attn_slot_load(uint32_t sdst, const bf16* src, int row_stride, int tid) {
+  constexpr int CH = C / 8, PITCH = C * 2;
+  for (int idx = tid; idx < 64 * CH; idx += 256) {
+    const int r = idx / CH, cc = idx - r * CH;
+    const uint32_t dst = sdst + r * PITCH + ((cc ^ (r & 7)) << 4);
+    const bf16* g = src + static_cast<size_t>(r) * row_stride + cc * 8;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+// acc[16 rows r0.. of A][64 rows of B] = A[.][:] . B[.][:] over the C channels (both [64, C] slots)
+template <int C>
+__device__ __forceinline__ void attn_rows_dot_rows(float (&acc)[8][4], uint32_t sA, uint32_t sB, int r0, int lane) {
+  constexpr int PITCH = C * 2;
+  const int mat = lane >> 3, rr = lane & 7;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+  const int arow = r0 + rr + (mat & 1) * 8;
+#pragma unroll 4
+  for (int ks = 0; ks < C / 16; ++ks) {
+    uint32_t a[4];
+    ldmatrix_x4(a, sA + arow * PITCH + (((2 * ks + (mat >> 1)) ^ (arow & 7)) << 4));
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {
+      const int key = 16 * jp + rr + (mat >> 1) * 8;
+      uint32_t b[4];
+      ldmatrix_x4(b, sB + key * PITCH + (((2 * ks + (mat & 1)) ^ (key & 7)) << 4));
+      mma_bf16_16816(acc[2 * jp], a, b[0], b[1]);
+      mma_bf16_16816(acc[2 * jp + 1], a, b[2], b[3]);
+    }
+  }
+}
+// out[r0 + 16 rows][cbase + C/2 channels] = M' [64 x 64] . X [64, C]; M' = M (TRANS = false) or M^T (TRANS = true),
+// M a bf16 [64][64] tile (128 B rows, swizzled chunks), X a [64, C] slot; rows of `out` are 3C apart (the qkv gradient).
+template <int C, bool TRANS>
+__device__ __forceinline__ void attn_tile_times_slot(bf16* out, uint32_t sM, uint32_t sX, int r0, int cbase, int lane) {
+  constexpr int PITCH = C * 2;
+  const int mat = lane >> 3, rr = lane & 7, g = lane >> 2, tq = lane & 3;
+  uint32_t ma[4][4];  // A fragments of the 4 k-steps over the 64 summed rows
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    if (!TRANS) {
+      const int arow = r0 + rr + (mat & 1) * 8;
+      ldmatrix_x4(ma[ks], sM + arow * 128 + (((2 * ks + (mat >> 1)) ^ (arow & 7)) << 4));
+    } else {  // A[m][k] = M[k][m]: 8 x 8 blocks of M read transposed
+      const int krow = 16 * ks + rr + (mat >> 1) * 8;
+      ldmatrix_x4_trans(ma[ks], sM + krow * 128 + ((((r0 >> 3) + (mat & 1)) ^ (krow & 7)) << 4));
+    }
+  }
+  bf16* orow0 = out + static_cast<size_t>(r0 + g) * 3 * C;
+  bf16* orow1 = orow0 + static_cast<size_t>(8) * 3 * C;
+#pragma unroll 1
+  for (int grp = 0; grp < C / 128; ++grp) {  // 64 channels at a time
+    const int c0 = cbase + 64 * grp;
+    float acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int key = 16 * ks + rr + (mat & 1) * 8;
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        const int chunk = (c0 >> 3) + 2 * jp + (mat >> 1);
+        uint32_t b[4];
+        ldmatrix_x4_trans(b, sX + key * PITCH + ((chunk ^ (key & 7)) << 4));
+        mma_bf16_16816(acc[2 * jp], ma[ks], b[0], b[1]);
+        mma_bf16_16816(acc[2 * jp + 1], ma[ks], b[2], b[3]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = c0 + 8 * j + 2 * tq;
+      *reinterpret_cast<uint32_t*>(orow0 + col) = pack_bf16x2(acc[j][0], acc[j][1]);
+      *reinterpret_cast<uint32_t*>(orow1 + col) = pack_bf16x2(acc[j][2], acc[j][3]);
+    }
+  }
+}
+inline size_t attention_bwd_mma_smem_bytes(int C) { return static_cast<size_t>(3) * 64 * C * 2 + 2 * 64 * 64 * 2; }
+template <int C>
+__global__ void __launch_bounds__(256) attention_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ go,
+                                                                bf16* __restrict__ gqkv, float scale2) {
+  constexpr int T = 64, PITCH = C * 2;
+  extern __shared__ __align__(128) uint8_t smraw[];
+  const uint32_t s0 = static_cast<uint32_t>(__cvta_generic_to_shared(smraw));
+  const uint32_t s1 = s0 + T * PITCH, s2 = s1 + T * PITCH, sP = s2 + T * PITCH, sG = sP + T * 128;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bf16* src = qkv + static_cast<size_t>(blockIdx.x) * T * 3 * C;
+  const bf16* gsrc = go + static_cast<size_t>(blockIdx.x) * T * C;
+  bf16* dst = gqkv + static_cast<size_t>(blockIdx.x) * T * 3 * C;
+  attn_slot_load<C>(s0, src, 3 * C, tid);          // q
+  attn_slot_load<C>(s1, src + C, 3 * C, tid);      // k
+  attn_slot_load<C>(s2, src + 2 * C, 3 * C, tid);  // v
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const int g = lane >> 2, tq = lane & 3;
+  const int r0 = 16 * (warp & 3);
+  float p[8][4];
+  if (warp < 4) {
+    attn_rows_dot_rows<C>(p, s0, s1, r0, lane);  // S
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) p[j][e] *= scale2;
+      m0 = fmaxf(m0, fmaxf(p[j][0], p[j][1]));
+      m1 = fmaxf(m1, fmaxf(p[j][2], p[j][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      p[j][0] = expf(p[j][0] - m0);
+      p[j][1] = expf(p[j][1] - m0);
+      p[j][2] = expf(p[j][2] - m1);
+      p[j][3] = expf(p[j][3] - m1);
+      sum0 += p[j][0] + p[j][1];
+      sum1 += p[j][2] + p[j][3];
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    const float i0 = 1.0f / sum0, i1 = 1.0f / sum1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      p[j][0] *= i0;
+      p[j][1] *= i0;
+      p[j][2] *= i1;
+      p[j][3] *= i1;
+    }
+  }
+  __syncthreads();                        // every warp is done with q
+  attn_slot_load<C>(s0, gsrc, C, tid);    // go over q
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (warp < 4) {
+    float gp[8][4];
+    attn_rows_dot_rows<C>(gp, s0, s2, r0, lane);  // gP = go v^T
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      d0 += gp[j][0] * p[j][0] + gp[j][1] * p[j][1];
+      d1 += gp[j][2] * p[j][2] + gp[j][3] * p[j][3];
+    }
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+    const int row0 = r0 + g, row1 = r0 + g + 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {  // [row][8 j + 2 tq, +1] (bf16): chunk j of the 128 B row, swizzled
+      const uint32_t o0 = (row0 * 128 + ((j ^ (row0 & 7)) << 4) + tq * 4), o1 = (row1 * 128 + ((j ^ (row1 & 7)) << 4) + tq * 4);
+      const uint32_t p0 = pack_bf16x2(p[j][0], p[j][1]), p1 = pack_bf16x2(p[j][2], p[j][3]);
+      const uint32_t g0 = pack_bf16x2(scale2 * p[j][0] * (gp[j][0] - d0), scale2 * p[j][1] * (gp[j][1] - d0));
+      const uint32_t g1 = pack_bf16x2(scale2 * p[j][2] * (gp[j][2] - d1), scale2 * p[j][3] * (gp[j][3] - d1));
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(sP + o0), "r"(p0) : "memory");
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(sP + o1), "r"(p1) : "memory");
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(sG + o0), "r"(g0) : "memory");
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(sG + o1), "r"(g1) : "memory");
+    }
+  }
+  __syncthreads();                                 // P, gS visible; v is dead
+  attn_slot_load<C>(s2, src, 3 * C, tid);          // q over v, under the next two products
+  const int cbase = (warp >> 2) * (C / 2);
+  attn_tile_times_slot<C, true>(dst + 2 * C, sP, s0, r0, cbase, lane);   // gv = P^T go
+  attn_tile_times_slot<C, false>(dst, sG, s1, r0, cbase, lane);          // gq = scale2 gS k
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  attn_tile_times_slot<C, true>(dst + C, sG, s2, r0, cbase, lane);       // gk = scale2 gS^T q
+}
+
 // ------------------------------------------------------------------------------------------------ VJP kernels
 // Backward of the channel LayerNorm (model/nn.py:154,183; zuko LayerNorm, unbiased variance):
 //   g_v = inv * (g_y - mean_C(g_y) - y * sum_C(g_y y) / (C - 1)),   out = gres + g_v

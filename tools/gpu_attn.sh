@@ -1,9 +1,8 @@
 #!/bin/bash
-for qb in 16 32 64; do
-  echo "== C2W_ATTN_QB=$qb"
-  C2W_ATTN_QB=$qb timeout 200 python bench.py --steps 8 --warmup 3 --no-cpu --no-e2e 2>&1 | grep '^{' | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); r=d['roofline']
-print('ms/step', d['ms_per_step'], 'k1_ms', r['k1_ms_per_step'], 'other_ms', r['other_fwd_kernels_ms_per_step'], 'clocks', d['clocks'])"
-done
-timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "attention" 2>&1 | tail -2
+TAG=${1:-at}
+OUT=gpurun_out
+mkdir -p $OUT
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_train.py -m gpu -q -x -k "attention or vjp or exact or train or grad" > $OUT/test_attn_$TAG.log 2>&1; echo "pytest exit=$?"
+tail -8 $OUT/test_attn_$TAG.log
+timeout 600 python bench.py --exact-grad --steps 10 --warmup 3 --no-cpu --no-e2e > $OUT/bench_exact_grad_$TAG.log 2>&1; echo "bench exit=$?"; tail -1 $OUT/bench_exact_grad_$TAG.log | cut -c1-250
+timeout 600 python bench.py --mode train --steps 5 --warmup 3 > $OUT/bench_train_n1_$TAG.log 2>&1; echo "train exit=$?"; tail -1 $OUT/bench_train_n1_$TAG.log | cut -c1-250
