@@ -131,6 +131,9 @@ struct c2w_handle {
   float *proj_w = nullptr, *proj_b = nullptr;
   long long *row_w = nullptr, *row_b = nullptr;  // per modulation channel: where its project.weight row / bias lives in the flat gradient
   float *mapf_w = nullptr, *mapf_b = nullptr;  // forcing branch: [E, forcing_pad] (columns zero-padded to 4), [E]
+  void* refresh_jobs = nullptr;  // c2w_refresh_weights: device table of re-pack jobs (built at the first call)
+  int* refresh_first = nullptr;
+  int refresh_n = 0, refresh_chunks = 0;
   int forcing_pad = 0;
   const float* forcing = nullptr;  // c2w_set_forcing: device [n, forcing_dim] for the next per-sample forwards
   float* zero_bias = nullptr;  // 512 zeros: the input-gradient convs have no bias
@@ -1540,46 +1543,79 @@ int c2w_refresh_weights(c2w_handle* h, const float* flat_dev, void* stream) {
   C2W_REQUIRE(h && flat_dev, "c2w_refresh_weights: bad argument");
   if (!h->finalized) return fail(C2W_ERR_STATE, "finalise the weights first");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  auto conv = [&](const ConvW& w) -> int {
-    if (w.gw < 0 || w.gb < 0) return fail(C2W_ERR_MISSING, "a conv has no slot in the flat parameter layout");
-    const long long total = static_cast<long long>(w.cout) * w.cin * w.taps;
-    repack_conv_kernel<<<grid_for(total, 256, h->sms), 256, 0, st>>>(flat_dev + w.gw, flat_dev + w.gb, w.w, w.wd, w.b, w.cout,
-                                                                     w.cin, w.taps, w.cin_pad, w.cout_pad);
-    return C2W_OK;
-  };
-  const int E = h->cfg.embedding_dim;
-  int rc;
-  for (LevelW& L : h->levels) {
-    if ((rc = conv(L.head)) || (rc = conv(L.tail))) return rc;
-    for (int side = 0; side < 2; ++side) {
-      std::vector<BlockW>& blocks = side == 0 ? L.desc : L.asc;
-      std::vector<AttnW>& attns = side == 0 ? L.dattn : L.aattn;
-      for (BlockW& bw : blocks) {
-        if ((rc = conv(bw.c1)) || (rc = conv(bw.c2))) return rc;
-        C2W_REQUIRE(bw.g_pw >= 0 && bw.g_pb >= 0, "a modulation projection has no slot in the flat parameter layout");
-        C2W_CUDA(cudaMemcpyAsync(h->proj_w + static_cast<size_t>(bw.mod_off) * E, flat_dev + bw.g_pw,
-                                 static_cast<size_t>(L.C) * E * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        C2W_CUDA(cudaMemcpyAsync(h->proj_b + bw.mod_off, flat_dev + bw.g_pb, L.C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (!h->refresh_jobs) {  // the job table is a function of the layout only: built and uploaded once
+    std::vector<RefreshJob> jobs;
+    auto copy = [&](long long src, float* dst, long long n) {
+      RefreshJob j{};
+      j.src = src, j.n = n, j.fdst = dst, j.kind = 1;
+      jobs.push_back(j);
+    };
+    auto conv = [&](const ConvW& w) -> int {
+      if (w.gw < 0 || w.gb < 0) return fail(C2W_ERR_MISSING, "a conv has no slot in the flat parameter layout");
+      RefreshJob j{};
+      j.src = w.gw, j.n = static_cast<long long>(w.cout) * w.cin * w.taps, j.wp = w.w, j.wd = w.wd, j.kind = 0;
+      j.cout = w.cout, j.cin = w.cin, j.taps = w.taps, j.cin_pad = w.cin_pad, j.cout_pad = w.cout_pad;
+      jobs.push_back(j);
+      copy(w.gb, w.b, w.cout);
+      return C2W_OK;
+    };
+    const int E = h->cfg.embedding_dim;
+    int rc;
+    for (LevelW& L : h->levels) {
+      if ((rc = conv(L.head)) || (rc = conv(L.tail))) return rc;
+      for (int side = 0; side < 2; ++side) {
+        std::vector<BlockW>& blocks = side == 0 ? L.desc : L.asc;
+        std::vector<AttnW>& attns = side == 0 ? L.dattn : L.aattn;
+        for (BlockW& bw : blocks) {
+          if ((rc = conv(bw.c1)) || (rc = conv(bw.c2))) return rc;
+          C2W_REQUIRE(bw.g_pw >= 0 && bw.g_pb >= 0, "a modulation projection has no slot in the flat parameter layout");
+          copy(bw.g_pw, h->proj_w + static_cast<size_t>(bw.mod_off) * E, static_cast<long long>(L.C) * E);
+          copy(bw.g_pb, h->proj_b + bw.mod_off, L.C);
+        }
+        for (AttnW& aw : attns)
+          if ((rc = conv(aw.qkv)) || (rc = conv(aw.proj))) return rc;
       }
-      for (AttnW& aw : attns)
-        if ((rc = conv(aw.qkv)) || (rc = conv(aw.proj))) return rc;
     }
+    if (h->cfg.forcing_dim > 0) {  // forcing branch: weight rows re-padded, bias copied
+      auto iw = h->param_off.find("map_forcing.weight"), ib = h->param_off.find("map_forcing.bias");
+      C2W_REQUIRE(iw != h->param_off.end() && ib != h->param_off.end(), "map_forcing has no slot in the flat layout");
+      RefreshJob j{};
+      j.src = iw->second, j.n = static_cast<long long>(E) * h->forcing_pad, j.fdst = h->mapf_w, j.kind = 2;
+      j.cin = h->cfg.forcing_dim, j.cin_pad = h->forcing_pad;
+      jobs.push_back(j);
+      copy(ib->second, h->mapf_b, E);
+    }
+    struct { const char* name; float* dst; long long n; } mlp[4] = {
+        {"map_layer0.weight", h->map0_w, static_cast<long long>(E) * h->cfg.noise_features}, {"map_layer0.bias", h->map0_b, E},
+        {"map_layer1.weight", h->map1_w, static_cast<long long>(E) * E}, {"map_layer1.bias", h->map1_b, E}};
+    for (auto& m : mlp) {
+      auto it = h->param_off.find(m.name);
+      C2W_REQUIRE(it != h->param_off.end(), "parameter '%s' has no slot in the flat layout", m.name);
+      copy(it->second, m.dst, m.n);
+    }
+    std::vector<int> first(jobs.size());
+    long long chunks = 0;
+    for (size_t i = 0; i < jobs.size(); ++i) {
+      first[i] = static_cast<int>(chunks);
+      chunks += (jobs[i].n + kRefreshChunk - 1) / kRefreshChunk;
+    }
+    RefreshJob* dj = nullptr;
+    int* df = nullptr;
+    C2W_CUDA(cudaMalloc(&dj, jobs.size() * sizeof(RefreshJob)));
+    h->allocs.push_back(dj);
+    C2W_CUDA(cudaMalloc(&df, first.size() * sizeof(int)));
+    h->allocs.push_back(df);
+    C2W_CUDA(cudaMemcpy(dj, jobs.data(), jobs.size() * sizeof(RefreshJob), cudaMemcpyHostToDevice));
+    C2W_CUDA(cudaMemcpy(df, first.data(), first.size() * sizeof(int), cudaMemcpyHostToDevice));
+    h->refresh_jobs = dj;
+    h->refresh_first = df;
+    h->refresh_n = static_cast<int>(jobs.size());
+    h->refresh_chunks = static_cast<int>(chunks);
   }
-  if (h->cfg.forcing_dim > 0) {  // forcing branch: weight rows re-padded, bias copied
-    auto iw = h->param_off.find("map_forcing.weight"), ib = h->param_off.find("map_forcing.bias");
-    C2W_REQUIRE(iw != h->param_off.end() && ib != h->param_off.end(), "map_forcing has no slot in the flat layout");
-    pad_rows_kernel<<<ceil_div(static_cast<long long>(E) * h->forcing_pad, 256), 256, 0, st>>>(flat_dev + iw->second, h->mapf_w, E,
-                                                                                             h->cfg.forcing_dim, h->forcing_pad);
-    C2W_CUDA(cudaMemcpyAsync(h->mapf_b, flat_dev + ib->second, E * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  }
-  struct { const char* name; float* dst; size_t n; } mlp[4] = {
-      {"map_layer0.weight", h->map0_w, static_cast<size_t>(E) * h->cfg.noise_features}, {"map_layer0.bias", h->map0_b, (size_t)E},
-      {"map_layer1.weight", h->map1_w, static_cast<size_t>(E) * E}, {"map_layer1.bias", h->map1_b, (size_t)E}};
-  for (auto& m : mlp) {
-    auto it = h->param_off.find(m.name);
-    C2W_REQUIRE(it != h->param_off.end(), "parameter '%s' has no slot in the flat layout", m.name);
-    C2W_CUDA(cudaMemcpyAsync(m.dst, flat_dev + it->second, m.n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  }
+  const int grid = std::min(h->refresh_chunks, 16 * h->sms);
+  refresh_weights_kernel<<<grid, 256, 0, st>>>(static_cast<const RefreshJob*>(h->refresh_jobs), h->refresh_first,
+                                               h->refresh_n, h->refresh_chunks, flat_dev);
+  ++g_launches;
   C2W_CUDA(cudaGetLastError());
   return C2W_OK;
 }

@@ -1125,23 +1125,50 @@ __global__ void dsm_loss_grad_kernel(const float* __restrict__ out, const float*
   }
 }
 
-// Device-side re-pack of one conv's weights after an optimiser step: fp32 OIHW (torch layout, in the flat parameter
+// Device-side re-pack of the weights after an optimiser step.  A conv: fp32 OIHW (torch layout, in the flat parameter
 // buffer) -> the bf16 forward operand [cout_pad][taps * cin_pad] (k = tap * cin_pad + c) and the flipped / transposed
 // input-gradient operand [cin_pad][taps * cout_pad] (k = (taps - 1 - tap) * cout_pad + o); padding entries stay zero.
-__global__ void repack_conv_kernel(const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ wp,
-                                   bf16* __restrict__ wd, float* __restrict__ bp, int cout, int cin, int taps, int cin_pad,
-                                   int cout_pad) {
-  const long long total = static_cast<long long>(cout) * cin * taps;
-  const size_t K = static_cast<size_t>(taps) * cin_pad, Kd = static_cast<size_t>(taps) * cout_pad;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int t = static_cast<int>(i % taps);
-    const long long oc = i / taps;
-    const int c = static_cast<int>(oc % cin), o = static_cast<int>(oc / cin);
-    const bf16 v = __float2bfloat16_rn(w[i]);
-    wp[o * K + static_cast<size_t>(t) * cin_pad + c] = v;
-    wd[c * Kd + static_cast<size_t>(taps - 1 - t) * cout_pad + o] = v;
-    if (i < cout) bp[i] = b[i];
+// The whole re-pack as ONE launch: a table of jobs (every conv's weights, every bias / projection / MLP copy, the
+// zero-padded forcing rows), 1024 elements per block step; `first_chunk[j]` = index of job j's first 1024-element chunk.
+struct RefreshJob {
+  long long src;   // offset in the flat fp32 parameter buffer
+  long long n;     // elements (conv: cout * cin * taps; copy: floats; padded rows: rows * cols_pad)
+  bf16* wp;        // conv: forward operand
+  bf16* wd;        // conv: input-gradient operand
+  float* fdst;     // copy / padded rows: destination
+  int kind;        // 0 conv weights, 1 fp32 copy, 2 rows of `cin` floats padded to `cin_pad`
+  int cout, cin, taps, cin_pad, cout_pad;
+};
+constexpr int kRefreshChunk = 1024;
+__global__ void refresh_weights_kernel(const RefreshJob* __restrict__ jobs, const int* __restrict__ first_chunk, int n_jobs,
+                                       int n_chunks, const float* __restrict__ flat) {
+  for (int ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    int lo = 0, hi = n_jobs - 1;  // last job whose first chunk <= ch
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (first_chunk[mid] <= ch) lo = mid;
+      else hi = mid - 1;
+    }
+    const RefreshJob jb = jobs[lo];
+    const float* src = flat + jb.src;
+    const long long i0 = static_cast<long long>(ch - first_chunk[lo]) * kRefreshChunk;
+    for (int k = threadIdx.x; k < kRefreshChunk; k += blockDim.x) {
+      const long long i = i0 + k;
+      if (i >= jb.n) break;
+      if (jb.kind == 0) {
+        const int t = static_cast<int>(i % jb.taps);
+        const long long oc = i / jb.taps;
+        const int c = static_cast<int>(oc % jb.cin), o = static_cast<int>(oc / jb.cin);
+        const bf16 v = __float2bfloat16_rn(src[i]);
+        jb.wp[o * (static_cast<size_t>(jb.taps) * jb.cin_pad) + static_cast<size_t>(t) * jb.cin_pad + c] = v;
+        jb.wd[c * (static_cast<size_t>(jb.taps) * jb.cout_pad) + static_cast<size_t>(jb.taps - 1 - t) * jb.cout_pad + o] = v;
+      } else if (jb.kind == 1) {
+        jb.fdst[i] = src[i];
+      } else {
+        const int r = static_cast<int>(i / jb.cin_pad), c = static_cast<int>(i - static_cast<long long>(r) * jb.cin_pad);
+        jb.fdst[i] = c < jb.cin ? src[static_cast<long long>(r) * jb.cin + c] : 0.f;
+      }
+    }
   }
 }
 
