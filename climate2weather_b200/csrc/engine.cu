@@ -1548,6 +1548,7 @@ int c2w_refresh_weights(c2w_handle* h, const float* flat_dev, void* stream) {
     auto copy = [&](long long src, float* dst, long long n) {
       RefreshJob j{};
       j.src = src, j.n = n, j.fdst = dst, j.kind = 1;
+      j.chunks = static_cast<int>((n + kRefreshChunk - 1) / kRefreshChunk);
       jobs.push_back(j);
     };
     auto conv = [&](const ConvW& w) -> int {
@@ -1555,6 +1556,8 @@ int c2w_refresh_weights(c2w_handle* h, const float* flat_dev, void* stream) {
       RefreshJob j{};
       j.src = w.gw, j.n = static_cast<long long>(w.cout) * w.cin * w.taps, j.wp = w.w, j.wd = w.wd, j.kind = 0;
       j.cout = w.cout, j.cin = w.cin, j.taps = w.taps, j.cin_pad = w.cin_pad, j.cout_pad = w.cout_pad;
+      if (w.taps > 9) return fail(C2W_ERR_INVALID, "weight re-pack handles up to 9 taps (got %d)", w.taps);
+      j.chunks = ((w.cout + kRefreshTile - 1) / kRefreshTile) * ((w.cin + kRefreshTile - 1) / kRefreshTile);
       jobs.push_back(j);
       copy(w.gb, w.b, w.cout);
       return C2W_OK;
@@ -1582,6 +1585,7 @@ int c2w_refresh_weights(c2w_handle* h, const float* flat_dev, void* stream) {
       RefreshJob j{};
       j.src = iw->second, j.n = static_cast<long long>(E) * h->forcing_pad, j.fdst = h->mapf_w, j.kind = 2;
       j.cin = h->cfg.forcing_dim, j.cin_pad = h->forcing_pad;
+      j.chunks = static_cast<int>((j.n + kRefreshChunk - 1) / kRefreshChunk);
       jobs.push_back(j);
       copy(ib->second, h->mapf_b, E);
     }
@@ -1597,7 +1601,7 @@ int c2w_refresh_weights(c2w_handle* h, const float* flat_dev, void* stream) {
     long long chunks = 0;
     for (size_t i = 0; i < jobs.size(); ++i) {
       first[i] = static_cast<int>(chunks);
-      chunks += (jobs[i].n + kRefreshChunk - 1) / kRefreshChunk;
+      chunks += jobs[i].chunks;
     }
     RefreshJob* dj = nullptr;
     int* df = nullptr;

@@ -1132,16 +1132,20 @@ __global__ void dsm_loss_grad_kernel(const float* __restrict__ out, const float*
 // zero-padded forcing rows), 1024 elements per block step; `first_chunk[j]` = index of job j's first 1024-element chunk.
 struct RefreshJob {
   long long src;   // offset in the flat fp32 parameter buffer
-  long long n;     // elements (conv: cout * cin * taps; copy: floats; padded rows: rows * cols_pad)
+  long long n;     // copy: floats; padded rows: rows * cols_pad; conv: unused
   bf16* wp;        // conv: forward operand
   bf16* wd;        // conv: input-gradient operand
   float* fdst;     // copy / padded rows: destination
   int kind;        // 0 conv weights, 1 fp32 copy, 2 rows of `cin` floats padded to `cin_pad`
   int cout, cin, taps, cin_pad, cout_pad;
+  int chunks;      // conv: ceil(cout / 32) * ceil(cin / 32) tiles; else ceil(n / 1024)
 };
 constexpr int kRefreshChunk = 1024;
-__global__ void refresh_weights_kernel(const RefreshJob* __restrict__ jobs, const int* __restrict__ first_chunk, int n_jobs,
-                                       int n_chunks, const float* __restrict__ flat) {
+constexpr int kRefreshTile = 32;  // conv jobs: [32 output x 32 input channels x taps] tiles through shared memory
+__global__ void __launch_bounds__(256)
+refresh_weights_kernel(const RefreshJob* __restrict__ jobs, const int* __restrict__ first_chunk, int n_jobs, int n_chunks,
+                       const float* __restrict__ flat) {
+  __shared__ float tile[kRefreshTile][kRefreshTile * 9 + 1];  // [o][c * taps + t], taps <= 9
   for (int ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
     int lo = 0, hi = n_jobs - 1;  // last job whose first chunk <= ch
     while (lo < hi) {
@@ -1151,18 +1155,37 @@ __global__ void refresh_weights_kernel(const RefreshJob* __restrict__ jobs, cons
     }
     const RefreshJob jb = jobs[lo];
     const float* src = flat + jb.src;
-    const long long i0 = static_cast<long long>(ch - first_chunk[lo]) * kRefreshChunk;
+    const int local = ch - first_chunk[lo];
+    if (jb.kind == 0) {
+      // tile (ob, cb): rows of 32 * taps contiguous floats in, 64-byte runs of c (forward operand) and o (gradient
+      // operand) out — the element-wise version wrote 2-byte values 2 * K bytes apart
+      const int c_tiles = (jb.cin + kRefreshTile - 1) / kRefreshTile;
+      const int o0 = (local / c_tiles) * kRefreshTile, c0 = (local % c_tiles) * kRefreshTile;
+      const int no = min(kRefreshTile, jb.cout - o0), nc = min(kRefreshTile, jb.cin - c0);
+      const int run = nc * jb.taps;
+      for (int k = threadIdx.x; k < no * run; k += blockDim.x) {
+        const int o = k / run, r = k - o * run;
+        tile[o][r] = src[(static_cast<long long>(o0 + o) * jb.cin + c0) * jb.taps + r];
+      }
+      __syncthreads();
+      const size_t K = static_cast<size_t>(jb.taps) * jb.cin_pad, Kd = static_cast<size_t>(jb.taps) * jb.cout_pad;
+      for (int k = threadIdx.x; k < no * jb.taps * nc; k += blockDim.x) {  // (o, t, c), c fastest
+        const int c = k % nc, ot = k / nc, t = ot % jb.taps, o = ot / jb.taps;
+        jb.wp[(o0 + o) * K + static_cast<size_t>(t) * jb.cin_pad + c0 + c] = __float2bfloat16_rn(tile[o][c * jb.taps + t]);
+      }
+      for (int k = threadIdx.x; k < nc * jb.taps * no; k += blockDim.x) {  // (c, t, o), o fastest
+        const int o = k % no, ct = k / no, t = ct % jb.taps, c = ct / jb.taps;
+        jb.wd[(c0 + c) * Kd + static_cast<size_t>(jb.taps - 1 - t) * jb.cout_pad + o0 + o] =
+            __float2bfloat16_rn(tile[o][c * jb.taps + t]);
+      }
+      __syncthreads();
+      continue;
+    }
+    const long long i0 = static_cast<long long>(local) * kRefreshChunk;
     for (int k = threadIdx.x; k < kRefreshChunk; k += blockDim.x) {
       const long long i = i0 + k;
       if (i >= jb.n) break;
-      if (jb.kind == 0) {
-        const int t = static_cast<int>(i % jb.taps);
-        const long long oc = i / jb.taps;
-        const int c = static_cast<int>(oc % jb.cin), o = static_cast<int>(oc / jb.cin);
-        const bf16 v = __float2bfloat16_rn(src[i]);
-        jb.wp[o * (static_cast<size_t>(jb.taps) * jb.cin_pad) + static_cast<size_t>(t) * jb.cin_pad + c] = v;
-        jb.wd[c * (static_cast<size_t>(jb.taps) * jb.cout_pad) + static_cast<size_t>(jb.taps - 1 - t) * jb.cout_pad + o] = v;
-      } else if (jb.kind == 1) {
+      if (jb.kind == 1) {
         jb.fdst[i] = src[i];
       } else {
         const int r = static_cast<int>(i / jb.cin_pad), c = static_cast<int>(i - static_cast<long long>(r) * jb.cin_pad);

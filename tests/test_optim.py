@@ -164,9 +164,11 @@ def test_engine_repacks_after_optimizer_and_ema_steps():
     opt = optim.AdamW(net.parameters(), lr=1e-2, weight_decay=0.0)
     ema = optim.StandardEMA(net, rates=[0.5])
     opt.fuse_ema(ema)
+    gout = torch.randn(2, 20, 32, 32, generator=torch.Generator().manual_seed(3)).to(dev)
     with torch.no_grad():
         y0 = net(x, t)
         e0 = ema.emas[0](x, t)
+        _, gin0 = net.engine(20, 1, 32, 32, dev, max_windows=2, vjp=True).unet_vjp(x, 0.4, gout)  # packed before the step
     assert torch.equal(y0, e0)
     opt.zero_grad()
     g = torch.Generator().manual_seed(2)
@@ -184,6 +186,12 @@ def test_engine_repacks_after_optimizer_and_ema_steps():
         with torch.no_grad():
             want = fresh.to(dev)(x, t)
         assert torch.equal(got, want)
+    # the flipped / transposed input-gradient operands are re-packed too
+    fresh = c2w.ScoreUNet(activation=torch.nn.SiLU, **cfg)
+    fresh.load_state_dict({k: v.detach().cpu().clone() for k, v in net.state_dict().items()})
+    _, gin1 = net.engine(20, 1, 32, 32, dev, max_windows=2, vjp=True).unet_vjp(x, 0.4, gout)
+    _, want = fresh.to(dev).engine(20, 1, 32, 32, dev, max_windows=2, vjp=True).unet_vjp(x, 0.4, gout)
+    assert torch.equal(gin1, want) and not torch.equal(gin1, gin0)
 
 
 @pytest.mark.gpu
