@@ -271,7 +271,7 @@ inline size_t attention_smem_bytes(int T, int C, int QB = 64) {
 template <int QB>
 __global__ void __launch_bounds__(kAttnThreads)
 attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, int C, float scale2) {
-  extern __shared__ __align__(16) uint8_t smraw[];
+  extern __shared__ __align__(128) uint8_t smraw[];
   const int pitch = C + 2;  // bf16 elements; +2 shifts consecutive rows by one bank
   bf16* sq = reinterpret_cast<bf16*>(smraw);
   bf16* sk = sq + QB * pitch;
@@ -1246,7 +1246,7 @@ __device__ __forceinline__ void attn_abt(const bf16* a, const bf16* b, float* ou
 __global__ void __launch_bounds__(kAttnThreads)
 attention_bwd_scores_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ go, float* __restrict__ Pm,
                             float* __restrict__ gSm, int T, int C, int QB, float scale2) {
-  extern __shared__ __align__(16) uint8_t smraw[];
+  extern __shared__ __align__(128) uint8_t smraw[];
   const int pitch = C + 2, sp = T + 1;
   bf16* sx = reinterpret_cast<bf16*>(smraw);                  // [T][pitch]: k, then v
   bf16* sq = sx + static_cast<size_t>(T) * pitch;             // [QB][pitch]: q block, then go block
@@ -1298,7 +1298,7 @@ attention_bwd_scores_kernel(const bf16* __restrict__ qkv, const bf16* __restrict
 __global__ void __launch_bounds__(kAttnThreads)
 attention_bwd_grads_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ go, const float* __restrict__ Pm,
                            const float* __restrict__ gSm, bf16* __restrict__ gqkv, int T, int C, int RB, float scale2) {
-  extern __shared__ __align__(16) uint8_t smraw[];
+  extern __shared__ __align__(128) uint8_t smraw[];
   const int pitch = C + 2, sp = T + 1;
   bf16* sx = reinterpret_cast<bf16*>(smraw);  // [T][pitch]
   float* sm = reinterpret_cast<float*>(sx + static_cast<size_t>(T) * pitch);  // [RB][sp]
