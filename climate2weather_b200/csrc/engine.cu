@@ -948,6 +948,16 @@ int run_ops(c2w_handle* h, std::vector<Op>& ops, int nn, const FinalSpec& fs, cu
         L.p.m_total = static_cast<int>(m_total);
         L.p.num_m_tiles = ceil_div(m_total, kBlockM);
         conv_set_grid(&L, h->sms);
+#ifdef C2W_DIAG
+        {  // diagnostics build only: timing experiments inside a real step (results are garbage) — C2W_SKIP_LOADS=1/3/4
+          static int skip = -1;
+          if (skip < 0) {
+            const char* e = getenv("C2W_SKIP_LOADS");
+            skip = e ? atoi(e) : 0;
+          }
+          L.p.dbg_skip_loads = skip;
+        }
+#endif
         if (op.is_final) {
           L.p.mode = fs.mode;
           L.p.out_f32 = P.out32;
