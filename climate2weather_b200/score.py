@@ -68,6 +68,24 @@ def _recognise_operator(A: Callable, L: int, C: int, H: int, W: int, y_shape) ->
                               "guidance kernel supports only that family (pass climate2weather_b200.CoarseGrain)")
 
 
+def observed_windows(win_lo: int, win_hi: int, n_win_global: int, L: int, k: int, t_step: int) -> list:
+    """Windows j in [win_lo, win_hi) whose part of the composed score meets an OBSERVED frame.  The likelihood's cotangent
+    g = A^T((y - A x0)/var) (src/thor/score.py:53-56) is non-zero on observed frames only — frame f with f % t_step == 0
+    (exp/downscaling.py:131) — and window j contributes frame j + k to the composed score (plus frames 0..k-1 if it is
+    the first window, L-k..L-1 if it is the last, src/thor/score.py:76-88): every other window has an identically zero
+    output cotangent, so its vector-Jacobian product vanishes and its backward pass is skipped."""
+    out = []
+    for j in range(win_lo, win_hi):
+        need = (j + k) % t_step == 0
+        if j == 0:
+            need = need or any(f % t_step == 0 for f in range(0, k))
+        if j == n_win_global - 1:
+            need = need or any(f % t_step == 0 for f in range(L - k, L))
+        if need:
+            out.append(j)
+    return out
+
+
 class _Runtime:
     """Device-resident state of one trajectory (or of this rank's time shard of it)."""
 
@@ -130,22 +148,9 @@ class _Runtime:
 
     # ------------------------------------------------------------------------------------------------ exact_grad
     def _selected_list(self):
-        """Global indices of this rank's windows whose OUTPUT carries a non-zero cotangent.  The likelihood's cotangent
-        g = A^T((y - A x0)/var) (src/thor/score.py:53-56) is non-zero on observed frames only — frame f with
-        f % t_step == 0 (exp/downscaling.py:131) — and window j contributes frame j + k to the composed score (plus
-        frames 0..k-1 if it is the first window, L-k..L-1 if it is the last, src/thor/score.py:76-88)."""
-        p, k = self.plan, self.sf.markov_order
-        t_step = self.cond["op"].t_step
-        out = []
-        for j in range(p.win_lo, p.win_hi):
-            need = (j + k) % t_step == 0
-            if j == 0:
-                need = need or any(f % t_step == 0 for f in range(0, k))
-            if j == p.n_win_global - 1:
-                need = need or any(f % t_step == 0 for f in range(self.L - k, self.L))
-            if need:
-                out.append(j)
-        return out
+        """Global indices of this rank's windows whose OUTPUT carries a non-zero cotangent (see `observed_windows`)."""
+        p = self.plan
+        return observed_windows(p.win_lo, p.win_hi, p.n_win_global, self.L, self.sf.markov_order, self.cond["op"].t_step)
 
     def _selection(self):
         """(chunks of (win_list_dev, pos_dev), n_selected) for the current conditioning, cached."""

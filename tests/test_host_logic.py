@@ -314,3 +314,27 @@ def test_bench_workload_selection():
     assert bench.pick_workload(A, 8) == ("config4", 8760, "weak", 2)
     A.config, A.weak = None, True
     assert bench.pick_workload(A, 4) == ("config2-weak", 12 + 4 * 156, "weak", 0)
+
+
+@pytest.mark.parametrize("L,k,t_step", [(13, 6, 6), (14, 6, 6), (25, 6, 6), (168, 6, 6), (40, 2, 3), (31, 3, 4), (720, 6, 6),
+                                        (50, 6, 1), (50, 6, 7)])
+def test_observed_window_selection_is_exactly_the_fold_preimage_of_the_observed_frames(L, k, t_step):
+    """exact_grad runs the UNet backward only for `observed_windows`: that must be EXACTLY the set of windows the
+    reference's fold (src/thor/score.py:76-88, oracle fold_index pinned against it) takes an observed frame
+    (f % t_step == 0, exp/downscaling.py:131) from — a missing window would drop a non-zero cotangent — and the shards
+    of a time-sharded run must partition it."""
+    from climate2weather_b200.score import observed_windows
+    from climate2weather_b200.sharding import make_plan
+    from oracle import score_ref
+    nw = L - 2 * k
+    f = score_ref.fold_index(L, k, 4)  # [L, C, (window, window-channel)]
+    want = sorted({int(f[fr, 0, 0]) for fr in range(L) if fr % t_step == 0})
+    assert observed_windows(0, nw, nw, L, k, t_step) == want
+    for world in (2, 3, 8):
+        if nw // world < max(k, 1):  # make_plan refuses shards narrower than the halo
+            continue
+        got = []
+        for r in range(world):
+            p = make_plan(L, k, r, world)
+            got += observed_windows(p.win_lo, p.win_hi, p.n_win_global, L, k, t_step)
+        assert got == want, world
