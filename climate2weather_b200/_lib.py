@@ -44,8 +44,8 @@ class Guide(C.Structure):
         ("eps", C.c_void_p),
         ("eps_out", C.c_void_p),
         ("y", C.c_void_p),
-        ("std2", C.c_float * 4),
-        ("gamma", C.c_float * 4),
+        ("std2", C.c_float * 8),   # C2W_MAX_VARS
+        ("gamma", C.c_float * 8),
         ("mu", C.c_float),
         ("sigma", C.c_float),
         ("mu_next", C.c_float),
@@ -64,6 +64,7 @@ class Guide(C.Structure):
         ("cot_out", C.c_void_p),
         ("halo", C.c_void_p),
         ("halo_k", C.c_int32),
+        ("channels", C.c_int32),
     ]
 
 
@@ -123,6 +124,8 @@ SIGNATURES = {
     "c2w_guided_step": (_i, [C.POINTER(Guide), _vp]),
     "c2w_reduce_partials": (_i, [_vp, C.c_int32, _vp, _vp]),
     "c2w_corrector_update": (_i, [_vp, _vp, _vp, _vp, _d, _f, _f, _i64, _i64, C.c_uint64, C.c_uint32, _vp, _vp]),
+    "c2w_corrector_update_c": (_i, [_vp, _vp, _vp, _vp, _d, _f, _f, _i64, _i64, C.c_int32, C.c_uint64, C.c_uint32, _vp,
+                                    _vp]),
     "c2w_op_conv_ex": (_i, [C.POINTER(ConvDesc), _vp]),
     "c2w_conv_tile_width": (_i, [_i, _i, _i, _i, _i, _i, _i]),
     "c2w_op_wgrad": (_i, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _i64,

@@ -1058,7 +1058,7 @@ int run_plan(c2w_handle* h, int nn, const FinalSpec& fs, cudaStream_t st) { retu
 
 extern "C" {
 
-int c2w_abi_version(void) { return 1; }
+int c2w_abi_version(void) { return 2; }
 const char* c2w_last_error(void) { return error_slot(); }
 
 int c2w_create(const c2w_config* cfg, c2w_handle** out) {
@@ -1371,7 +1371,7 @@ int c2w_window_score(c2w_handle* h, const float* traj, int32_t n_frames_local, i
   C2W_REQUIRE(win_first >= frame_global0 && win_first + n_win - 1 + w <= frame_global0 + n_frames_local,
               "windows [%d,%d) need frames outside the local range [%d,%d)", win_first, win_first + n_win,
               frame_global0, frame_global0 + n_frames_local);
-  C2W_REQUIRE(C == 4, "fused compose supports 4 variables per frame (got %d)", C);
+  C2W_REQUIRE(C >= 1 && C <= 8, "1 to 8 variables per frame (got %d)", C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Plan& P = h->plan;
   const int hw = h->cfg.height * h->cfg.width;
@@ -1383,14 +1383,23 @@ int c2w_window_score(c2w_handle* h, const float* traj, int32_t n_frames_local, i
     if ((rc = launch_gather(traj, P.xin, nn, hw, C, w, h->cin_pad, j0 - frame_global0, h->sms, st))) return rc;
     ++g_launches;
     FinalSpec fs;
-    fs.mode = EPI_COMPOSE;
-    fs.eps = eps;
-    fs.order_k = k;
-    fs.win_first = j0;
-    fs.win_last_global = n_win_global - 1;
-    fs.frame_base = frame_global0;
-    rc = run_plan(h, nn, fs, st);
-    if (rc) return rc;
+    if (C == 4) {  // the fold is the last conv's epilogue
+      fs.mode = EPI_COMPOSE;
+      fs.eps = eps;
+      fs.order_k = k;
+      fs.win_first = j0;
+      fs.win_last_global = n_win_global - 1;
+      fs.frame_base = frame_global0;
+      if ((rc = run_plan(h, nn, fs, st))) return rc;
+    } else {       // any other variable count: fp32 window outputs, then the fold as its own pass
+      fs.mode = EPI_F32;
+      if ((rc = run_plan(h, nn, fs, st))) return rc;
+      const long long items = static_cast<long long>(nn) * hw * C;
+      compose_generic_kernel<<<grid_for(items, 256, h->sms), 256, 0, st>>>(P.out32, eps, nn, hw, h->levels[0].tail.cout_pad, C,
+                                                                           k, j0, n_win_global - 1, frame_global0, nullptr);
+      ++g_launches;
+      C2W_CUDA(cudaGetLastError());
+    }
   }
   return C2W_OK;
 }
@@ -1845,12 +1854,16 @@ int c2w_guided_step(const c2w_guide* g, void* stream) {
   C2W_REQUIRE(g->mode != 1 || (g->eps_out && g->partials), "mode 1 needs eps_out and partials");
   C2W_REQUIRE(g->mode != 2 || (g->cot_out && g->y), "mode 2 needs cot_out and an observation");
   C2W_REQUIRE(g->own_n >= 1 && g->t_step >= 1, "own_n and t_step must be positive");
+  const int C = g->channels == 0 ? 4 : g->channels;
+  C2W_REQUIRE(C >= 1 && C <= C2W_MAX_VARS, "c2w_guided_step: 1 to %d variables per frame (got %d)", C2W_MAX_VARS, C);
+  C2W_REQUIRE(C == 4 || g->halo == nullptr, "c2w_guided_step: the fused halo push handles 4 variables per frame");
   GuideParams p;
   p.x = g->x;
   p.eps = g->eps;
   p.eps_out = g->eps_out;
   p.y = g->y;
-  for (int i = 0; i < 4; ++i) {
+  p.C = C;
+  for (int i = 0; i < C2W_MAX_VARS; ++i) {
     p.std2[i] = g->std2[i];
     p.gamma[i] = g->gamma[i];
   }
@@ -1888,7 +1901,8 @@ int c2w_guided_step(const c2w_guide* g, void* stream) {
     p.publish = pub;
   }
   dim3 grid(g->H / g->s_step, g->own_n);
-  guided_step_kernel<<<grid, 32 * (g->W / g->s_step), 0, static_cast<cudaStream_t>(stream)>>>(p);
+  if (C == 4) guided_step_kernel<<<grid, 32 * (g->W / g->s_step), 0, static_cast<cudaStream_t>(stream)>>>(p);
+  else guided_step_generic_kernel<<<grid, 32 * (g->W / g->s_step), 0, static_cast<cudaStream_t>(stream)>>>(p);
   ++g_launches;
   C2W_CUDA(cudaGetLastError());
   return C2W_OK;
@@ -1902,15 +1916,29 @@ int c2w_reduce_partials(const float* partials, int32_t n, double* sumsq, void* s
   return C2W_OK;
 }
 
-int c2w_corrector_update(float* x, const float* eps, const float* z, const double* sumsq, double count, float tau,
-                         float sigma_next, int64_t pix0_global, int64_t npix, uint64_t seed, uint32_t step_id,
-                         int32_t* nan_flag, void* stream) {
+int c2w_corrector_update_c(float* x, const float* eps, const float* z, const double* sumsq, double count, float tau,
+                           float sigma_next, int64_t pix0_global, int64_t npix, int32_t channels, uint64_t seed,
+                           uint32_t step_id, int32_t* nan_flag, void* stream) {
   C2W_REQUIRE(x && eps && sumsq && nan_flag && npix >= 1 && count > 0, "c2w_corrector_update: bad argument");
-  corrector_update_kernel<<<grid_for(npix, 256, c2w_num_sms()), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, eps, z, sumsq, count, tau, sigma_next, pix0_global, npix, seed, step_id, nan_flag);
+  C2W_REQUIRE(channels >= 1 && channels <= C2W_MAX_VARS, "c2w_corrector_update: 1 to %d variables per frame (got %d)",
+              C2W_MAX_VARS, channels);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (channels == 4)
+    corrector_update_kernel<<<grid_for(npix, 256, c2w_num_sms()), 256, 0, st>>>(x, eps, z, sumsq, count, tau, sigma_next,
+                                                                                pix0_global, npix, seed, step_id, nan_flag);
+  else
+    corrector_update_generic_kernel<<<grid_for(npix, 256, c2w_num_sms()), 256, 0, st>>>(
+        x, eps, z, sumsq, count, tau, sigma_next, pix0_global, npix, channels, seed, step_id, nan_flag);
   ++g_launches;
   C2W_CUDA(cudaGetLastError());
   return C2W_OK;
+}
+
+int c2w_corrector_update(float* x, const float* eps, const float* z, const double* sumsq, double count, float tau,
+                         float sigma_next, int64_t pix0_global, int64_t npix, uint64_t seed, uint32_t step_id,
+                         int32_t* nan_flag, void* stream) {
+  return c2w_corrector_update_c(x, eps, z, sumsq, count, tau, sigma_next, pix0_global, npix, 4, seed, step_id, nan_flag,
+                                stream);
 }
 
 // ---------------------------------------------------------------------------------------------- op-level hooks

@@ -1503,8 +1503,9 @@ struct GuideParams {
   const float* eps;  // unguided window-composed score (K1 compose epilogue)
   float* eps_out;    // mode 1: guided eps
   const float* y;    // null => unconditioned
-  float std2[4];     // likelihood std^2 per variable
-  float gamma[4];
+  float std2[8];     // likelihood std^2 per variable
+  float gamma[8];
+  int C;             // variables per frame: 4 -> guided_step_kernel (one float4 per pixel), else the generic kernel
   float mu, sigma;            // at the time the score was evaluated
   float mu_next, sigma_next;  // mode 0: target of the predictor step
   int t_step, s_step, H, W;
@@ -1642,6 +1643,112 @@ __global__ void guided_step_kernel(const GuideParams p) {
   }
 }
 
+// ---- any number of variables per frame (1 <= C <= 8, C != 4): the same arithmetic on [frames, H, W, C] with scalar
+// lanes.  The shipped configs have C = 4 (exp/downscaling.py:101) and never launch these; they keep the reference's
+// generality (src/thor/score.py:68-88 is written for any C) at HBM-bound-kernel cost, without the fused halo push.
+__global__ void guided_step_generic_kernel(const GuideParams p) {
+  constexpr int MC = 8;
+  const int C = p.C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = p.s_step;
+  const int fl = p.own_lo + blockIdx.y;
+  const int fg = p.frame_global0 + fl;
+  const int h0 = blockIdx.x * s, w0 = warp * s;
+  const long long fbase = (static_cast<long long>(fl) * p.H) * p.W;
+  const bool observed = (p.y != nullptr) && (fg % p.t_step == 0);
+  const float inv_mu = 1.0f / p.mu;
+  float corr[MC];
+#pragma unroll
+  for (int c = 0; c < MC; ++c) corr[c] = 0.f;
+  if (observed) {
+    float acc[MC];
+#pragma unroll
+    for (int c = 0; c < MC; ++c) acc[c] = 0.f;
+    for (int i = lane; i < s * s; i += 32) {
+      const long long o = (fbase + static_cast<long long>(h0 + i / s) * p.W + (w0 + i % s)) * C;
+#pragma unroll
+      for (int c = 0; c < MC; ++c)
+        if (c < C) acc[c] += (p.x[o + c] - p.sigma * p.eps[o + c]) * inv_mu;
+    }
+    const float inv_area = 1.0f / static_cast<float>(s * s);
+    const int Hs = p.H / s, Ws = p.W / s;
+    const int m = fg / p.t_step;
+    const float r2 = (p.sigma * inv_mu) * (p.sigma * inv_mu);
+#pragma unroll
+    for (int c = 0; c < MC; ++c) {
+      if (c < C) {  // C is uniform over the warp: every lane takes part in the shuffle
+        const float mean = warp_sum(acc[c]) * inv_area;
+        const float yv = __ldg(p.y + ((static_cast<long long>(m) * C + c) * Hs + blockIdx.x) * Ws + warp);
+        corr[c] = ((yv - mean) / (p.std2[c] + p.gamma[c] * r2)) * inv_area;
+      }
+    }
+  }
+  if (p.mode == 2) {
+    for (int i = lane; i < s * s; i += 32) {
+      const long long o = (fbase + static_cast<long long>(h0 + i / s) * p.W + (w0 + i % s)) * C;
+#pragma unroll
+      for (int c = 0; c < MC; ++c)
+        if (c < C) p.cot_out[o + c] = corr[c];
+    }
+    return;
+  }
+  const float sg_mu = p.sigma * inv_mu;
+  float sq = 0.f;
+  bool bad = false;
+  for (int i = lane; i < s * s; i += 32) {
+    const long long o = (fbase + static_cast<long long>(h0 + i / s) * p.W + (w0 + i % s)) * C;
+#pragma unroll
+    for (int c = 0; c < MC; ++c) {
+      if (c < C) {
+        float gv = corr[c];
+        if (p.vjp != nullptr) gv -= p.sigma * p.vjp[o + c];
+        const float ev = p.eps[o + c] - sg_mu * gv;
+        if (p.mode == 0) {
+          const float xv = p.mu_next * ((p.x[o + c] - p.sigma * ev) * inv_mu) + p.sigma_next * ev;
+          bad |= !isfinite(xv);
+          p.x[o + c] = xv;
+        } else {
+          sq += ev * ev;
+          p.eps_out[o + c] = ev;
+        }
+      }
+    }
+  }
+  if (p.mode == 0) {
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(p.nan_flag, 1);
+  } else {
+    __shared__ float wsum[32];
+    sq = warp_sum(sq);
+    if (lane == 0) wsum[warp] = sq;
+    __syncthreads();
+    if (warp == 0) {
+      float v = (lane < (blockDim.x >> 5)) ? wsum[lane] : 0.f;
+      v = warp_sum(v);
+      if (lane == 0) p.partials[blockIdx.y * gridDim.x + blockIdx.x] = v;
+    }
+  }
+}
+
+// Fold of the window outputs (fp32 [n, hw, cpad], EPI_F32 of the last conv) into the composed score [frames, hw, C]:
+// the centre slot of every window, the head slots of window 0 and the tail slots of the last window
+// (src/thor/score.py:76-88) — what the K1 compose epilogue does for C = 4.
+__global__ void compose_generic_kernel(const float* __restrict__ out32, float* __restrict__ eps, int n, int hw, int cpad,
+                                       int C, int k, int win_first, int win_last_global, int frame_base,
+                                       const int* __restrict__ win_list) {
+  const long long total = static_cast<long long>(n) * hw * C;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % C);
+    const long long ip = idx / C;
+    const int pix = static_cast<int>(ip % hw), i = static_cast<int>(ip / hw);
+    const int win = win_list ? win_list[i] : win_first + i;
+    const float* src = out32 + (static_cast<long long>(i) * hw + pix) * cpad + c;
+    const int t0 = (win == 0) ? 0 : k, t1 = (win == win_last_global) ? 2 * k : k;
+    for (int tau = t0; tau <= t1; ++tau)
+      eps[((static_cast<long long>(win + tau - frame_base)) * hw + pix) * C + c] = src[tau * C];
+  }
+}
+
 // N2 (optimiser half): torch.optim.AdamW.step() (training_loop.py:384; decoupled weight decay, bias
 // correction, eps added to sqrt(v)/sqrt(bias2)) and StandardEMA.update() (src/thor/ema.py:24-27: ema = ema * rate +
 // p * (1 - rate), evaluated on the UPDATED parameters) as ONE pass over the flat parameter buffer: reads p, g, m, v,
@@ -1747,6 +1854,38 @@ __global__ void corrector_update_kernel(float* __restrict__ x, const float* __re
     xv.w -= (delta * ev.w + zs * zv.w) * sigma_next;
     bad |= !(isfinite(xv.x) && isfinite(xv.y) && isfinite(xv.z) && isfinite(xv.w));
     *reinterpret_cast<float4*>(x + i * 4) = xv;
+  }
+  if (bad) atomicOr(nan_flag, 1);
+}
+// The same for C != 4 variables per pixel: one Philox block of four normals per group of four variables (counter word 3
+// = group index, so C = 4 would draw exactly what the kernel above draws).
+__global__ void corrector_update_generic_kernel(float* __restrict__ x, const float* __restrict__ eps,
+                                                const float* __restrict__ z, const double* __restrict__ sumsq, double count,
+                                                float tau, float sigma_next, long long pix0_global, long long npix, int C,
+                                                unsigned long long seed, unsigned int step_id, int* nan_flag) {
+  const float delta = tau / static_cast<float>(sumsq[0] / count);
+  const float zs = sqrtf(2.0f * delta);
+  bool bad = false;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < npix;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const unsigned long long g = static_cast<unsigned long long>(pix0_global + i);
+    for (int b = 0; 4 * b < C; ++b) {
+      float zv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!z) {
+        const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), step_id,
+                                                 static_cast<uint32_t>(b)),
+                                      make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+        const float2 n0 = box_muller(r.x, r.y), n1 = box_muller(r.z, r.w);
+        zv[0] = n0.x, zv[1] = n0.y, zv[2] = n1.x, zv[3] = n1.y;
+      }
+      for (int e = 0; e < 4 && 4 * b + e < C; ++e) {
+        const long long o = i * C + 4 * b + e;
+        const float zz = z ? z[o] : zv[e];
+        const float xv = x[o] - (delta * eps[o] + zs * zz) * sigma_next;
+        bad |= !isfinite(xv);
+        x[o] = xv;
+      }
+    }
   }
   if (bad) atomicOr(nan_flag, 1);
 }

@@ -91,8 +91,10 @@ class _Runtime:
 
     def __init__(self, sf: "AbstractScoreFunction", L: int, C: int, H: int, W: int, device: torch.device,
                  plan: ShardPlan, max_windows: int, exact: bool = False):
-        if C != 4:
-            raise NotImplementedError(f"the fused path keeps 4 variables per pixel (float4); got C={C}")
+        if not 1 <= C <= 8:
+            raise NotImplementedError(f"1 to 8 variables per frame (c2w_b200.h: C2W_MAX_VARS); got C={C}")
+        if C != 4 and exact:
+            raise NotImplementedError(f"exact_grad=True runs on the 4-variable path (the shipped configs); got C={C}")
         self.sf, self.L, self.C, self.H, self.W, self.device, self.plan = sf, L, C, H, W, device, plan
         self.lib = _lib.load()
         k = sf.markov_order
@@ -259,7 +261,7 @@ class _Runtime:
             s = cg.s_step
             g.y = self.y_dev.data_ptr()
             g.t_step = cg.t_step
-            for i in range(4):
+            for i in range(self.C):
                 g.std2[i] = self.cond["std"][i] ** 2
                 g.gamma[i] = self.cond["gamma"][i]
         else:
@@ -271,6 +273,7 @@ class _Runtime:
         if frames is not None:
             g.own_lo, g.own_n = frames
         g.mode = mode
+        g.channels = self.C
         g.nan_flag = self.nan_flag.data_ptr()
         g.vjp = self.vjp.data_ptr() if (self.exact and self.cond is not None and mode != 2) else None
         g.cot_out = self.cot.data_ptr() if mode == 2 else None
@@ -330,14 +333,16 @@ class _Runtime:
                 zl = z[lo:lo + p.own_n]
                 assert zl.is_contiguous()
                 zp = zl.data_ptr()
-            _lib.check(self.lib.c2w_corrector_update(
+            _lib.check(self.lib.c2w_corrector_update_c(
                 self.x[lo:].data_ptr(), self.eps_g[lo:].data_ptr(), zp, self.sumsq.data_ptr(),
-                float(self.L * self.C * hw), float(tau), float(sigma_next), p.own_lo * hw, p.own_n * hw, int(seed),
-                int(step_id), self.nan_flag.data_ptr(), self.stream), "c2w_corrector_update")
+                float(self.L * self.C * hw), float(tau), float(sigma_next), p.own_lo * hw, p.own_n * hw, self.C, int(seed),
+                int(step_id), self.nan_flag.data_ptr(), self.stream), "c2w_corrector_update_c")
 
     def _ensure_peer_halo(self) -> Optional[PeerHalo]:
         """The peer-memory mailboxes (set up collectively on first use by every rank at the same point)."""
         if self.plan.world == 1:
+            return None
+        if self.C != 4:  # the mailboxes and the fused push move one float4 per pixel
             return None
         if self._peer_halo is None and self._peer_halo_ok and halo_transport() != "nccl":
             group = self.sf.shard[2] if self.sf.shard else None

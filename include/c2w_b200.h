@@ -46,13 +46,14 @@ typedef struct c2w_handle c2w_handle;
  * Replaces AbstractScoreFunction.condition_on/log_p + __call__ (src/thor/score.py:24-60, exact_grad=False closed
  * form), the observation operator A and its adjoint (exp/downscaling.py:129-132) and SDAPipeline._sample_step
  * (src/thor/pipelines.py:41-46) / the corrector body (src/thor/pipelines.py:81-88). */
+#define C2W_MAX_VARS 8
 typedef struct c2w_guide {
-  float* x;             /* [frames_local, H, W, 4] state, updated in place (mode 0)                       */
-  const float* eps;     /* [frames_local, H, W, 4] window-composed score                                   */
+  float* x;             /* [frames_local, H, W, C] state, updated in place (mode 0)                       */
+  const float* eps;     /* [frames_local, H, W, C] window-composed score                                   */
   float* eps_out;       /* mode 1: guided score                                                            */
-  const float* y;       /* [ceil(L / t_step), 4, H / s_step, W / s_step] observation; NULL = unconditioned */
-  float std2[4];        /* likelihood std^2 per variable (exp/downscaling.py:221-227)                      */
-  float gamma[4];
+  const float* y;       /* [ceil(L / t_step), C, H / s_step, W / s_step] observation; NULL = unconditioned */
+  float std2[C2W_MAX_VARS]; /* likelihood std^2 per variable (exp/downscaling.py:221-227)                  */
+  float gamma[C2W_MAX_VARS];
   float mu, sigma;           /* schedule at the score's time (src/thor/pipelines.py:13-20)                 */
   float mu_next, sigma_next; /* schedule at t - dt                                                         */
   int32_t t_step, s_step, H, W;
@@ -69,6 +70,8 @@ typedef struct c2w_guide {
                             updated pixels of the first / last k owned frames are also stored into the neighbours'
                             mailboxes over NVLink and the last CTA publishes the step; complete with c2w_halo_pull  */
   int32_t halo_k;        /* Markov order k (frames per side)                                                       */
+  int32_t channels;      /* C, variables per frame: 0 or 4 = the shipped configs (one float4 per pixel, every fused
+                            path); 1..8 otherwise run the generic kernels (no fused halo push, no exact_grad)      */
 } c2w_guide;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------ */
@@ -180,6 +183,10 @@ int c2w_reduce_partials(const float* partials, int32_t n, double* sumsq, void* s
 int c2w_corrector_update(float* x, const float* eps, const float* z, const double* sumsq, double count, float tau,
                          float sigma_next, int64_t pix0_global, int64_t npix, uint64_t seed, uint32_t step_id,
                          int32_t* nan_flag, void* stream);
+/* the same for `channels` variables per pixel (1..8; 4 = the call above) */
+int c2w_corrector_update_c(float* x, const float* eps, const float* z, const double* sumsq, double count, float tau,
+                           float sigma_next, int64_t pix0_global, int64_t npix, int32_t channels, uint64_t seed,
+                           uint32_t step_id, int32_t* nan_flag, void* stream);
 
 /* ---- op-level hooks (parity tests of single kernels; same kernels the calls above launch) ----------------- */
 /* One launch of K1 (Conv2d 3x3 pad 1, stride 1 or 2 — model/nn.py:155,157,169,185,193,194 — or a plain GEMM for the

@@ -684,6 +684,63 @@ def test_sampler_vs_reference_golden(dev, golden_dir):
     assert relerr(s2, torch.from_numpy(g["sample_one_window"])) < 5e-2
 
 
+@pytest.mark.parametrize("C", [1, 3, 6])
+def test_other_variable_counts_vs_oracle(dev, C):
+    """The reference's score functions and sampler are written for any number of variables per frame
+    (src/thor/score.py:68-88, :111-154); the shipped configs have C = 4 (exp/downscaling.py:101), which is the fused
+    float4 path.  C != 4 runs the generic fold / guidance / corrector kernels: composed score, closed-form guided score
+    and a short predictor-corrector run against the fp32 oracle, same tolerances as the 4-variable tests; the fold is
+    index work -> chunk-invariant to the bit."""
+    import climate2weather_b200 as c2w
+    k, L, H, W = 2, 11, 32, 32
+    cfg = dict(SMALL, channels=C * (2 * k + 1))
+    torch.manual_seed(11 + C)
+    net = c2w.ScoreUNet(activation=torch.nn.SiLU, **cfg)
+    ref = unet_ref.RefNet({n: v.detach().clone() for n, v in net.state_dict().items()}, cfg)
+    net = net.to(dev)
+    g = torch.Generator().manual_seed(50 + C)
+    x = torch.randn(L, C, H, W, generator=g)
+    y = score_ref.coarse_grain(torch.randn(L, C, H, W, generator=g), 3, 8)
+    std = torch.tensor([0.1 + 0.05 * c for c in range(C)]).reshape(1, C, 1, 1)
+    t = torch.tensor(0.45)
+    pipe = c2w.SDAPipeline()
+    with torch.no_grad():
+        want = score_ref.window_score(ref, x, t, k)
+    outs = []
+    for mw in (None, 3):
+        sf = c2w.DefaultScoreFunction(net, markov_order=k, noise_process=pipe)
+        sf.max_windows = mw
+        outs.append(sf.score_fn(x.to(dev), t).cpu())
+    e = relerr(outs[0], want)
+    assert outs[0].shape == x.shape and e < 3e-2, e
+    assert torch.equal(outs[0], outs[1])
+    # closed-form guidance (exact_grad=False, every shipped config)
+    sf = c2w.BatchedScoreFunction(net, markov_order=k, noise_process=pipe, batch_size=4, device=dev)
+    sf.condition_on(A=c2w.CoarseGrain(3, 8), y=y, std=std, gamma=GAMMA, exact_grad=False)
+    with torch.no_grad():
+        want_g = score_ref.guided_score(ref, x, t, k, y, std, GAMMA, 3, 8, exact_grad=False)
+    eg = relerr(sf(x, t), want_g)
+    assert eg < 3e-2, eg
+    # predictor + one Langevin correction per step, the corrector noise drawn as the reference draws it
+    ref_pipe = pipeline_ref.RefPipeline()
+    score = lambda xx, tt: score_ref.guided_score(ref, xx, tt, k, y, std, GAMMA, 3, 8, exact_grad=False)
+    torch.manual_seed(5)
+    want_s = ref_pipe.sample(score, x, steps=3, corrections=1, tau=0.5)
+    pipe.rng = "reference"
+    torch.manual_seed(5)
+    got_s = pipe.sample(sf, x, steps=3, corrections=1, tau=0.5, show_progressbar=False)
+    es, ls = relerr(got_s, want_s), rel_l2(got_s, want_s)
+    print(f"\nC={C}: score {e:.3e}, guided {eg:.3e}, sampler max-abs ratio {es:.3e} rel-L2 {ls:.3e}")
+    assert got_s.shape == x.shape and es < 5e-2 and ls < 3e-2
+    # on-chip Philox noise: finite, and exact_grad is refused clearly for C != 4
+    pipe2 = c2w.SDAPipeline()
+    assert torch.isfinite(pipe2.sample(sf, x, steps=2, corrections=1, tau=0.5, show_progressbar=False, seed=3)).all()
+    sfe = c2w.DefaultScoreFunction(net, markov_order=k, noise_process=pipe2)
+    sfe.condition_on(A=c2w.CoarseGrain(3, 8), y=y, std=std, gamma=GAMMA, exact_grad=True)
+    with pytest.raises(NotImplementedError):
+        sfe(x.to(dev), t)
+
+
 def test_per_sample_times_and_dsm_loss(dev, golden_dir):
     """ScoreUNet with one diffusion time per sample (model/score.py:61) and SDAPipeline.loss
     (src/thor/pipelines.py:27-35) against the oracle with the same t and eps; chunked through a 2-window workspace."""
