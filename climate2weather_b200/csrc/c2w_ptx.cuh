@@ -222,8 +222,13 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t ra
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
+// Arrive on a barrier in the peer CTA's shared memory.  CTA-scope release (the default), as CUTLASS's ClusterBarrier
+// does: what the arrive publishes here is "my tcgen05.ld's of this accumulator have completed" (tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync precede it), no generic-proxy memory.  (`.release.cluster` compiles to
+// MEMBAR.ALL.GPU + ERRBAR in every epilogue warp of the non-leader CTA once per tile — 10 % of K1's warp-stall samples
+// in the ncu source page; A/B inside the real step: no measurable change either way, the accumulator ring has the slack.)
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads of a CTA pair: data lands in the executing CTA's shared memory, the transaction bytes are
 // counted on `bar_cluster_addr`, a shared::cluster address (the leader CTA's full barrier).
