@@ -101,6 +101,7 @@ SIGNATURES = {
     "c2w_destroy": (None, [_vp]),
     "c2w_last_error": (C.c_char_p, []),
     "c2w_abi_version": (_i, []),
+    "c2w_struct_size": (_i, [_i]),
     "c2w_load_weight": (_i, [_vp, C.c_char_p, _vp, _i64]),
     "c2w_finalize_weights": (_i, [_vp]),
     "c2w_workspace_bytes": (_i64, [_vp, C.c_int32]),

@@ -1059,6 +1059,16 @@ int run_plan(c2w_handle* h, int nn, const FinalSpec& fs, cudaStream_t st) { retu
 extern "C" {
 
 int c2w_abi_version(void) { return 2; }
+
+int c2w_struct_size(int which) {
+  switch (which) {
+    case 0: return static_cast<int>(sizeof(c2w_config));
+    case 1: return static_cast<int>(sizeof(c2w_guide));
+    case 2: return static_cast<int>(sizeof(c2w_adamw));
+    case 3: return static_cast<int>(sizeof(c2w_conv_desc));
+    default: return -1;
+  }
+}
 const char* c2w_last_error(void) { return error_slot(); }
 
 int c2w_create(const c2w_config* cfg, c2w_handle** out) {

@@ -79,6 +79,9 @@ int c2w_create(const c2w_config* cfg, c2w_handle** out);
 void c2w_destroy(c2w_handle* h);
 const char* c2w_last_error(void);
 int c2w_abi_version(void);
+/* sizeof() of the structs of this header as the library was compiled, for bindings to check their own layout against:
+ * which = 0 c2w_config, 1 c2w_guide, 2 c2w_adamw, 3 c2w_conv_desc; -1 for an unknown index */
+int c2w_struct_size(int which);
 
 /* ---- weights: reference state_dict entries by name, fp32 host memory -------------------- */
 int c2w_load_weight(c2w_handle* h, const char* name, const float* host_data, int64_t numel);

@@ -3,6 +3,7 @@ declares (no compute calls), the time-shard plan partitions trajectories correct
 frame gather work with world_size 2 over gloo.  The sharded-score equivalence is checked with the oracle's window
 composition standing in for the UNet (src/thor/score.py:68-93 makes frame i depend on frames i-k..i+k only).
 """
+import ctypes
 import os
 import re
 import socket
@@ -33,7 +34,11 @@ def test_library_exports_every_header_symbol():
     lib = _lib.load()  # raises C2WError if the library is missing, AttributeError if a symbol is
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.c2w_abi_version() >= 1
+    assert lib.c2w_abi_version() >= 2
+    # the ctypes mirrors of the header's structs have the layout the library was compiled with
+    for which, mirror in enumerate((_lib.Config, _lib.Guide, _lib.AdamW, _lib.ConvDesc)):
+        assert lib.c2w_struct_size(which) == ctypes.sizeof(mirror), mirror.__name__
+    assert lib.c2w_struct_size(99) == -1
 
 
 def test_no_cpu_path():
