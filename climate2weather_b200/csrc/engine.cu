@@ -1431,7 +1431,6 @@ int c2w_window_score_sel(c2w_handle* h, const float* traj, int32_t n_frames_loca
               P.n_max);
   C2W_REQUIRE(eps || P.vjp, "c2w_window_score_sel: no output asked for on a plain workspace");
   const int w = h->cfg.window, k = w / 2, C = h->cfg.frame_channels;
-  C2W_REQUIRE(!eps || C == 4, "fused compose supports 4 variables per frame (got %d)", C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int hw = h->cfg.height * h->cfg.width;
   (void)n_frames_local;
@@ -1446,7 +1445,7 @@ int c2w_window_score_sel(c2w_handle* h, const float* traj, int32_t n_frames_loca
     C2W_CUDA(cudaGetLastError());
     FinalSpec fs;
     fs.mode = EPI_F32;
-    if (eps) {
+    if (eps && C == 4) {
       fs.mode = EPI_COMPOSE;
       fs.eps = eps;
       fs.order_k = k;
@@ -1455,6 +1454,13 @@ int c2w_window_score_sel(c2w_handle* h, const float* traj, int32_t n_frames_loca
       fs.win_list = win_list_dev + c0;
     }
     if ((rc = run_plan(h, nn, fs, st))) return rc;
+    if (eps && C != 4) {  // the fold as its own pass over the fp32 window outputs
+      const long long it2 = static_cast<long long>(nn) * hw * C;
+      compose_generic_kernel<<<grid_for(it2, 256, h->sms), 256, 0, st>>>(P.out32, eps, nn, hw, h->levels[0].tail.cout_pad, C, k, 0,
+                                                                          n_win_global - 1, frame_global0, win_list_dev + c0);
+      ++g_launches;
+      C2W_CUDA(cudaGetLastError());
+    }
   }
   return C2W_OK;
 }
@@ -1470,22 +1476,31 @@ int c2w_window_score_backward_sel(c2w_handle* h, const float* cot, int32_t n_fra
   if (P.n_max < 1 || !P.vjp) return fail(C2W_ERR_STATE, "bind a VJP workspace first (c2w_bind_workspace_vjp)");
   C2W_REQUIRE(n_sel <= P.n_max, "backward handles one chunk: %d windows, workspace %d", n_sel, P.n_max);
   const int w = h->cfg.window, k = w / 2, C = h->cfg.frame_channels;
-  C2W_REQUIRE(C == 4, "fused compose supports 4 variables per frame (got %d)", C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int hw = h->cfg.height * h->cfg.width;
   const int cpad = h->levels[0].tail.cout_pad;
   const long long items = static_cast<long long>(n_sel) * hw * (cpad / 8);
-  compose_adjoint_kernel<<<grid_for(items, 256, h->sms), 256, 0, st>>>(cot, P.cot, n_sel, hw, cpad, k, 0, n_win_global - 1,
-                                                                         frame_global0, win_list_dev);
+  if (C == 4)
+    compose_adjoint_kernel<<<grid_for(items, 256, h->sms), 256, 0, st>>>(cot, P.cot, n_sel, hw, cpad, k, 0, n_win_global - 1,
+                                                                           frame_global0, win_list_dev);
+  else
+    compose_adjoint_generic_kernel<<<grid_for(items, 256, h->sms), 256, 0, st>>>(cot, P.cot, n_sel, hw, cpad, C, k, 0,
+                                                                                   n_win_global - 1, frame_global0, win_list_dev);
   ++g_launches;
   C2W_CUDA(cudaGetLastError());
   FinalSpec fs;
   fs.mode = EPI_F32;
   int rc = run_ops(h, P.bwd, n_sel, fs, st);
   if (rc) return rc;
-  const long long items2 = static_cast<long long>(n_frames_local) * hw;
-  unfold_adjoint_sel_kernel<<<grid_for(items2, 256, h->sms), 256, 0, st>>>(P.out32, vjp, n_frames_local, hw, h->cin_pad, w,
-                                                                             frame_global0, n_win_global, pos_dev);
+  if (C == 4) {
+    const long long items2 = static_cast<long long>(n_frames_local) * hw;
+    unfold_adjoint_sel_kernel<<<grid_for(items2, 256, h->sms), 256, 0, st>>>(P.out32, vjp, n_frames_local, hw, h->cin_pad, w,
+                                                                               frame_global0, n_win_global, pos_dev);
+  } else {
+    const long long items2 = static_cast<long long>(n_frames_local) * hw * C;
+    unfold_adjoint_generic_kernel<<<grid_for(items2, 256, h->sms), 256, 0, st>>>(
+        P.out32, vjp, n_sel, n_frames_local, hw, h->cin_pad, C, w, 0, frame_global0, n_win_global, pos_dev);
+  }
   ++g_launches;
   C2W_CUDA(cudaGetLastError());
   return C2W_OK;
@@ -1537,22 +1552,31 @@ int c2w_window_score_backward(c2w_handle* h, const float* cot, int32_t n_frames_
   C2W_REQUIRE(win_first >= frame_global0 && win_first + n_win - 1 + w <= frame_global0 + n_frames_local,
               "windows [%d,%d) need frames outside the local range [%d,%d)", win_first, win_first + n_win,
               frame_global0, frame_global0 + n_frames_local);
-  C2W_REQUIRE(C == 4, "fused compose supports 4 variables per frame (got %d)", C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int hw = h->cfg.height * h->cfg.width;
   const int cpad = h->levels[0].tail.cout_pad;
   const long long items = static_cast<long long>(n_win) * hw * (cpad / 8);
-  compose_adjoint_kernel<<<grid_for(items, 256, h->sms), 256, 0, st>>>(cot, P.cot, n_win, hw, cpad, k, win_first,
-                                                                         n_win_global - 1, frame_global0);
+  if (C == 4)
+    compose_adjoint_kernel<<<grid_for(items, 256, h->sms), 256, 0, st>>>(cot, P.cot, n_win, hw, cpad, k, win_first,
+                                                                           n_win_global - 1, frame_global0);
+  else
+    compose_adjoint_generic_kernel<<<grid_for(items, 256, h->sms), 256, 0, st>>>(cot, P.cot, n_win, hw, cpad, C, k, win_first,
+                                                                                   n_win_global - 1, frame_global0, nullptr);
   ++g_launches;
   C2W_CUDA(cudaGetLastError());
   FinalSpec fs;
   fs.mode = EPI_F32;
   int rc = run_ops(h, P.bwd, n_win, fs, st);
   if (rc) return rc;
-  const long long items2 = static_cast<long long>(n_win + w - 1) * hw;
-  unfold_adjoint_kernel<<<grid_for(items2, 256, h->sms), 256, 0, st>>>(P.out32, vjp, n_win, hw, h->cin_pad, w, win_first,
-                                                                         frame_global0);
+  if (C == 4) {
+    const long long items2 = static_cast<long long>(n_win + w - 1) * hw;
+    unfold_adjoint_kernel<<<grid_for(items2, 256, h->sms), 256, 0, st>>>(P.out32, vjp, n_win, hw, h->cin_pad, w, win_first,
+                                                                           frame_global0);
+  } else {
+    const long long items2 = static_cast<long long>(n_frames_local) * hw * C;
+    unfold_adjoint_generic_kernel<<<grid_for(items2, 256, h->sms), 256, 0, st>>>(
+        P.out32, vjp, n_win, n_frames_local, hw, h->cin_pad, C, w, win_first, frame_global0, n_win_global, nullptr);
+  }
   ++g_launches;
   C2W_CUDA(cudaGetLastError());
   return C2W_OK;

@@ -1495,6 +1495,62 @@ __global__ void unfold_adjoint_sel_kernel(const float* __restrict__ gin, float* 
   }
 }
 
+// The three adjoints above for any number of variables per frame (C != 4; g / vjp: fp32 [frames, HW, C]).
+__global__ void compose_adjoint_generic_kernel(const float* __restrict__ g, bf16* __restrict__ cot, int n, int hw, int cpad,
+                                               int C, int order_k, int win_first, int win_last_global, int frame_base,
+                                               const int* __restrict__ win_list) {
+  const int groups = cpad >> 3;
+  const long long total = static_cast<long long>(n) * hw * groups;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int gq = static_cast<int>(idx % groups);
+    const long long pw = idx / groups;
+    const int pix = static_cast<int>(pw % hw);
+    const int i = static_cast<int>(pw / hw);
+    const int win = win_list ? win_list[i] : win_first + i;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ch = 8 * gq + e;
+      const int tau = ch / C, c = ch - tau * C;
+      const bool take = tau <= 2 * order_k && ((tau == order_k) || (win == 0 && tau < order_k) ||
+                                               (win == win_last_global && tau > order_k));
+      v[e] = take ? __ldg(g + (static_cast<long long>(win + tau - frame_base) * hw + pix) * C + c) : 0.f;
+    }
+    *reinterpret_cast<uint4*>(cot + (static_cast<long long>(i) * hw + pix) * cpad + 8 * gq) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+// pos == null: the contiguous windows [win_first, win_first + n); else pos[j] = batch index of global window j or -1
+__global__ void unfold_adjoint_generic_kernel(const float* __restrict__ gin, float* __restrict__ vjp, int n, int n_frames,
+                                              int hw, int cpad, int C, int window, int win_first, int frame_base,
+                                              int n_win_global, const int* __restrict__ pos) {
+  const long long total = static_cast<long long>(n_frames) * hw * C;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % C);
+    const long long fp = idx / C;
+    const int pix = static_cast<int>(fp % hw);
+    const int fl = static_cast<int>(fp / hw);
+    const int fg = frame_base + fl;
+    float acc = 0.f;
+    for (int tau = 0; tau < window; ++tau) {
+      const int j = fg - tau;  // global window whose slot tau is this frame
+      int i;
+      if (pos) {
+        if (j < 0 || j >= n_win_global) continue;
+        i = pos[j];
+      } else {
+        i = j - win_first;
+        if (i >= n) i = -1;
+      }
+      if (i < 0) continue;
+      acc += gin[(static_cast<long long>(i) * hw + pix) * cpad + tau * C + c];
+    }
+    vjp[idx] += acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ K6 / K7
 // State layout: x, eps, z are fp32 [frames, H, W, 4] (one float4 per pixel).  Observation y: fp32 [n_obs, 4, Hs, Ws]
 // exactly as the reference builds it (exp/downscaling.py:129-132: every t_step-th frame, s x s tile means).

@@ -93,8 +93,6 @@ class _Runtime:
                  plan: ShardPlan, max_windows: int, exact: bool = False):
         if not 1 <= C <= 8:
             raise NotImplementedError(f"1 to 8 variables per frame (c2w_b200.h: C2W_MAX_VARS); got C={C}")
-        if C != 4 and exact:
-            raise NotImplementedError(f"exact_grad=True runs on the 4-variable path (the shipped configs); got C={C}")
         self.sf, self.L, self.C, self.H, self.W, self.device, self.plan = sf, L, C, H, W, device, plan
         self.lib = _lib.load()
         k = sf.markov_order

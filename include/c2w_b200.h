@@ -71,7 +71,7 @@ typedef struct c2w_guide {
                             mailboxes over NVLink and the last CTA publishes the step; complete with c2w_halo_pull  */
   int32_t halo_k;        /* Markov order k (frames per side)                                                       */
   int32_t channels;      /* C, variables per frame: 0 or 4 = the shipped configs (one float4 per pixel, every fused
-                            path); 1..8 otherwise run the generic kernels (no fused halo push, no exact_grad)      */
+                            path); 1..8 otherwise run the generic kernels (no fused halo push)                     */
 } c2w_guide;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------ */

@@ -688,9 +688,9 @@ def test_sampler_vs_reference_golden(dev, golden_dir):
 def test_other_variable_counts_vs_oracle(dev, C):
     """The reference's score functions and sampler are written for any number of variables per frame
     (src/thor/score.py:68-88, :111-154); the shipped configs have C = 4 (exp/downscaling.py:101), which is the fused
-    float4 path.  C != 4 runs the generic fold / guidance / corrector kernels: composed score, closed-form guided score
-    and a short predictor-corrector run against the fp32 oracle, same tolerances as the 4-variable tests; the fold is
-    index work -> chunk-invariant to the bit."""
+    float4 path.  C != 4 runs the generic fold / guidance / corrector / adjoint kernels: composed score, closed-form and
+    exact-gradient guided score and a short predictor-corrector run against the fp32 oracle, same tolerances as the
+    4-variable tests; the fold is index work -> chunk-invariant to the bit."""
     import climate2weather_b200 as c2w
     k, L, H, W = 2, 11, 32, 32
     cfg = dict(SMALL, channels=C * (2 * k + 1))
@@ -732,13 +732,17 @@ def test_other_variable_counts_vs_oracle(dev, C):
     es, ls = relerr(got_s, want_s), rel_l2(got_s, want_s)
     print(f"\nC={C}: score {e:.3e}, guided {eg:.3e}, sampler max-abs ratio {es:.3e} rel-L2 {ls:.3e}")
     assert got_s.shape == x.shape and es < 5e-2 and ls < 3e-2
-    # on-chip Philox noise: finite, and exact_grad is refused clearly for C != 4
+    # on-chip Philox noise: finite
     pipe2 = c2w.SDAPipeline()
     assert torch.isfinite(pipe2.sample(sf, x, steps=2, corrections=1, tau=0.5, show_progressbar=False, seed=3)).all()
-    sfe = c2w.DefaultScoreFunction(net, markov_order=k, noise_process=pipe2)
-    sfe.condition_on(A=c2w.CoarseGrain(3, 8), y=y, std=std, gamma=GAMMA, exact_grad=True)
-    with pytest.raises(NotImplementedError):
-        sfe(x.to(dev), t)
+    # exact_grad=True (gradient through the UNet, src/thor/score.py:28-35): one stashing chunk and several
+    want_e = score_ref.guided_score(ref, x, t, k, y, std, GAMMA, 3, 8, exact_grad=True)
+    for mw in (None, 2):
+        sfe = c2w.DefaultScoreFunction(net, markov_order=k, noise_process=pipe2)
+        sfe.max_windows = mw
+        sfe.condition_on(A=c2w.CoarseGrain(3, 8), y=y, std=std, gamma=GAMMA, exact_grad=True)
+        ee = relerr(sfe(x.to(dev), t).cpu(), want_e)
+        assert ee < 4e-2 and ee < 0.5 * relerr(want_g, want_e), (mw, ee)
 
 
 def test_per_sample_times_and_dsm_loss(dev, golden_dir):
