@@ -321,6 +321,31 @@ def test_bench_workload_selection():
     assert bench.pick_workload(A, 4) == ("config2-weak", 12 + 4 * 156, "weak", 0)
 
 
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the same metric, unit,
+    direction and workload part of `config` as our arm, `impl: reference`, a `cpu_baseline` describing the run, an `e2e`
+    equal to the line's value with zero copies — and exactly the steps / warm-up it was asked for (a bounded 13-window
+    step here so the test stays short)."""
+    import json
+    import subprocess
+
+    sys.path.insert(0, str(ROOT))
+    import bench
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-windows-ref", "13"], capture_output=True, text=True, timeout=600, cwd=str(ROOT))
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "guided-sampling frames/sec" and line["unit"] == "frames/s"
+    assert line["higher_is_better"] is True and line["steps"] == 1 and line["warmup"] == 0 and line["n_gpus"] == 1
+    ours = bench.workload_config("config2", 168, 1, 0, False)
+    assert {k: line["config"][k] for k in ours} == ours
+    assert line["config"]["windows_per_step"] == 13
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "13 of the 156 windows" in cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["value"] > 0 and line["ms_per_step"] > 0
+
+
 @pytest.mark.parametrize("L,k,t_step", [(13, 6, 6), (14, 6, 6), (25, 6, 6), (168, 6, 6), (40, 2, 3), (31, 3, 4), (720, 6, 6),
                                         (50, 6, 1), (50, 6, 7)])
 def test_observed_window_selection_is_exactly_the_fold_preimage_of_the_observed_frames(L, k, t_step):
